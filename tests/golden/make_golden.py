@@ -1,0 +1,177 @@
+"""Generate golden fixtures from the REAL reference (imported read-only from /root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+Reference commits: Flow-Factory a0b2bc5, diffusers submodule f7fd76a.  torch 2.11.0 CPU.
+Writes tests/golden/*.pt (small).  The oracle (oracle/sd3_oracle.py) and the CUDA engine are both
+checked against these files by the test-suite; nothing here is imported by the product.
+"""
+import os, sys, json, math
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [os.path.join(HERE, "ref_stubs"), "/root/reference/diffusers/src", "/root/reference/src", ROOT]
+
+import torch
+from diffusers.models.transformers.transformer_sd3 import SD3Transformer2DModel
+from flow_factory.scheduler import FlowMatchEulerDiscreteSDEScheduler, set_scheduler_timesteps
+from flow_factory.utils.trajectory_collector import (compute_trajectory_indices, create_trajectory_collector)
+from oracle import sd3_oracle as O
+
+torch.set_num_threads(8)
+
+
+def ref_model(cfg, weights, dtype):
+    m = SD3Transformer2DModel(**cfg.ref_kwargs())
+    missing, unexpected = m.load_state_dict(weights, strict=True), None
+    return m.to(dtype).eval()
+
+
+def golden_schedule():
+    out = {}
+    for T, seq in ((4, 256), (30, 4096), (10, 1024)):
+        s = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0, num_sde_steps=None, dynamics_type="Flow-SDE")
+        ts = set_scheduler_timesteps(s, T, seq_len=seq, device="cpu")
+        out[f"T{T}"] = dict(timesteps=ts.clone(), sigmas=s.sigmas.clone(), sde=s.current_sde_steps.clone())
+    for seed in (0, 42, 43):
+        for n in (1, 3):
+            s = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0, num_sde_steps=n, seed=seed)
+            set_scheduler_timesteps(s, 30, seq_len=4096, device="cpu")
+            out[f"sde_seed{seed}_n{n}"] = s.current_sde_steps.clone()
+            out[f"noise_levels_seed{seed}_n{n}"] = s.get_noise_levels().clone()
+    return out
+
+
+def golden_step():
+    """scheduler.step for the 4 dynamics, sampled + teacher-forced, incl. the sigma==1 first step."""
+    out = {}
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 16, 8, 8, generator=g).half()
+    v = torch.randn(2, 16, 8, 8, generator=g).bfloat16()
+    out["x"], out["v"] = x, v
+    for dyn in ("Flow-SDE", "Dance-SDE", "CPS", "ODE"):
+        s = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0, num_sde_steps=None, dynamics_type=dyn)
+        ts = set_scheduler_timesteps(s, 30, seq_len=4096, device="cpu")
+        for i in (0, 5, 28, 29):
+            t = ts[i]
+            tn = ts[i + 1] if i + 1 < len(ts) else torch.tensor(0.0)
+            nl = s.get_noise_level_for_timestep(t)
+            torch.manual_seed(123 + i)
+            r = s.step(noise_pred=v, timestep=t, latents=x, timestep_next=tn, noise_level=nl, compute_log_prob=True)
+            noise = torch.randn(v.shape, generator=torch.Generator().manual_seed(123 + i), dtype=torch.float32)
+            key = f"{dyn}_{i}"
+            out[key] = dict(t=t.clone(), tn=tn.clone(), nl=float(nl), noise=noise,
+                            next_latents=r.next_latents, mean=r.next_latents_mean, std=r.std_dev_t, dt=r.dt,
+                            log_prob=r.log_prob)
+            if dyn != "ODE" and nl > 0:  # teacher forced replay of a perturbed stored sample
+                stored = (r.next_latents + 0.01).half()
+                r2 = s.step(noise_pred=v, timestep=t, latents=x, timestep_next=tn, noise_level=nl,
+                            next_latents=stored, compute_log_prob=True)
+                out[key]["tf_next"] = stored
+                out[key]["tf_log_prob"] = r2.log_prob
+    return out
+
+
+def golden_forward():
+    """Tiny SD3.5-style transformer (dual layer 0, qk rms_norm): fp32 truth and bf16 CPU-autocast outputs."""
+    out = {}
+    cfg = O.tiny_config()
+    w32 = O.make_weights(cfg, seed=0)
+    inp = O.make_inputs(cfg, batch=2, lat_h=16, lat_w=16, n_text=13, seed=1)
+    t = torch.tensor([988.5, 250.0])
+    m32 = ref_model(cfg, w32, torch.float32)
+    with torch.no_grad():
+        y32 = m32(hidden_states=inp["x0"], timestep=t, encoder_hidden_states=inp["prompt_embeds"],
+                  pooled_projections=inp["pooled"], return_dict=False)[0]
+        mb = ref_model(cfg, w32, torch.bfloat16)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            yb = mb(hidden_states=inp["x0"].half(), timestep=t.half(),
+                    encoder_hidden_states=inp["prompt_embeds"].bfloat16(),
+                    pooled_projections=inp["pooled"].bfloat16(), return_dict=False)[0]
+    out["tiny"] = dict(t=t, y32=y32, y_bf16_cpu_autocast=yb, pos_embed=m32.pos_embed.pos_embed.clone(),
+                       keys=sorted(m32.state_dict().keys()))
+    # 3-layer config: 2 dual layers, last layer context_pre_only, non-square latent, 3 heads
+    cfg2 = O.tiny_config(num_layers=3, heads=3, dual=(0, 1), joint_dim=96, pooled_dim=48, pos_max=24, sample_size=32)
+    w2 = O.make_weights(cfg2, seed=5)
+    inp2 = O.make_inputs(cfg2, batch=1, lat_h=24, lat_w=16, n_text=21, seed=6)
+    t2 = torch.tensor([612.0])
+    m2 = ref_model(cfg2, w2, torch.float32)
+    with torch.no_grad():
+        y2 = m2(hidden_states=inp2["x0"], timestep=t2, encoder_hidden_states=inp2["prompt_embeds"],
+                pooled_projections=inp2["pooled"], return_dict=False)[0]
+    out["tiny3"] = dict(t=t2, y32=y2)
+    return out
+
+
+def golden_rollout():
+    """The loop body of SD3_5Adapter.inference/forward (sd3_5.py:266-304, 392-446) driven with the REAL
+    reference transformer + scheduler: T=4, CFG on, Flow-SDE, fp16 latent storage, bf16 CPU autocast and fp32."""
+    out = {}
+    cfg = O.tiny_config()
+    w32 = O.make_weights(cfg, seed=0)
+    inp = O.make_inputs(cfg, batch=2, lat_h=16, lat_w=16, n_text=13, seed=1)
+    T, gs = 4, 4.5
+    for mode in ("fp32", "bf16"):
+        dt = torch.float32 if mode == "fp32" else torch.bfloat16
+        m = ref_model(cfg, w32, dt)
+        s = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0, num_sde_steps=None, dynamics_type="Flow-SDE")
+        ts = set_scheduler_timesteps(s, T, seq_len=64, device="cpu")
+        s.rollout()
+        pe, pp = inp["prompt_embeds"].to(dt), inp["pooled"].to(dt)
+        npe, npp = inp["neg_prompt_embeds"].to(dt), inp["neg_pooled"].to(dt)
+        latents = inp["x0"].to(dt).half()                      # cast_latents -> fp16 storage
+        lat_list, lps, vps = [latents], {}, []
+        torch.manual_seed(123)
+        with torch.no_grad():
+            for i, t in enumerate(ts):
+                nl = s.get_noise_level_for_timestep(t)
+                tn = ts[i + 1] if i + 1 < len(ts) else torch.tensor(0.0)
+                timestep = t.expand(2).to(latents.dtype)
+                li = torch.cat([latents, latents]); ti = timestep.repeat(2)
+                pei = torch.cat([npe, pe]); ppi = torch.cat([npp, pp])
+                if mode == "bf16":
+                    with torch.autocast("cpu", dtype=torch.bfloat16):
+                        v = m(hidden_states=li, timestep=ti, encoder_hidden_states=pei, pooled_projections=ppi,
+                              return_dict=False)[0]
+                else:
+                    v = m(hidden_states=li.float(), timestep=ti, encoder_hidden_states=pei, pooled_projections=ppi,
+                          return_dict=False)[0]
+                vu, vc = v.chunk(2)
+                v = vu + gs * (vc - vu)
+                clp = nl > 0
+                r = s.step(noise_pred=v, timestep=t, latents=latents, timestep_next=tn, noise_level=nl,
+                           compute_log_prob=clp)
+                latents = r.next_latents.half()
+                lat_list.append(latents); vps.append(v)
+                if clp:
+                    lps[i] = r.log_prob
+        out[mode] = dict(latents=lat_list, log_probs=lps, noise_preds=vps, timesteps=ts.clone())
+    return out
+
+
+def golden_traj():
+    cases = []
+    for T in (4, 10, 30):
+        for idx in ([0], [2, 5, 8], [0, 1, 2], [T - 2], list(range(T - 1)), [T - 1]):
+            idx = [i for i in idx if i < T]
+            for inc in (False, True):
+                cases.append(dict(T=T, idx=idx, inc=inc, out=compute_trajectory_indices(idx, T, inc)))
+    maps = []
+    for T, ind in ((4, "all"), (4, None), (6, [0, -1]), (6, [1, 2, 5]), (30, [3, 4, 29, 30])):
+        c = create_trajectory_collector(ind, T)
+        for p in range(T + 1):
+            c.collect(torch.tensor(float(p)), p)
+        im = c.get_index_map()
+        res = c.get_result()
+        maps.append(dict(T=T, ind=ind, index_map=None if im is None else im.tolist(),
+                         collected=None if res is None else [float(x) for x in res]))
+    return dict(cases=cases, maps=maps)
+
+
+if __name__ == "__main__":
+    torch.save(golden_schedule(), os.path.join(HERE, "schedule.pt"))
+    torch.save(golden_step(), os.path.join(HERE, "sde_step.pt"))
+    torch.save(golden_forward(), os.path.join(HERE, "forward_tiny.pt"))
+    torch.save(golden_rollout(), os.path.join(HERE, "rollout_tiny.pt"))
+    with open(os.path.join(HERE, "trajectory.json"), "w") as f:
+        json.dump(golden_traj(), f)
+    print("golden written:", sorted(os.listdir(HERE)))
