@@ -1,0 +1,237 @@
+"""B200SD3_5Adapter - the drop-in for Flow-Factory's SD3_5Adapter on the rollout path.
+
+Mirrors FF/models/stable_diffusion/sd3_5.py: `inference()` (175-349, the trajectory sampler; `compute_log_prob`
+and `trajectory_indices` are keyword arguments exactly as in the reference) and `forward()` (352-448, one denoise
+step, optionally teacher-forced through `next_latents`).  Parameter names are the ABI: the trainers call these through
+`filter_kwargs(adapter.inference|forward, **kw)` (FF/utils/base.py:38-63, grpo.py:159-166, 242-263).
+
+What differs from the reference: the T-step loop runs inside the native engine with zero host synchronisation
+(the reference syncs >= 4 times per step: SURVEY.md section 3.2); CFG, the Euler/SDE update, the fp16 round trip,
+cast_latents' overflow clamp and the Gaussian log-prob are one kernel; kept latents/log-probs land directly in compact
+per-sample buffers.  `forward()` with autograd enabled is NOT served here (training replay stays on the reference's
+diffusers path - INTEGRATION.md); there is no CPU / PyTorch fallback for the rollout.
+"""
+from __future__ import annotations
+
+import inspect
+from typing import Any, Callable, Dict, List, Optional, Union
+
+import torch
+
+from . import _lib
+from .engine import RolloutEngine
+from .samples import SD3_5Sample
+from .scheduler import FlowMatchEulerDiscreteSDEScheduler, SDESchedulerOutput, set_scheduler_timesteps
+from .trajectory import TrajectoryIndicesType, compute_trajectory_indices, plan_slots
+from .weights import EngineConfig
+
+
+def filter_kwargs(fn: Callable, **kwargs) -> Dict[str, Any]:
+    """FF/utils/base.py:38-63: keep only the keyword arguments `fn` names."""
+    names = set(inspect.signature(fn).parameters)
+    return {k: v for k, v in kwargs.items() if k in names}
+
+
+class B200SD3_5Adapter:
+    """Construct from a transformer config + state dict (or `from_reference_adapter`)."""
+
+    def __init__(self, model_config, state_dict: Dict[str, torch.Tensor], device: Union[str, torch.device] = "cuda",
+                 scheduler: Optional[FlowMatchEulerDiscreteSDEScheduler] = None, latent_storage_dtype: str = "fp16",
+                 decode_fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, vae_scale_factor: int = 8,
+                 rng: str = "torch", use_graph: bool = True):
+        if latent_storage_dtype != "fp16":
+            raise ValueError("the fused step kernel stores latents as fp16 (Flow-Factory's default latent_storage_dtype)")
+        if rng not in ("torch", "philox"):
+            raise ValueError("rng must be 'torch' (reference-identical noise stream) or 'philox' (in-kernel)")
+        self.device = torch.device(device)
+        self.engine = RolloutEngine(model_config, state_dict, self.device)
+        self.model_config = self.engine.cfg
+        self.scheduler = scheduler or FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0, dynamics_type="Flow-SDE")
+        self.decode_fn = decode_fn
+        self.vae_scale_factor = vae_scale_factor
+        self.rng = rng
+        self.use_graph = use_graph
+        self._mode = "rollout"
+        self.overflow_seen = False
+
+    # -------------------------------------------------------------- construction from the reference objects
+    @classmethod
+    def from_reference_adapter(cls, ref_adapter, **kw) -> "B200SD3_5Adapter":
+        """`ref_adapter`: a flow_factory SD3_5Adapter; borrows its transformer weights, scheduler settings and VAE decode."""
+        tr = ref_adapter.transformer
+        tr = getattr(tr, "module", tr)
+        sched = ref_adapter.scheduler
+        mine = FlowMatchEulerDiscreteSDEScheduler(noise_level=sched.noise_level,
+                                                  sde_steps=None if sched._sde_steps is None else sched._sde_steps.tolist(),
+                                                  num_sde_steps=sched._num_sde_steps, seed=sched.seed,
+                                                  dynamics_type=sched.dynamics_type, **dict(sched.config))
+        return cls(tr.config, tr.state_dict(), device=ref_adapter.device, scheduler=mine,
+                   decode_fn=lambda lat: ref_adapter.decode_latents(lat, output_type="pt"), **kw)
+
+    def refresh_weights(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        self.engine.refresh_weights(state_dict)
+
+    # -------------------------------------------------------------- mode switches (FF/models/abc.py:356-378)
+    def rollout(self):
+        self._mode = "rollout"; self.scheduler.rollout()
+
+    def train(self):
+        self._mode = "train"; self.scheduler.train()
+
+    def eval(self):
+        self._mode = "eval"; self.scheduler.eval()
+
+    def cast_latents(self, latents: torch.Tensor, default_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+        """FF/models/abc.py:172-182, without the per-call host sync: clamp is a no-op unless something overflowed."""
+        if latents.dtype == torch.float16:
+            return latents
+        return latents.clamp(-65504.0, 65504.0).to(torch.float16)
+
+    def decode_latents(self, latents: torch.Tensor, output_type: str = "pt"):
+        if self.decode_fn is None:
+            return None
+        return self.decode_fn(latents)
+
+    # -------------------------------------------------------------- the trajectory sampler
+    @torch.no_grad()
+    def inference(
+        self,
+        prompt: Union[str, List[str], None] = None,
+        negative_prompt: Optional[Union[str, List[str]]] = None,
+        height: Optional[int] = 1024,
+        width: Optional[int] = 1024,
+        num_inference_steps: Optional[int] = 50,
+        guidance_scale: float = 7.5,
+        generator: Optional[torch.Generator] = None,
+        joint_attention_kwargs: Optional[Dict[str, Any]] = None,
+        prompt_ids: Optional[torch.Tensor] = None,
+        prompt_embeds: Optional[torch.Tensor] = None,
+        pooled_prompt_embeds: Optional[torch.Tensor] = None,
+        negative_prompt_ids: Optional[torch.Tensor] = None,
+        negative_prompt_embeds: Optional[torch.Tensor] = None,
+        negative_pooled_prompt_embeds: Optional[torch.Tensor] = None,
+        compute_log_prob: bool = True,
+        extra_call_back_kwargs: List[str] = [],
+        trajectory_indices: TrajectoryIndicesType = "all",
+        latents: Optional[torch.Tensor] = None,
+        noise: Optional[torch.Tensor] = None,
+    ) -> List[SD3_5Sample]:
+        if prompt_embeds is None or pooled_prompt_embeds is None:
+            raise ValueError("B200SD3_5Adapter.inference needs pre-encoded prompt_embeds / pooled_prompt_embeds "
+                             "(Flow-Factory's dataloader caches them; text encoders are outside the rollout path)")
+        if joint_attention_kwargs:
+            raise NotImplementedError("joint_attention_kwargs (IP-adapter / LoRA scale) are not on the accelerated path")
+        unsupported = set(extra_call_back_kwargs) - {"noise_pred", "next_latents_mean", "noise_level"}
+        if unsupported:
+            raise NotImplementedError(f"extra_call_back_kwargs {sorted(unsupported)} are not produced by the fused step")
+        if extra_call_back_kwargs:
+            raise NotImplementedError("per-step callbacks need the step-by-step path: call forward() in a loop")
+        dev = self.device
+        T = int(num_inference_steps)
+        do_cfg = guidance_scale > 1.0 and negative_prompt_embeds is not None and negative_pooled_prompt_embeds is not None
+        B = len(prompt_embeds)
+        C = self.model_config.in_channels
+        lh, lw = int(height) // self.vae_scale_factor, int(width) // self.vae_scale_factor
+        n_text = prompt_embeds.shape[1]
+        plan = self.engine.plan(B, do_cfg, lh, lw, n_text)
+        self.engine.set_prompts(plan, prompt_embeds, pooled_prompt_embeds,
+                                negative_prompt_embeds if do_cfg else None, negative_pooled_prompt_embeds if do_cfg else None)
+        # 3. initial latents: randn in the transformer dtype (pipeline_stable_diffusion_3.py:633-662), then cast_latents
+        if latents is None:
+            latents = torch.randn((B, C, lh, lw), generator=generator, device=dev, dtype=torch.bfloat16)
+        x0 = self.cast_latents(latents.to(dev))
+        # 5. schedule (host only, no device syncs)
+        seq_len = (lh // self.model_config.patch_size) * (lw // self.model_config.patch_size)
+        sch = self.scheduler
+        timesteps = set_scheduler_timesteps(sch, T, seq_len=seq_len)
+        sde_now = set(sch.current_sde_steps.tolist())
+        nls = [(sch.noise_level if (i in sde_now and not sch.is_eval) else 0.0) for i in range(T)]
+        has_lp = [bool(compute_log_prob and nls[i] > 0) for i in range(T)]
+        lat_slot, lp_slot, lat_map, lp_map = plan_slots(trajectory_indices, T, has_lp)
+        if not compute_log_prob:
+            lp_slot, lp_map = [-1] * T, None
+        coefs = []
+        for i in range(T):
+            t, tn = timesteps[i], (timesteps[i + 1] if i + 1 < T else torch.tensor(0.0))
+            t_model = float(t.to(torch.float16))                      # sd3_5.py:394: timestep cast to the latents dtype
+            coefs.append(sch.step_coef(t, tn, nls[i], compute_log_prob=has_lp[i], t_model=t_model,
+                                       store_slot=lat_slot[i + 1], logp_slot=lp_slot[i]))
+        n_lat = sum(1 for s in lat_slot if s >= 0)
+        n_lp = sum(1 for s in lp_slot if s >= 0)
+        # 6. noise: reference draws a full fp32 tensor from the device RNG EVERY step (flow_match...py:350-357)
+        if noise is None and self.rng == "torch" and sch.dynamics_type != "ODE":
+            noise = torch.stack([torch.randn((B, C, lh, lw), device=dev, dtype=torch.float32) for _ in range(T)])
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if noise is None else 0
+        r = self.engine.rollout(plan, x0, coefs, guidance_scale if do_cfg else 1.0, n_lat, lat_slot[0], n_lp,
+                                noise=noise, seed=seed, use_graph=self.use_graph)
+        final = r["final_latents"]
+        images = self.decode_latents(final, output_type="pt")
+        samples = []
+        for b in range(B):
+            samples.append(SD3_5Sample(
+                timesteps=timesteps,
+                all_latents=r["all_latents"][b, :n_lat] if n_lat else None,
+                log_probs=(r["log_probs"][b, :n_lp] if n_lp else (torch.zeros(0, device=dev) if compute_log_prob and lp_map is not None else None)),
+                latent_index_map=lat_map,
+                log_prob_index_map=lp_map if compute_log_prob else None,
+                prompt=prompt[b] if isinstance(prompt, list) else prompt,
+                prompt_ids=prompt_ids[b] if prompt_ids is not None else None,
+                prompt_embeds=prompt_embeds[b],
+                pooled_prompt_embeds=pooled_prompt_embeds[b],
+                negative_prompt=negative_prompt[b] if isinstance(negative_prompt, list) else negative_prompt,
+                negative_prompt_ids=negative_prompt_ids[b] if negative_prompt_ids is not None else None,
+                negative_prompt_embeds=negative_prompt_embeds[b] if negative_prompt_embeds is not None else None,
+                negative_pooled_prompt_embeds=negative_pooled_prompt_embeds[b] if negative_pooled_prompt_embeds is not None else None,
+                height=height, width=width,
+                image=images[b] if images is not None else None,
+                extra_kwargs={"callback_index_map": None, "final_latents": final[b]},
+            ))
+        self._last_overflow = r["overflow"]
+        return samples
+
+    # -------------------------------------------------------------- one denoise step
+    def forward(
+        self,
+        t: torch.Tensor,
+        latents: torch.Tensor,
+        prompt_embeds: torch.Tensor,
+        pooled_prompt_embeds: torch.Tensor,
+        negative_prompt_embeds: Optional[torch.Tensor] = None,
+        negative_pooled_prompt_embeds: Optional[torch.Tensor] = None,
+        guidance_scale: float = 7.5,
+        t_next: Optional[torch.Tensor] = None,
+        next_latents: Optional[torch.Tensor] = None,
+        noise_level: Optional[float] = None,
+        joint_attention_kwargs: Optional[Dict[str, Any]] = None,
+        compute_log_prob: bool = True,
+        return_kwargs: List[str] = ["noise_pred", "next_latents", "next_latents_mean", "std_dev_t", "dt", "log_prob"],
+        noise: Optional[torch.Tensor] = None,
+    ) -> SDESchedulerOutput:
+        if torch.is_grad_enabled() and any(isinstance(x, torch.Tensor) and x.requires_grad for x in (latents, prompt_embeds)):
+            raise RuntimeError("B200SD3_5Adapter.forward serves the no-grad path (rollout step, teacher-forced old-log-prob / "
+                               "KL-reference recompute). Keep the autograd replay on the reference adapter (INTEGRATION.md).")
+        if joint_attention_kwargs:
+            raise NotImplementedError("joint_attention_kwargs are not on the accelerated path")
+        do_cfg = negative_prompt_embeds is not None and negative_pooled_prompt_embeds is not None and guidance_scale > 1.0
+        B, C, lh, lw = latents.shape
+        plan = self.engine.plan(B, do_cfg, lh, lw, prompt_embeds.shape[1])
+        self.engine.set_prompts(plan, prompt_embeds, pooled_prompt_embeds, negative_prompt_embeds if do_cfg else None,
+                                negative_pooled_prompt_embeds if do_cfg else None)
+        sch = self.scheduler
+        t0 = t if isinstance(t, torch.Tensor) else torch.tensor(float(t))
+        t0 = t0.flatten()[0].detach().cpu().float()
+        if t_next is None:
+            i = sch.index_for_timestep(t0)
+            t_next = sch.timesteps[i + 1] if i + 1 < len(sch.timesteps) else torch.tensor(0.0)
+        tn = (t_next if isinstance(t_next, torch.Tensor) else torch.tensor(float(t_next))).flatten()[0].detach().cpu().float()
+        coef = sch.step_coef(t0, tn, noise_level, compute_log_prob=compute_log_prob, t_model=float(t0.to(latents.dtype)))
+        if noise is None and next_latents is None and self.rng == "torch" and sch.dynamics_type != "ODE":
+            noise = torch.randn(latents.shape, device=self.device, dtype=torch.float32)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if noise is None else 0
+        r = self.engine.step(plan, latents, coef, guidance_scale if do_cfg else 1.0, noise=noise, next_latents=next_latents,
+                             seed=seed, want_mean="next_latents_mean" in return_kwargs)
+        d = dict(next_latents=(next_latents.float() if next_latents is not None else r["next_latents"].float()),
+                 next_latents_mean=r["next_latents_mean"], log_prob=r["log_prob"], noise_pred=r["noise_pred"],
+                 std_dev_t=torch.full((B, 1, 1, 1), coef.std_dev_t, dtype=torch.float32, device=self.device),
+                 dt=torch.full((B, 1, 1, 1), coef.dt, dtype=torch.float32, device=self.device))
+        return SDESchedulerOutput.from_dict({k: d[k] for k in return_kwargs if k in d})

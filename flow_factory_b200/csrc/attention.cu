@@ -1,0 +1,271 @@
+// tcgen05 / TMEM flash attention for the MMDiT joint (image+text) attention, head_dim 64, non-causal.
+//
+// Replaces F.scaled_dot_product_attention at DF/models/attention_processor.py:1484 together with the
+// torch.cat of image/text q,k,v (1480-1482) and the head transposes (1451-1452, 1485): q, k, v are read
+// straight out of the fused-QKV GEMM's token-major [B, S, 3D] buffer with 3-D TMA boxes (one per head),
+// so there is no concat copy and no [B,H,S,d] transpose in HBM.
+//
+// One CTA per (128 query rows, head, batch):
+//   warps 0-3 : softmax + output accumulation; thread == query row == TMEM lane (no shuffles)
+//   warp  4   : TMA producer (Q once; K/V ring of kStages 128x64 tiles)
+//   warp  5   : MMA issuer  (S = Q K^T : M128 N128 K64 ; O_part = P V : M128 N64 K128, V as MN-major operand)
+// S is double-buffered in TMEM so QK^T of tile j+1 runs on the tensor core while the softmax warps
+// work on tile j; P (bf16) goes through shared memory in the canonical 128B-swizzled K-major layout.
+// The running output lives in registers (fp32) and is rescaled FA2-style per KV tile.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ffb {
+
+constexpr int ATT_BM = 128;     // query rows per CTA
+constexpr int ATT_BN = 128;     // kv rows per tile
+constexpr int ATT_D = 64;
+constexpr int ATT_STAGES = 3;
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
+constexpr int ATT_SMEM = ATT_TILE_BYTES /*Q*/ + 2 * ATT_STAGES * ATT_TILE_BYTES /*K,V*/ + 2 * 2 * ATT_TILE_BYTES /*P x2*/ +
+                         1024 + 512;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATT_TILE_BYTES;
+  uint8_t* sV = sK + ATT_STAGES * ATT_TILE_BYTES;
+  uint8_t* sP = sV + ATT_STAGES * ATT_TILE_BYTES;  // [2 buffers][2 k-atoms][128 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;                       // 1
+  uint64_t* k_full = bars + 1;                   // [ST]
+  uint64_t* k_empty = k_full + ATT_STAGES;       // [ST]
+  uint64_t* v_full = k_empty + ATT_STAGES;       // [ST]
+  uint64_t* v_empty = v_full + ATT_STAGES;       // [ST]
+  uint64_t* s_full = v_empty + ATT_STAGES;       // [2]
+  uint64_t* s_empty = s_full + 2;                // [2]
+  uint64_t* p_full = s_empty + 2;                // [2]
+  uint64_t* o_full = p_full + 2;                 // [2]
+  uint64_t* o_empty = o_full + 2;                // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BM;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int S = p.seq_len;
+  const int n_tiles = (S + ATT_BN - 1) / ATT_BN;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&p.tmQKV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < ATT_STAGES; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tS = tmem_base;         // S buffers at columns 0 / 128
+  const uint32_t tO = tmem_base + 256;   // O_part buffers at columns 256 / 320
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int cq = head * ATT_D, ck = p.inner_dim + head * ATT_D, cv = 2 * p.inner_dim + head * ATT_D;
+      mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_3d(sQ, &p.tmQKV, q_full, cq, q0, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % ATT_STAGES;
+        const uint32_t ph = (j / ATT_STAGES) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1, 0x40);
+        mbar_arrive_expect_tx(&k_full[st], ATT_TILE_BYTES);
+        tma_load_3d(sK + st * ATT_TILE_BYTES, &p.tmQKV, &k_full[st], ck, j * ATT_BN, b);
+        mbar_wait(&v_empty[st], ph ^ 1, 0x41);
+        mbar_arrive_expect_tx(&v_full[st], ATT_TILE_BYTES);
+        tma_load_3d(sV + st * ATT_TILE_BYTES, &p.tmQKV, &v_full[st], cv, j * ATT_BN, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);  // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);   // P (K-major) x V (MN-major)
+      const uint32_t q_addr = smem_u32(sQ);
+      auto issue_qk = [&](int j) {
+        const int st = j % ATT_STAGES;
+        const uint32_t ph = (j / ATT_STAGES) & 1;
+        const int sb = j & 1;
+        mbar_wait(&k_full[st], ph, 0x50);
+        mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1, 0x51);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_bf16(tS + sb * ATT_BN, desc_kmajor_sw128(q_addr + k * 32), desc_kmajor_sw128(k_addr + k * 32), idesc_s,
+                    k != 0 ? 1u : 0u);
+        umma_commit(&s_full[sb]);
+        umma_commit(&k_empty[st]);
+      };
+      mbar_wait(q_full, 0, 0x52);
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_qk(j + 1);
+        const int st = j % ATT_STAGES;
+        const uint32_t ph = (j / ATT_STAGES) & 1;
+        const int pb = j & 1;
+        const uint32_t pph = (j >> 1) & 1;
+        mbar_wait(&v_full[st], ph, 0x53);
+        mbar_wait(&p_full[pb], pph, 0x54);
+        mbar_wait(&o_empty[pb], pph ^ 1, 0x55);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(sP + pb * 2 * ATT_TILE_BYTES);
+        const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; ++k) {
+          // P: two 64-wide K atoms (16 KB apart), 32 B per K=16 step inside an atom.  V: 16 kv rows = 2048 B per step.
+          const uint64_t da = desc_kmajor_sw128(p_addr + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32);
+          const uint64_t db = desc_mnmajor_sw128(v_addr + k * 2048, ATT_TILE_BYTES);
+          umma_bf16(tO + pb * ATT_D, da, db, idesc_o, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&o_full[pb]);
+        umma_commit(&v_empty[st]);
+      }
+    }
+  } else {
+    // ===================== softmax / accumulate (warps 0-3) =====================
+    const int r = warp * 32 + lane;                 // query row in tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const float sc = p.scale_log2;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o_acc[ATT_D];
+#pragma unroll
+    for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.f;
+    float alpha_prev = 0.f;
+
+    auto softmax_tile = [&](int j) -> float {
+      const int sb = j & 1;
+      mbar_wait(&s_full[sb], (j >> 1) & 1, 0x60);
+      tc_fence_after();
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      tmem_ld32(tS + lane_off + sb * ATT_BN + 0, s0);
+      tmem_ld32(tS + lane_off + sb * ATT_BN + 32, s1);
+      tmem_ld32(tS + lane_off + sb * ATT_BN + 64, s2);
+      tmem_ld32(tS + lane_off + sb * ATT_BN + 96, s3);
+      tmem_ld_wait();
+      // S buffer is free for QK^T of tile j+2
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sb]);
+
+      const int kv_valid = S - j * ATT_BN;  // >= 1
+      float mx = m_run;
+      auto max32 = [&](uint32_t(&a)[32], int base) {
+        if (kv_valid < ATT_BN) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (base + c >= kv_valid) a[c] = 0xFF800000u;  // -inf: key beyond the sequence
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(a[c]));
+      };
+      max32(s0, 0); max32(s1, 32); max32(s2, 64); max32(s3, 96);
+      const float alpha = ex2_approx((m_run - mx) * sc);
+      const float mneg = -mx * sc;
+      float sum = 0.f;
+      uint8_t* prow = sP + sb * 2 * ATT_TILE_BYTES + r * 128;
+      auto exp32 = [&](uint32_t(&a)[32], int quarter) {
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {   // 16-byte chunks of 8 kv columns
+          float e[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            e[t] = ex2_approx(fmaf(__uint_as_float(a[c4 * 8 + t]), sc, mneg));
+            sum += e[t];
+          }
+          uint4 o;
+          o.x = pack_bf16x2(e[0], e[1]); o.y = pack_bf16x2(e[2], e[3]);
+          o.z = pack_bf16x2(e[4], e[5]); o.w = pack_bf16x2(e[6], e[7]);
+          const int ch = quarter * 4 + c4;
+          const int atom = ch >> 3, cc = ch & 7;
+          *reinterpret_cast<uint4*>(prow + atom * ATT_TILE_BYTES + ((cc ^ (r & 7)) << 4)) = o;
+        }
+      };
+      exp32(s0, 0); exp32(s1, 1); exp32(s2, 2); exp32(s3, 3);
+      l_run = l_run * alpha + sum;
+      m_run = mx;
+      fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[sb]);
+      return alpha;
+    };
+
+    alpha_prev = softmax_tile(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      float alpha_next = 0.f;
+      if (j + 1 < n_tiles) alpha_next = softmax_tile(j + 1);
+      const int ob = j & 1;
+      mbar_wait(&o_full[ob], (j >> 1) & 1, 0x61);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld32(tO + lane_off + ob * ATT_D + 0, o0);
+      tmem_ld32(tO + lane_off + ob * ATT_D + 32, o1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[ob]);
+      // invariant: o_acc = sum_{i<j} P_i V_i relative to the running max M_{j-1}; O_part_j is relative to M_j;
+      // alpha_prev == alpha_j = exp2((M_{j-1} - M_j) * scale).
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        o_acc[i] = o_acc[i] * alpha_prev + __uint_as_float(o0[i]);
+        o_acc[32 + i] = o_acc[32 + i] * alpha_prev + __uint_as_float(o1[i]);
+      }
+      alpha_prev = alpha_next;
+    }
+    // o_acc and l_run are both relative to the final running max m_run.
+    const int q = q0 + r;
+    if (q < S) {
+      const float inv = 1.0f / l_run;
+      bf16* dst = p.out + static_cast<long>(b) * p.out_batch_stride + static_cast<long>(q) * p.inner_dim + head * ATT_D;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 o;
+        o.x = pack_bf16x2(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
+        o.y = pack_bf16x2(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
+        o.z = pack_bf16x2(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv);
+        o.w = pack_bf16x2(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
+        reinterpret_cast<uint4*>(dst)[c] = o;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((p.seq_len + ATT_BM - 1) / ATT_BM, p.num_heads, p.batch);
+  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace ffb

@@ -1,0 +1,425 @@
+// HBM-bound pieces of the denoise step (coalesced 16-byte vector access, warp-shuffle reductions):
+//   ln_modulate      : LayerNorm(no affine) + adaLN-Zero modulate            (normalization.py:120-126,167-169,348-351)
+//   small_linear     : skinny-batch Linear (timestep/pooled MLPs, all-layer adaLN GEMV)  (embeddings.py:1294-1306,2213-2217)
+//   timestep_proj    : 256-ch sinusoid                                        (embeddings.py:26-77)
+//   patchify         : im2col for the 2x2 stride-2 patch-embed conv           (embeddings.py:559)
+//   sde_step         : CFG combine + Euler/SDE update + noise + fp16 round-trip + Gaussian log-prob
+//                      (sd3_5.py:431-433 ; flow_match_euler_discrete.py:309-420 ; abc.py:172-182)
+#include "common.cuh"
+#include "kernels.h"
+#include <algorithm>
+
+namespace ffb {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm + modulate.  One warp per token row, row kept in registers (D <= 2048, D % 8 == 0).
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_MAXC = 8;  // 16-byte chunks per lane
+
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rows = p.rows_per_batch * p.num_batch;
+  if (warp >= rows) return;
+  const int b = warp / p.rows_per_batch;
+  const int nchunk = p.D >> 3;
+  const bf16* xr = p.x + static_cast<long>(warp) * p.D;
+  float v[LN_MAXC][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXC; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunk) {
+      const uint4 u = *reinterpret_cast<const uint4*>(xr + c * 8);
+      unpack8(u, v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += v[i][e];
+    }
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(p.D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXC; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunk) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; sq += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(p.D) + p.eps);
+  const long mo = static_cast<long>(b) * p.mod_batch_stride;
+#pragma unroll
+  for (int i = 0; i < LN_MAXC; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunk) {
+      float y[8], sc[8], sh[8], o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = (v[i][e] - mean) * rstd;
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.scale1 + mo + c * 8)), sc);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.shift1 + mo + c * 8)), sh);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = __fadd_rn(__fmul_rn(y[e], bf16_round(1.0f + sc[e])), sh[e]);
+      *reinterpret_cast<uint4*>(p.out1 + static_cast<long>(warp) * p.D + c * 8) = pack8(o);
+      if (p.out2 != nullptr) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p.scale2 + mo + c * 8)), sc);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p.shift2 + mo + c * 8)), sh);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __fadd_rn(__fmul_rn(y[e], bf16_round(1.0f + sc[e])), sh[e]);
+        *reinterpret_cast<uint4*>(p.out2 + static_cast<long>(warp) * p.D + c * 8) = pack8(o);
+      }
+    }
+  }
+}
+
+cudaError_t launch_ln_modulate(const LnModParams& p, cudaStream_t stream) {
+  if (p.D % 8 != 0 || p.D > LN_MAXC * 32 * 8) return cudaErrorInvalidValue;
+  const long rows = static_cast<long>(p.rows_per_batch) * p.num_batch;
+  const int wpb = 8;
+  const int grid = static_cast<int>((rows + wpb - 1) / wpb);
+  ln_modulate_kernel<<<grid, wpb * 32, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// small_linear: out[b, n] = bf16(bf16(acc + bias) + addend), batch <= 32 handled 8 rows at a time;
+// one warp per output feature n; weights streamed once per batch chunk with 16-byte loads.
+// ------------------------------------------------------------------------------------------------
+constexpr int SL_BCHUNK = 8;
+constexpr int SL_WARPS = 8;
+
+__global__ void __launch_bounds__(SL_WARPS * 32) small_linear_kernel(const SmallLinearParams p) {
+  extern __shared__ __align__(16) uint8_t sl_smem[];
+  bf16* xin = reinterpret_cast<bf16*>(sl_smem);  // [SL_BCHUNK][K]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * SL_WARPS + warp;
+  const int b0 = blockIdx.y * SL_BCHUNK;
+  const int nb = min(SL_BCHUNK, p.batch - b0);
+  const int kc = p.K >> 3;
+  for (int i = threadIdx.x; i < nb * kc; i += blockDim.x) {
+    const int bb = i / kc, c = i % kc;
+    uint4 u = *reinterpret_cast<const uint4*>(p.in + static_cast<long>(b0 + bb) * p.in_stride + c * 8);
+    if (p.silu_input) {
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = __fdividef(f[e], 1.0f + __expf(-f[e]));  // F.silu, then bf16
+      u = pack8(f);
+    }
+    *reinterpret_cast<uint4*>(xin + bb * p.K + c * 8) = u;
+  }
+  __syncthreads();
+  if (n >= p.N) return;
+  float acc[SL_BCHUNK];
+#pragma unroll
+  for (int i = 0; i < SL_BCHUNK; ++i) acc[i] = 0.f;
+  const bf16* wr = p.W + static_cast<long>(n) * p.K;
+  for (int c = lane; c < kc; c += 32) {
+    float wf[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(wr + c * 8)), wf);
+#pragma unroll
+    for (int bb = 0; bb < SL_BCHUNK; ++bb) {
+      if (bb < nb) {
+        float xf[8];
+        unpack8(*reinterpret_cast<const uint4*>(xin + bb * p.K + c * 8), xf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[bb] = fmaf(wf[e], xf[e], acc[bb]);
+      }
+    }
+  }
+#pragma unroll
+  for (int bb = 0; bb < SL_BCHUNK; ++bb) acc[bb] = warp_sum(acc[bb]);
+  if (lane == 0) {
+    const float bias = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
+    for (int bb = 0; bb < nb; ++bb) {
+      float y = bf16_round(acc[bb] + bias);
+      if (p.addend) y = y + __bfloat162float(p.addend[static_cast<long>(b0 + bb) * p.addend_stride + n]);
+      p.out[static_cast<long>(b0 + bb) * p.out_stride + n] = __float2bfloat16_rn(y);
+    }
+  }
+}
+
+cudaError_t launch_small_linear(const SmallLinearParams& p, cudaStream_t stream) {
+  if (p.K % 8 != 0) return cudaErrorInvalidValue;
+  const int smem = SL_BCHUNK * p.K * 2;
+  static int max_smem = 48 * 1024;
+  if (smem > max_smem) {
+    cudaError_t e = cudaFuncSetAttribute(small_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    max_smem = smem;
+  }
+  dim3 grid((p.N + SL_WARPS - 1) / SL_WARPS, (p.batch + SL_BCHUNK - 1) / SL_BCHUNK);
+  small_linear_kernel<<<grid, SL_WARPS * 32, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// timestep sinusoid: out[b, 0:128] = cos(t * f_i), out[b, 128:256] = sin(t * f_i), f_i = exp(-ln(1e4) * i / 128)
+// ------------------------------------------------------------------------------------------------
+__global__ void timestep_proj_kernel(const StepCoef* table, const int* step_ptr, int index, int batch, bf16* out) {
+  const int i = threadIdx.x;  // 0..127
+  const float t = table[step_ptr ? *step_ptr : index].t_model;
+  const float exponent = (-9.210340371976184f * static_cast<float>(i)) / 128.0f;
+  const float f = expf(exponent);
+  const float a = t * f;
+  const bf16 c = __float2bfloat16_rn(cosf(a)), s = __float2bfloat16_rn(sinf(a));
+  for (int b = 0; b < batch; ++b) {
+    out[b * 256 + i] = c;
+    out[b * 256 + 128 + i] = s;
+  }
+}
+cudaError_t launch_timestep_proj(const StepCoef* table, const int* step_ptr, int index, int batch, bf16* out, cudaStream_t stream) {
+  timestep_proj_kernel<<<1, 128, 0, stream>>>(table, step_ptr, index, batch, out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// patchify (im2col): out[(r*B + b)*Ni + i*wp + j][c*p*p + py*p + px] = bf16(x[b, c, i*p+py, j*p+px])
+// ------------------------------------------------------------------------------------------------
+__global__ void patchify_kernel(const __half* x, int B, int reps, int C, int H, int W, int patch, bf16* out) {
+  const int hp = H / patch, wp = W / patch;
+  const int KK = C * patch * patch;
+  const long total = static_cast<long>(B) * hp * wp * KK;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(idx % KK);
+    const long tok = idx / KK;
+    const int j = static_cast<int>(tok % wp);
+    const int i = static_cast<int>((tok / wp) % hp);
+    const int b = static_cast<int>(tok / (static_cast<long>(wp) * hp));
+    const int px = k % patch, py = (k / patch) % patch, c = k / (patch * patch);
+    const float v = __half2float(x[((static_cast<long>(b) * C + c) * H + i * patch + py) * W + j * patch + px]);
+    const bf16 o = __float2bfloat16_rn(v);
+    for (int r = 0; r < reps; ++r)
+      out[((static_cast<long>(r) * B + b) * hp * wp + static_cast<long>(i) * wp + j) * KK + k] = o;
+  }
+}
+cudaError_t launch_patchify(const __half* x, int B, int reps, int C, int H, int W, int patch, bf16* out, cudaStream_t stream) {
+  const long total = static_cast<long>(B) * (H / patch) * (W / patch) * C * patch * patch;
+  const int grid = static_cast<int>(std::min<long>((total + 255) / 256, 148 * 8));
+  patchify_kernel<<<grid, 256, 0, stream>>>(x, B, reps, C, H, W, patch, out);
+  return cudaGetLastError();
+}
+
+__global__ void cast_f32_bf16_kernel(const float* in, bf16* out, long n) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+cudaError_t launch_cast_f32_to_bf16(const float* in, bf16* out, long n, cudaStream_t stream) {
+  const int grid = static_cast<int>(std::min<long>((n + 255) / 256, 148 * 16));
+  cast_f32_bf16_kernel<<<grid, 256, 0, stream>>>(in, out, n);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller (counter = element-quad index, step; key = seed)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ void box_muller(uint32_t u0, uint32_t u1, float* z0, float* z1) {
+  const float a = (static_cast<float>(u0) + 1.0f) * 2.3283064365386963e-10f;  // (0, 1]
+  const float b = static_cast<float>(u1) * 2.3283064365386963e-10f;           // [0, 1)
+  const float rad = sqrtf(-2.0f * logf(a));
+  float s, c;
+  sincosf(6.283185307179586f * b, &s, &c);
+  *z0 = rad * c; *z1 = rad * s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused CFG + Euler/SDE step + log-prob.  Each thread owns 4 consecutive pixels of one (b, c, y) row.
+// ------------------------------------------------------------------------------------------------
+constexpr int SDE_THREADS = 256;
+
+__global__ void __launch_bounds__(SDE_THREADS) sde_step_kernel(const SdeStepParams p) {
+  const int sidx = p.step_ptr ? *p.step_ptr : p.coef_index;
+  const StepCoef k = p.coef_table[sidx];
+  const int b = blockIdx.y;
+  const float* noise = p.noise ? p.noise + static_cast<long>(sidx) * p.noise_step_stride : nullptr;
+  __half* traj = (p.traj != nullptr && k.store_slot >= 0) ? p.traj + static_cast<long>(b) * p.traj_batch_stride + static_cast<long>(k.store_slot) * (p.C * p.H * p.W) : nullptr;
+  const int CHW = p.C * p.H * p.W;
+  const int quads = CHW >> 2;
+  float part = 0.f;
+  const int hp = p.H / p.patch, wp = p.W / p.patch;
+  const int ntok = hp * wp;
+  const int vch = p.patch * p.patch * p.C;
+  for (int qd = blockIdx.x * SDE_THREADS + threadIdx.x; qd < quads; qd += gridDim.x * SDE_THREADS) {
+    const int e0 = qd << 2;
+    const int x0 = e0 % p.W;
+    const int y = (e0 / p.W) % p.H;
+    const int c = e0 / (p.W * p.H);
+    const long base = static_cast<long>(b) * CHW + e0;
+    // ---- noise prediction (with CFG) ----
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float vc;
+      if (p.v_tokens != nullptr) {
+        const int xx = x0 + i;
+        const int tok = (y / p.patch) * wp + xx / p.patch;
+        const int n = ((y % p.patch) * p.patch + (xx % p.patch)) * p.C + c;   // "nhwpqc"
+        if (p.cfg) {
+          const float vu = __bfloat162float(p.v_tokens[(static_cast<long>(b) * ntok + tok) * vch + n]);
+          const float vt = __bfloat162float(p.v_tokens[(static_cast<long>(p.B + b) * ntok + tok) * vch + n]);
+          vc = bf16_round(vu + bf16_round(p.guidance * bf16_round(vt - vu)));
+        } else {
+          vc = __bfloat162float(p.v_tokens[(static_cast<long>(b) * ntok + tok) * vch + n]);
+        }
+      } else {
+        vc = __bfloat162float(p.v_direct[base + i]);
+      }
+      v[i] = vc;
+    }
+    // ---- current latents ----
+    const uint2 xr = *reinterpret_cast<const uint2*>(p.x + base);
+    const __half2 xa = *reinterpret_cast<const __half2*>(&xr.x), xb = *reinterpret_cast<const __half2*>(&xr.y);
+    const float xs[4] = {__low2float(xa), __high2float(xa), __low2float(xb), __high2float(xb)};
+    // ---- mean ----
+    float mean[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (k.dynamics == DYN_ODE) {
+        mean[i] = __fadd_rn(xs[i], __fmul_rn(v[i], k.dt));
+      } else if (k.dynamics == DYN_FLOW_SDE) {
+        mean[i] = __fadd_rn(__fmul_rn(xs[i], k.c_x), __fmul_rn(__fmul_rn(v[i], k.c_v), k.dt));
+      } else if (k.dynamics == DYN_DANCE_SDE) {
+        const float x0p = __fsub_rn(xs[i], __fmul_rn(k.sigma, v[i]));
+        const float num = __fmul_rn(k.c_x /* 0.5*eta^2 */, __fsub_rn(xs[i], __fmul_rn(x0p, k.c_v /* 1-sigma */)));
+        const float lt = __fdiv_rn(num, __fmul_rn(k.sigma, k.sigma));
+        mean[i] = __fadd_rn(xs[i], __fmul_rn(__fadd_rn(v[i], lt), k.dt));
+      } else {  // CPS
+        const float x0p = __fsub_rn(xs[i], __fmul_rn(k.sigma, v[i]));
+        const float x1p = __fadd_rn(xs[i], __fmul_rn(v[i], k.c_v /* 1-sigma */));
+        mean[i] = __fadd_rn(__fmul_rn(x0p, k.cps_a), __fmul_rn(x1p, k.cps_b));
+      }
+    }
+    // ---- next sample ----
+    float nxt[4];
+    if (p.next_given != nullptr) {
+      const uint2 nr = *reinterpret_cast<const uint2*>(p.next_given + base);
+      const __half2 na = *reinterpret_cast<const __half2*>(&nr.x), nb = *reinterpret_cast<const __half2*>(&nr.y);
+      nxt[0] = __low2float(na); nxt[1] = __high2float(na); nxt[2] = __low2float(nb); nxt[3] = __high2float(nb);
+    } else if (k.dynamics == DYN_ODE) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) nxt[i] = mean[i];
+    } else {
+      float z[4];
+      if (noise != nullptr) {
+        const float4 nz = *reinterpret_cast<const float4*>(noise + base);
+        z[0] = nz.x; z[1] = nz.y; z[2] = nz.z; z[3] = nz.w;
+      } else {
+        uint32_t r[4];
+        philox4x32_10(static_cast<uint32_t>(qd), static_cast<uint32_t>(b), static_cast<uint32_t>(sidx), 0x5DEu,
+                      static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32), r);
+        box_muller(r[0], r[1], &z[0], &z[1]);
+        box_muller(r[2], r[3], &z[2], &z[3]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float s = __fadd_rn(mean[i], __fmul_rn(k.noise_scale, z[i]));
+        nxt[i] = __half2float(__float2half_rn(s));  // .to(storage dtype).float()  (flow_match...py:362)
+      }
+    }
+    // ---- store (cast_latents: clamp to +-65504 on overflow) ----
+    if (p.x_next != nullptr || traj != nullptr) {
+      __half h[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float s = nxt[i];
+        if (fabsf(s) > 65504.0f) { s = copysignf(65504.0f, s); if (p.overflow_flag) *p.overflow_flag = 1; }
+        h[i] = __float2half_rn(s);
+      }
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&h[0]);
+      o.y = *reinterpret_cast<uint32_t*>(&h[2]);
+      if (p.x_next) *reinterpret_cast<uint2*>(p.x_next + base) = o;
+      if (traj) *reinterpret_cast<uint2*>(traj + e0) = o;
+    }
+    if (p.mean_out) *reinterpret_cast<float4*>(p.mean_out + base) = make_float4(mean[0], mean[1], mean[2], mean[3]);
+    if (p.v_out) {
+      uint2 vo;
+      vo.x = pack_bf16x2(v[0], v[1]); vo.y = pack_bf16x2(v[2], v[3]);
+      *reinterpret_cast<uint2*>(p.v_out + base) = vo;
+    }
+    // ---- log-prob terms ----
+    if (k.compute_log_prob && k.dynamics != DYN_ODE) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float d = __fsub_rn(nxt[i], mean[i]);
+        const float d2 = __fmul_rn(d, d);
+        if (k.dynamics == DYN_CPS) part += -d2;
+        else part += __fdiv_rn(-d2, k.two_var /* = 2*var */);
+      }
+    }
+  }
+  // block reduce -> logp_partial[b, blockIdx.x]
+  if (k.compute_log_prob && p.logp_partial != nullptr) {
+    __shared__ float red[SDE_THREADS / 32];
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < SDE_THREADS / 32; ++i) t += red[i];
+      p.logp_partial[b * gridDim.x + blockIdx.x] = t;
+    }
+  }
+}
+
+// One block: per-sample deterministic reduction of the block partials, normaliser, slot stores, step advance.
+__global__ void sde_finalize_kernel(const SdeStepParams p, int nblk) {
+  const int sidx = p.step_ptr ? *p.step_ptr : p.coef_index;
+  const StepCoef k = p.coef_table[sidx];
+  const int chw = p.C * p.H * p.W;
+  if (k.compute_log_prob) {
+    for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
+      float lp = 0.f;
+      if (k.dynamics != DYN_ODE) {
+        float t = 0.f;
+        for (int i = 0; i < nblk; ++i) t += p.logp_partial[b * nblk + i];
+        lp = t / static_cast<float>(chw) - k.log_norm;
+      }
+      if (p.log_prob) p.log_prob[b] = lp;
+      if (p.logp_traj && k.logp_slot >= 0) p.logp_traj[b * p.logp_batch_stride + k.logp_slot] = lp;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && p.step_ptr) *p.step_ptr = sidx + 1;
+}
+
+constexpr int SDE_MAX_BLOCKS = 64;
+
+cudaError_t launch_sde_step(const SdeStepParams& p, cudaStream_t stream) {
+  if (p.W % 4 != 0) return cudaErrorInvalidValue;
+  const int quads = p.C * p.H * p.W / 4;
+  int nblk = (quads + SDE_THREADS - 1) / SDE_THREADS;
+  if (nblk > SDE_MAX_BLOCKS) nblk = SDE_MAX_BLOCKS;
+  dim3 grid(nblk, p.B);
+  sde_step_kernel<<<grid, SDE_THREADS, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  sde_finalize_kernel<<<1, 32, 0, stream>>>(p, nblk);
+  e = cudaGetLastError();
+  return e;
+}
+
+}  // namespace ffb

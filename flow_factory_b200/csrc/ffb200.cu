@@ -1,0 +1,5 @@
+// Single translation unit of libffb200.so (keeps the device error word and helper templates in one module).
+#include "gemm.cu"
+#include "attention.cu"
+#include "elementwise.cu"
+#include "engine.cu"

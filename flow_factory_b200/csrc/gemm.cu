@@ -1,0 +1,292 @@
+// tcgen05 / TMEM / TMA bf16 GEMM for the MMDiT linears:  out = epilogue( A[M,K] * W[N,K]^T )
+//
+// Replaces every nn.Linear / Conv2d(k=s=patch) call site on the hot path
+// (DF/models/attention_processor.py:1443-1445,1461-1463,1495-1498; attention.py:1731; activations.py:87-90;
+//  transformers/transformer_sd3.py:293,327; embeddings.py:559) with one persistent warp-specialised kernel:
+//   warp 0    : TMA producer   (A tile 128x64, W tile BNx64, SWIZZLE_128B, mbarrier ring)
+//   warp 1    : MMA issuer     (one thread, tcgen05.mma cta_group::1 kind::f16, M=128 N=BN K=16, fp32 accum in TMEM)
+//   warp 2    : TMEM allocator
+//   warps 4-7 : epilogue       (tcgen05.ld 32x32b -> registers; thread == accumulator row; fused bias /
+//                               GELU-tanh / adaLN gate + residual / per-head RMSNorm(q,k) / row-table add; bf16 stores)
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// A is addressed as a 3-D tensor [batch][rows_per_batch][K] so that token sub-ranges of a joint
+// [B, S, D] buffer (image rows / text rows) are separate GEMM problems with zero-filled ragged tails.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ffb {
+
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN> struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
+  static constexpr int kBBytes = BN * GEMM_BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // 0.5*x*(1+tanh(u)) == x * sigmoid(2u), u = sqrt(2/pi)*(x + 0.044715 x^3)   (F.gelu(approximate='tanh'))
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return __fdividef(x, 1.0f + __expf(-2.0f * u));
+}
+
+// 8 consecutive bf16 (16-B aligned) -> fp32
+__device__ __forceinline__ void load8_bf16(const bf16* ptr, float* f) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(ptr));
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+template <int N8>
+__device__ __forceinline__ void load_vec_bf16(const bf16* ptr, float* f) {
+  if (ptr == nullptr) {
+#pragma unroll
+    for (int i = 0; i < N8 * 8; ++i) f[i] = 0.f;
+  } else {
+#pragma unroll
+    for (int i = 0; i < N8; ++i) load8_bf16(ptr + i * 8, f + i * 8);
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                          // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;          // [kStages]
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;      // [2]
+  uint64_t* tmem_empty = bars + 2 * Cfg::kStages + 2; // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int tiles_m = p.num_batch * p.tiles_m_per_batch;
+  const int tiles_n = p.N / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile % tiles_m, tn = tile / tiles_m;
+        const int b = tm / p.tiles_m_per_batch, row0 = (tm % p.tiles_m_per_batch) * GEMM_BM;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 0x10);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_3d(smem_a + stage * Cfg::kABytes, &p.tmA, &full_bar[stage], kb * GEMM_BK, row0, b);
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.tmB, &full_bar[stage], kb * GEMM_BK, tn * BN);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 0x20);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 0x21);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            umma_bf16(d_tmem, desc_kmajor_sw128(a_addr + k * 32), desc_kmajor_sw128(b_addr + k * 32), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                 // smem slot free once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;                 // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    const int r_in_tile = ew * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int tm = tile % tiles_m, tn = tile / tiles_m;
+      const int b = tm / p.tiles_m_per_batch;
+      const int row = (tm % p.tiles_m_per_batch) * GEMM_BM + r_in_tile;
+      const bool row_ok = row < p.rows_per_batch;
+      mbar_wait(&tmem_full[acc], acc_phase, 0x30);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+      bf16* out_row = p.out + static_cast<long>(b) * p.out_batch_stride + static_cast<long>(p.out_row_offset + row) * p.ldo;
+
+      if (p.epi == EPI_QKV_RMSNORM) {
+        // 64 columns == one attention head per step; q/k heads get RMSNorm (normalization.py:553-561)
+        for (int c = 0; c < BN / 64; ++c) {
+          const int n0 = tn * BN + c * 64;
+          uint32_t r0[32], r1[32];
+          tmem_ld32(t_row + c * 64, r0);
+          tmem_ld32(t_row + c * 64 + 32, r1);
+          tmem_ld_wait();
+          float v[64];
+          float ss = 0.f;
+          load_vec_bf16<8>(p.bias ? p.bias + n0 : nullptr, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = bf16_round(__uint_as_float(r0[j]) + v[j]);
+            v[32 + j] = bf16_round(__uint_as_float(r1[j]) + v[32 + j]);
+          }
+          const int which = n0 / p.qk_dim;   // 0 = q, 1 = k, 2 = v
+          if (which < 2) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) ss += v[j] * v[j];
+            const float rs = rsqrtf(ss * (1.0f / 64.0f) + p.eps);
+            const bf16* wn = which == 0 ? p.norm_q : p.norm_k;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float wf[8];
+              load8_bf16(wn + q * 8, wf);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[q * 8 + e] = bf16_round(v[q * 8 + e] * rs) * wf[e];
+            }
+          }
+          if (row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(out_row + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              uint4 o;
+              o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+              o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+              o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+              o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+              dst[q] = o;
+            }
+          }
+        }
+      } else {
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n0 = tn * BN + c * 32;
+          uint32_t r[32];
+          tmem_ld32(t_row + c * 32, r);
+          tmem_ld_wait();
+          float v[32];
+          load_vec_bf16<4>(p.bias ? p.bias + n0 : nullptr, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = bf16_round(__uint_as_float(r[j]) + v[j]);
+          if (p.epi == EPI_BIAS_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+          } else if (p.epi == EPI_GATE_RESIDUAL) {
+            // h = h + gate[b,:] * y   in bf16 steps (attention.py:711-712, 726-728)
+            const bf16* g = p.gate + static_cast<long>(b) * p.gate_batch_stride + n0;
+            if (row_ok) {
+              const uint4* hsrc = reinterpret_cast<const uint4*>(out_row + n0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 h4 = hsrc[q];
+                const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
+                float gf[8];
+                load8_bf16(g + q * 8, gf);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int j = q * 8 + e * 2;
+                  v[j] = bf16_lo(hw[e]) + bf16_round(gf[e * 2] * v[j]);
+                  v[j + 1] = bf16_hi(hw[e]) + bf16_round(gf[e * 2 + 1] * v[j + 1]);
+                }
+              }
+            }
+          } else if (p.epi == EPI_BIAS_ADD_ROWTABLE) {
+            // (latent + pos_embed).to(latent.dtype)   (embeddings.py:583)
+            if (row_ok) {
+              const float* t = p.row_table + static_cast<long>(row) * p.N + n0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = v[j] + t[j];
+            }
+          }
+          if (row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(out_row + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+              o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+              o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+              o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+              dst[q] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN>
+static cudaError_t launch_bn(const GemmParams& p, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int tiles = p.num_batch * p.tiles_m_per_batch * (p.N / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(p);
+  return cudaGetLastError();
+}
+
+int gemm_pick_bn(int N) { return (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : 64); }
+
+cudaError_t launch_gemm(const GemmParams& p, int num_sms, cudaStream_t stream) {
+  switch (p.bn) {
+    case 256: return launch_bn<256>(p, num_sms, stream);
+    case 128: return launch_bn<128>(p, num_sms, stream);
+    case 64: return launch_bn<64>(p, num_sms, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace ffb

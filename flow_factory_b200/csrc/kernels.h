@@ -1,0 +1,138 @@
+// Internal launch interfaces shared by the .cu files and the C-ABI layer (capi.cu / engine.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace ffb {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------ GEMM
+enum GemmEpilogue : int {
+  EPI_BIAS = 0,               // out = bf16(acc + bias)
+  EPI_BIAS_GELU = 1,          // out = bf16(gelu_tanh(bf16(acc + bias)))
+  EPI_GATE_RESIDUAL = 2,      // out = bf16(out + bf16(gate[b,:] * bf16(acc + bias)))      (in place on the residual stream)
+  EPI_QKV_RMSNORM = 3,        // fused q|k|v projection: per-head RMSNorm on the q and k column blocks
+  EPI_BIAS_ADD_ROWTABLE = 4,  // out = bf16(bf16(acc + bias) + table[row, :])             (patch-embed + pos-embed)
+};
+
+struct GemmParams {
+  CUtensorMap tmA;  // 3-D {K, rows_per_batch, num_batch}, box {64, 128, 1}, SWIZZLE_128B
+  CUtensorMap tmB;  // 2-D {K, N},                          box {64, bn},    SWIZZLE_128B
+  int rows_per_batch, num_batch, N, K;
+  int tiles_m_per_batch;
+  int bn;   // N tile: 256 / 128 / 64 (must divide N)
+  int epi;
+  const bf16* bias;  // [N] or null
+  bf16* out;         // out[b*out_batch_stride + (out_row_offset + row)*ldo + n]
+  long out_batch_stride;
+  int out_row_offset;
+  int ldo;
+  const bf16* gate;  // EPI_GATE_RESIDUAL: gate[b*gate_batch_stride + n]
+  long gate_batch_stride;
+  const bf16* norm_q;  // EPI_QKV_RMSNORM: [64] weights for the q / k column blocks
+  const bf16* norm_k;
+  int qk_dim;        // width of each of the q|k|v column blocks (= inner_dim)
+  float eps;
+  const float* row_table;  // EPI_BIAS_ADD_ROWTABLE: fp32 [rows_per_batch, N]
+};
+
+int gemm_pick_bn(int N);
+cudaError_t launch_gemm(const GemmParams& p, int num_sms, cudaStream_t stream);
+
+// ------------------------------------------------------------------ attention
+struct AttnParams {
+  CUtensorMap tmQKV;  // 3-D {3*D, S, B}, box {64, 128, 1}, SWIZZLE_128B over the joint qkv buffer [B, S, 3D]
+  int seq_len;        // S (q and kv length)
+  int num_heads;      // H
+  int inner_dim;      // D = 64*H
+  int batch;
+  bf16* out;          // [B, S, D]
+  long out_batch_stride;
+  float scale_log2;   // (1/sqrt(64)) * log2(e)
+};
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
+
+// ------------------------------------------------------------------ per-step scalars
+enum Dynamics : int { DYN_FLOW_SDE = 0, DYN_DANCE_SDE = 1, DYN_CPS = 2, DYN_ODE = 3 };
+
+// Per-step scalars, computed on the host in fp32 exactly as the reference's (B,1,1,1) tensors are.
+struct StepCoef {
+  float t_model;      // fp16-rounded timestep fed to the sinusoid (sd3_5.py:394)
+  float sigma, sigma_prev, dt, noise_level, std_dev_t;
+  float c_x;          // Flow-SDE: 1 + std^2/(2 sigma) * dt
+  float c_v;          // Flow-SDE: 1 + std^2 (1-sigma)/(2 sigma)
+  float noise_scale;  // std_dev_t * sqrt(-dt)   (CPS: std_dev_t)
+  float two_var;      // 2 * noise_scale^2 (per-element divisor of the Gaussian log-density)
+  float log_norm;     // log(noise_scale) + log(sqrt(2 pi))   (0 for CPS)
+  float cps_a, cps_b; // CPS: (1 - sigma_prev), sqrt(sigma_prev^2 - std^2)
+  int dynamics;
+  int compute_log_prob;
+  int store_slot;     // index into all_latents for the *result* of this step, or -1
+  int logp_slot;      // index into log_probs for this step, or -1
+};
+
+// ------------------------------------------------------------------ elementwise / small ops
+// LayerNorm (no affine, eps) + adaLN modulate: out = bf16( LN(x) * bf16(1 + scale[b]) + shift[b] ), up to two outputs.
+struct LnModParams {
+  const bf16* x;    // [num_batch * rows_per_batch, D]
+  int rows_per_batch, num_batch, D;
+  float eps;
+  const bf16* shift1; const bf16* scale1; bf16* out1;  // vectors: ptr + b*mod_batch_stride
+  const bf16* shift2; const bf16* scale2; bf16* out2;  // optional second modulation (SD35AdaLayerNormZeroX)
+  long mod_batch_stride;
+};
+cudaError_t launch_ln_modulate(const LnModParams& p, cudaStream_t stream);
+
+// out[b, n] = bf16( bf16(sum_k in'[b,k] * W[n,k] + bias[n]) (+ addend[b,n]) ),  in' = silu(in) if silu_input
+struct SmallLinearParams {
+  const bf16* in; int batch; int K; long in_stride;
+  const bf16* W; const bf16* bias; int N;
+  bf16* out; long out_stride;
+  const bf16* addend; long addend_stride;  // optional
+  int silu_input;
+};
+cudaError_t launch_small_linear(const SmallLinearParams& p, cudaStream_t stream);
+
+// sinusoidal timestep projection (embeddings.py:26-77, flip_sin_to_cos, shift 0) -> bf16 [batch, 256]
+cudaError_t launch_timestep_proj(const StepCoef* table, const int* step_ptr, int index, int batch, bf16* out, cudaStream_t stream);
+
+// im2col for the 2x2/stride-2 patch-embed conv: fp16 latents [B,C,H,W] -> bf16 [Bp*Ni, C*p*p] (Bp = B*reps)
+cudaError_t launch_patchify(const __half* x, int B, int reps, int C, int H, int W, int patch, bf16* out, cudaStream_t stream);
+
+// cast helpers
+cudaError_t launch_cast_f32_to_bf16(const float* in, bf16* out, long n, cudaStream_t stream);
+
+// ------------------------------------------------------------------ fused Euler/SDE step + log-prob (K14)
+
+struct SdeStepParams {
+  const bf16* v_tokens;   // [Bp*Ni, p*p*C] proj_out rows (token-major, "nhwpqc"), uncond half first when cfg
+  const bf16* v_direct;   // alternatively an NCHW bf16 noise_pred [B,C,H,W] (op-level entry); one of the two
+  int B, C, H, W, patch;
+  int cfg;                // 1: v = vu + g*(vc - vu) in bf16 steps (sd3_5.py:431-433)
+  float guidance;
+  const __half* x;        // [B,C,H,W] fp16 current latents
+  const float* noise;     // fp32 N(0,1) [(steps,) B,C,H,W] or null -> in-kernel Philox4x32-10 + Box-Muller
+  long noise_step_stride; // elements between steps (0 for a single step)
+  unsigned long long seed;
+  const __half* next_given; // teacher-forced next latents (fp16) or null
+  __half* x_next;         // [B,C,H,W] fp16 (next_latents rounded to storage dtype, +-65504 clamp); may alias x
+  __half* traj;           // all_latents base [B, n_slots, C,H,W] or null; slot = coef.store_slot
+  long traj_batch_stride; // elements
+  float* mean_out;        // optional fp32 next_latents_mean or null
+  bf16* v_out;            // optional bf16 [B,C,H,W] noise_pred after CFG or null
+  float* logp_partial;    // [B, SDE_MAX_BLOCKS] scratch
+  float* log_prob;        // direct [B] output or null
+  float* logp_traj;       // log_probs base [B, n_logp_slots] or null; slot = coef.logp_slot
+  int logp_batch_stride;
+  int* overflow_flag;     // sticky fp16-overflow flag (cast_latents, abc.py:172-182)
+  const StepCoef* coef_table;
+  int* step_ptr;          // device step counter (entry = *step_ptr, incremented by the finalize kernel) or null
+  int coef_index;         // used when step_ptr == null
+};
+cudaError_t launch_sde_step(const SdeStepParams& p, cudaStream_t stream);
+
+}  // namespace ffb

@@ -1,0 +1,172 @@
+/* ffb200 - C ABI of the B200-native rollout engine for Flow-Factory's SD3.5 path.
+ *
+ * Plain C: pointers and sizes only, no torch / C++ types.  Every entry point returns 0 on success,
+ * a positive cudaError_t, or a negative engine code; ffb200_last_error() returns the message.
+ * All device pointers are borrowed for the duration of the call and used on `stream`
+ * (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *
+ * Each function names the reference interface it replaces (paths relative to /root/reference;
+ * FF = src/flow_factory, DF = diffusers/src/diffusers).  The reference is pure Python, so the
+ * "FFI" a maintainer adds is a ctypes binding - see INTEGRATION.md and flow_factory_b200/_lib.py.
+ */
+#ifndef FFB200_H
+#define FFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFB200_ABI_VERSION 1
+
+/* ---------------------------------------------------------------- errors */
+const char* ffb200_last_error(void);
+/* Reads (and clears) the device-side error word written by a kernel before it trapped. */
+int ffb200_device_error(unsigned int out[4]);
+int ffb200_abi_version(void);
+
+/* ---------------------------------------------------------------- model description
+ * DF/models/transformers/transformer_sd3.py:117-141 (register_to_config arguments). head_dim must be 64. */
+typedef struct ffb200_model_config {
+  int num_layers;
+  int num_heads;           /* inner_dim D = 64 * num_heads */
+  int patch_size;          /* 2 */
+  int in_channels;         /* 16 (== out_channels) */
+  int joint_attention_dim; /* 4096 */
+  int pooled_projection_dim; /* 2048 */
+  int pos_embed_max_size;  /* 384 */
+  int num_dual_layers;     /* layers [0, num_dual_layers) carry attn2 (SD3.5: 13) */
+} ffb200_model_config;
+
+/* Per-layer weights, bf16, row-major [out_features, in_features] exactly as nn.Linear stores them.
+ * q|k|v projections are concatenated along out_features (host side: torch.cat at load / refresh time). */
+typedef struct ffb200_layer_weights {
+  const void *qkv_w, *qkv_b, *norm_q, *norm_k;             /* attn.to_{q,k,v}, attn.norm_{q,k}            */
+  const void *add_qkv_w, *add_qkv_b, *norm_added_q, *norm_added_k; /* attn.add_{q,k,v}_proj, norm_added_* */
+  const void *out_w, *out_b;                               /* attn.to_out.0                               */
+  const void *add_out_w, *add_out_b;                       /* attn.to_add_out (NULL on the last layer)    */
+  const void *qkv2_w, *qkv2_b, *norm_q2, *norm_k2, *out2_w, *out2_b; /* attn2.* (NULL if not dual)        */
+  const void *ff1_w, *ff1_b, *ff2_w, *ff2_b;               /* ff.net.0.proj, ff.net.2                     */
+  const void *cff1_w, *cff1_b, *cff2_w, *cff2_b;           /* ff_context.* (NULL on the last layer)       */
+} ffb200_layer_weights;
+
+typedef struct ffb200_weights {
+  const void *pe_w, *pe_b;      /* pos_embed.proj as [D, C*p*p], [D]                                       */
+  const float* pos_embed;       /* fp32 [pos_embed_max_size^2, D]                                         */
+  const void *t1_w, *t1_b, *t2_w, *t2_b; /* time_text_embed.timestep_embedder.linear_{1,2}               */
+  const void *p1_w, *p1_b, *p2_w, *p2_b; /* time_text_embed.text_embedder.linear_{1,2}                   */
+  const void *ctx_w, *ctx_b;    /* context_embedder                                                       */
+  /* all adaLN projections stacked row-wise: for each layer [norm1.linear ; norm1_context.linear], then norm_out.linear */
+  const void *mod_w, *mod_b;
+  const void *proj_w, *proj_b;  /* proj_out                                                               */
+  const ffb200_layer_weights* layers; /* [num_layers] */
+} ffb200_weights;
+
+typedef struct ffb200_engine ffb200_engine;
+typedef struct ffb200_plan ffb200_plan;
+
+/* Replaces BaseAdapter.load_pipeline()'s transformer for the rollout path (FF/models/abc.py:185-188;
+ * FF/models/stable_diffusion/sd3_5.py:60-120).  Weight pointers are borrowed and may be refreshed with
+ * ffb200_engine_set_weights() after an optimizer / EMA / LoRA-merge step. */
+int ffb200_engine_create(const ffb200_model_config* cfg, const ffb200_weights* w, ffb200_engine** out);
+int ffb200_engine_set_weights(ffb200_engine* e, const ffb200_weights* w);
+void ffb200_engine_destroy(ffb200_engine* e);
+/* total rows of the stacked adaLN matrix (for the host-side packer) */
+int ffb200_engine_mod_rows(const ffb200_engine* e);
+
+/* A plan fixes the geometry (batch, CFG on/off, latent H x W, text tokens) and owns the workspace + TMA descriptors. */
+int ffb200_plan_create(ffb200_engine* e, int batch, int cfg, int lat_h, int lat_w, int n_text, ffb200_plan** out);
+void ffb200_plan_destroy(ffb200_plan* p);
+long long ffb200_plan_workspace_bytes(const ffb200_plan* p);
+
+/* Prompt conditioning for the next forward()/rollout() calls: bf16 [Bp, n_text, joint_dim] and [Bp, pooled_dim]
+ * with Bp = batch * (cfg ? 2 : 1), negative (unconditional) half FIRST (sd3_5.py:409-413).  Runs context_embedder
+ * and the pooled-text MLP once (they do not depend on the timestep). */
+int ffb200_plan_set_prompts(ffb200_plan* p, const void* prompt_embeds_bf16, const void* pooled_bf16, void* stream);
+
+/* Per-step scalars computed on the host in fp32 exactly as FlowMatchEulerDiscreteSDEScheduler.step builds its
+ * (B,1,1,1) tensors (FF/scheduler/flow_match_euler_discrete.py:299-420).  Filled by flow_factory_b200.scheduler. */
+typedef struct ffb200_step_coef {
+  float t_model;
+  float sigma, sigma_prev, dt, noise_level, std_dev_t;
+  float c_x, c_v, noise_scale, two_var, log_norm, cps_a, cps_b;
+  int dynamics;          /* 0 Flow-SDE, 1 Dance-SDE, 2 CPS, 3 ODE */
+  int compute_log_prob;
+  int store_slot;        /* slot of all_latents receiving this step's result, or -1 */
+  int logp_slot;         /* slot of log_probs receiving this step's log-prob, or -1 */
+} ffb200_step_coef;
+
+/* SD3Transformer2DModel.forward + CFG batching (DF/models/transformers/transformer_sd3.py:249-345;
+ * sd3_5.py:409-428): latents fp16 [B,C,H,W] -> proj_out rows bf16 [Bp*Ni, p*p*C] (token-major, pre-unpatchify).
+ * `noise_pred_nchw` (optional, bf16 [Bp,C,H,W]) receives the unpatchified prediction for inspection. */
+int ffb200_transformer_forward(ffb200_plan* p, const void* latents_fp16, float t_model, void* noise_pred_nchw, void* stream);
+
+/* SD3_5Adapter.forward under no_grad (sd3_5.py:352-448): one denoise step = transformer + CFG + scheduler.step. */
+typedef struct ffb200_step_args {
+  const void* latents;        /* fp16 [B,C,H,W] */
+  ffb200_step_coef coef;
+  float guidance_scale;
+  const float* noise;         /* fp32 [B,C,H,W] or NULL (in-kernel Philox) */
+  unsigned long long seed;
+  int step_index;
+  const void* next_latents;   /* teacher-forced fp16 [B,C,H,W] or NULL */
+  void* out_next_latents;     /* fp16 [B,C,H,W] or NULL */
+  float* out_mean;            /* fp32 [B,C,H,W] or NULL */
+  float* out_log_prob;        /* fp32 [B] or NULL */
+  void* out_noise_pred;       /* bf16 [B,C,H,W] (after CFG) or NULL */
+  int* overflow_flag;         /* device int or NULL */
+} ffb200_step_args;
+int ffb200_step(ffb200_plan* p, const ffb200_step_args* a, void* stream);
+
+/* SD3_5Adapter.inference's denoising loop (sd3_5.py:266-304): T steps, no host sync inside.
+ * all_latents: fp16 [B, n_latent_slots, C,H,W]; log_probs: fp32 [B, n_logp_slots]. */
+typedef struct ffb200_rollout_args {
+  int num_steps;
+  const ffb200_step_coef* coefs;  /* host array [num_steps] */
+  float guidance_scale;
+  const void* x0;                 /* fp16 [B,C,H,W] (already cast to the storage dtype) */
+  const float* noise;             /* fp32 [num_steps,B,C,H,W] or NULL -> in-kernel Philox keyed by (seed, step) */
+  unsigned long long seed;
+  void* all_latents; int n_latent_slots; int store_initial_slot; /* slot for position 0 or -1 */
+  float* log_probs; int n_logp_slots;
+  void* final_latents;            /* fp16 [B,C,H,W] */
+  int* overflow_flag;
+  int use_graph;                  /* 1: replay one captured per-step CUDA graph */
+} ffb200_rollout_args;
+int ffb200_rollout(ffb200_plan* p, const ffb200_rollout_args* a, void* stream);
+/* Same, but every pointer in `a` (and the prompts) is a HOST buffer: copies in/out are part of the call. */
+int ffb200_rollout_host(ffb200_plan* p, const ffb200_rollout_args* a, const void* prompt_embeds_bf16,
+                        const void* pooled_bf16, void* stream);
+/* number of kernels the last ffb200_rollout / ffb200_step / ffb200_transformer_forward launched */
+long long ffb200_last_launch_count(void);
+
+/* ---------------------------------------------------------------- op-level entries (one reference call site each) */
+/* nn.Linear + fused epilogue. A: bf16 [num_batch][rows_per_batch][K] (row stride lda, batch stride a_batch_stride, in
+ * elements); W: bf16 [N,K]; epilogue: 0 bias, 1 bias+GELU-tanh, 2 gate*y + residual (in place), 3 fused qkv + RMSNorm,
+ * 4 bias + fp32 row table. */
+int ffb200_linear(const void* A, int num_batch, int rows_per_batch, long long a_batch_stride, int lda, int K,
+                  const void* W, int N, const void* bias, void* out, long long out_batch_stride, int out_row_offset,
+                  int ldo, int epilogue, const void* gate, long long gate_batch_stride, const void* norm_q,
+                  const void* norm_k, int qk_dim, float eps, const float* row_table, void* stream);
+/* F.scaled_dot_product_attention over a fused token-major qkv buffer bf16 [B, S, 3*64*H] -> out bf16 [B, S, 64*H]
+ * (DF/models/attention_processor.py:1480-1486). */
+int ffb200_attention(const void* qkv, int batch, int seq_len, int num_heads, void* out, void* stream);
+/* LayerNorm(no affine) * (1 + scale) + shift  (DF/models/normalization.py:120-126). vectors: [num_batch, *] with stride. */
+int ffb200_ln_modulate(const void* x, int num_batch, int rows_per_batch, int D, float eps, const void* shift1,
+                       const void* scale1, void* out1, const void* shift2, const void* scale2, void* out2,
+                       long long mod_batch_stride, void* stream);
+/* skinny-batch nn.Linear (optionally SiLU on the input, optional bf16 addend). */
+int ffb200_small_linear(const void* in, int batch, int K, long long in_stride, const void* W, const void* bias, int N,
+                        void* out, long long out_stride, const void* addend, long long addend_stride, int silu_input,
+                        void* stream);
+/* FlowMatchEulerDiscreteSDEScheduler.step on an NCHW bf16 noise_pred (FF/scheduler/flow_match_euler_discrete.py:243-438). */
+int ffb200_sde_step(const void* noise_pred_bf16, const void* latents_fp16, int B, int C, int H, int W,
+                    const ffb200_step_coef* coef, const float* noise, unsigned long long seed, int step_index,
+                    const void* next_latents_fp16, void* out_next_fp16, float* out_mean, float* out_log_prob,
+                    int* overflow_flag, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFB200_H */

@@ -91,21 +91,25 @@ def sincos_pos_embed_2d(embed_dim: int, grid_size: int, base_size: int, interpol
 # ----------------------------------------------------------------------------------------------
 # Deterministic random-init weights with diffusers state-dict key names
 # ----------------------------------------------------------------------------------------------
-def make_weights(cfg: SD3Config, seed: int = 0, dtype: torch.dtype = torch.float32) -> Dict[str, torch.Tensor]:
+def make_weights(cfg: SD3Config, seed: int = 0, dtype: torch.dtype = torch.float32, device: str = "cpu") -> Dict[str, torch.Tensor]:
     """Random weights (seeded, checkpoint-independent) keyed like SD3Transformer2DModel.state_dict().
-    Scale ~ 1/sqrt(fan_in) keeps activations O(1) through 24 layers; adaLN rows get a smaller scale."""
-    g = torch.Generator().manual_seed(seed)
+    Scale ~ 1/sqrt(fan_in) keeps activations O(1) through 24 layers; adaLN rows get a smaller scale.
+    `device='cuda'` draws from a CUDA generator (different stream than CPU; used only for full-size GPU tests)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    _randn = torch.randn
+    def randn(*shape, generator=None):
+        return _randn(*shape, generator=generator, device=device)
     D = cfg.inner_dim
     w: Dict[str, torch.Tensor] = {}
 
     def lin(name: str, out_f: int, in_f: int, scale: float = 1.0, bias_std: float = 0.02):
-        w[name + ".weight"] = torch.randn(out_f, in_f, generator=g) * (scale / math.sqrt(in_f))
-        w[name + ".bias"] = torch.randn(out_f, generator=g) * bias_std
+        w[name + ".weight"] = randn(out_f, in_f, generator=g) * (scale / math.sqrt(in_f))
+        w[name + ".bias"] = randn(out_f, generator=g) * bias_std
 
     p = cfg.patch_size
-    w["pos_embed.proj.weight"] = torch.randn(D, cfg.in_channels, p, p, generator=g) / math.sqrt(cfg.in_channels * p * p)
-    w["pos_embed.proj.bias"] = torch.randn(D, generator=g) * 0.02
-    w["pos_embed.pos_embed"] = sincos_pos_embed_2d(D, cfg.pos_embed_max_size, cfg.sample_size // p).unsqueeze(0)
+    w["pos_embed.proj.weight"] = randn(D, cfg.in_channels, p, p, generator=g) / math.sqrt(cfg.in_channels * p * p)
+    w["pos_embed.proj.bias"] = randn(D, generator=g) * 0.02
+    w["pos_embed.pos_embed"] = sincos_pos_embed_2d(D, cfg.pos_embed_max_size, cfg.sample_size // p).unsqueeze(0).to(device)
     lin("time_text_embed.timestep_embedder.linear_1", D, 256)
     lin("time_text_embed.timestep_embedder.linear_2", D, D)
     lin("time_text_embed.text_embedder.linear_1", D, cfg.pooled_projection_dim)
@@ -120,14 +124,14 @@ def make_weights(cfg: SD3Config, seed: int = 0, dtype: torch.dtype = torch.float
         for a in (["attn", "attn2"] if dual else ["attn"]):
             for nm in ("to_q", "to_k", "to_v"):
                 lin(pre + f"{a}.{nm}", D, D)
-            w[pre + f"{a}.norm_q.weight"] = 1.0 + 0.1 * torch.randn(cfg.attention_head_dim, generator=g)
-            w[pre + f"{a}.norm_k.weight"] = 1.0 + 0.1 * torch.randn(cfg.attention_head_dim, generator=g)
+            w[pre + f"{a}.norm_q.weight"] = 1.0 + 0.1 * randn(cfg.attention_head_dim, generator=g)
+            w[pre + f"{a}.norm_k.weight"] = 1.0 + 0.1 * randn(cfg.attention_head_dim, generator=g)
             lin(pre + f"{a}.to_out.0", D, D)
             if a == "attn":
                 for nm in ("add_q_proj", "add_k_proj", "add_v_proj"):
                     lin(pre + f"attn.{nm}", D, D)
-                w[pre + "attn.norm_added_q.weight"] = 1.0 + 0.1 * torch.randn(cfg.attention_head_dim, generator=g)
-                w[pre + "attn.norm_added_k.weight"] = 1.0 + 0.1 * torch.randn(cfg.attention_head_dim, generator=g)
+                w[pre + "attn.norm_added_q.weight"] = 1.0 + 0.1 * randn(cfg.attention_head_dim, generator=g)
+                w[pre + "attn.norm_added_k.weight"] = 1.0 + 0.1 * randn(cfg.attention_head_dim, generator=g)
                 if not last:
                     lin(pre + "attn.to_add_out", D, D)
         lin(pre + "ff.net.0.proj", 4 * D, D)

@@ -1,0 +1,56 @@
+"""Helpers for the -m gpu parity tests: call the C ABI through ctypes on torch-owned device memory."""
+import ctypes as C
+import json
+import os
+
+import torch
+
+from flow_factory_b200 import _lib
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def dump(name, obj):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, name), "w") as f:
+        json.dump(obj, f, indent=1, default=lambda o: o.tolist() if hasattr(o, "tolist") else str(o))
+
+
+def err_report(got: torch.Tensor, ref: torch.Tensor, tag: str):
+    g, r = got.float(), ref.float()
+    d = (g - r).abs()
+    rep = dict(tag=tag, shape=list(g.shape), max_abs=float(d.max()), mean_abs=float(d.mean()), ref_absmax=float(r.abs().max()),
+               got_absmax=float(g.abs().max()), n_nan=int(torch.isnan(g).sum()),
+               frac_bad=float((d > 0.05 * r.abs().max()).float().mean()))
+    if g.dim() == 2:
+        bad = d > 0.05 * r.abs().max()
+        rep["bad_rows_first"] = bad.any(1).nonzero().flatten()[:16].tolist()
+        rep["bad_cols_first"] = bad.any(0).nonzero().flatten()[:16].tolist()
+        rep["got_00"] = g[:2, :8].tolist()
+        rep["ref_00"] = r[:2, :8].tolist()
+    return rep
+
+
+def linear(A, W, bias, out, *, num_batch=1, rows_per_batch=None, a_batch_stride=0, out_batch_stride=0, out_row_offset=0,
+           epi=0, gate=None, gate_batch_stride=0, norm_q=None, norm_k=None, qk_dim=0, eps=1e-6, row_table=None):
+    K = W.shape[1]
+    N = W.shape[0]
+    rows_per_batch = rows_per_batch if rows_per_batch is not None else A.numel() // K // num_batch
+    code = _lib.lib().ffb200_linear(ptr(A), num_batch, rows_per_batch, a_batch_stride, A.stride(-2), K, ptr(W), N, ptr(bias),
+                                    ptr(out), out_batch_stride, out_row_offset, out.stride(-2), epi, ptr(gate),
+                                    gate_batch_stride, ptr(norm_q), ptr(norm_k), qk_dim, eps, ptr(row_table), stream())
+    _lib.check(code, "ffb200_linear")
+
+
+def device_error():
+    buf = (C.c_uint * 4)()
+    _lib.lib().ffb200_device_error(C.byref(buf))
+    return [hex(x) for x in buf]

@@ -1,0 +1,191 @@
+"""-m gpu parity: the whole MMDiT forward, the fused step and the T-step rollout through the C ABI, against
+(a) golden fixtures minted from the reference, (b) the oracle run on the same device, (c) invariants at full size."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import sd3_oracle as O
+from tests.gpu_util import dump
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _engine(cfg, w):
+    from flow_factory_b200 import RolloutEngine
+    return RolloutEngine(cfg, w, "cuda")
+
+
+def _oracle_fwd(cfg, w32, x, pe, pp, t, mode):
+    """mode 'fp32' = ground truth, 'bf16' = reference numerics on this device (bf16 weights + CUDA autocast)."""
+    dev = "cuda"
+    tt = torch.full((x.shape[0],), float(t), device=dev)
+    if mode == "fp32":
+        w = {k: v.to(dev) for k, v in w32.items()}
+        with torch.no_grad():
+            return O.transformer_forward(w, cfg, x.float().to(dev), pe.float().to(dev), pp.float().to(dev), tt)
+    w = {k: v.to(dev).bfloat16() for k, v in w32.items()}
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        return O.transformer_forward(w, cfg, x.half().to(dev), pe.bfloat16().to(dev), pp.bfloat16().to(dev), tt.half())
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm())
+
+
+@pytest.mark.parametrize("name,kw,B,lh,lw,nt", [
+    ("tiny", dict(), 2, 16, 16, 13),
+    ("tiny3", dict(num_layers=3, heads=3, dual=(0, 1), joint_dim=96, pooled_dim=48, pos_max=24, sample_size=32), 1, 24, 16, 21),
+    ("mid", dict(num_layers=4, heads=4, dual=(0, 1), joint_dim=256, pooled_dim=128, pos_max=48, sample_size=64), 2, 32, 32, 77),
+])
+def test_forward_vs_oracle(name, kw, B, lh, lw, nt):
+    """Engine error against the fp32 truth must be comparable to the bf16 reference's own error."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = O.tiny_config(**kw)
+    w32 = O.make_weights(cfg, seed=3)
+    inp = O.make_inputs(cfg, B, lh, lw, nt, seed=4)
+    t = float(torch.tensor(612.3).half())
+    eng = _engine(cfg, w32)
+    plan = eng.plan(B, False, lh, lw, nt)
+    eng.set_prompts(plan, inp["prompt_embeds"], inp["pooled"])
+    v = eng.transformer_forward(plan, inp["x0"].half(), t)
+    torch.cuda.synchronize()
+    truth = _oracle_fwd(cfg, w32, inp["x0"].half(), inp["prompt_embeds"].bfloat16(), inp["pooled"].bfloat16(), t, "fp32")
+    ref = _oracle_fwd(cfg, w32, inp["x0"], inp["prompt_embeds"], inp["pooled"], t, "bf16")
+    e_eng, e_ref, e_cross = _rel(v, truth), _rel(ref, truth), _rel(v, ref)
+    dump(f"fwd_{name}.json", dict(err_engine_vs_fp32=e_eng, err_ref_bf16_vs_fp32=e_ref, err_engine_vs_ref=e_cross,
+                                  launches=eng.last_launch_count()))
+    assert not torch.isnan(v).any()
+    assert e_eng <= 2.5 * e_ref + 2e-3, (e_eng, e_ref, e_cross)
+
+
+def test_forward_cfg_batching_order():
+    """CFG: uncond half first, both halves share the latents (sd3_5.py:409-413)."""
+    cfg = O.tiny_config()
+    w32 = O.make_weights(cfg, seed=0)
+    inp = O.make_inputs(cfg, 2, 16, 16, 13, seed=1)
+    eng = _engine(cfg, w32)
+    t = 988.5
+    p2 = eng.plan(2, True, 16, 16, 13)
+    eng.set_prompts(p2, inp["prompt_embeds"], inp["pooled"], inp["neg_prompt_embeds"], inp["neg_pooled"])
+    v2 = eng.transformer_forward(p2, inp["x0"].half(), t)
+    p1 = eng.plan(2, False, 16, 16, 13)
+    eng.set_prompts(p1, inp["neg_prompt_embeds"], inp["neg_pooled"])
+    vu = eng.transformer_forward(p1, inp["x0"].half(), t)
+    eng.set_prompts(p1, inp["prompt_embeds"], inp["pooled"])
+    vc = eng.transformer_forward(p1, inp["x0"].half(), t)
+    assert torch.equal(v2[:2], vu) and torch.equal(v2[2:], vc)
+
+
+def test_rollout_tiny_vs_reference_golden(golden_dir):
+    """T=4, CFG 4.5, Flow-SDE, fp16 storage, same noise stream: latents and log-probs against the fixture minted from
+    the reference loop (bf16 autocast) and its fp32 twin.  log-prob tolerance: 1e-3 relative (north-star)."""
+    g = _load(golden_dir, "rollout_tiny.pt")
+    from flow_factory_b200.adapter import B200SD3_5Adapter
+    from flow_factory_b200 import FlowMatchEulerDiscreteSDEScheduler
+    cfg = O.tiny_config()
+    w32 = O.make_weights(cfg, seed=0)
+    inp = O.make_inputs(cfg, 2, 16, 16, 13, seed=1)
+    noises = torch.stack(O.make_noises(4, (2, 16, 16, 16), seed=123))
+    ad = B200SD3_5Adapter(cfg, w32, scheduler=FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0))
+    ad.rollout()
+    for use_graph in (False, True):
+        ad.use_graph = use_graph
+        samples = ad.inference(height=128, width=128, num_inference_steps=4, guidance_scale=4.5,
+                               prompt_embeds=inp["prompt_embeds"].cuda(), pooled_prompt_embeds=inp["pooled"].cuda(),
+                               negative_prompt_embeds=inp["neg_prompt_embeds"].cuda(), negative_pooled_prompt_embeds=inp["neg_pooled"].cuda(),
+                               compute_log_prob=True, trajectory_indices="all", latents=inp["x0"].bfloat16().cuda(), noise=noises.cuda())
+        assert len(samples) == 2
+        assert torch.equal(samples[0].timesteps, g["bf16"]["timesteps"])
+        rep = {}
+        for b in range(2):
+            s = samples[b]
+            assert s.all_latents.shape == (5, 16, 16, 16) and s.log_probs.shape == (3,)
+            assert s.latent_index_map.tolist() == [0, 1, 2, 3, 4]
+            for pos in range(5):
+                got = s.all_latents[pos].float().cpu()
+                t32, tb = g["fp32"]["latents"][pos][b].float(), g["bf16"]["latents"][pos][b].float()
+                e_eng, e_ref = float((got - t32).abs().max()), float((tb - t32).abs().max())
+                rep[f"b{b}_pos{pos}"] = (e_eng, e_ref)
+                assert e_eng <= 3 * e_ref + 4e-3, (b, pos, e_eng, e_ref)
+            for i in range(3):
+                lp, lp_ref = float(s.log_probs[i]), float(g["bf16"]["log_probs"][i][b])
+                assert abs(lp - lp_ref) <= 1e-3 * abs(lp_ref), (i, lp, lp_ref)
+        dump(f"rollout_tiny_graph{int(use_graph)}.json", rep)
+
+
+def test_teacher_forced_replay_reproduces_rollout_log_probs():
+    """The GRPO invariant ratio == exp(new_logp - old_logp) == 1 before the first update (grpo.py:271): replaying a stored
+    transition through forward(next_latents=stored) returns the rollout's log-prob."""
+    from flow_factory_b200.adapter import B200SD3_5Adapter
+    from flow_factory_b200 import FlowMatchEulerDiscreteSDEScheduler
+    from flow_factory_b200.trajectory import compute_trajectory_indices
+    cfg = O.tiny_config()
+    w32 = O.make_weights(cfg, seed=0)
+    inp = {k: v.cuda() for k, v in O.make_inputs(cfg, 2, 16, 16, 13, seed=1).items()}
+    sch = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0, num_sde_steps=2, seed=5)
+    ad = B200SD3_5Adapter(cfg, w32, scheduler=sch, rng="philox")
+    ad.rollout()
+    sch.set_timesteps(6, seq_len=64)
+    train_steps = sch.train_timesteps.tolist()
+    idx = compute_trajectory_indices(train_steps, 6)
+    kw = dict(prompt_embeds=inp["prompt_embeds"], pooled_prompt_embeds=inp["pooled"],
+              negative_prompt_embeds=inp["neg_prompt_embeds"], negative_pooled_prompt_embeds=inp["neg_pooled"], guidance_scale=4.5)
+    samples = ad.inference(height=128, width=128, num_inference_steps=6, compute_log_prob=True, trajectory_indices=idx,
+                           latents=inp["x0"].bfloat16(), **kw)
+    st = type(samples[0]).stack(samples)
+    for i in sorted(train_steps):
+        li, lj = int(samples[0].latent_index_map[i]), int(samples[0].latent_index_map[i + 1])
+        lp_slot = int(samples[0].log_prob_index_map[i])
+        assert li >= 0 and lj >= 0 and lp_slot >= 0
+        t = sch.timesteps[i]
+        tn = sch.timesteps[i + 1] if i + 1 < 6 else torch.tensor(0.0)
+        out = ad.forward(t=t, t_next=tn, latents=st["all_latents"][:, li], next_latents=st["all_latents"][:, lj],
+                         noise_level=sch.noise_level, compute_log_prob=True, return_kwargs=["log_prob", "next_latents_mean"], **kw)
+        old = st["log_probs"][:, lp_slot]
+        ratio = torch.exp(out.log_prob - old)
+        assert float((ratio - 1).abs().max()) <= 1e-5, (i, ratio)
+
+
+def test_adapter_trajectory_subset_and_no_logprob():
+    from flow_factory_b200.adapter import B200SD3_5Adapter
+    cfg = O.tiny_config()
+    w32 = O.make_weights(cfg, seed=0)
+    inp = {k: v.cuda() for k, v in O.make_inputs(cfg, 1, 16, 16, 13, seed=2).items()}
+    ad = B200SD3_5Adapter(cfg, w32, rng="philox")
+    s = ad.inference(height=128, width=128, num_inference_steps=5, guidance_scale=1.0, prompt_embeds=inp["prompt_embeds"],
+                     pooled_prompt_embeds=inp["pooled"], compute_log_prob=False, trajectory_indices=[-1])[0]
+    assert s.all_latents.shape[0] == 1 and s.latent_index_map.tolist() == [-1, -1, -1, -1, -1, 0]
+    assert s.log_probs is None and s.log_prob_index_map is None
+    assert torch.equal(s.all_latents[0], s.extra_kwargs["final_latents"])
+    ad.eval()   # ODE sampling, noise_level 0 everywhere (scheduler.eval)
+    s2 = ad.inference(height=128, width=128, num_inference_steps=5, guidance_scale=1.0, prompt_embeds=inp["prompt_embeds"],
+                      pooled_prompt_embeds=inp["pooled"], compute_log_prob=True, trajectory_indices=None,
+                      latents=torch.zeros(1, 16, 16, 16, device="cuda"))[0]
+    assert s2.all_latents is None and s2.latent_index_map is None
+
+
+def test_forward_sd35_medium_1024_vs_oracle():
+    """Full-size config C2 (24 layers, 13 dual, D=1536, 1024^2 -> 4096+333 tokens), one CFG forward, random-init weights."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = O.sd35_medium()
+    w32 = O.make_weights(cfg, seed=0, device="cuda")
+    inp = O.make_inputs(cfg, 1, 128, 128, 333, seed=1)
+    t = 612.5
+    eng = _engine(cfg, w32)
+    plan = eng.plan(1, False, 128, 128, 333)
+    eng.set_prompts(plan, inp["prompt_embeds"], inp["pooled"])
+    v = eng.transformer_forward(plan, inp["x0"].half(), t)
+    torch.cuda.synchronize()
+    ref = _oracle_fwd(cfg, w32, inp["x0"], inp["prompt_embeds"], inp["pooled"], t, "bf16")
+    wb = None
+    truth = _oracle_fwd(cfg, w32, inp["x0"].half(), inp["prompt_embeds"].bfloat16(), inp["pooled"].bfloat16(), t, "fp32")
+    e_eng, e_ref, e_cross = _rel(v, truth), _rel(ref, truth), _rel(v, ref)
+    dump("fwd_sd35_medium_1024.json", dict(err_engine_vs_fp32=e_eng, err_ref_bf16_vs_fp32=e_ref, err_engine_vs_ref=e_cross,
+                                           launches=eng.last_launch_count(), workspace_gb=plan.workspace_bytes / 2 ** 30))
+    assert not torch.isnan(v).any()
+    assert e_eng <= 2.5 * e_ref + 2e-3, (e_eng, e_ref, e_cross)

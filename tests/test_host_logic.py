@@ -1,0 +1,141 @@
+"""CPU tests of the host-side mirror of the reference interface (scheduler bookkeeping, trajectory slots, samples,
+C-ABI symbols).  No GPU, no compute calls."""
+import ctypes as C
+import json
+import os
+import re
+
+import pytest
+import torch
+
+import flow_factory_b200 as F
+from flow_factory_b200 import _lib, trajectory as TR
+from flow_factory_b200.samples import SD3_5Sample
+from oracle import sd3_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def test_schedule_and_sde_window_match_reference(golden_dir):
+    g = _load(golden_dir, "schedule.pt")
+    for T, seq in ((4, 256), (30, 4096), (10, 1024)):
+        s = F.FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0)
+        ts = F.set_scheduler_timesteps(s, T, seq_len=seq)
+        assert torch.equal(ts, g[f"T{T}"]["timesteps"]) and torch.equal(s.sigmas, g[f"T{T}"]["sigmas"])
+        assert torch.equal(s.current_sde_steps, g[f"T{T}"]["sde"])
+    for seed in (0, 42, 43):
+        for n in (1, 3):
+            s = F.FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0, num_sde_steps=n, seed=seed)
+            F.set_scheduler_timesteps(s, 30, seq_len=4096)
+            assert torch.equal(s.current_sde_steps, g[f"sde_seed{seed}_n{n}"])
+            assert torch.equal(s.get_noise_levels(), g[f"noise_levels_seed{seed}_n{n}"])
+            assert torch.equal(s.train_timesteps, s.current_sde_steps)
+    s.set_seed(7); assert s.seed == 7
+    s.eval(); assert s.is_eval
+    s.rollout(); assert not s.is_eval
+
+
+@pytest.mark.parametrize("dyn", ["Flow-SDE", "Dance-SDE", "CPS", "ODE"])
+def test_step_coefficients_match_reference_scalars(golden_dir, dyn):
+    """std_dev_t and dt of the packed coefficient block equal the reference's (B,1,1,1) tensors bit for bit."""
+    g = _load(golden_dir, "sde_step.pt")
+    s = F.FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0, dynamics_type=dyn)
+    s.set_timesteps(30, seq_len=4096)
+    for i in (0, 5, 28, 29):
+        e = g[f"{dyn}_{i}"]
+        c = s.step_coef(e["t"], e["tn"], e["nl"])
+        assert c.std_dev_t == float(e["std"].flatten()[0])
+        assert c.dt == float(e["dt"].flatten()[0])
+        assert c.dynamics == {"Flow-SDE": 0, "Dance-SDE": 1, "CPS": 2, "ODE": 3}[dyn]
+    assert s.get_noise_level_for_timestep(s.timesteps[3]) == 0.7
+    assert s.get_noise_level_for_timestep(s.timesteps[29]) == 0.0     # default window excludes the last step
+
+
+def test_trajectory_indices_and_maps_match_reference(golden_dir):
+    with open(os.path.join(golden_dir, "trajectory.json")) as f:
+        g = json.load(f)
+    for c in g["cases"]:
+        assert TR.compute_trajectory_indices(c["idx"], c["T"], c["inc"]) == c["out"]
+    for m in g["maps"]:
+        col = TR.create_trajectory_collector(m["ind"], m["T"])
+        for p in range(m["T"] + 1):
+            col.collect(torch.tensor(float(p)), p)
+        im = col.get_index_map()
+        assert (None if im is None else im.tolist()) == m["index_map"]
+        res = col.get_result()
+        assert (None if res is None else [float(x) for x in res]) == m["collected"]
+        # slot planner == what the collector does when every position is offered
+        lat_slot, _, lat_map, _ = TR.plan_slots(m["ind"], m["T"], [True] * m["T"])
+        assert (None if lat_map is None else lat_map.tolist()) == m["index_map"]
+        assert [p for p, s in enumerate(lat_slot) if s >= 0] == ([] if m["collected"] is None else [int(x) for x in m["collected"]])
+
+
+def test_plan_slots_grpo_default():
+    # num_sde_steps=1 at step 7 of 30: trainer needs positions 7 and 8 and the log-prob of step 7
+    idx = TR.compute_trajectory_indices([7], 30)
+    has = [i == 7 for i in range(30)]
+    lat_slot, lp_slot, lat_map, lp_map = TR.plan_slots(idx, 30, has)
+    assert idx == [7, 8] and lat_slot[7] == 0 and lat_slot[8] == 1 and sum(s >= 0 for s in lat_slot) == 2
+    assert lp_slot[7] == 0 and sum(s >= 0 for s in lp_slot) == 1
+    assert lat_map[7] == 0 and lat_map[8] == 1 and lp_map[7] == 0 and int((lp_map >= 0).sum()) == 1
+
+
+def test_sample_record_stack_and_unique_id():
+    a = SD3_5Sample(prompt="a cat", all_latents=torch.zeros(2, 16, 4, 4), log_probs=torch.zeros(1), height=32, width=32)
+    b = SD3_5Sample(prompt="a cat", all_latents=torch.ones(2, 16, 4, 4), log_probs=torch.ones(1), height=32, width=32)
+    c = SD3_5Sample(prompt="a dog")
+    assert a.unique_id == b.unique_id != c.unique_id
+    st = SD3_5Sample.stack([a, b])
+    assert st["all_latents"].shape == (2, 2, 16, 4, 4) and st["log_probs"].shape == (2, 1) and st["prompt"] == ["a cat", "a cat"]
+
+
+def test_filter_kwargs_is_the_abi():
+    from flow_factory_b200.adapter import B200SD3_5Adapter, filter_kwargs
+    kw = filter_kwargs(B200SD3_5Adapter.inference, height=512, width=512, num_inference_steps=10, guidance_scale=4.5,
+                       compute_log_prob=True, trajectory_indices=[1, 2], prompt_embeds=1, per_device_batch_size=8, lr=1e-4)
+    assert set(kw) == {"height", "width", "num_inference_steps", "guidance_scale", "compute_log_prob", "trajectory_indices", "prompt_embeds"}
+    # every parameter of the reference's inference()/forward() (sd3_5.py:176-199, 352-370) is accepted by name
+    ref_inf = ["prompt", "negative_prompt", "height", "width", "num_inference_steps", "guidance_scale", "generator",
+               "joint_attention_kwargs", "prompt_ids", "prompt_embeds", "pooled_prompt_embeds", "negative_prompt_ids",
+               "negative_prompt_embeds", "negative_pooled_prompt_embeds", "compute_log_prob", "extra_call_back_kwargs",
+               "trajectory_indices"]
+    ref_fwd = ["t", "latents", "prompt_embeds", "pooled_prompt_embeds", "negative_prompt_embeds", "negative_pooled_prompt_embeds",
+               "guidance_scale", "t_next", "next_latents", "noise_level", "joint_attention_kwargs", "compute_log_prob", "return_kwargs"]
+    import inspect
+    assert set(ref_inf) <= set(inspect.signature(B200SD3_5Adapter.inference).parameters)
+    assert set(ref_fwd) <= set(inspect.signature(B200SD3_5Adapter.forward).parameters)
+
+
+def test_c_abi_library_loads_and_exports_every_declared_symbol():
+    L = _lib.lib()
+    assert L.ffb200_abi_version() == 1
+    with open(os.path.join(ROOT, "include", "ffb200.h")) as f:
+        hdr = f.read()
+    declared = set(re.findall(r"\b(ffb200_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    # struct layouts the ABI depends on
+    assert C.sizeof(_lib.StepCoef) == 13 * 4 + 4 * 4
+    assert C.sizeof(_lib.ModelConfig) == 8 * 4
+    assert C.sizeof(_lib.LayerWeights) == 26 * 8
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "flow_factory_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+
+
+def test_engine_refuses_to_run_without_a_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    cfg = O.tiny_config()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        F.RolloutEngine(cfg, O.make_weights(cfg))
