@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py - rollout latents/sec, SD3.5-medium 1024^2 30-step GRPO sampling (BASELINE.json metric, config C2).
+
+  python bench.py --gpus N --steps K --warmup W              # our arm (one rank per GPU; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port) on host cores
+
+A "step" is ONE ROLLOUT: `batch` prompts per rank x 30 denoise steps x (2 transformer forwards with CFG) + the fused
+Euler/SDE + log-prob step, synthetic inputs of the BASELINE shape, random-init weights of the SD3.5-medium architecture
+(no checkpoints offline).  `value` = whole-job latents/s with inputs resident in HBM, device-timed (CUDA events, max over
+ranks); `e2e` = the same metric through the public adapter API with HOST (pinned) inputs and host outputs, copies inside
+the timed region.  Working set (4.5 GB of weights + GBs of activations per step) is far larger than the 126 MB L2.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rollout latents/sec SD3.5-medium 1024^2 30-step"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4, help="prompts per rank per rollout")
+    ap.add_argument("--height", type=int, default=1024)
+    ap.add_argument("--width", type=int, default=1024)
+    ap.add_argument("--num-inference-steps", type=int, default=30)
+    ap.add_argument("--guidance", type=float, default=4.5)
+    ap.add_argument("--n-text", type=int, default=333)
+    ap.add_argument("--num-sde-steps", type=int, default=1)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-res", type=int, default=1024)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def flops_per_latent(cfg, ni, nt, T, cfg_on):
+    from flow_factory_b200.synth import flops_per_forward
+    lin, att = flops_per_forward(cfg, ni, nt)
+    return (lin + att) * T * (2 if cfg_on else 1)
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
+def cpu_reference_sample(cfg, weights_bf16_cpu, res, n_text, T, guidance, threads, reps=1):
+    """Times the reference's CPU path restated in oracle/ (diffusers SD3 forward + scheduler.step, bf16 CPU autocast):
+    ONE transformer forward at B=1 (no CFG doubling) + one scheduler step; a latent costs T x (2 if CFG) of those."""
+    from oracle import sd3_oracle as O
+    torch.set_num_threads(threads)
+    lat = res // 8
+    inp = O.make_inputs(cfg, 1, lat, lat, n_text, seed=1)
+    ts, sig = O.make_schedule(T, 3.0)
+    x = inp["x0"].half()
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            v = O.transformer_forward(weights_bf16_cpu, cfg, x, inp["prompt_embeds"].bfloat16(), inp["pooled"].bfloat16(),
+                                      ts[3].expand(1).half())
+        O.sde_step(v, x, (ts[3] / 1000).item(), (ts[4] / 1000).item(), 0.7, float(sig[1]),
+                   noise=torch.randn(x.shape), compute_log_prob=True)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    fwd_per_latent = T * (2 if guidance > 1.0 else 1)
+    return 1.0 / (best * fwd_per_latent), best
+
+
+def make_cpu_weights(cfg):
+    from oracle import sd3_oracle as O
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    w = O.make_weights(cfg, seed=0, dtype=torch.bfloat16, device=dev)
+    return {k: v.cpu() for k, v in w.items()}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle port; /root/reference is absent on the
+    GPU box and pure Python/diffusers cannot be vendored) on all host threads; each step = a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import sd3_oracle as O
+    cfg = O.sd35_medium()
+    threads = os.cpu_count() or 1
+    w = make_cpu_weights(cfg)
+    T = args.num_inference_steps
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_reference_sample(cfg, w, args.cpu_sample_res, args.n_text, T, args.guidance, threads)
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(args.steps):
+        v, dt = cpu_reference_sample(cfg, w, args.cpu_sample_res, args.n_text, T, args.guidance, threads)
+        vals.append(v)
+    wall = time.perf_counter() - t0
+    value = sum(vals) / len(vals)
+    sample = (f"1 transformer forward + scheduler.step at {args.cpu_sample_res}^2, B=1, bf16 CPU autocast, extrapolated x{T} steps"
+              f" x{2 if args.guidance > 1 else 1} (CFG); {args.steps} timed samples")
+    line = {"metric": METRIC, "value": value, "unit": "latents/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"SD3.5-medium {args.height}x{args.width} {T}-step GRPO rollout, guidance {args.guidance}, random-init weights",
+                       "timing": "host wall clock of a bounded sample, extrapolated"},
+            "cpu_baseline": {"value": value, "unit": "latents/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "latents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_b200(args):
+    import torch.distributed as dist
+    from flow_factory_b200 import FlowMatchEulerDiscreteSDEScheduler, RolloutEngine, _lib
+    from flow_factory_b200.adapter import B200SD3_5Adapter
+    from flow_factory_b200.dist import all_gather_rollout
+    from flow_factory_b200.trajectory import compute_trajectory_indices
+    from flow_factory_b200.synth import random_inputs, random_weights, sd35_medium   # the engine arm never touches oracle/
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = sd35_medium()
+    T, B = args.num_inference_steps, args.batch
+    lat_h, lat_w = args.height // 8, args.width // 8
+    ni = (lat_h // 2) * (lat_w // 2)
+    cfg_on = args.guidance > 1.0
+    w = random_weights(cfg, seed=0, dtype=torch.bfloat16, device=f"cuda:{local}")
+    sched = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0, num_sde_steps=args.num_sde_steps, seed=42)
+    adapter = B200SD3_5Adapter(cfg, w, device=dev, scheduler=sched, rng="philox", use_graph=not args.no_graph)
+    adapter.rollout()
+    del w
+    sched.set_timesteps(T, seq_len=ni)
+    traj_idx = compute_trajectory_indices(sched.train_timesteps, T)
+    inp = random_inputs(cfg, B, lat_h, lat_w, args.n_text, seed=1 + rank, device=dev)
+    kw = dict(height=args.height, width=args.width, num_inference_steps=T, guidance_scale=args.guidance, compute_log_prob=True,
+              trajectory_indices=traj_idx)
+
+    def rollout_device():
+        s = adapter.inference(prompt_embeds=inp["prompt_embeds"], pooled_prompt_embeds=inp["pooled"],
+                              negative_prompt_embeds=inp["neg_prompt_embeds"], negative_pooled_prompt_embeds=inp["neg_pooled"],
+                              latents=inp["x0"], **kw)
+        if world > 1:   # the single collective of the path: one all-gather of {kept latents | log-probs} per rollout
+            lat = torch.stack([x.all_latents for x in s]); lp = torch.stack([x.log_probs for x in s])
+            all_gather_rollout(lat, lp)
+        return s
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing ----------------
+    for _ in range(args.warmup):
+        rollout_device()
+    barrier()
+    launches_per_rollout = RolloutEngine.last_launch_count()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        rollout_device()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t_wall
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    clk = clocks.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---------------- end to end through the public API with host buffers ----------------
+    host = {k: v.cpu().pin_memory() for k, v in inp.items() if k != "x0"}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def rollout_e2e():
+        s = adapter.inference(prompt_embeds=host["prompt_embeds"].to(dev, non_blocking=True),
+                              pooled_prompt_embeds=host["pooled"].to(dev, non_blocking=True),
+                              negative_prompt_embeds=host["neg_prompt_embeds"].to(dev, non_blocking=True),
+                              negative_pooled_prompt_embeds=host["neg_pooled"].to(dev, non_blocking=True), **kw)
+        lat = torch.stack([x.all_latents for x in s]); lp = torch.stack([x.log_probs for x in s])
+        fin = torch.stack([x.extra_kwargs["final_latents"] for x in s])
+        if world > 1:
+            lat, lp = all_gather_rollout(lat, lp)
+        out = (lat.cpu(), lp.cpu(), fin.cpu())     # device -> host read of the rollout's result
+        return sum(t.numel() * t.element_size() for t in out)
+
+    d2h = rollout_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rollout_e2e()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(e2e_s)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (tcgen05 GEMM, MLP-up shape of this batch), timed live ----------------
+    peaks, peak_kind = load_peaks()
+    from flow_factory_b200.ops import linear as op_linear
+    Bp = B * (2 if cfg_on else 1)
+    M, N, K = Bp * ni, 4 * cfg.inner_dim, cfg.inner_dim
+    A = torch.randn(M, K, device=dev).bfloat16(); Wt = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    bb = torch.zeros(N, device=dev).bfloat16(); oo = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        op_linear(A, Wt, bb, oo, epi=1)
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); op_linear(A, Wt, bb, oo, epi=1); b_.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b_))
+    gemm_ms = sorted(ts)[len(ts) // 2]
+    gemm_tf = 2.0 * M * N * K / gemm_ms / 1e9
+    fl_latent = flops_per_latent(cfg, ni, args.n_text, T, cfg_on)
+    step_tf = value * fl_latent / 1e12
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel<256> (MLP up, bias+GELU epilogue)", "achieved": gemm_tf,
+                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["bf16_tflops"], "traffic": None,
+                "peak_source": f"{peak_kind} cuBLAS bf16 burst", "flops_per_launch": 2.0 * M * N * K, "launch_ms": gemm_ms,
+                "whole_step_achieved": step_tf, "whole_step_frac_of_sustained": step_tf / peaks["bf16_tflops_sustained"],
+                "flops_per_latent": fl_latent}
+
+    # ---------------- CPU baseline: the oracle port on this box's host cores, bounded sample ----------------
+    cpu = None
+    if not args.skip_cpu_baseline:
+        threads = os.cpu_count() or 1
+        wcpu = make_cpu_weights(cfg)
+        v, dt = cpu_reference_sample(cfg, wcpu, args.cpu_sample_res, args.n_text, T, args.guidance, threads)
+        cpu = {"value": v, "unit": "latents/s", "cores": threads, "kind": "port",
+               "sample": f"1 transformer forward + scheduler.step at {args.cpu_sample_res}^2 B=1 bf16 CPU autocast ({dt:.1f} s), extrapolated x{T} steps x{2 if cfg_on else 1} (CFG)"}
+
+    line = {"metric": METRIC, "value": value, "unit": "latents/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "impl": "b200",
+            "config": {"workload": f"SD3.5-medium {args.height}x{args.width} {T}-step GRPO rollout (Flow-SDE, noise 0.7, num_sde_steps {args.num_sde_steps}), "
+                                   f"guidance {args.guidance}, {args.n_text} text tokens, random-init weights",
+                       "per_rank_batch": B, "global_batch": B * world, "parallelism": f"dp{world} (prompt-sharded, 1 all-gather/rollout)",
+                       "l2": "working set >> 126 MB L2 (4.5 GB weights re-read every forward)", "cuda_graph": not args.no_graph,
+                       "rng": "in-kernel Philox4x32-10"},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "latents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches_per_rollout * args.steps),
+            "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": wall}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a B200 (no CPU fallback for the engine arm); use --impl reference for the CPU baseline")
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

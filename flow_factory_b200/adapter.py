@@ -43,8 +43,8 @@ class B200SD3_5Adapter:
             raise ValueError("the fused step kernel stores latents as fp16 (Flow-Factory's default latent_storage_dtype)")
         if rng not in ("torch", "philox"):
             raise ValueError("rng must be 'torch' (reference-identical noise stream) or 'philox' (in-kernel)")
-        self.device = torch.device(device)
-        self.engine = RolloutEngine(model_config, state_dict, self.device)
+        self.engine = RolloutEngine(model_config, state_dict, torch.device(device))
+        self.device = self.engine.device
         self.model_config = self.engine.cfg
         self.scheduler = scheduler or FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0, dynamics_type="Flow-SDE")
         self.decode_fn = decode_fn
@@ -229,9 +229,14 @@ class B200SD3_5Adapter:
             noise = torch.randn(latents.shape, device=self.device, dtype=torch.float32)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if noise is None else 0
         r = self.engine.step(plan, latents, coef, guidance_scale if do_cfg else 1.0, noise=noise, next_latents=next_latents,
-                             seed=seed, want_mean="next_latents_mean" in return_kwargs)
-        d = dict(next_latents=(next_latents.float() if next_latents is not None else r["next_latents"].float()),
-                 next_latents_mean=r["next_latents_mean"], log_prob=r["log_prob"], noise_pred=r["noise_pred"],
+                             seed=seed, want_mean=("next_latents_mean" in return_kwargs) or sch.dynamics_type == "ODE")
+        if next_latents is not None:
+            nxt = next_latents.float()
+        elif sch.dynamics_type == "ODE" and r["next_latents_mean"] is not None:
+            nxt = r["next_latents_mean"]            # ODE: next_latents IS the mean, no storage round trip (flow_match...py:333-334)
+        else:
+            nxt = r["next_latents"].float()
+        d = dict(next_latents=nxt, next_latents_mean=r["next_latents_mean"], log_prob=r["log_prob"], noise_pred=r["noise_pred"],
                  std_dev_t=torch.full((B, 1, 1, 1), coef.std_dev_t, dtype=torch.float32, device=self.device),
                  dt=torch.full((B, 1, 1, 1), coef.dt, dtype=torch.float32, device=self.device))
         return SDESchedulerOutput.from_dict({k: d[k] for k in return_kwargs if k in d})

@@ -41,6 +41,8 @@ class RolloutEngine:
         if not torch.cuda.is_available():
             raise RuntimeError("flow_factory_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device(device if device is not None else "cuda")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         torch.cuda.set_device(self.device)
         self.cfg = model_config if isinstance(model_config, EngineConfig) else EngineConfig.from_model_config(model_config)
         self.weights = PackedWeights(self.cfg, state_dict, self.device)

@@ -1,0 +1,53 @@
+"""Op-level Python entry points over the C ABI (one reference call site each; see include/ffb200.h).
+Tensors are torch CUDA tensors (device memory + stream plumbing); the kernels are ours; no fallback."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+EPI_BIAS, EPI_BIAS_GELU, EPI_GATE_RESIDUAL, EPI_QKV_RMSNORM, EPI_BIAS_ADD_ROWTABLE = range(5)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def linear(A, W, bias, out, *, num_batch=1, rows_per_batch=None, a_batch_stride=0, out_batch_stride=0, out_row_offset=0,
+           epi=EPI_BIAS, gate=None, gate_batch_stride=0, norm_q=None, norm_k=None, qk_dim=0, eps=1e-6, row_table=None) -> None:
+    """out = epilogue(A @ W^T + bias) on the tcgen05 GEMM (nn.Linear call sites of the MMDiT block)."""
+    K, N = W.shape[1], W.shape[0]
+    rows_per_batch = rows_per_batch if rows_per_batch is not None else A.numel() // K // num_batch
+    code = _lib.lib().ffb200_linear(_ptr(A), num_batch, rows_per_batch, a_batch_stride, A.stride(-2), K, _ptr(W), N, _ptr(bias),
+                                    _ptr(out), out_batch_stride, out_row_offset, out.stride(-2), epi, _ptr(gate),
+                                    gate_batch_stride, _ptr(norm_q), _ptr(norm_k), qk_dim, eps, _ptr(row_table), _stream(A))
+    _lib.check(code, "ffb200_linear")
+
+
+def attention(qkv: torch.Tensor, num_heads: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Joint attention over a fused token-major qkv buffer bf16 [B, S, 3*64*H] -> bf16 [B, S, 64*H]."""
+    B, S, _ = qkv.shape
+    if out is None:
+        out = torch.empty((B, S, 64 * num_heads), dtype=torch.bfloat16, device=qkv.device)
+    _lib.check(_lib.lib().ffb200_attention(_ptr(qkv), B, S, num_heads, _ptr(out), _stream(qkv)), "ffb200_attention")
+    return out
+
+
+def ln_modulate(x, shift1, scale1, out1, shift2=None, scale2=None, out2=None, *, mod_batch_stride, eps=1e-6) -> None:
+    B, R, D = x.shape
+    _lib.check(_lib.lib().ffb200_ln_modulate(_ptr(x), B, R, D, eps, _ptr(shift1), _ptr(scale1), _ptr(out1), _ptr(shift2),
+                                             _ptr(scale2), _ptr(out2), mod_batch_stride, _stream(x)), "ffb200_ln_modulate")
+
+
+def small_linear(x, W, bias, out, *, addend=None, silu_input=False) -> None:
+    B, K = x.shape
+    N = W.shape[0]
+    _lib.check(_lib.lib().ffb200_small_linear(_ptr(x), B, K, x.stride(0), _ptr(W), _ptr(bias), N, _ptr(out), out.stride(0),
+                                              _ptr(addend), addend.stride(0) if addend is not None else 0, int(silu_input),
+                                              _stream(x)), "ffb200_small_linear")

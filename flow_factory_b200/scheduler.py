@@ -257,7 +257,13 @@ class FlowMatchEulerDiscreteSDEScheduler:
                                      nz.data_ptr() if nz is not None else None, seed, step_index,
                                      ng.data_ptr() if ng is not None else None, out_next.data_ptr(), out_mean.data_ptr(),
                                      out_lp.data_ptr() if out_lp is not None else None, flag.data_ptr(), st), "ffb200_sde_step")
-        d = dict(next_latents=(next_latents.float() if next_latents is not None else out_next.float()),
+        if next_latents is not None:
+            nxt = next_latents.float()
+        elif dyn == "ODE":
+            nxt = out_mean                        # ODE: next_latents IS the mean, no storage round trip (flow_match...py:333-334)
+        else:
+            nxt = out_next.float()
+        d = dict(next_latents=nxt,
                  next_latents_mean=out_mean,
                  std_dev_t=torch.full((B, 1, 1, 1), c.std_dev_t, dtype=torch.float32, device=latents.device),
                  dt=torch.full((B, 1, 1, 1), c.dt, dtype=torch.float32, device=latents.device),

@@ -167,11 +167,37 @@ def golden_traj():
     return dict(cases=cases, maps=maps)
 
 
+def golden_advantage():
+    """AdvantageProcessor.compute_weighted_sum / compute_gdpo (FF/advantage/advantage_processor.py:314-481) driven with a
+    minimal fake self (no accelerator): the numpy fp64 group-normalisation math only."""
+    import numpy as np
+    from flow_factory.advantage.advantage_processor import AdvantageProcessor
+    rng = np.random.default_rng(0)
+    n_groups, k = 6, 4
+    gid = np.repeat(np.arange(n_groups), k)
+    perm = rng.permutation(len(gid))
+    gid = gid[perm]
+    rewards = {"pick": rng.normal(size=len(gid)), "ocr": rng.uniform(size=len(gid))}
+    weights = {"pick": 1.0, "ocr": 0.5}
+    out = dict(gid=gid, rewards=rewards, weights=weights)
+    for global_std in (True, False):
+        ap = AdvantageProcessor.__new__(AdvantageProcessor)
+        ap.reward_weights, ap.global_std, ap.group_size, ap.group_on_same_rank = weights, global_std, k, False
+        ap.collect_group_rewards = lambda samples, rw: ({kk: np.asarray(v, dtype=np.float64) for kk, v in rw.items()}, gid)
+        ap._to_local = lambda a: a
+        ap._build_weighted_sum_log_data = lambda *a, **kw: {}
+        ap._build_gdpo_log_data = lambda *a, **kw: {}
+        out[f"sum_global{int(global_std)}"] = np.asarray(ap.compute_weighted_sum([], rewards, False))
+        out[f"gdpo_global{int(global_std)}"] = np.asarray(ap.compute_gdpo([], rewards, False))
+    return out
+
+
 if __name__ == "__main__":
     torch.save(golden_schedule(), os.path.join(HERE, "schedule.pt"))
     torch.save(golden_step(), os.path.join(HERE, "sde_step.pt"))
     torch.save(golden_forward(), os.path.join(HERE, "forward_tiny.pt"))
     torch.save(golden_rollout(), os.path.join(HERE, "rollout_tiny.pt"))
+    torch.save(golden_advantage(), os.path.join(HERE, "advantage.pt"))
     with open(os.path.join(HERE, "trajectory.json"), "w") as f:
         json.dump(golden_traj(), f)
     print("golden written:", sorted(os.listdir(HERE)))

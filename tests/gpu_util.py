@@ -39,15 +39,7 @@ def err_report(got: torch.Tensor, ref: torch.Tensor, tag: str):
     return rep
 
 
-def linear(A, W, bias, out, *, num_batch=1, rows_per_batch=None, a_batch_stride=0, out_batch_stride=0, out_row_offset=0,
-           epi=0, gate=None, gate_batch_stride=0, norm_q=None, norm_k=None, qk_dim=0, eps=1e-6, row_table=None):
-    K = W.shape[1]
-    N = W.shape[0]
-    rows_per_batch = rows_per_batch if rows_per_batch is not None else A.numel() // K // num_batch
-    code = _lib.lib().ffb200_linear(ptr(A), num_batch, rows_per_batch, a_batch_stride, A.stride(-2), K, ptr(W), N, ptr(bias),
-                                    ptr(out), out_batch_stride, out_row_offset, out.stride(-2), epi, ptr(gate),
-                                    gate_batch_stride, ptr(norm_q), ptr(norm_k), qk_dim, eps, ptr(row_table), stream())
-    _lib.check(code, "ffb200_linear")
+from flow_factory_b200.ops import linear  # noqa: E402,F401
 
 
 def device_error():

@@ -139,3 +139,47 @@ def test_engine_refuses_to_run_without_a_gpu():
     cfg = O.tiny_config()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         F.RolloutEngine(cfg, O.make_weights(cfg))
+
+
+def test_advantage_mirror_matches_reference(golden_dir):
+    import numpy as np
+    from flow_factory_b200 import advantage as A
+    g = _load(golden_dir, "advantage.pt")
+    for gs in (True, False):
+        a = A.advantages_sum(g["rewards"], g["weights"], g["gid"], global_std=gs)
+        np.testing.assert_allclose(a, g[f"sum_global{int(gs)}"], rtol=1e-12, atol=1e-12)
+    a = A.advantages_gdpo(g["rewards"], g["weights"], g["gid"])
+    np.testing.assert_allclose(a, g["gdpo_global1"], rtol=1e-12, atol=1e-12)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from flow_factory_b200 import dist as D
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        B = 3
+        lat = (torch.arange(B * 2 * 4, dtype=torch.float32).reshape(B, 2, 4) + 100 * rank).half()
+        lp = torch.arange(B * 2, dtype=torch.float32).reshape(B, 2) - 10 * rank
+        gl, glp = D.all_gather_rollout(lat, lp)
+        ok = gl.shape == (world * B, 2, 4) and glp.shape == (world * B, 2)
+        for r in range(world):
+            ok &= torch.equal(gl[r * B:(r + 1) * B], (torch.arange(B * 2 * 4, dtype=torch.float32).reshape(B, 2, 4) + 100 * r).half())
+            ok &= torch.equal(glp[r * B:(r + 1) * B], torch.arange(B * 2, dtype=torch.float32).reshape(B, 2) - 10 * r)
+        lo, hi = D.shard_range(10, rank, world)
+        q.put((rank, bool(ok), lo, hi))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_prompt_sharding_and_single_allgather_world2_gloo():
+    import torch.multiprocessing as mp
+    from flow_factory_b200 import dist as D
+    assert [D.shard_range(10, r, 3) for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29611
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in ps]
+    assert res == [(0, True, 0, 5), (1, True, 5, 10)]
