@@ -5,42 +5,48 @@
 // straight out of the fused-QKV GEMM's token-major [B, S, 3D] buffer with 3-D TMA boxes (one per head),
 // so there is no concat copy and no [B,H,S,d] transpose in HBM.
 //
-// One CTA per (128 query rows, head, batch):
-//   warps 0-3 : softmax + output accumulation; thread == query row == TMEM lane (no shuffles)
-//   warp  4   : TMA producer (Q once; K/V ring of kStages 128x64 tiles)
-//   warp  5   : MMA issuer  (S = Q K^T : M128 N128 K64 ; O_part = P V : M128 N64 K128, V as MN-major operand)
-// S is double-buffered in TMEM so QK^T of tile j+1 runs on the tensor core while the softmax warps
-// work on tile j; P (bf16) goes through shared memory in the canonical 128B-swizzled K-major layout.
-// The running output lives in registers (fp32) and is rescaled FA2-style per KV tile.
+// One CTA per (256 query rows = two 128-row sub-tiles A/B, head, batch), 12 warps:
+//   warps 0-3 / 4-7 : softmax + output accumulation of sub-tile A / B; thread == query row == TMEM lane.
+//                     Two warps per SM sub-partition, so one sub-tile's TMEM-load / barrier latency hides
+//                     behind the other's exp2 work (the MUFU unit is the binding resource at d = 64).
+//   warp  8         : TMA producer (Q once; K/V ring of 128x64 tiles shared by both sub-tiles)
+//   warp  9         : MMA issuer  (S = Q K^T : M128 N128 K64 ; O_part = P V : M128 N64 K128, V as MN-major operand)
+//   setmaxnreg moves registers from warps 8-11 to the softmax warps (232 each).
+// S_A/S_B and the per-tile partial outputs live in TMEM; P (bf16) goes through shared memory in the canonical
+// 128B-swizzled K-major layout; the running output is kept in registers (fp32) and rescaled FA2-style.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace ffb {
 
-constexpr int ATT_BM = 128;     // query rows per CTA
+constexpr int ATT_BM = 128;     // query rows per sub-tile
+constexpr int ATT_QB = 256;     // query rows per CTA
 constexpr int ATT_BN = 128;     // kv rows per tile
 constexpr int ATT_D = 64;
 constexpr int ATT_STAGES = 3;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 384;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
-constexpr int ATT_SMEM = ATT_TILE_BYTES /*Q*/ + 2 * ATT_STAGES * ATT_TILE_BYTES /*K,V*/ + 2 * 2 * ATT_TILE_BYTES /*P x2*/ +
+constexpr int ATT_SMEM = 2 * ATT_TILE_BYTES /*Q_A,Q_B*/ + 2 * ATT_STAGES * ATT_TILE_BYTES /*K,V*/ + 2 * 2 * ATT_TILE_BYTES /*P_A,P_B*/ +
                          1024 + 512;
+
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + ATT_TILE_BYTES;
-  uint8_t* sV = sK + ATT_STAGES * ATT_TILE_BYTES;
-  uint8_t* sP = sV + ATT_STAGES * ATT_TILE_BYTES;  // [2 buffers][2 k-atoms][128 rows][128 B]
+  uint8_t* sQ = smem;                                   // [2 sub-tiles][128][64]
+  uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;                // [stages]
+  uint8_t* sV = sK + ATT_STAGES * ATT_TILE_BYTES;       // [stages]
+  uint8_t* sP = sV + ATT_STAGES * ATT_TILE_BYTES;       // [2 sub-tiles][2 k-atoms][128 rows][128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATT_TILE_BYTES);
   uint64_t* q_full = bars;                       // 1
   uint64_t* k_full = bars + 1;                   // [ST]
   uint64_t* k_empty = k_full + ATT_STAGES;       // [ST]
   uint64_t* v_full = k_empty + ATT_STAGES;       // [ST]
   uint64_t* v_empty = v_full + ATT_STAGES;       // [ST]
-  uint64_t* s_full = v_empty + ATT_STAGES;       // [2]
+  uint64_t* s_full = v_empty + ATT_STAGES;       // [2]  per sub-tile
   uint64_t* s_empty = s_full + 2;                // [2]
   uint64_t* p_full = s_empty + 2;                // [2]
   uint64_t* o_full = p_full + 2;                 // [2]
@@ -49,13 +55,14 @@ attention_kernel(const __grid_constant__ AttnParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * ATT_BM;
+  const int q0 = blockIdx.x * ATT_QB;
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   const int S = p.seq_len;
   const int n_tiles = (S + ATT_BN - 1) / ATT_BN;
+  const int n_sub = (q0 + ATT_BM < S) ? 2 : 1;   // sub-tile B exists only if it holds at least one valid row
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&p.tmQKV);
     mbar_init(q_full, 1);
     for (int i = 0; i < ATT_STAGES; ++i) {
@@ -69,188 +76,190 @@ attention_kernel(const __grid_constant__ AttnParams p) {
     }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_ptr_smem, 512);
+  if (warp == 9) tmem_alloc(tmem_ptr_smem, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tS = tmem_base;         // S buffers at columns 0 / 128
-  const uint32_t tO = tmem_base + 256;   // O_part buffers at columns 256 / 320
+  const uint32_t tS = tmem_base;         // S_A / S_B at columns 0 / 128
+  const uint32_t tO = tmem_base + 256;   // O_part A / B at columns 256 / 320
 
-  if (warp == 4) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      const int cq = head * ATT_D, ck = p.inner_dim + head * ATT_D, cv = 2 * p.inner_dim + head * ATT_D;
-      mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_3d(sQ, &p.tmQKV, q_full, cq, q0, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % ATT_STAGES;
-        const uint32_t ph = (j / ATT_STAGES) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1, 0x40);
-        mbar_arrive_expect_tx(&k_full[st], ATT_TILE_BYTES);
-        tma_load_3d(sK + st * ATT_TILE_BYTES, &p.tmQKV, &k_full[st], ck, j * ATT_BN, b);
-        mbar_wait(&v_empty[st], ph ^ 1, 0x41);
-        mbar_arrive_expect_tx(&v_full[st], ATT_TILE_BYTES);
-        tma_load_3d(sV + st * ATT_TILE_BYTES, &p.tmQKV, &v_full[st], cv, j * ATT_BN, b);
-      }
-    }
-  } else if (warp == 5) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);  // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);   // P (K-major) x V (MN-major)
-      const uint32_t q_addr = smem_u32(sQ);
-      auto issue_qk = [&](int j) {
-        const int st = j % ATT_STAGES;
-        const uint32_t ph = (j / ATT_STAGES) & 1;
-        const int sb = j & 1;
-        mbar_wait(&k_full[st], ph, 0x50);
-        mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1, 0x51);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < ATT_D / 16; ++k)
-          umma_bf16(tS + sb * ATT_BN, desc_kmajor_sw128(q_addr + k * 32), desc_kmajor_sw128(k_addr + k * 32), idesc_s,
-                    k != 0 ? 1u : 0u);
-        umma_commit(&s_full[sb]);
-        umma_commit(&k_empty[st]);
-      };
-      mbar_wait(q_full, 0, 0x52);
-      issue_qk(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) issue_qk(j + 1);
-        const int st = j % ATT_STAGES;
-        const uint32_t ph = (j / ATT_STAGES) & 1;
-        const int pb = j & 1;
-        const uint32_t pph = (j >> 1) & 1;
-        mbar_wait(&v_full[st], ph, 0x53);
-        mbar_wait(&p_full[pb], pph, 0x54);
-        mbar_wait(&o_empty[pb], pph ^ 1, 0x55);
-        tc_fence_after();
-        const uint32_t p_addr = smem_u32(sP + pb * 2 * ATT_TILE_BYTES);
-        const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < ATT_BN / 16; ++k) {
-          // P: two 64-wide K atoms (16 KB apart), 32 B per K=16 step inside an atom.  V: 16 kv rows = 2048 B per step.
-          const uint64_t da = desc_kmajor_sw128(p_addr + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32);
-          const uint64_t db = desc_mnmajor_sw128(v_addr + k * 2048, ATT_TILE_BYTES);
-          umma_bf16(tO + pb * ATT_D, da, db, idesc_o, k != 0 ? 1u : 0u);
+  if (warp >= 8) {
+    setmaxnreg_dec<40>();
+    if (warp == 8) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        const int cq = head * ATT_D, ck = p.inner_dim + head * ATT_D, cv = 2 * p.inner_dim + head * ATT_D;
+        mbar_arrive_expect_tx(q_full, n_sub * ATT_TILE_BYTES);
+        for (int x = 0; x < n_sub; ++x) tma_load_3d(sQ + x * ATT_TILE_BYTES, &p.tmQKV, q_full, cq, q0 + x * ATT_BM, b);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int st = j % ATT_STAGES;
+          const uint32_t ph = (j / ATT_STAGES) & 1;
+          mbar_wait(&k_empty[st], ph ^ 1, 0x40);
+          mbar_arrive_expect_tx(&k_full[st], ATT_TILE_BYTES);
+          tma_load_3d(sK + st * ATT_TILE_BYTES, &p.tmQKV, &k_full[st], ck, j * ATT_BN, b);
+          mbar_wait(&v_empty[st], ph ^ 1, 0x41);
+          mbar_arrive_expect_tx(&v_full[st], ATT_TILE_BYTES);
+          tma_load_3d(sV + st * ATT_TILE_BYTES, &p.tmQKV, &v_full[st], cv, j * ATT_BN, b);
         }
-        umma_commit(&o_full[pb]);
-        umma_commit(&v_empty[st]);
+      }
+    } else if (warp == 9) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);  // Q (K-major) x K (K-major)
+        constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);   // P (K-major) x V (MN-major)
+        auto issue_qk = [&](int j) {
+          const int st = j % ATT_STAGES;
+          mbar_wait(&k_full[st], (j / ATT_STAGES) & 1, 0x50);
+          const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
+          for (int x = 0; x < n_sub; ++x) {
+            mbar_wait(&s_empty[x], (j & 1) ^ 1, 0x51);   // softmax has pulled S_x(j-1) into registers
+            tc_fence_after();
+            const uint32_t q_addr = smem_u32(sQ + x * ATT_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < ATT_D / 16; ++k)
+              umma_bf16(tS + x * ATT_BN, desc_kmajor_sw128(q_addr + k * 32), desc_kmajor_sw128(k_addr + k * 32), idesc_s,
+                        k != 0 ? 1u : 0u);
+            umma_commit(&s_full[x]);
+          }
+          umma_commit(&k_empty[st]);
+        };
+        mbar_wait(q_full, 0, 0x52);
+        issue_qk(0);
+        for (int j = 0; j < n_tiles; ++j) {
+          if (j + 1 < n_tiles) issue_qk(j + 1);
+          const int st = j % ATT_STAGES;
+          mbar_wait(&v_full[st], (j / ATT_STAGES) & 1, 0x53);
+          const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
+          for (int x = 0; x < n_sub; ++x) {
+            mbar_wait(&p_full[x], j & 1, 0x54);
+            mbar_wait(&o_empty[x], (j & 1) ^ 1, 0x55);
+            tc_fence_after();
+            const uint32_t p_addr = smem_u32(sP + x * 2 * ATT_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < ATT_BN / 16; ++k) {
+              // P: two 64-wide K atoms (16 KB apart), 32 B per K=16 step inside an atom.  V: 16 kv rows = 2048 B per step.
+              const uint64_t da = desc_kmajor_sw128(p_addr + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32);
+              const uint64_t db = desc_mnmajor_sw128(v_addr + k * 2048, ATT_TILE_BYTES);
+              umma_bf16(tO + x * ATT_D, da, db, idesc_o, k != 0 ? 1u : 0u);
+            }
+            umma_commit(&o_full[x]);
+          }
+          umma_commit(&v_empty[st]);
+        }
       }
     }
   } else {
-    // ===================== softmax / accumulate (warps 0-3) =====================
-    const int r = warp * 32 + lane;                 // query row in tile == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    const float sc = p.scale_log2;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o_acc[ATT_D];
+    // ===================== softmax / accumulate: warps 0-3 -> sub-tile A, warps 4-7 -> sub-tile B =====================
+    setmaxnreg_inc<232>();
+    const int x = warp >> 2;                          // sub-tile
+    if (x < n_sub) {
+      const int wq = warp & 3;                        // TMEM lane quadrant
+      const int r = wq * 32 + lane;                   // query row in the sub-tile == TMEM lane
+      const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+      const uint32_t tSx = tS + lane_off + x * ATT_BN;
+      const uint32_t tOx = tO + lane_off + x * ATT_D;
+      uint8_t* prow = sP + x * 2 * ATT_TILE_BYTES + r * 128;
+      const float sc = p.scale_log2;
+      float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+      float o_acc[ATT_D];
 #pragma unroll
-    for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.f;
-    float alpha_prev = 0.f;
+      for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.f;
 
-    auto softmax_tile = [&](int j) -> float {
-      const int sb = j & 1;
-      mbar_wait(&s_full[sb], (j >> 1) & 1, 0x60);
-      tc_fence_after();
-      uint32_t s0[32], s1[32], s2[32], s3[32];
-      tmem_ld32(tS + lane_off + sb * ATT_BN + 0, s0);
-      tmem_ld32(tS + lane_off + sb * ATT_BN + 32, s1);
-      tmem_ld32(tS + lane_off + sb * ATT_BN + 64, s2);
-      tmem_ld32(tS + lane_off + sb * ATT_BN + 96, s3);
-      tmem_ld_wait();
-      // S buffer is free for QK^T of tile j+2
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[sb]);
-
-      const int kv_valid = S - j * ATT_BN;  // >= 1
-      float mx = m_run;
-      auto max32 = [&](uint32_t(&a)[32], int base) {
-        if (kv_valid < ATT_BN) {
+      auto accumulate = [&](int j, float alpha) {   // o_acc = o_acc * alpha_j + O_part(j)
+        mbar_wait(&o_full[x], j & 1, 0x61);
+        tc_fence_after();
+        uint32_t o0[32], o1[32];
+        tmem_ld32(tOx, o0);
+        tmem_ld32(tOx + 32, o1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[x]);
 #pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (base + c >= kv_valid) a[c] = 0xFF800000u;  // -inf: key beyond the sequence
+        for (int i = 0; i < 32; ++i) {
+          o_acc[i] = o_acc[i] * alpha + __uint_as_float(o0[i]);
+          o_acc[32 + i] = o_acc[32 + i] * alpha + __uint_as_float(o1[i]);
         }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(a[c]));
       };
-      max32(s0, 0); max32(s1, 32); max32(s2, 64); max32(s3, 96);
-      const float alpha = ex2_approx((m_run - mx) * sc);
-      const float mneg = -mx * sc;
-      float sum = 0.f;
-      uint8_t* prow = sP + sb * 2 * ATT_TILE_BYTES + r * 128;
-      auto exp32 = [&](uint32_t(&a)[32], int quarter) {
+
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(&s_full[x], j & 1, 0x60);
+        tc_fence_after();
+        uint32_t s0[32], s1[32], s2[32], s3[32];
+        tmem_ld32(tSx + 0, s0);
+        tmem_ld32(tSx + 32, s1);
+        tmem_ld32(tSx + 64, s2);
+        tmem_ld32(tSx + 96, s3);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[x]);     // S_x is free for QK^T of tile j+1
+
+        const int kv_valid = S - j * ATT_BN;  // >= 1
+        float mx = m_run;
+        auto max32 = [&](uint32_t(&a)[32], int base) {
+          if (kv_valid < ATT_BN) {
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {   // 16-byte chunks of 8 kv columns
-          float e[8];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            e[t] = ex2_approx(fmaf(__uint_as_float(a[c4 * 8 + t]), sc, mneg));
-            sum += e[t];
+            for (int c = 0; c < 32; ++c)
+              if (base + c >= kv_valid) a[c] = 0xFF800000u;  // -inf: key beyond the sequence
           }
-          uint4 o;
-          o.x = pack_bf16x2(e[0], e[1]); o.y = pack_bf16x2(e[2], e[3]);
-          o.z = pack_bf16x2(e[4], e[5]); o.w = pack_bf16x2(e[6], e[7]);
-          const int ch = quarter * 4 + c4;
-          const int atom = ch >> 3, cc = ch & 7;
-          *reinterpret_cast<uint4*>(prow + atom * ATT_TILE_BYTES + ((cc ^ (r & 7)) << 4)) = o;
-        }
-      };
-      exp32(s0, 0); exp32(s1, 1); exp32(s2, 2); exp32(s3, 3);
-      l_run = l_run * alpha + sum;
-      m_run = mx;
-      fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[sb]);
-      return alpha;
-    };
+#pragma unroll
+          for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(a[c]));
+        };
+        max32(s0, 0); max32(s1, 32); max32(s2, 64); max32(s3, 96);
+        const float alpha = ex2_approx((m_run - mx) * sc);
+        const float mneg = -mx * sc;
+        float sum = 0.f;
+        uint32_t pk[64];                               // P(j) as packed bf16 pairs, held until P smem is free
+        auto exp32 = [&](uint32_t(&a)[32], int quarter) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(a[2 * c]), sc, mneg));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(a[2 * c + 1]), sc, mneg));
+            sum += e0 + e1;
+            pk[quarter * 16 + c] = pack_bf16x2(e0, e1);
+          }
+        };
+        exp32(s0, 0); exp32(s1, 1); exp32(s2, 2); exp32(s3, 3);
+        l_run = l_run * alpha + sum;
+        m_run = mx;
 
-    alpha_prev = softmax_tile(0);
-    for (int j = 0; j < n_tiles; ++j) {
-      float alpha_next = 0.f;
-      if (j + 1 < n_tiles) alpha_next = softmax_tile(j + 1);
-      const int ob = j & 1;
-      mbar_wait(&o_full[ob], (j >> 1) & 1, 0x61);
-      tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld32(tO + lane_off + ob * ATT_D + 0, o0);
-      tmem_ld32(tO + lane_off + ob * ATT_D + 32, o1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_empty[ob]);
-      // invariant: o_acc = sum_{i<j} P_i V_i relative to the running max M_{j-1}; O_part_j is relative to M_j;
-      // alpha_prev == alpha_j = exp2((M_{j-1} - M_j) * scale).
+        // PV(j-1) finished <=> O_part(j-1) is ready and the tensor core no longer reads P smem
+        if (j > 0) accumulate(j - 1, alpha_prev);
+        alpha_prev = alpha;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        o_acc[i] = o_acc[i] * alpha_prev + __uint_as_float(o0[i]);
-        o_acc[32 + i] = o_acc[32 + i] * alpha_prev + __uint_as_float(o1[i]);
+        for (int ch = 0; ch < 16; ++ch) {              // 16-byte chunks of 8 kv columns
+          const int atom = ch >> 3, cc = ch & 7;
+          *reinterpret_cast<uint4*>(prow + atom * ATT_TILE_BYTES + ((cc ^ (r & 7)) << 4)) =
+              make_uint4(pk[ch * 4 + 0], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+        }
+        fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[x]);
       }
-      alpha_prev = alpha_next;
-    }
-    // o_acc and l_run are both relative to the final running max m_run.
-    const int q = q0 + r;
-    if (q < S) {
-      const float inv = 1.0f / l_run;
-      bf16* dst = p.out + static_cast<long>(b) * p.out_batch_stride + static_cast<long>(q) * p.inner_dim + head * ATT_D;
+      accumulate(n_tiles - 1, alpha_prev);
+      // o_acc and l_run are both relative to the final running max m_run.
+      const int q = q0 + x * ATT_BM + r;
+      if (q < S) {
+        const float inv = 1.0f / l_run;
+        bf16* dst = p.out + static_cast<long>(b) * p.out_batch_stride + static_cast<long>(q) * p.inner_dim + head * ATT_D;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 o;
-        o.x = pack_bf16x2(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
-        o.y = pack_bf16x2(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
-        o.z = pack_bf16x2(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv);
-        o.w = pack_bf16x2(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
-        reinterpret_cast<uint4*>(dst)[c] = o;
+        for (int c = 0; c < 8; ++c) {
+          uint4 o;
+          o.x = pack_bf16x2(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
+          o.y = pack_bf16x2(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
+          o.z = pack_bf16x2(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv);
+          o.w = pack_bf16x2(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
+          reinterpret_cast<uint4*>(dst)[c] = o;
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -263,7 +272,7 @@ cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  dim3 grid((p.seq_len + ATT_BM - 1) / ATT_BM, p.num_heads, p.batch);
+  dim3 grid((p.seq_len + ATT_QB - 1) / ATT_QB, p.num_heads, p.batch);
   attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(p);
   return cudaGetLastError();
 }

@@ -419,7 +419,7 @@ def rollout(w, cfg: SD3Config, x0: torch.Tensor, prompt_embeds: torch.Tensor, po
         t = timesteps[i]
         t_next = timesteps[i + 1] if i + 1 < num_inference_steps else torch.tensor(0.0)
         nl = noise_level if i in sde_step_indices else 0.0
-        timestep = t.expand(B).to(latents.dtype)                       # sd3_5.py:394 (fp16-rounded t)
+        timestep = t.expand(B).to(device=latents.device, dtype=latents.dtype)   # sd3_5.py:394 (fp16-rounded t)
         if do_cfg:
             pe = torch.cat([neg_prompt_embeds, prompt_embeds], dim=0)  # sd3_5.py:409-413
             pp = torch.cat([neg_pooled, pooled], dim=0)
