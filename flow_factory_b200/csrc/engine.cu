@@ -106,7 +106,7 @@ static int build_gemm(const GemmSpec& s, GemmParams* p) {
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(s.K), static_cast<uint64_t>(s.N)};
     const uint64_t str[1] = {static_cast<uint64_t>(s.K)};
-    const uint32_t box[2] = {64, static_cast<uint32_t>(p->bn)};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(p->bn / 2)};   // each CTA of the pair fetches half of the W tile
     int r = make_tmap(&p->tmB, s.W, 2, dims, str, box);
     if (r) return r;
   }

@@ -9,6 +9,9 @@
 //   warps 4-7 : epilogue       (tcgen05.ld 32x32b -> registers; thread == accumulator row; fused bias /
 //                               GELU-tanh / adaLN gate + residual / per-head RMSNorm(q,k) / row-table add; bf16 stores)
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+// CTAs run as clusters of 2 on vertically adjacent output tiles: each CTA fetches half of the shared W tile and
+// TMA-multicasts it into both CTAs' shared memory, halving the L2 -> SM operand traffic (128x256 tiles alone need
+// ~19 TB/s of L2 bandwidth at tensor peak; with the shared W tile the pair is at 128 FLOP/B).
 //
 // A is addressed as a 3-D tensor [batch][rows_per_batch][K] so that token sub-ranges of a joint
 // [B, S, D] buffer (image rows / text rows) are separate GEMM problems with zero-filled ragged tails.
@@ -55,7 +58,7 @@ __device__ __forceinline__ void load_vec_bf16(const bf16* ptr, float* f) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -77,33 +80,40 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
     tma_prefetch_desc(&p.tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    // a slot is free only when BOTH CTAs' MMAs have drained it (the peer multicasts half of W into it)
+    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 2); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();   // barrier inits visible cluster-wide before any remote arrive / multicast; also a CTA barrier
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  const uint32_t cta_rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int tiles_m = p.num_batch * p.tiles_m_per_batch;
+  const int pairs_m = (tiles_m + 1) >> 1;
   const int tiles_n = p.N / BN;
-  const int num_tiles = tiles_m * tiles_n;
+  const int num_units = pairs_m * tiles_n;      // unit = two vertically adjacent 128 x BN tiles sharing one W tile
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile % tiles_m, tn = tile / tiles_m;
-        const int b = tm / p.tiles_m_per_batch, row0 = (tm % p.tiles_m_per_batch) * GEMM_BM;
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+        const int tm = 2 * (unit % pairs_m) + static_cast<int>(cta_rank), tn = unit / pairs_m;
+        // a ghost tile (odd tile count) still takes part in the W multicast; its A rows are out of bounds -> zeros
+        const int b = tm < tiles_m ? tm / p.tiles_m_per_batch : p.num_batch;
+        const int row0 = tm < tiles_m ? (tm % p.tiles_m_per_batch) * GEMM_BM : 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 0x10);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           tma_load_3d(smem_a + stage * Cfg::kABytes, &p.tmA, &full_bar[stage], kb * GEMM_BK, row0, b);
-          tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.tmB, &full_bar[stage], kb * GEMM_BK, tn * BN);
+          tma_load_2d_multicast(smem_b + stage * Cfg::kBBytes + cta_rank * (Cfg::kBBytes / 2), &p.tmB, &full_bar[stage],
+                                kb * GEMM_BK, tn * BN + static_cast<int>(cta_rank) * (BN / 2), 0x3);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -113,7 +123,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
       int stage = 0; uint32_t phase = 0; int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 0x20);
@@ -129,7 +139,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
             umma_bf16(d_tmem, desc_kmajor_sw128(a_addr + k * 32), desc_kmajor_sw128(b_addr + k * 32), idesc,
                       (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                 // smem slot free once these MMAs retire
+          umma_commit_multicast(&empty_bar[stage], 0x3);  // slot free (in both CTAs) once these MMAs retire
           if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -140,13 +150,13 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
     const int ew = warp - 4;                 // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
     const int r_in_tile = ew * 32 + lane;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int tm = tile % tiles_m, tn = tile / tiles_m;
-      const int b = tm / p.tiles_m_per_batch;
+      const int tm = 2 * (unit % pairs_m) + static_cast<int>(cta_rank), tn = unit / pairs_m;
+      const int b = tm < tiles_m ? tm / p.tiles_m_per_batch : 0;
       const int row = (tm % p.tiles_m_per_batch) * GEMM_BM + r_in_tile;
-      const bool row_ok = row < p.rows_per_batch;
+      const bool row_ok = tm < tiles_m && row < p.rows_per_batch;
       mbar_wait(&tmem_full[acc], acc_phase, 0x30);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
@@ -256,7 +266,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();   // no CTA may exit while its peer can still multicast into its smem / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -272,8 +282,9 @@ static cudaError_t launch_bn(const GemmParams& p, int num_sms, cudaStream_t stre
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int tiles = p.num_batch * p.tiles_m_per_batch * (p.N / BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  const int units = ((p.num_batch * p.tiles_m_per_batch + 1) / 2) * (p.N / BN);
+  const int max_clusters = num_sms / 2;
+  const int grid = 2 * (units < max_clusters ? units : max_clusters);
   gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(p);
   return cudaGetLastError();
 }

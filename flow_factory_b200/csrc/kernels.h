@@ -21,7 +21,7 @@ enum GemmEpilogue : int {
 
 struct GemmParams {
   CUtensorMap tmA;  // 3-D {K, rows_per_batch, num_batch}, box {64, 128, 1}, SWIZZLE_128B
-  CUtensorMap tmB;  // 2-D {K, N},                          box {64, bn},    SWIZZLE_128B
+  CUtensorMap tmB;  // 2-D {K, N},                          box {64, bn/2},  SWIZZLE_128B (one half per CTA of the cluster pair)
   int rows_per_batch, num_batch, N, K;
   int tiles_m_per_batch;
   int bn;   // N tile: 256 / 128 / 64 (must divide N)
