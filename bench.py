@@ -109,12 +109,18 @@ def flops_per_latent(cfg, ni, nt, T, cfg_on):
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
+CPU_SAMPLE_LAYERS = 2
+
+
 def cpu_reference_sample(cfg, weights_bf16_cpu, res, n_text, T, guidance, threads, reps=1):
-    """Times the reference's CPU path restated in oracle/ (diffusers SD3 forward + scheduler.step, bf16 CPU autocast):
-    ONE transformer forward at B=1 (no CFG doubling) + one scheduler step; a latent costs T x (2 if CFG) of those."""
+    """Times the reference's CPU path restated in oracle/ (diffusers SD3 forward + scheduler.step, bf16 CPU autocast) on a
+    BOUNDED sample: embeddings + the first CPU_SAMPLE_LAYERS (dual-attention) blocks + norm_out/proj_out of ONE forward at
+    B=1 (no CFG doubling) + one scheduler step, scaled to a full forward by the FLOP model (a block is >99.9 % GEMM +
+    attention work) and to a latent by T x (2 if CFG)."""
     from oracle import sd3_oracle as O
     torch.set_num_threads(threads)
     lat = res // 8
+    ni = (lat // 2) ** 2
     inp = O.make_inputs(cfg, 1, lat, lat, n_text, seed=1)
     ts, sig = O.make_schedule(T, 3.0)
     x = inp["x0"].half()
@@ -123,13 +129,17 @@ def cpu_reference_sample(cfg, weights_bf16_cpu, res, n_text, T, guidance, thread
         t0 = time.perf_counter()
         with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
             v = O.transformer_forward(weights_bf16_cpu, cfg, x, inp["prompt_embeds"].bfloat16(), inp["pooled"].bfloat16(),
-                                      ts[3].expand(1).half())
+                                      ts[3].expand(1).half(), max_layers=CPU_SAMPLE_LAYERS)
         O.sde_step(v, x, (ts[3] / 1000).item(), (ts[4] / 1000).item(), 0.7, float(sig[1]),
                    noise=torch.randn(x.shape), compute_log_prob=True)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
+    D, S, n = cfg.inner_dim, ni + n_text, CPU_SAMPLE_LAYERS
+    fl_sample = n * (24 * ni * D * D + 24 * n_text * D * D + 8 * ni * D * D + 4 * S * S * D + 4 * ni * ni * D)
+    lin, att = O.flops_per_forward(cfg, ni, n_text)
+    t_forward = best * (lin + att) / fl_sample
     fwd_per_latent = T * (2 if guidance > 1.0 else 1)
-    return 1.0 / (best * fwd_per_latent), best
+    return 1.0 / (t_forward * fwd_per_latent), best
 
 
 def make_cpu_weights(cfg):
@@ -159,8 +169,8 @@ def run_reference(args):
         vals.append(v)
     wall = time.perf_counter() - t0
     value = sum(vals) / len(vals)
-    sample = (f"1 transformer forward + scheduler.step at {args.cpu_sample_res}^2, B=1, bf16 CPU autocast, extrapolated x{T} steps"
-              f" x{2 if args.guidance > 1 else 1} (CFG); {args.steps} timed samples")
+    sample = (f"{CPU_SAMPLE_LAYERS} of 24 blocks of 1 transformer forward + scheduler.step at {args.cpu_sample_res}^2, B=1, bf16 CPU autocast, "
+              f"scaled to 24 blocks by FLOPs, x{T} steps x{2 if args.guidance > 1 else 1} (CFG); {args.steps} timed samples")
     line = {"metric": METRIC, "value": value, "unit": "latents/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "impl": "reference",
@@ -306,7 +316,8 @@ def run_b200(args):
         wcpu = make_cpu_weights(cfg)
         v, dt = cpu_reference_sample(cfg, wcpu, args.cpu_sample_res, args.n_text, T, args.guidance, threads)
         cpu = {"value": v, "unit": "latents/s", "cores": threads, "kind": "port",
-               "sample": f"1 transformer forward + scheduler.step at {args.cpu_sample_res}^2 B=1 bf16 CPU autocast ({dt:.1f} s), extrapolated x{T} steps x{2 if cfg_on else 1} (CFG)"}
+               "sample": f"{CPU_SAMPLE_LAYERS} of 24 blocks of 1 forward + scheduler.step at {args.cpu_sample_res}^2 B=1 bf16 CPU autocast ({dt:.1f} s), "
+                         f"scaled to 24 blocks by FLOPs, x{T} steps x{2 if cfg_on else 1} (CFG)"}
 
     line = {"metric": METRIC, "value": value, "unit": "latents/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",

@@ -248,6 +248,41 @@ __device__ __forceinline__ void box_muller(uint32_t u0, uint32_t u1, float* z0, 
 // ------------------------------------------------------------------------------------------------
 // Fused CFG + Euler/SDE step + log-prob.  Each thread owns 4 consecutive pixels of one (b, c, y) row.
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// Per-element pieces of scheduler.step, shared by the standalone kernel and the fused proj_out epilogue.
+// fp32, reference operation order, no FMA contraction.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cfg_combine_bf16(float vu, float vt, float g) {   // sd3_5.py:431-433 on bf16 tensors
+  return bf16_round(vu + bf16_round(g * bf16_round(vt - vu)));
+}
+__device__ __forceinline__ float sde_mean(const StepCoef& k, float x, float v) {
+  if (k.dynamics == DYN_ODE) return __fadd_rn(x, __fmul_rn(v, k.dt));
+  if (k.dynamics == DYN_FLOW_SDE) return __fadd_rn(__fmul_rn(x, k.c_x), __fmul_rn(__fmul_rn(v, k.c_v), k.dt));
+  if (k.dynamics == DYN_DANCE_SDE) {
+    const float x0p = __fsub_rn(x, __fmul_rn(k.sigma, v));
+    const float num = __fmul_rn(k.c_x /* 0.5*eta^2 */, __fsub_rn(x, __fmul_rn(x0p, k.c_v /* 1-sigma */)));
+    const float lt = __fdiv_rn(num, __fmul_rn(k.sigma, k.sigma));
+    return __fadd_rn(x, __fmul_rn(__fadd_rn(v, lt), k.dt));
+  }
+  const float x0p = __fsub_rn(x, __fmul_rn(k.sigma, v));                 // CPS
+  const float x1p = __fadd_rn(x, __fmul_rn(v, k.c_v /* 1-sigma */));
+  return __fadd_rn(__fmul_rn(x0p, k.cps_a), __fmul_rn(x1p, k.cps_b));
+}
+// mean + scale*z, rounded through the fp16 storage dtype (flow_match...py:359-362)
+__device__ __forceinline__ float sde_sample(const StepCoef& k, float mean, float z) {
+  return __half2float(__float2half_rn(__fadd_rn(mean, __fmul_rn(k.noise_scale, z))));
+}
+__device__ __forceinline__ float sde_logp_term(const StepCoef& k, float nxt, float mean) {
+  const float d = __fsub_rn(nxt, mean);
+  const float d2 = __fmul_rn(d, d);
+  return k.dynamics == DYN_CPS ? -d2 : __fdiv_rn(-d2, k.two_var);
+}
+// cast_latents (abc.py:172-182): clamp to the fp16 range, raise the sticky flag
+__device__ __forceinline__ __half sde_store_half(float s, int* overflow_flag) {
+  if (fabsf(s) > 65504.0f) { s = copysignf(65504.0f, s); if (overflow_flag) *overflow_flag = 1; }
+  return __float2half_rn(s);
+}
+
 constexpr int SDE_THREADS = 256;
 
 __global__ void __launch_bounds__(SDE_THREADS) sde_step_kernel(const SdeStepParams p) {
@@ -280,7 +315,7 @@ __global__ void __launch_bounds__(SDE_THREADS) sde_step_kernel(const SdeStepPara
         if (p.cfg) {
           const float vu = __bfloat162float(p.v_tokens[(static_cast<long>(b) * ntok + tok) * vch + n]);
           const float vt = __bfloat162float(p.v_tokens[(static_cast<long>(p.B + b) * ntok + tok) * vch + n]);
-          vc = bf16_round(vu + bf16_round(p.guidance * bf16_round(vt - vu)));
+          vc = cfg_combine_bf16(vu, vt, p.guidance);
         } else {
           vc = __bfloat162float(p.v_tokens[(static_cast<long>(b) * ntok + tok) * vch + n]);
         }
@@ -296,22 +331,7 @@ __global__ void __launch_bounds__(SDE_THREADS) sde_step_kernel(const SdeStepPara
     // ---- mean ----
     float mean[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (k.dynamics == DYN_ODE) {
-        mean[i] = __fadd_rn(xs[i], __fmul_rn(v[i], k.dt));
-      } else if (k.dynamics == DYN_FLOW_SDE) {
-        mean[i] = __fadd_rn(__fmul_rn(xs[i], k.c_x), __fmul_rn(__fmul_rn(v[i], k.c_v), k.dt));
-      } else if (k.dynamics == DYN_DANCE_SDE) {
-        const float x0p = __fsub_rn(xs[i], __fmul_rn(k.sigma, v[i]));
-        const float num = __fmul_rn(k.c_x /* 0.5*eta^2 */, __fsub_rn(xs[i], __fmul_rn(x0p, k.c_v /* 1-sigma */)));
-        const float lt = __fdiv_rn(num, __fmul_rn(k.sigma, k.sigma));
-        mean[i] = __fadd_rn(xs[i], __fmul_rn(__fadd_rn(v[i], lt), k.dt));
-      } else {  // CPS
-        const float x0p = __fsub_rn(xs[i], __fmul_rn(k.sigma, v[i]));
-        const float x1p = __fadd_rn(xs[i], __fmul_rn(v[i], k.c_v /* 1-sigma */));
-        mean[i] = __fadd_rn(__fmul_rn(x0p, k.cps_a), __fmul_rn(x1p, k.cps_b));
-      }
-    }
+    for (int i = 0; i < 4; ++i) mean[i] = sde_mean(k, xs[i], v[i]);
     // ---- next sample ----
     float nxt[4];
     if (p.next_given != nullptr) {
@@ -334,20 +354,13 @@ __global__ void __launch_bounds__(SDE_THREADS) sde_step_kernel(const SdeStepPara
         box_muller(r[2], r[3], &z[2], &z[3]);
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float s = __fadd_rn(mean[i], __fmul_rn(k.noise_scale, z[i]));
-        nxt[i] = __half2float(__float2half_rn(s));  // .to(storage dtype).float()  (flow_match...py:362)
-      }
+      for (int i = 0; i < 4; ++i) nxt[i] = sde_sample(k, mean[i], z[i]);
     }
     // ---- store (cast_latents: clamp to +-65504 on overflow) ----
     if (p.x_next != nullptr || traj != nullptr) {
       __half h[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float s = nxt[i];
-        if (fabsf(s) > 65504.0f) { s = copysignf(65504.0f, s); if (p.overflow_flag) *p.overflow_flag = 1; }
-        h[i] = __float2half_rn(s);
-      }
+      for (int i = 0; i < 4; ++i) h[i] = sde_store_half(nxt[i], p.overflow_flag);
       uint2 o;
       o.x = *reinterpret_cast<uint32_t*>(&h[0]);
       o.y = *reinterpret_cast<uint32_t*>(&h[2]);
@@ -363,12 +376,7 @@ __global__ void __launch_bounds__(SDE_THREADS) sde_step_kernel(const SdeStepPara
     // ---- log-prob terms ----
     if (k.compute_log_prob && k.dynamics != DYN_ODE) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float d = __fsub_rn(nxt[i], mean[i]);
-        const float d2 = __fmul_rn(d, d);
-        if (k.dynamics == DYN_CPS) part += -d2;
-        else part += __fdiv_rn(-d2, k.two_var /* = 2*var */);
-      }
+      for (int i = 0; i < 4; ++i) part += sde_logp_term(k, nxt[i], mean[i]);
     }
   }
   // block reduce -> logp_partial[b, blockIdx.x]

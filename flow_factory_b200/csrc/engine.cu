@@ -9,6 +9,7 @@
 #include "kernels.h"
 #include "../../include/ffb200.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <functional>
@@ -165,7 +166,10 @@ struct ffb200_plan {
   float* logp_partial;
   int* d_step;
   StepCoef* d_coefs; int coef_cap;
-  std::vector<Op> fwd_ops;      // transformer forward (reads x_cur, writes vout)
+  std::vector<Op> fwd_ops;      // transformer forward up to norm_out (reads x_cur, leaves LN-modulated hidden states in a1)
+  Op proj_op;                   // plain proj_out GEMM -> vout (inspection path: ffb200_transformer_forward)
+  FinalStepParams fs;           // fused proj_out + CFG + unpatchify + scheduler.step (step / rollout path)
+  unsigned int* d_done;
   bool prompts_set;
   const void* prompt_ptr;
   // per-step graph
@@ -210,7 +214,7 @@ int ffb200_engine_set_weights(ffb200_engine* e, const ffb200_weights* w) {
 int ffb200_engine_create(const ffb200_model_config* cfg, const ffb200_weights* w, ffb200_engine** out) {
   FFB_CHECK(cfg && w && out, "null argument");
   FFB_CHECK(cfg->num_layers > 0 && cfg->num_heads > 0, "bad config");
-  FFB_CHECK(cfg->patch_size * cfg->patch_size * cfg->in_channels == 64, "patch_size^2 * in_channels must be 64");
+  FFB_CHECK(cfg->patch_size == 2 && cfg->in_channels == 16, "patch_size 2 / 16 latent channels (SD3 family) required");
   FFB_CHECK(cfg->joint_attention_dim % 8 == 0 && cfg->pooled_projection_dim % 8 == 0, "joint/pooled dims must be multiples of 8");
   int dev = 0, major = 0;
   FFB_CUDA(cudaGetDevice(&dev));
@@ -316,8 +320,10 @@ int ffb200_plan_create(ffb200_engine* e, int batch, int cfg, int lat_h, int lat_
   ALLOC(ffc, static_cast<size_t>(Bp) * Nt * 4 * D, bf16);
   ALLOC(vout, static_cast<size_t>(Bp) * Ni * 64, bf16);
   ALLOC(x_cur, static_cast<size_t>(p->B) * p->C * p->H * p->W, __half);
-  ALLOC(logp_partial, static_cast<size_t>(p->B) * 64, float);
+  ALLOC(logp_partial, static_cast<size_t>(p->B) * std::max(64, (Ni + 127) / 128), float);
   ALLOC(d_step, 1, int);
+  ALLOC(d_done, 1, unsigned int);
+  if (!r) cudaMemset(p->d_done, 0, sizeof(unsigned int));
 #undef ALLOC
   if (r) { ffb200_plan_destroy(p); return r; }
   // cropped positional table (DF/models/embeddings.py:531-552)
@@ -408,7 +414,19 @@ int ffb200_plan_create(ffb200_engine* e, int batch, int cfg, int lat_h, int lat_
     add_lnmod(p, p->h_img, Ni, mo + 1 * D, mo + 0 * D, p->a1, nullptr, nullptr, nullptr);
     GemmSpec po = {p->a1, Bp, Ni, 0, D, D, w.proj_w, 64, w.proj_b, p->vout, static_cast<long>(Ni) * 64, 0, 64,
                    EPI_BIAS, nullptr, 0, nullptr, nullptr, 0, 0.f, nullptr};
-    r = add_gemm(p, po);
+    GemmParams gp;
+    r = build_gemm(po, &gp);
+    if (!r) {
+      const int sms = num_sms();
+      p->proj_op = [gp, sms](cudaStream_t st) { ++g_launch_count; return launch_gemm(gp, sms, st); };
+      memset(&p->fs, 0, sizeof(p->fs));
+      p->fs.tmA = gp.tmA;
+      const uint64_t dims[2] = {static_cast<uint64_t>(D), 64};
+      const uint64_t str[1] = {static_cast<uint64_t>(D)};
+      const uint32_t box[2] = {64, 64};
+      r = make_tmap(&p->fs.tmW, w.proj_w, 2, dims, str, box);
+      p->fs.K = D; p->fs.bias = static_cast<const bf16*>(w.proj_b); p->fs.done_counter = p->d_done;
+    }
   }
   if (r) { ffb200_plan_destroy(p); return r; }
   *out = p;
@@ -470,7 +488,7 @@ __global__ void unpatchify_kernel(const bf16* v_tokens, int Bp, int C, int H, in
 
 static void fill_sde(const ffb200_plan* p, SdeStepParams* sp) {
   memset(sp, 0, sizeof(*sp));
-  sp->v_tokens = p->vout; sp->B = p->B; sp->C = p->C; sp->H = p->H; sp->W = p->W; sp->patch = p->e->cfg.patch_size;
+  sp->B = p->B; sp->C = p->C; sp->H = p->H; sp->W = p->W; sp->patch = p->e->cfg.patch_size;
   sp->cfg = p->cfg; sp->x = p->x_cur; sp->logp_partial = p->logp_partial; sp->coef_table = p->d_coefs;
 }
 
@@ -486,6 +504,7 @@ int ffb200_transformer_forward(ffb200_plan* p, const void* latents_fp16, float t
   FFB_CUDA(cudaMemsetAsync(p->d_step, 0, sizeof(int), st));
   FFB_CUDA(cudaMemcpyAsync(p->x_cur, latents_fp16, static_cast<size_t>(p->B) * p->C * p->H * p->W * 2, cudaMemcpyDeviceToDevice, st));
   if ((r = run_forward(p, st))) return r;
+  FFB_CUDA(p->proj_op(st));
   if (noise_pred_nchw) {
     ++g_launch_count;
     unpatchify_kernel<<<148 * 4, 256, 0, st>>>(p->vout, p->Bp, p->C, p->H, p->W, p->e->cfg.patch_size, static_cast<bf16*>(noise_pred_nchw));
@@ -512,8 +531,10 @@ int ffb200_step(ffb200_plan* p, const ffb200_step_args* a, void* stream) {
   sp.x_next = static_cast<__half*>(a->out_next_latents);
   sp.mean_out = a->out_mean; sp.log_prob = a->out_log_prob; sp.v_out = static_cast<bf16*>(a->out_noise_pred);
   sp.overflow_flag = a->overflow_flag;
-  g_launch_count += 2;
-  FFB_CUDA(launch_sde_step(sp, st));
+  FinalStepParams fs = p->fs;
+  fs.sde = sp;
+  ++g_launch_count;
+  FFB_CUDA(launch_final_step(fs, st));
   return 0;
 }
 
@@ -538,12 +559,14 @@ static int rollout_impl(ffb200_plan* p, const ffb200_rollout_args* a, cudaStream
   sp.logp_traj = a->log_probs; sp.logp_batch_stride = a->n_logp_slots;
   sp.overflow_flag = a->overflow_flag; sp.step_ptr = p->d_step;
 
+  FinalStepParams fs = p->fs;
+  fs.sde = sp;
   auto one_step = [&](cudaStream_t s) -> int {
     int rr = run_forward(p, s);
     if (rr) return rr;
-    g_launch_count += 2;
-    cudaError_t e = launch_sde_step(sp, s);
-    if (e != cudaSuccess) return fail(static_cast<int>(e), "sde_step launch");
+    ++g_launch_count;
+    cudaError_t e = launch_final_step(fs, s);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "final_step launch");
     return 0;
   };
 
@@ -563,7 +586,7 @@ static int rollout_impl(ffb200_plan* p, const ffb200_rollout_args* a, cudaStream
       cudaGraphDestroy(graph);
       p->graph_sde = sp; p->graph_valid = true;
     }
-    const long long per_step = static_cast<long long>(p->fwd_ops.size()) - 1 /*memcpy*/ + 2;
+    const long long per_step = static_cast<long long>(p->fwd_ops.size()) - 1 /*memcpy*/ + 1;
     for (int i = 0; i < T; ++i) FFB_CUDA(cudaGraphLaunch(p->graph_exec, st));
     g_launch_count += per_step * T;
   } else {

@@ -2,4 +2,5 @@
 #include "gemm.cu"
 #include "attention.cu"
 #include "elementwise.cu"
+#include "final_step.cu"
 #include "engine.cu"

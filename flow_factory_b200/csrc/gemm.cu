@@ -9,9 +9,10 @@
 //   warps 4-7 : epilogue       (tcgen05.ld 32x32b -> registers; thread == accumulator row; fused bias /
 //                               GELU-tanh / adaLN gate + residual / per-head RMSNorm(q,k) / row-table add; bf16 stores)
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
-// CTAs run as clusters of 2 on vertically adjacent output tiles: each CTA fetches half of the shared W tile and
-// TMA-multicasts it into both CTAs' shared memory, halving the L2 -> SM operand traffic (128x256 tiles alone need
-// ~19 TB/s of L2 bandwidth at tensor peak; with the shared W tile the pair is at 128 FLOP/B).
+// CTAs run as pairs (cluster of 2, tcgen05 cta_group::2): one MMA instruction spans both SMs (M = 256 x BN): each CTA
+// stages its own 128 A rows and HALF of the W tile, the tensor cores read the other half from the peer's shared memory.
+// Per CTA that is 32 KB per k-block instead of 48 KB: deeper TMA pipeline (6 stages) for the same shared memory and
+// 128 FLOP/B of L2 -> SM traffic instead of 85 (a 128x256 tile alone would need ~19 TB/s of L2 bandwidth at peak).
 //
 // A is addressed as a 3-D tensor [batch][rows_per_batch][K] so that token sub-ranges of a joint
 // [B, S, D] buffer (image rows / text rows) are separate GEMM problems with zero-filled ragged tails.
@@ -26,9 +27,9 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 256;
 
 template <int BN> struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (BN == 256) ? 6 : 8;
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
-  static constexpr int kBBytes = BN * GEMM_BK * 2;
+  static constexpr int kBBytes = (BN / 2) * GEMM_BK * 2;   // this CTA's half of the W tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -80,18 +81,21 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
     tma_prefetch_desc(&p.tmB);
   }
   if (warp == 1 && lane == 0) {
-    // a slot is free only when BOTH CTAs' MMAs have drained it (the peer multicasts half of W into it)
-    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 2); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    // full: the LEADER's barrier collects the bytes of both CTAs' loads; empty / tmem_full: the leader's commits arrive in
+    // both CTAs; tmem_empty: the leader's barrier collects the 4 + 4 epilogue warps of the pair
+    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+  cluster_sync_all();   // both CTAs resident + barrier inits visible cluster-wide before the pair-wide TMEM allocation
+  if (warp == 2) tmem_alloc_2sm(tmem_ptr_smem, Cfg::kTmemCols);
   tc_fence_before();
-  cluster_sync_all();   // barrier inits visible cluster-wide before any remote arrive / multicast; also a CTA barrier
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int tiles_m = p.num_batch * p.tiles_m_per_batch;
   const int pairs_m = (tiles_m + 1) >> 1;
@@ -110,18 +114,18 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
         const int row0 = tm < tiles_m ? (tm % p.tiles_m_per_batch) * GEMM_BM : 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 0x10);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_3d(smem_a + stage * Cfg::kABytes, &p.tmA, &full_bar[stage], kb * GEMM_BK, row0, b);
-          tma_load_2d_multicast(smem_b + stage * Cfg::kBBytes + cta_rank * (Cfg::kBBytes / 2), &p.tmB, &full_bar[stage],
-                                kb * GEMM_BK, tn * BN + static_cast<int>(cta_rank) * (BN / 2), 0x3);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          tma_load_3d_2sm(smem_a + stage * Cfg::kABytes, &p.tmA, &full_bar[stage], kb * GEMM_BK, row0, b);
+          tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &p.tmB, &full_bar[stage], kb * GEMM_BK,
+                          tn * BN + static_cast<int>(cta_rank) * (BN / 2));
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
+    // ===================== MMA issuer (leader CTA only; M = 256 across the pair) =====================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN, 0, 0);
       int stage = 0; uint32_t phase = 0; int it = 0;
       for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++it) {
         const int acc = it & 1;
@@ -136,11 +140,11 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
           const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
-            umma_bf16(d_tmem, desc_kmajor_sw128(a_addr + k * 32), desc_kmajor_sw128(b_addr + k * 32), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_2sm(d_tmem, desc_kmajor_sw128(a_addr + k * 32), desc_kmajor_sw128(b_addr + k * 32), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit_multicast(&empty_bar[stage], 0x3);  // slot free (in both CTAs) once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);  // accumulator complete
+          umma_commit_2sm(&empty_bar[stage], 0x3);                       // slot free in both CTAs once these MMAs retire
+          if (kb == num_kb - 1) umma_commit_2sm(&tmem_full[acc], 0x3);   // accumulators (both halves) complete
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -261,7 +265,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);   // the leader's MMA thread waits for all 8 epilogue warps
     }
   }
 
@@ -269,7 +273,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
   cluster_sync_all();   // no CTA may exit while its peer can still multicast into its smem / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
   }
 }
 

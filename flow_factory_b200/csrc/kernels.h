@@ -135,4 +135,15 @@ struct SdeStepParams {
 };
 cudaError_t launch_sde_step(const SdeStepParams& p, cudaStream_t stream);
 
+// proj_out GEMM whose epilogue is the whole denoise step (final_step.cu); `sde.v_tokens/v_direct` are unused.
+struct FinalStepParams {
+  CUtensorMap tmA;   // 3-D {K, Ni, Bp} over the norm_out-modulated hidden states, box {64, 128, 1}
+  CUtensorMap tmW;   // 2-D {K, 64} proj_out weight, box {64, 64}
+  int K;
+  const bf16* bias;  // [64]
+  SdeStepParams sde;
+  unsigned int* done_counter;  // device word, zero between launches
+};
+cudaError_t launch_final_step(const FinalStepParams& p, cudaStream_t stream);
+
 }  // namespace ffb

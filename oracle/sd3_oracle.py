@@ -256,8 +256,9 @@ def _block(w, i: int, cfg: SD3Config, hs: torch.Tensor, ehs: torch.Tensor, temb:
 
 def transformer_forward(w: Dict[str, torch.Tensor], cfg: SD3Config, hidden_states: torch.Tensor,
                         encoder_hidden_states: torch.Tensor, pooled_projections: torch.Tensor,
-                        timestep: torch.Tensor, return_intermediates: bool = False):
-    """SD3Transformer2DModel.forward (DF/models/transformers/transformer_sd3.py:288-345)."""
+                        timestep: torch.Tensor, return_intermediates: bool = False, max_layers: Optional[int] = None):
+    """SD3Transformer2DModel.forward (DF/models/transformers/transformer_sd3.py:288-345).
+    `max_layers` (timing only): run just the first blocks - used by bench.py's bounded CPU sample."""
     inter = {}
     p = cfg.patch_size
     height, width = hidden_states.shape[-2:]
@@ -280,7 +281,7 @@ def transformer_forward(w: Dict[str, torch.Tensor], cfg: SD3Config, hidden_state
     ehs = _linear(w, "context_embedder", encoder_hidden_states)
     if return_intermediates:
         inter["temb"], inter["hs0"], inter["ehs0"] = temb, hs, ehs
-    for i in range(cfg.num_layers):
+    for i in range(cfg.num_layers if max_layers is None else min(max_layers, cfg.num_layers)):
         ehs, hs = _block(w, i, cfg, hs, ehs, temb)
         if return_intermediates:
             inter[f"hs_{i}"] = hs

@@ -189,3 +189,42 @@ def test_forward_sd35_medium_1024_vs_oracle():
                                            launches=eng.last_launch_count(), workspace_gb=plan.workspace_bytes / 2 ** 30))
     assert not torch.isnan(v).any()
     assert e_eng <= 2.5 * e_ref + 2e-3, (e_eng, e_ref, e_cross)
+
+
+@pytest.mark.parametrize("dyn", ["Flow-SDE", "CPS", "ODE"])
+@pytest.mark.parametrize("cfg_on", [True, False])
+def test_fused_final_step_equals_unfused_composition(dyn, cfg_on):
+    """The fused proj_out+CFG+unpatchify+scheduler.step epilogue (final_step.cu) against the same result assembled from
+    pieces that are each pinned elsewhere: plain proj_out GEMM -> unpatchify -> bf16 CFG (torch) -> sde_step kernel
+    (which is bit-checked against the reference-minted fixtures)."""
+    from flow_factory_b200 import FlowMatchEulerDiscreteSDEScheduler
+    cfg = O.tiny_config(num_layers=2, heads=2, dual=(0,), pos_max=24, sample_size=32)
+    w32 = O.make_weights(cfg, seed=9)
+    B, lh, lw, nt = 3, 24, 16, 17                    # 96 tokens: ragged 128-token tile
+    inp = {k: v.cuda() for k, v in O.make_inputs(cfg, B, lh, lw, nt, seed=10).items()}
+    eng = _engine(cfg, w32)
+    sch = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0, dynamics_type=dyn)
+    ts = sch.set_timesteps(8, seq_len=96)
+    plan = eng.plan(B, cfg_on, lh, lw, nt)
+    eng.set_prompts(plan, inp["prompt_embeds"], inp["pooled"], inp["neg_prompt_embeds"] if cfg_on else None,
+                    inp["neg_pooled"] if cfg_on else None)
+    x = inp["x0"].half()
+    g = 4.5 if cfg_on else 1.0
+    noise = torch.randn(B, 16, lh, lw, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    t_model = float(ts[2].half())
+    for use_noise in (True, False):
+        coef = sch.step_coef(ts[2], ts[3], 0.7, t_model=t_model)
+        r = eng.step(plan, x, coef, g, noise=noise if use_noise else None, seed=77, step_index=0)
+        v = eng.transformer_forward(plan, x, t_model)
+        if cfg_on:
+            vu, vc = v.chunk(2)
+            v = vu + g * (vc - vu)                    # bf16 tensor ops, as sd3_5.py:431-433
+        assert torch.equal(r["noise_pred"], v)
+        ref = sch.step(noise_pred=v, timestep=ts[2], latents=x, timestep_next=ts[3], noise_level=0.7, compute_log_prob=True,
+                       noise=noise if use_noise else None, seed=77, step_index=0)
+        torch.testing.assert_close(r["next_latents_mean"], ref.next_latents_mean, rtol=0, atol=0)
+        if dyn == "ODE":
+            assert torch.equal(r["next_latents"].float(), ref.next_latents.half().float())
+        else:
+            assert torch.equal(r["next_latents"].float(), ref.next_latents)      # same Philox stream in both kernels
+        torch.testing.assert_close(r["log_prob"], ref.log_prob, rtol=1e-6, atol=1e-7)
