@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libffb200.so")
+LIB_PATH = os.environ.get("FFB200_LIB", os.path.join(_HERE, "libffb200.so"))
 
 vp, ci, cf, cll, cull = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_ulonglong
 
@@ -90,7 +90,7 @@ def lib() -> C.CDLL:
 
 
 EXPORTED_SYMBOLS = (
-    "ffb200_last_error", "ffb200_device_error", "ffb200_abi_version", "ffb200_engine_create",
+    "ffb200_last_error", "ffb200_device_error", "ffb200_abi_version", "ffb200_debug_read_prof", "ffb200_engine_create",
     "ffb200_engine_set_weights", "ffb200_engine_destroy", "ffb200_engine_mod_rows", "ffb200_plan_create",
     "ffb200_plan_destroy", "ffb200_plan_workspace_bytes", "ffb200_plan_set_prompts", "ffb200_transformer_forward",
     "ffb200_step", "ffb200_rollout", "ffb200_rollout_host", "ffb200_last_launch_count", "ffb200_linear",

@@ -165,6 +165,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       float o_acc[ATT_D];
 #pragma unroll
       for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.f;
+      const long long pc0 = prof_begin();
 
       auto accumulate = [&](int j, float alpha) {   // o_acc = o_acc * alpha_j + O_part(j)
         mbar_wait(&o_full[x], j & 1, 0x61);
@@ -197,7 +198,10 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         if (lane == 0) mbar_arrive(&s_empty[x]);     // S_x is free for QK^T of tile j+1
 
         const int kv_valid = S - j * ATT_BN;  // >= 1
-        float mx = m_run;
+        // running max: 8 independent chains (a single serial fmax chain costs 128 x 4 cycles of pure latency per tile)
+        float mxs[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mxs[i] = -INFINITY;
         auto max32 = [&](uint32_t(&a)[32], int base) {
           if (kv_valid < ATT_BN) {
 #pragma unroll
@@ -205,23 +209,25 @@ attention_kernel(const __grid_constant__ AttnParams p) {
               if (base + c >= kv_valid) a[c] = 0xFF800000u;  // -inf: key beyond the sequence
           }
 #pragma unroll
-          for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(a[c]));
+          for (int c = 0; c < 32; c += 2) mxs[(c >> 1) & 7] = fmax3(mxs[(c >> 1) & 7], __uint_as_float(a[c]), __uint_as_float(a[c + 1]));
         };
         max32(s0, 0); max32(s1, 32); max32(s2, 64); max32(s3, 96);
+        const float mx = fmax3(fmax3(mxs[0], mxs[1], mxs[2]), fmax3(mxs[3], mxs[4], mxs[5]), fmax3(mxs[6], mxs[7], m_run));
         const float alpha = ex2_approx((m_run - mx) * sc);
         const float mneg = -mx * sc;
-        float sum = 0.f;
+        float sums[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[64];                               // P(j) as packed bf16 pairs, held until P smem is free
         auto exp32 = [&](uint32_t(&a)[32], int quarter) {
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
             const float e0 = ex2_approx(fmaf(__uint_as_float(a[2 * c]), sc, mneg));
             const float e1 = ex2_approx(fmaf(__uint_as_float(a[2 * c + 1]), sc, mneg));
-            sum += e0 + e1;
+            sums[c & 3] += e0 + e1;
             pk[quarter * 16 + c] = pack_bf16x2(e0, e1);
           }
         };
         exp32(s0, 0); exp32(s1, 1); exp32(s2, 2); exp32(s3, 3);
+        const float sum = (sums[0] + sums[1]) + (sums[2] + sums[3]);
         l_run = l_run * alpha + sum;
         m_run = mx;
 
@@ -239,6 +245,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         if (lane == 0) mbar_arrive(&p_full[x]);
       }
       accumulate(n_tiles - 1, alpha_prev);
+      prof_end(pc0, 0x78 + warp);
       // o_acc and l_run are both relative to the final running max m_run.
       const int q = q0 + x * ATT_BM + r;
       if (q < S) {

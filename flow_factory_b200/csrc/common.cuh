@@ -15,6 +15,8 @@ typedef __nv_bfloat16 bf16;
 // Device-side error word (set before a __trap() so the host can tell *why* a kernel died).
 // ---------------------------------------------------------------------------------------------
 __device__ unsigned int g_dev_error[4];  // single translation unit (ffb200.cu includes every .cu)
+// Wait-cycle attribution per mbarrier tag (only filled by the -DFFB_PROFILE build; CTA (0,0,0) only).
+__device__ unsigned long long g_prof[256];
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -56,12 +58,38 @@ __device__ __noinline__ void mbar_timeout(uint32_t tag) {
   __threadfence_system();
   __trap();
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag) {
+__device__ __forceinline__ void mbar_wait_impl(uint64_t* bar, uint32_t parity, uint32_t tag) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = globaltimer_ns();
   while (!mbar_try_wait(bar, parity)) {
     if (globaltimer_ns() - t0 > 4000000000ull) mbar_timeout(tag);
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag) {
+#ifdef FFB_PROFILE
+  const long long c0 = clock64();
+  mbar_wait_impl(bar, parity, tag);
+  if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (threadIdx.x & 31) == 0) {
+    atomicAdd(&g_prof[tag & 0x7F], static_cast<unsigned long long>(clock64() - c0));
+    atomicAdd(&g_prof[128 + (tag & 0x7F)], 1ull);
+  }
+#else
+  mbar_wait_impl(bar, parity, tag);
+#endif
+}
+// total cycles of a role (profile build only): call at role start / end
+__device__ __forceinline__ long long prof_begin() {
+#ifdef FFB_PROFILE
+  return clock64();
+#else
+  return 0;
+#endif
+}
+__device__ __forceinline__ void prof_end(long long c0, int slot) {
+#ifdef FFB_PROFILE
+  if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (threadIdx.x & 31) == 0)
+    atomicAdd(&g_prof[slot & 0x7F], static_cast<unsigned long long>(clock64() - c0));
+#endif
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -249,6 +277,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {   // 3-input max (sm_100)
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -202,6 +202,16 @@ int ffb200_device_error(unsigned int out[4]) {
   return 0;
 }
 
+int ffb200_debug_read_prof(unsigned long long* out, int n) {
+  unsigned long long buf[256];
+  cudaError_t e = cudaMemcpyFromSymbol(buf, g_prof, sizeof(buf));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  for (int i = 0; i < n && i < 256; ++i) out[i] = buf[i];
+  memset(buf, 0, sizeof(buf));
+  cudaMemcpyToSymbol(g_prof, buf, sizeof(buf));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 int ffb200_engine_set_weights(ffb200_engine* e, const ffb200_weights* w) {
   FFB_CHECK(e && w && w->layers, "null engine/weights");

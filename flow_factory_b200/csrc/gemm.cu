@@ -106,6 +106,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      const long long pc0 = prof_begin();
       int stage = 0; uint32_t phase = 0;
       for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
         const int tm = 2 * (unit % pairs_m) + static_cast<int>(cta_rank), tn = unit / pairs_m;
@@ -121,11 +122,13 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
+      prof_end(pc0, 0x70);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only; M = 256 across the pair) =====================
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN, 0, 0);
+      const long long pc0 = prof_begin();
       int stage = 0; uint32_t phase = 0; int it = 0;
       for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++it) {
         const int acc = it & 1;
@@ -148,11 +151,13 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
+      prof_end(pc0, 0x71);
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int ew = warp - 4;                 // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
     const int r_in_tile = ew * 32 + lane;
+    const long long pc0 = prof_begin();
     int it = 0;
     for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++it) {
       const int acc = it & 1;
@@ -267,6 +272,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);   // the leader's MMA thread waits for all 8 epilogue warps
     }
+    prof_end(pc0, 0x72 + ew);
   }
 
   tc_fence_before();

@@ -25,6 +25,9 @@ const char* ffb200_last_error(void);
 /* Reads (and clears) the device-side error word written by a kernel before it trapped. */
 int ffb200_device_error(unsigned int out[4]);
 int ffb200_abi_version(void);
+/* Developer aid: per-mbarrier-tag wait cycles of CTA 0 (out[tag], counts at out[128+tag]); all zero unless the library was built
+ * with -DFFB_PROFILE (tools/prof_waits.py). Reading clears the counters. */
+int ffb200_debug_read_prof(unsigned long long* out, int n);
 
 /* ---------------------------------------------------------------- model description
  * DF/models/transformers/transformer_sd3.py:117-141 (register_to_config arguments). head_dim must be 64. */
