@@ -11,7 +11,7 @@
 //                     behind the other's exp2 work (the MUFU unit is the binding resource at d = 64).
 //   warp  8         : TMA producer (Q once; K/V ring of 128x64 tiles shared by both sub-tiles)
 //   warp  9         : MMA issuer  (S = Q K^T : M128 N128 K64 ; O_part = P V : M128 N64 K128, V as MN-major operand)
-//   setmaxnreg moves registers from warps 8-11 to the softmax warps (232 each).
+//   setmaxnreg moves registers from warps 8-11 (24 each) to the softmax warps (240 each).
 // S_A/S_B and the per-tile partial outputs live in TMEM; P (bf16) goes through shared memory in the canonical
 // 128B-swizzled K-major layout; the running output is kept in registers (fp32) and rescaled FA2-style.
 #include "common.cuh"
@@ -85,7 +85,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   const uint32_t tO = tmem_base + 256;   // O_part A / B at columns 256 / 320
 
   if (warp >= 8) {
-    setmaxnreg_dec<40>();
+    setmaxnreg_dec<24>();
     if (warp == 8) {
       // ===================== TMA producer =====================
       if (lane == 0) {
@@ -104,38 +104,43 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         }
       }
     } else if (warp == 9) {
-      // ===================== MMA issuer =====================
-      if (lane == 0) {
-        constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);  // Q (K-major) x K (K-major)
-        constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);   // P (K-major) x V (MN-major)
-        auto issue_qk = [&](int j) {
-          const int st = j % ATT_STAGES;
-          mbar_wait(&k_full[st], (j / ATT_STAGES) & 1, 0x50);
-          const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
-          for (int x = 0; x < n_sub; ++x) {
-            mbar_wait(&s_empty[x], (j & 1) ^ 1, 0x51);   // softmax has pulled S_x(j-1) into registers
-            tc_fence_after();
-            const uint32_t q_addr = smem_u32(sQ + x * ATT_TILE_BYTES);
+      // ===================== MMA issuer: the whole warp walks the loop (warp-uniform state -> uniform registers feed
+      // UTCHMMA directly), one elected lane issues =====================
+      constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);  // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);   // P (K-major) x V (MN-major)
+      const uint32_t sQ_addr = smem_u32(sQ), sK_addr = smem_u32(sK), sV_addr = smem_u32(sV), sP_addr = smem_u32(sP);
+      auto issue_qk = [&](int j) {
+        const int st = j % ATT_STAGES;
+        mbar_wait(&k_full[st], (j / ATT_STAGES) & 1, 0x50);
+        const uint32_t k_addr = sK_addr + st * ATT_TILE_BYTES;
+        for (int x = 0; x < n_sub; ++x) {
+          mbar_wait(&s_empty[x], (j & 1) ^ 1, 0x51);   // softmax has pulled S_x(j-1) into registers
+          tc_fence_after();
+          const uint32_t q_addr = sQ_addr + x * ATT_TILE_BYTES;
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < ATT_D / 16; ++k)
               umma_bf16(tS + x * ATT_BN, desc_kmajor_sw128(q_addr + k * 32), desc_kmajor_sw128(k_addr + k * 32), idesc_s,
                         k != 0 ? 1u : 0u);
             umma_commit(&s_full[x]);
+            if (x == n_sub - 1) umma_commit(&k_empty[st]);
           }
-          umma_commit(&k_empty[st]);
-        };
-        mbar_wait(q_full, 0, 0x52);
-        issue_qk(0);
-        for (int j = 0; j < n_tiles; ++j) {
-          if (j + 1 < n_tiles) issue_qk(j + 1);
-          const int st = j % ATT_STAGES;
-          mbar_wait(&v_full[st], (j / ATT_STAGES) & 1, 0x53);
-          const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
-          for (int x = 0; x < n_sub; ++x) {
-            mbar_wait(&p_full[x], j & 1, 0x54);
-            mbar_wait(&o_empty[x], (j & 1) ^ 1, 0x55);
-            tc_fence_after();
-            const uint32_t p_addr = smem_u32(sP + x * 2 * ATT_TILE_BYTES);
+          __syncwarp();
+        }
+      };
+      mbar_wait(q_full, 0, 0x52);
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_qk(j + 1);
+        const int st = j % ATT_STAGES;
+        mbar_wait(&v_full[st], (j / ATT_STAGES) & 1, 0x53);
+        const uint32_t v_addr = sV_addr + st * ATT_TILE_BYTES;
+        for (int x = 0; x < n_sub; ++x) {
+          mbar_wait(&p_full[x], j & 1, 0x54);
+          mbar_wait(&o_empty[x], (j & 1) ^ 1, 0x55);
+          tc_fence_after();
+          const uint32_t p_addr = sP_addr + x * 2 * ATT_TILE_BYTES;
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < ATT_BN / 16; ++k) {
               // P: two 64-wide K atoms (16 KB apart), 32 B per K=16 step inside an atom.  V: 16 kv rows = 2048 B per step.
@@ -144,14 +149,15 @@ attention_kernel(const __grid_constant__ AttnParams p) {
               umma_bf16(tO + x * ATT_D, da, db, idesc_o, k != 0 ? 1u : 0u);
             }
             umma_commit(&o_full[x]);
+            if (x == n_sub - 1) umma_commit(&v_empty[st]);
           }
-          umma_commit(&v_empty[st]);
+          __syncwarp();
         }
       }
     }
   } else {
     // ===================== softmax / accumulate: warps 0-3 -> sub-tile A, warps 4-7 -> sub-tile B =====================
-    setmaxnreg_inc<232>();
+    setmaxnreg_inc<240>();
     const int x = warp >> 2;                          // sub-tile
     if (x < n_sub) {
       const int wq = warp & 3;                        // TMEM lane quadrant
@@ -159,7 +165,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
       const uint32_t tSx = tS + lane_off + x * ATT_BN;
       const uint32_t tOx = tO + lane_off + x * ATT_D;
-      uint8_t* prow = sP + x * 2 * ATT_TILE_BYTES + r * 128;
+      const uint32_t prow = smem_u32(sP) + x * 2 * ATT_TILE_BYTES + r * 128;   // 32-bit shared address of this row of P
       const float sc = p.scale_log2;
       float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
       float o_acc[ATT_D];
@@ -214,20 +220,24 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         max32(s0, 0); max32(s1, 32); max32(s2, 64); max32(s3, 96);
         const float mx = fmax3(fmax3(mxs[0], mxs[1], mxs[2]), fmax3(mxs[3], mxs[4], mxs[5]), fmax3(mxs[6], mxs[7], m_run));
         const float alpha = ex2_approx((m_run - mx) * sc);
-        const float mneg = -mx * sc;
-        float sums[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint64_t sc2 = pack_f32x2(sc, sc), mneg2 = pack_f32x2(-mx * sc, -mx * sc);
+        uint64_t sums2[2] = {0ull, 0ull};              // 4 partial row sums as two packed pairs
         uint32_t pk[64];                               // P(j) as packed bf16 pairs, held until P smem is free
         auto exp32 = [&](uint32_t(&a)[32], int quarter) {
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
-            const float e0 = ex2_approx(fmaf(__uint_as_float(a[2 * c]), sc, mneg));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(a[2 * c + 1]), sc, mneg));
-            sums[c & 3] += e0 + e1;
+            float t0, t1;
+            unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(a[2 * c]), __uint_as_float(a[2 * c + 1])), sc2, mneg2), t0, t1);
+            const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+            sums2[c & 1] = fadd2(sums2[c & 1], pack_f32x2(e0, e1));
             pk[quarter * 16 + c] = pack_bf16x2(e0, e1);
           }
         };
         exp32(s0, 0); exp32(s1, 1); exp32(s2, 2); exp32(s3, 3);
-        const float sum = (sums[0] + sums[1]) + (sums[2] + sums[3]);
+        float sa, sb, sc_, sd;
+        unpack_f32x2(sums2[0], sa, sb);
+        unpack_f32x2(sums2[1], sc_, sd);
+        const float sum = (sa + sb) + (sc_ + sd);
         l_run = l_run * alpha + sum;
         m_run = mx;
 
@@ -237,8 +247,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
 #pragma unroll
         for (int ch = 0; ch < 16; ++ch) {              // 16-byte chunks of 8 kv columns
           const int atom = ch >> 3, cc = ch & 7;
-          *reinterpret_cast<uint4*>(prow + atom * ATT_TILE_BYTES + ((cc ^ (r & 7)) << 4)) =
-              make_uint4(pk[ch * 4 + 0], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+          st_shared_v4(prow + atom * ATT_TILE_BYTES + ((cc ^ (r & 7)) << 4), pk[ch * 4 + 0], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
         }
         fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();

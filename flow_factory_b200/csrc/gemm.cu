@@ -3,16 +3,19 @@
 // Replaces every nn.Linear / Conv2d(k=s=patch) call site on the hot path
 // (DF/models/attention_processor.py:1443-1445,1461-1463,1495-1498; attention.py:1731; activations.py:87-90;
 //  transformers/transformer_sd3.py:293,327; embeddings.py:559) with one persistent warp-specialised kernel:
-//   warp 0    : TMA producer   (A tile 128x64, W tile BNx64, SWIZZLE_128B, mbarrier ring)
-//   warp 1    : MMA issuer     (one thread, tcgen05.mma cta_group::1 kind::f16, M=128 N=BN K=16, fp32 accum in TMEM)
+//   warp 0    : TMA producer   (A tile 128x64, half W tile (BN/2)x64, SWIZZLE_128B, mbarrier ring)
+//   warp 1    : MMA issuer     (one elected thread, tcgen05.mma cta_group::2 kind::f16, M=256 N=BN K=16, fp32 accum in TMEM)
 //   warp 2    : TMEM allocator
 //   warps 4-7 : epilogue       (tcgen05.ld 32x32b -> registers; thread == accumulator row; fused bias /
-//                               GELU-tanh / adaLN gate + residual / per-head RMSNorm(q,k) / row-table add; bf16 stores)
+//                               GELU-tanh / adaLN gate + residual / per-head RMSNorm(q,k) / row-table add)
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 // CTAs run as pairs (cluster of 2, tcgen05 cta_group::2): one MMA instruction spans both SMs (M = 256 x BN): each CTA
 // stages its own 128 A rows and HALF of the W tile, the tensor cores read the other half from the peer's shared memory.
 // Per CTA that is 32 KB per k-block instead of 48 KB: deeper TMA pipeline (6 stages) for the same shared memory and
-// 128 FLOP/B of L2 -> SM traffic instead of 85 (a 128x256 tile alone would need ~19 TB/s of L2 bandwidth at peak).
+// 128 FLOP/B of L2 -> SM traffic instead of 85.
+// The epilogue goes through a per-warp shared-memory staging tile so that every global load/store instruction moves
+// whole 128-byte lines (a thread-per-row store touches 32 different lines per instruction); bias / gate vectors are staged
+// in shared memory once per tile, the q/k RMSNorm weights once per kernel.
 //
 // A is addressed as a 3-D tensor [batch][rows_per_batch][K] so that token sub-ranges of a joint
 // [B, S, D] buffer (image rows / text rows) are separate GEMM problems with zero-filled ragged tails.
@@ -20,7 +23,6 @@
 #include "kernels.h"
 
 namespace ffb {
-
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
@@ -32,7 +34,9 @@ template <int BN> struct GemmCfg {
   static constexpr int kBBytes = (BN / 2) * GEMM_BK * 2;   // this CTA's half of the W tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 4 * 32 * 128;        // per epilogue warp: 32 rows x 64 bf16
+  static constexpr int kVecBytes = 4 * (2 * BN * 2 + 2 * 64 * 2);  // per warp: bias[BN], gate[BN], norm_q[64], norm_k[64]
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kVecBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
@@ -41,32 +45,22 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   return __fdividef(x, 1.0f + __expf(-2.0f * u));
 }
 
-// 8 consecutive bf16 (16-B aligned) -> fp32
-__device__ __forceinline__ void load8_bf16(const bf16* ptr, float* f) {
-  const uint4 u = __ldg(reinterpret_cast<const uint4*>(ptr));
+__device__ __forceinline__ void unpack8_bf16(const uint4& u, float* f) {
   f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
   f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
 }
-template <int N8>
-__device__ __forceinline__ void load_vec_bf16(const bf16* ptr, float* f) {
-  if (ptr == nullptr) {
-#pragma unroll
-    for (int i = 0; i < N8 * 8; ++i) f[i] = 0.f;
-  } else {
-#pragma unroll
-    for (int i = 0; i < N8; ++i) load8_bf16(ptr + i * 8, f + i * 8);
-  }
-}
-
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + Cfg::kStages * Cfg::kABytes;
+  const uint32_t smem_stage = smem_base + Cfg::kStages * Cfg::kStageBytes;   // epilogue staging tiles
+  const uint32_t smem_vec = smem_stage + Cfg::kStagingBytes;                   // epilogue vectors
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes + Cfg::kVecBytes);
   uint64_t* full_bar = bars;                          // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;          // [kStages]
   uint64_t* tmem_full = bars + 2 * Cfg::kStages;      // [2]
@@ -104,29 +98,32 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      const long long pc0 = prof_begin();
-      int stage = 0; uint32_t phase = 0;
-      for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
-        const int tm = 2 * (unit % pairs_m) + static_cast<int>(cta_rank), tn = unit / pairs_m;
-        // a ghost tile (odd tile count) still takes part in the W multicast; its A rows are out of bounds -> zeros
-        const int b = tm < tiles_m ? tm / p.tiles_m_per_batch : p.num_batch;
-        const int row0 = tm < tiles_m ? (tm % p.tiles_m_per_batch) * GEMM_BM : 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1, 0x10);
+    // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
+    const long long pc0 = prof_begin();
+    int stage = 0; uint32_t phase = 0;
+    for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
+      const int tm = 2 * (unit % pairs_m) + static_cast<int>(cta_rank), tn = unit / pairs_m;
+      // a ghost tile (odd tile count) still feeds its half of W to the pair; its A rows are out of bounds -> zeros
+      const int b = tm < tiles_m ? tm / p.tiles_m_per_batch : p.num_batch;
+      const int row0 = tm < tiles_m ? (tm % p.tiles_m_per_batch) * GEMM_BM : 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, 0x10);
+        if (elect_one()) {
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-          tma_load_3d_2sm(smem_a + stage * Cfg::kABytes, &p.tmA, &full_bar[stage], kb * GEMM_BK, row0, b);
-          tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &p.tmB, &full_bar[stage], kb * GEMM_BK,
+          tma_load_3d_2sm(smem + stage * Cfg::kABytes, &p.tmA, &full_bar[stage], kb * GEMM_BK, row0, b);
+          tma_load_2d_2sm(smem + Cfg::kStages * Cfg::kABytes + stage * Cfg::kBBytes, &p.tmB, &full_bar[stage], kb * GEMM_BK,
                           tn * BN + static_cast<int>(cta_rank) * (BN / 2));
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
-      prof_end(pc0, 0x70);
     }
+    prof_end(pc0, 0x70);
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only; M = 256 across the pair) =====================
-    if (lane == 0 && leader) {
+    // The whole warp walks the loop so that stage / phase / descriptors stay warp-uniform (uniform registers feed
+    // UTCHMMA directly; a lane-0-only loop pays a vector->uniform move per operand per MMA).
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN, 0, 0);
       const long long pc0 = prof_begin();
       int stage = 0; uint32_t phase = 0; int it = 0;
@@ -139,15 +136,18 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase, 0x21);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * Cfg::kABytes);
-          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::kBBytes);
+          const uint32_t a_addr = smem_a + stage * Cfg::kABytes;
+          const uint32_t b_addr = smem_b + stage * Cfg::kBBytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            umma_bf16_2sm(d_tmem, desc_kmajor_sw128(a_addr + k * 32), desc_kmajor_sw128(b_addr + k * 32), idesc,
-                          (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              umma_bf16_2sm(d_tmem, desc_kmajor_sw128(a_addr + k * 32), desc_kmajor_sw128(b_addr + k * 32), idesc,
+                            (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty_bar[stage], 0x3);                       // slot free in both CTAs once these MMAs retire
+            if (kb == num_kb - 1) umma_commit_2sm(&tmem_full[acc], 0x3);   // accumulators (both halves) complete
           }
-          umma_commit_2sm(&empty_bar[stage], 0x3);                       // slot free in both CTAs once these MMAs retire
-          if (kb == num_kb - 1) umma_commit_2sm(&tmem_full[acc], 0x3);   // accumulators (both halves) complete
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -156,127 +156,135 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int ew = warp - 4;                 // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
-    const int r_in_tile = ew * 32 + lane;
+    const uint32_t stg = smem_stage + ew * (32 * 128);                    // this warp's 32 x 128 B staging tile
+    const uint32_t vec_bias = smem_vec + ew * (2 * BN * 2 + 256);         // bias[BN] | gate[BN] | norm_q[64] | norm_k[64]
+    const uint32_t vec_gate = vec_bias + BN * 2;
+    const uint32_t vec_nq = vec_gate + BN * 2, vec_nk = vec_nq + 128;
+    const int coop_row = lane >> 3, coop_c = lane & 7;                    // cooperative (coalesced) access: 8 lanes per 128-B row
     const long long pc0 = prof_begin();
+    if (p.epi == EPI_QKV_RMSNORM) {
+      if (lane < 8) st_shared_v4x(vec_nq + lane * 16, __ldg(reinterpret_cast<const uint4*>(p.norm_q) + lane));
+      else if (lane < 16) st_shared_v4x(vec_nk + (lane - 8) * 16, __ldg(reinterpret_cast<const uint4*>(p.norm_k) + (lane - 8)));
+      __syncwarp();
+    }
     int it = 0;
     for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int tm = 2 * (unit % pairs_m) + static_cast<int>(cta_rank), tn = unit / pairs_m;
-      const int b = tm < tiles_m ? tm / p.tiles_m_per_batch : 0;
-      const int row = (tm % p.tiles_m_per_batch) * GEMM_BM + r_in_tile;
-      const bool row_ok = tm < tiles_m && row < p.rows_per_batch;
+      const bool tile_ok = tm < tiles_m;
+      const int b = tile_ok ? tm / p.tiles_m_per_batch : 0;
+      const int row_base = (tm % p.tiles_m_per_batch) * GEMM_BM + ew * 32;   // first row (within the batch) of this warp
+      bf16* out_base = p.out + static_cast<long>(b) * p.out_batch_stride + static_cast<long>(p.out_row_offset + row_base) * p.ldo + tn * BN;
+      // stage this tile's bias / gate slices while the MMAs of the tile are still running
+      if (lane * 8 < BN) {
+        uint4 bv = make_uint4(0, 0, 0, 0);
+        if (p.bias) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + tn * BN) + lane);
+        st_shared_v4x(vec_bias + lane * 16, bv);
+        if (p.epi == EPI_GATE_RESIDUAL)
+          st_shared_v4x(vec_gate + lane * 16, __ldg(reinterpret_cast<const uint4*>(p.gate + static_cast<long>(b) * p.gate_batch_stride + tn * BN) + lane));
+      }
+      __syncwarp();
       mbar_wait(&tmem_full[acc], acc_phase, 0x30);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
-      bf16* out_row = p.out + static_cast<long>(b) * p.out_batch_stride + static_cast<long>(p.out_row_offset + row) * p.ldo;
 
-      if (p.epi == EPI_QKV_RMSNORM) {
-        // 64 columns == one attention head per step; q/k heads get RMSNorm (normalization.py:553-561)
-        for (int c = 0; c < BN / 64; ++c) {
-          const int n0 = tn * BN + c * 64;
-          uint32_t r0[32], r1[32];
-          tmem_ld32(t_row + c * 64, r0);
-          tmem_ld32(t_row + c * 64 + 32, r1);
-          tmem_ld_wait();
-          float v[64];
-          float ss = 0.f;
-          load_vec_bf16<8>(p.bias ? p.bias + n0 : nullptr, v);
+      for (int c = 0; c < BN / 64; ++c) {
+        const int n0 = tn * BN + c * 64;       // global column of this 64-wide chunk
+        // (1) residual mode: pull the h chunk in with whole-line loads -> staging tile (16-B chunks XOR-swizzled by row)
+        if (p.epi == EPI_GATE_RESIDUAL) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = bf16_round(__uint_as_float(r0[j]) + v[j]);
-            v[32 + j] = bf16_round(__uint_as_float(r1[j]) + v[32 + j]);
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + coop_row;
+            if (tile_ok && row_base + rr < p.rows_per_batch) {
+              const uint4 hv = *reinterpret_cast<const uint4*>(out_base + static_cast<long>(rr) * p.ldo + c * 64 + coop_c * 8);
+              st_shared_v4x(stg + rr * 128 + ((coop_c ^ (rr & 7)) << 4), hv);
+            }
           }
+          __syncwarp();
+        }
+        // (2) thread == row: accumulator chunk -> registers -> fused math -> bf16 -> own row of the staging tile
+        uint32_t r0[32], r1[32];
+        tmem_ld32(t_row + c * 64, r0);
+        tmem_ld32(t_row + c * 64 + 32, r1);
+        tmem_ld_wait();
+        float v[64];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float bf[8];
+          unpack8_bf16(ld_shared_v4(vec_bias + (c * 64 + q * 8) * 2), bf);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int j = q * 8 + e;
+            v[j] = bf16_round(__uint_as_float(j < 32 ? r0[j] : r1[j - 32]) + bf[e]);
+          }
+        }
+        if (p.epi == EPI_QKV_RMSNORM) {
+          // 64 columns == one attention head; q/k heads get RMSNorm (normalization.py:553-561)
           const int which = n0 / p.qk_dim;   // 0 = q, 1 = k, 2 = v
           if (which < 2) {
+            float ss = 0.f;
 #pragma unroll
             for (int j = 0; j < 64; ++j) ss += v[j] * v[j];
             const float rs = rsqrtf(ss * (1.0f / 64.0f) + p.eps);
-            const bf16* wn = which == 0 ? p.norm_q : p.norm_k;
+            const uint32_t wn = which == 0 ? vec_nq : vec_nk;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               float wf[8];
-              load8_bf16(wn + q * 8, wf);
+              unpack8_bf16(ld_shared_v4(wn + q * 16), wf);
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[q * 8 + e] = bf16_round(v[q * 8 + e] * rs) * wf[e];
             }
           }
-          if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(out_row + n0);
+        } else if (p.epi == EPI_BIAS_GELU) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              uint4 o;
-              o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-              o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-              o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-              o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-              dst[q] = o;
+          for (int j = 0; j < 64; ++j) v[j] = gelu_tanh_f(v[j]);
+        } else if (p.epi == EPI_GATE_RESIDUAL) {
+          // h = h + gate[b,:] * y   in bf16 steps (attention.py:711-712, 726-728)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float gf[8], hf[8];
+            unpack8_bf16(ld_shared_v4(vec_gate + (c * 64 + q * 8) * 2), gf);
+            unpack8_bf16(ld_shared_v4(stg + lane * 128 + ((q ^ (lane & 7)) << 4)), hf);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[q * 8 + e] = hf[e] + bf16_round(gf[e] * v[q * 8 + e]);
+          }
+        } else if (p.epi == EPI_BIAS_ADD_ROWTABLE) {
+          // (latent + pos_embed).to(latent.dtype)   (embeddings.py:583)
+          if (tile_ok && row_base + lane < p.rows_per_batch) {
+            const float* t = p.row_table + static_cast<long>(row_base + lane) * p.N + n0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const float4 t4 = *reinterpret_cast<const float4*>(t + q * 4);
+              v[q * 4 + 0] += t4.x; v[q * 4 + 1] += t4.y; v[q * 4 + 2] += t4.z; v[q * 4 + 3] += t4.w;
             }
           }
         }
-      } else {
-        for (int c = 0; c < BN / 32; ++c) {
-          const int n0 = tn * BN + c * 32;
-          uint32_t r[32];
-          tmem_ld32(t_row + c * 32, r);
-          tmem_ld_wait();
-          float v[32];
-          load_vec_bf16<4>(p.bias ? p.bias + n0 : nullptr, v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = bf16_round(__uint_as_float(r[j]) + v[j]);
-          if (p.epi == EPI_BIAS_GELU) {
+        for (int q = 0; q < 8; ++q)
+          st_shared_v4(stg + lane * 128 + ((q ^ (lane & 7)) << 4), pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]),
+                       pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]), pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]),
+                       pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+        __syncwarp();
+        // (3) whole-line stores: 8 lanes per 128-B row, 4 rows per instruction
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
-          } else if (p.epi == EPI_GATE_RESIDUAL) {
-            // h = h + gate[b,:] * y   in bf16 steps (attention.py:711-712, 726-728)
-            const bf16* g = p.gate + static_cast<long>(b) * p.gate_batch_stride + n0;
-            if (row_ok) {
-              const uint4* hsrc = reinterpret_cast<const uint4*>(out_row + n0);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 h4 = hsrc[q];
-                const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w};
-                float gf[8];
-                load8_bf16(g + q * 8, gf);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int j = q * 8 + e * 2;
-                  v[j] = bf16_lo(hw[e]) + bf16_round(gf[e * 2] * v[j]);
-                  v[j + 1] = bf16_hi(hw[e]) + bf16_round(gf[e * 2 + 1] * v[j + 1]);
-                }
-              }
-            }
-          } else if (p.epi == EPI_BIAS_ADD_ROWTABLE) {
-            // (latent + pos_embed).to(latent.dtype)   (embeddings.py:583)
-            if (row_ok) {
-              const float* t = p.row_table + static_cast<long>(row) * p.N + n0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = v[j] + t[j];
-            }
-          }
-          if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(out_row + n0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-              o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-              o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-              o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-              dst[q] = o;
-            }
-          }
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + coop_row;
+          if (tile_ok && row_base + rr < p.rows_per_batch)
+            *reinterpret_cast<uint4*>(out_base + static_cast<long>(rr) * p.ldo + c * 64 + coop_c * 8) =
+                ld_shared_v4(stg + rr * 128 + ((coop_c ^ (rr & 7)) << 4));
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);   // the leader's MMA thread waits for all 8 epilogue warps
+      if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);   // the leader's MMA warp waits for all 8 epilogue warps
     }
     prof_end(pc0, 0x72 + ew);
   }
 
   tc_fence_before();
-  cluster_sync_all();   // no CTA may exit while its peer can still multicast into its smem / arrive on its barriers
+  cluster_sync_all();   // no CTA may exit while its peer can still read its smem / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
