@@ -12,8 +12,10 @@
 //   warp  8         : TMA producer (Q once; K/V ring of 128x64 tiles shared by both sub-tiles)
 //   warp  9         : MMA issuer  (S = Q K^T : M128 N128 K64 ; O_part = P V : M128 N64 K128, V as MN-major operand)
 //   setmaxnreg moves registers from warps 8-11 (24 each) to the softmax warps (240 each).
-// S_A/S_B and the per-tile partial outputs live in TMEM; P (bf16) goes through shared memory in the canonical
-// 128B-swizzled K-major layout; the running output is kept in registers (fp32) and rescaled FA2-style.
+// S_A/S_B and the output accumulators O_A/O_B live in TMEM: P V accumulates into O on the tensor core across KV tiles and the
+// softmax warps touch O only (a) in the rare tiles where the running row max grows by more than 2^8 (lazy rescale: otherwise the
+// stale max is kept and P may exceed 1, harmless in fp32/bf16) and (b) once at the end.  P (bf16) goes through shared memory in
+// the canonical 128B-swizzled K-major layout.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -136,8 +138,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         mbar_wait(&v_full[st], (j / ATT_STAGES) & 1, 0x53);
         const uint32_t v_addr = sV_addr + st * ATT_TILE_BYTES;
         for (int x = 0; x < n_sub; ++x) {
-          mbar_wait(&p_full[x], j & 1, 0x54);
-          mbar_wait(&o_empty[x], (j & 1) ^ 1, 0x55);
+          mbar_wait(&p_full[x], j & 1, 0x54);   // P(j) in smem (and any rescale of O_x done)
           tc_fence_after();
           const uint32_t p_addr = sP_addr + x * 2 * ATT_TILE_BYTES;
           if (elect_one()) {
@@ -146,7 +147,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
               // P: two 64-wide K atoms (16 KB apart), 32 B per K=16 step inside an atom.  V: 16 kv rows = 2048 B per step.
               const uint64_t da = desc_kmajor_sw128(p_addr + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32);
               const uint64_t db = desc_mnmajor_sw128(v_addr + k * 2048, ATT_TILE_BYTES);
-              umma_bf16(tO + x * ATT_D, da, db, idesc_o, k != 0 ? 1u : 0u);
+              umma_bf16(tO + x * ATT_D, da, db, idesc_o, (j | k) != 0 ? 1u : 0u);   // O_x accumulates across KV tiles
             }
             umma_commit(&o_full[x]);
             if (x == n_sub - 1) umma_commit(&v_empty[st]);
@@ -167,32 +168,14 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       const uint32_t tOx = tO + lane_off + x * ATT_D;
       const uint32_t prow = smem_u32(sP) + x * 2 * ATT_TILE_BYTES + r * 128;   // 32-bit shared address of this row of P
       const float sc = p.scale_log2;
-      float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-      float o_acc[ATT_D];
-#pragma unroll
-      for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f;
       const long long pc0 = prof_begin();
-
-      auto accumulate = [&](int j, float alpha) {   // o_acc = o_acc * alpha_j + O_part(j)
-        mbar_wait(&o_full[x], j & 1, 0x61);
-        tc_fence_after();
-        uint32_t o0[32], o1[32];
-        tmem_ld32(tOx, o0);
-        tmem_ld32(tOx + 32, o1);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_empty[x]);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          o_acc[i] = o_acc[i] * alpha + __uint_as_float(o0[i]);
-          o_acc[32 + i] = o_acc[32 + i] * alpha + __uint_as_float(o1[i]);
-        }
-      };
-
+      long long lap = prof_begin();
       for (int j = 0; j < n_tiles; ++j) {
+        prof_lap(&lap, 0x67);                          // loop overhead / previous arrive
         mbar_wait(&s_full[x], j & 1, 0x60);
         tc_fence_after();
+        prof_lap(&lap, 0x68);                          // wait s_full
         uint32_t s0[32], s1[32], s2[32], s3[32];
         tmem_ld32(tSx + 0, s0);
         tmem_ld32(tSx + 32, s1);
@@ -202,9 +185,10 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[x]);     // S_x is free for QK^T of tile j+1
+        prof_lap(&lap, 0x62);                          // TMEM load of S
 
         const int kv_valid = S - j * ATT_BN;  // >= 1
-        // running max: 8 independent chains (a single serial fmax chain costs 128 x 4 cycles of pure latency per tile)
+        // row max of this tile: 8 independent chains (a single serial fmax chain is 128 x 4 cycles of pure latency)
         float mxs[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) mxs[i] = -INFINITY;
@@ -218,9 +202,18 @@ attention_kernel(const __grid_constant__ AttnParams p) {
           for (int c = 0; c < 32; c += 2) mxs[(c >> 1) & 7] = fmax3(mxs[(c >> 1) & 7], __uint_as_float(a[c]), __uint_as_float(a[c + 1]));
         };
         max32(s0, 0); max32(s1, 32); max32(s2, 64); max32(s3, 96);
-        const float mx = fmax3(fmax3(mxs[0], mxs[1], mxs[2]), fmax3(mxs[3], mxs[4], mxs[5]), fmax3(mxs[6], mxs[7], m_run));
-        const float alpha = ex2_approx((m_run - mx) * sc);
-        const uint64_t sc2 = pack_f32x2(sc, sc), mneg2 = pack_f32x2(-mx * sc, -mx * sc);
+        const float mt = fmax3(fmax3(mxs[0], mxs[1], mxs[2]), fmax3(mxs[3], mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7]));
+        // lazy rescale: adopt the new max only if some row of the warp grew by more than 2^8 (warp-uniform decision)
+        const bool grow = (mt - m_run) * sc > 8.0f;           // true on the first tile (m_run = -inf)
+        const bool rescale = __any_sync(0xffffffffu, grow);
+        float alpha = 1.0f;
+        if (rescale) {
+          const float mnew = fmaxf(m_run, mt);
+          alpha = ex2_approx((m_run - mnew) * sc);             // 0 on the first tile
+          m_run = mnew;
+        }
+        prof_lap(&lap, 0x63);                          // row max
+        const uint64_t sc2 = pack_f32x2(sc, sc), mneg2 = pack_f32x2(-m_run * sc, -m_run * sc);
         uint64_t sums2[2] = {0ull, 0ull};              // 4 partial row sums as two packed pairs
         uint32_t pk[64];                               // P(j) as packed bf16 pairs, held until P smem is free
         auto exp32 = [&](uint32_t(&a)[32], int quarter) {
@@ -237,13 +230,30 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         float sa, sb, sc_, sd;
         unpack_f32x2(sums2[0], sa, sb);
         unpack_f32x2(sums2[1], sc_, sd);
-        const float sum = (sa + sb) + (sc_ + sd);
-        l_run = l_run * alpha + sum;
-        m_run = mx;
+        l_run = l_run * alpha + ((sa + sb) + (sc_ + sd));
+        prof_lap(&lap, 0x64);                          // exp2 + sum + pack
 
-        // PV(j-1) finished <=> O_part(j-1) is ready and the tensor core no longer reads P smem
-        if (j > 0) accumulate(j - 1, alpha_prev);
-        alpha_prev = alpha;
+        // PV(j-1) retired <=> the tensor core no longer reads P smem and O_x holds tiles < j
+        if (j > 0) {
+          mbar_wait(&o_full[x], (j - 1) & 1, 0x61);
+          if (rescale) {                                 // rare: O_x *= alpha in TMEM
+            tc_fence_after();
+            uint32_t o0[32], o1[32];
+            tmem_ld32(tOx, o0);
+            tmem_ld32(tOx + 32, o1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
+              o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
+            }
+            tmem_st32(tOx, o0);
+            tmem_st32(tOx + 32, o1);
+            tmem_st_wait();
+            tc_fence_before();
+          }
+        }
+        prof_lap(&lap, 0x65);                          // wait PV(j-1) (+ rare O rescale)
 #pragma unroll
         for (int ch = 0; ch < 16; ++ch) {              // 16-byte chunks of 8 kv columns
           const int atom = ch >> 3, cc = ch & 7;
@@ -252,10 +262,22 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[x]);
+        prof_lap(&lap, 0x66);                          // P -> smem, proxy fence, arrive
       }
-      accumulate(n_tiles - 1, alpha_prev);
+      // final output: O_x / l
+      mbar_wait(&o_full[x], (n_tiles - 1) & 1, 0x61);
+      tc_fence_after();
+      float o_acc[ATT_D];
+      {
+        uint32_t o0[32], o1[32];
+        tmem_ld32(tOx, o0);
+        tmem_ld32(tOx + 32, o1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { o_acc[i] = __uint_as_float(o0[i]); o_acc[32 + i] = __uint_as_float(o1[i]); }
+      }
       prof_end(pc0, 0x78 + warp);
-      // o_acc and l_run are both relative to the final running max m_run.
+      // O_x and l_run are both relative to the final running max m_run.
       const int q = q0 + x * ATT_BM + r;
       if (q < S) {
         const float inv = 1.0f / l_run;

@@ -12,6 +12,8 @@ NAMES = {0x10: "gemm.tma wait empty", 0x20: "gemm.mma wait tmem_empty", 0x21: "g
          0x40: "attn.tma wait k_empty", 0x41: "attn.tma wait v_empty", 0x50: "attn.mma wait k_full", 0x51: "attn.mma wait s_empty",
          0x52: "attn.mma wait q_full", 0x53: "attn.mma wait v_full", 0x54: "attn.mma wait p_full", 0x55: "attn.mma wait o_empty",
          0x60: "attn.softmax wait s_full (8 warps)", 0x61: "attn.softmax wait o_full (8 warps)",
+         0x62: "attn.softmax phase: ld S (8 warps)", 0x63: "attn.softmax phase: max", 0x64: "attn.softmax phase: exp+sum+pack",
+         0x65: "attn.softmax phase: O readback+accumulate", 0x66: "attn.softmax phase: P store+fence+arrive", 0x67: "attn.softmax phase: loop", 0x68: "attn.softmax phase: wait s_full",
          0x78: "attn.softmax w0 total", 0x79: "attn.softmax w1 total", 0x7c: "attn.softmax w4 total"}
 
 
