@@ -45,7 +45,8 @@ cudaError_t launch_gemm(const GemmParams& p, int num_sms, cudaStream_t stream);
 
 // ------------------------------------------------------------------ attention
 struct AttnParams {
-  CUtensorMap tmQKV;  // 3-D {3*D, S, B}, box {64, 128, 1}, SWIZZLE_128B over the joint qkv buffer [B, S, 3D]
+  CUtensorMap tmQKV;  // 3-D {3*D, S, B}, box {64, 128, 1}, SWIZZLE_128B over the joint qkv buffer [B, S, 3D] (Q sub-tiles)
+  CUtensorMap tmKV;   // same tensor, box {64, 64, 1} (K / V tiles)
   int seq_len;        // S (q and kv length)
   int num_heads;      // H
   int inner_dim;      // D = 64*H
