@@ -306,7 +306,7 @@ def run_b200(args):
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel<256> (MLP up, bias+GELU epilogue)", "achieved": gemm_tf,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["bf16_tflops"], "traffic": None,
                 "peak_source": f"{peak_kind} cuBLAS bf16 burst", "flops_per_launch": 2.0 * M * N * K, "launch_ms": gemm_ms,
-                "whole_step_achieved": step_tf, "whole_step_frac_of_sustained": step_tf / peaks["bf16_tflops_sustained"],
+                "whole_step_achieved_per_gpu": step_tf / world, "whole_step_frac_of_sustained": step_tf / world / peaks["bf16_tflops_sustained"],
                 "flops_per_latent": fl_latent}
 
     # ---------------- CPU baseline: the oracle port on this box's host cores, bounded sample ----------------

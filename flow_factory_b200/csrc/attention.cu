@@ -57,8 +57,8 @@ __device__ __forceinline__ void exp2_poly_pair(uint64_t x2, float& e0, float& e1
   e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(r0) << 23));
   e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
 }
-constexpr int ATT_POLY_PERIOD = 2;   // of every ATT_POLY_PERIOD element pairs ...
-constexpr int ATT_POLY_NUM = 1;      // ... this many go through exp2_poly_pair, the rest through MUFU.EX2
+constexpr int ATT_POLY_PERIOD = 8;   // of every ATT_POLY_PERIOD element pairs ...
+constexpr int ATT_POLY_NUM = 3;      // ... this many go through exp2_poly_pair, the rest through MUFU.EX2
 
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }

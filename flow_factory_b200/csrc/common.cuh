@@ -345,6 +345,13 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {   // 3-input
   return d;
 }
 
+// round a PAIR to bf16 with one F2FP (ALU pipe) instead of two F2F (quarter-rate XU pipe)
+__device__ __forceinline__ void bf16_round2(float& a, float& b) {
+  const uint32_t p = pack_bf16x2(a, b);
+  a = bf16_lo(p);
+  b = bf16_hi(p);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -216,8 +216,10 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int j = q * 8 + e;
-            v[j] = bf16_round(__uint_as_float(j < 32 ? r0[j] : r1[j - 32]) + bf[e]);
+            v[j] = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]) + bf[e];
           }
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) bf16_round2(v[q * 8 + e], v[q * 8 + e + 1]);   // nn.Linear output is a bf16 tensor
         }
         if (p.epi == EPI_QKV_RMSNORM) {
           // 64 columns == one attention head; q/k heads get RMSNorm (normalization.py:553-561)
@@ -233,7 +235,12 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
               float wf[8];
               unpack8_bf16(ld_shared_v4(wn + q * 16), wf);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[q * 8 + e] = bf16_round(v[q * 8 + e] * rs) * wf[e];
+              for (int e = 0; e < 8; e += 2) {
+                float a = v[q * 8 + e] * rs, b = v[q * 8 + e + 1] * rs;
+                bf16_round2(a, b);                                     // .to(weight.dtype) before the weight multiply
+                v[q * 8 + e] = a * wf[e];
+                v[q * 8 + e + 1] = b * wf[e + 1];
+              }
             }
           }
         } else if (p.epi == EPI_BIAS_GELU) {
@@ -247,7 +254,12 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
             unpack8_bf16(ld_shared_v4(vec_gate + (c * 64 + q * 8) * 2), gf);
             unpack8_bf16(ld_shared_v4(stg + lane * 128 + ((q ^ (lane & 7)) << 4)), hf);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[q * 8 + e] = hf[e] + bf16_round(gf[e] * v[q * 8 + e]);
+            for (int e = 0; e < 8; e += 2) {
+              float a = gf[e] * v[q * 8 + e], b = gf[e + 1] * v[q * 8 + e + 1];
+              bf16_round2(a, b);                                       // gate * y is a bf16 tensor
+              v[q * 8 + e] = hf[e] + a;
+              v[q * 8 + e + 1] = hf[e + 1] + b;
+            }
           }
         } else if (p.epi == EPI_BIAS_ADD_ROWTABLE) {
           // (latent + pos_embed).to(latent.dtype)   (embeddings.py:583)

@@ -228,3 +228,90 @@ def test_fused_final_step_equals_unfused_composition(dyn, cfg_on):
         else:
             assert torch.equal(r["next_latents"].float(), ref.next_latents)      # same Philox stream in both kernels
         torch.testing.assert_close(r["log_prob"], ref.log_prob, rtol=1e-6, atol=1e-7)
+
+
+def test_refresh_weights_tracks_the_trainer():
+    """Weights move under the engine (optimizer / EMA / LoRA merge, SURVEY 7.2 #4): refresh_weights re-packs in place."""
+    cfg = O.tiny_config()
+    w32 = O.make_weights(cfg, seed=0)
+    inp = O.make_inputs(cfg, 1, 16, 16, 13, seed=1)
+    eng = _engine(cfg, w32)
+    plan = eng.plan(1, False, 16, 16, 13)
+    eng.set_prompts(plan, inp["prompt_embeds"], inp["pooled"])
+    v0 = eng.transformer_forward(plan, inp["x0"].half(), 500.0).clone()
+    w2 = {k: v.clone() for k, v in w32.items()}
+    w2["transformer_blocks.1.ff.net.2.weight"] *= 1.5
+    w2["transformer_blocks.0.attn.to_q.weight"] += 0.05
+    eng.refresh_weights(w2)
+    v1 = eng.transformer_forward(plan, inp["x0"].half(), 500.0)
+    assert not torch.equal(v0, v1)
+    truth = _oracle_fwd(cfg, w2, inp["x0"].half(), inp["prompt_embeds"].bfloat16(), inp["pooled"].bfloat16(), 500.0, "fp32")
+    ref = _oracle_fwd(cfg, w2, inp["x0"], inp["prompt_embeds"], inp["pooled"], 500.0, "bf16")
+    assert _rel(v1, truth) <= 2.5 * _rel(ref, truth) + 2e-3
+    eng.refresh_weights(w32)
+    assert torch.equal(eng.transformer_forward(plan, inp["x0"].half(), 500.0), v0)
+
+
+def test_rollout_host_entry_matches_device_entry():
+    """ffb200_rollout_host (host buffers in/out, copies inside the call) == ffb200_rollout on device buffers (same Philox seed)."""
+    from flow_factory_b200 import FlowMatchEulerDiscreteSDEScheduler
+    from flow_factory_b200.trajectory import plan_slots
+    cfg = O.tiny_config()
+    w32 = O.make_weights(cfg, seed=0)
+    inp = O.make_inputs(cfg, 2, 16, 16, 13, seed=1)
+    eng = _engine(cfg, w32)
+    sch = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0)
+    T = 5
+    ts = sch.set_timesteps(T, seq_len=64)
+    has = [i < T - 1 for i in range(T)]
+    lat_slot, lp_slot, _, _ = plan_slots("all", T, has)
+    coefs = [sch.step_coef(ts[i], ts[i + 1] if i + 1 < T else torch.tensor(0.0), 0.7 if has[i] else 0.0, compute_log_prob=has[i],
+                           t_model=float(ts[i].half()), store_slot=lat_slot[i + 1], logp_slot=lp_slot[i]) for i in range(T)]
+    plan = eng.plan(2, True, 16, 16, 13)
+    pe = torch.cat([inp["neg_prompt_embeds"], inp["prompt_embeds"]]).bfloat16().contiguous()
+    pp = torch.cat([inp["neg_pooled"], inp["pooled"]]).bfloat16().contiguous()
+    x0 = inp["x0"].half().contiguous()
+    rh = eng.rollout_host(plan, x0, pe, pp, coefs, 4.5, T + 1, 0, T - 1, seed=99, use_graph=True)
+    eng.set_prompts(plan, inp["prompt_embeds"], inp["pooled"], inp["neg_prompt_embeds"], inp["neg_pooled"])
+    rd = eng.rollout(plan, x0, coefs, 4.5, T + 1, 0, T - 1, seed=99, use_graph=False)
+    torch.cuda.synchronize()
+    assert torch.equal(rh["all_latents"], rd["all_latents"].cpu())
+    assert torch.equal(rh["log_probs"], rd["log_probs"].cpu())
+    assert torch.equal(rh["final_latents"], rd["final_latents"].cpu())
+    assert torch.equal(rd["all_latents"][:, 0].cpu(), x0) and torch.equal(rd["all_latents"][:, T], rd["final_latents"])
+    assert int(rh["overflow"]) == 0
+
+
+@pytest.mark.parametrize("B,nt,lh,lw", [(3, 77, 32, 32), (1, 333, 16, 48), (5, 1, 16, 16)])
+def test_odd_batch_text_length_and_aspect(B, nt, lh, lw):
+    cfg = O.tiny_config(num_layers=2, heads=2, dual=(0,), pos_max=32, sample_size=32)
+    w32 = O.make_weights(cfg, seed=11)
+    inp = O.make_inputs(cfg, B, lh, lw, nt, seed=12)
+    eng = _engine(cfg, w32)
+    plan = eng.plan(B, False, lh, lw, nt)
+    eng.set_prompts(plan, inp["prompt_embeds"], inp["pooled"])
+    v = eng.transformer_forward(plan, inp["x0"].half(), 250.0)
+    truth = _oracle_fwd(cfg, w32, inp["x0"].half(), inp["prompt_embeds"].bfloat16(), inp["pooled"].bfloat16(), 250.0, "fp32")
+    ref = _oracle_fwd(cfg, w32, inp["x0"], inp["prompt_embeds"], inp["pooled"], 250.0, "bf16")
+    assert not torch.isnan(v).any()
+    assert _rel(v, truth) <= 2.5 * _rel(ref, truth) + 2e-3, (_rel(v, truth), _rel(ref, truth))
+
+
+def test_dance_sde_step_through_the_engine():
+    from flow_factory_b200 import FlowMatchEulerDiscreteSDEScheduler
+    cfg = O.tiny_config()
+    w32 = O.make_weights(cfg, seed=0)
+    inp = {k: v.cuda() for k, v in O.make_inputs(cfg, 2, 16, 16, 13, seed=1).items()}
+    eng = _engine(cfg, w32)
+    sch = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.5, shift=3.0, dynamics_type="Dance-SDE")
+    ts = sch.set_timesteps(10, seq_len=64)
+    plan = eng.plan(2, False, 16, 16, 13)
+    eng.set_prompts(plan, inp["prompt_embeds"], inp["pooled"])
+    x = inp["x0"].half()
+    noise = torch.randn(2, 16, 16, 16, device="cuda")
+    coef = sch.step_coef(ts[4], ts[5], 0.5, t_model=float(ts[4].half()))
+    r = eng.step(plan, x, coef, 1.0, noise=noise)
+    ro = O.sde_step(r["noise_pred"], x, (ts[4] / 1000).item(), (ts[5] / 1000).item(), 0.5, float(sch.sigmas[1]), "Dance-SDE", noise=noise)
+    torch.testing.assert_close(r["next_latents_mean"], ro["next_latents_mean"], rtol=1e-6, atol=1e-6)
+    assert torch.equal(r["next_latents"].float(), ro["next_latents"])
+    torch.testing.assert_close(r["log_prob"], ro["log_prob"], rtol=1e-5, atol=1e-6)
