@@ -226,7 +226,11 @@ attention_kernel(const __grid_constant__ AttnParams p) {
 #pragma unroll
           for (int c = 0; c < 32; c += 2) mxs[(c >> 1) & 7] = fmax3(mxs[(c >> 1) & 7], __uint_as_float(a[c]), __uint_as_float(a[c + 1]));
         };
+#ifndef ATT_EXP_NO_MAX
         max32(s0, 0); max32(s1, 32);
+#else
+        mxs[0] = 8.0f;
+#endif
         const float mt = fmax3(fmax3(mxs[0], mxs[1], mxs[2]), fmax3(mxs[3], mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7]));
         // lazy rescale: adopt the new max only if some row of the warp grew by more than 2^8 (warp-uniform decision)
         const bool grow = (mt - m_run) * sc > 8.0f;           // true on the first tile (m_run = -inf)
@@ -246,6 +250,9 @@ attention_kernel(const __grid_constant__ AttnParams p) {
           for (int c = 0; c < 16; ++c) {
             const uint64_t x2 = ffma2(pack_f32x2(__uint_as_float(a[2 * c]), __uint_as_float(a[2 * c + 1])), sc2, mneg2);
             float e0, e1;
+#ifdef ATT_EXP_NO_EXP
+            if (true) { unpack_f32x2(x2, e0, e1); } else
+#endif
             if ((c % ATT_POLY_PERIOD) < ATT_POLY_NUM) {
               exp2_poly_pair(x2, e0, e1);
             } else {
@@ -266,7 +273,9 @@ attention_kernel(const __grid_constant__ AttnParams p) {
 
         // PV(j-1) retired <=> the tensor core no longer reads P smem and O_x holds tiles < j
         if (j > 0) {
+#ifndef ATT_EXP_NO_OWAIT
           mbar_wait(&o_full[x], (j - 1) & 1, 0x61);
+#endif
           if (rescale) {                                 // rare: O_x *= alpha in TMEM
             tc_fence_after();
             uint32_t o0[32], o1[32];
@@ -286,9 +295,13 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         }
         prof_lap(&lap, 0x65);                          // wait PV(j-1) (+ rare O rescale)
 #pragma unroll
+#ifndef ATT_EXP_NO_STORE
         for (int cc = 0; cc < 8; ++cc)                 // 16-byte chunks of 8 kv columns
           st_shared_v4(prow + ((cc ^ (r & 7)) << 4), pk[cc * 4 + 0], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
-        fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        fence_proxy_async_smem();
+#else
+        if (pk[0] == 0x12345678u && pk[31] == 0x9abcdefu) st_shared_v4(prow, pk[0], pk[5], pk[17], pk[31]);   // keep pk alive
+#endif   // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[x]);
         prof_lap(&lap, 0x66);                          // P -> smem, proxy fence, arrive
