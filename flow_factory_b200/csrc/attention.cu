@@ -15,8 +15,10 @@
 //   i.e. four softmax warps per SM sub-partition hide each other's TMEM-load / barrier / fence latencies.
 // S_A/S_B and the output accumulators O_A/O_B live in TMEM: P V accumulates into O on the tensor core across KV tiles and the
 // softmax warps touch O only (a) in the rare tiles where the running row max grows by more than 2^8 (lazy rescale: otherwise the
-// stale max is kept and P may exceed 1, harmless in fp32/bf16) and (b) once at the end.  P (bf16) goes through shared memory in
-// the canonical 128B-swizzled K-major layout.
+// stale max is kept and P may exceed 1, harmless in fp32/bf16) and (b) once at the end.  P (bf16 pairs) is written back into the
+// first 32 columns of S_x with tcgen05.st and consumed by the P V MMA as its TMEM A-operand: no shared-memory round trip, no
+// generic->async proxy fence.  Per sub-tile the tensor-core order is  QK(j) -> [softmax j] -> PV(j) -> QK(j+1) ...; the four
+// softmax warps that share an SM sub-partition (2 CTAs x 2 sub-tiles) cover each other's tensor-core latency.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -26,12 +28,12 @@ constexpr int ATT_BM = 128;     // query rows per sub-tile
 constexpr int ATT_QB = 256;     // query rows per CTA
 constexpr int ATT_BN = 64;      // kv rows per tile
 constexpr int ATT_D = 64;
-constexpr int ATT_STAGES = 3;
+constexpr int ATT_STAGES = 4;
 constexpr int ATT_THREADS = 384;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;      // 16 KB: a Q sub-tile or a P sub-tile (128 rows x 64 bf16)
 constexpr int ATT_KV_BYTES = ATT_BN * 64 * 2;     // 8 KB: a K or V tile
-// two CTAs per SM (4 softmax warps per SM sub-partition): 112.5 KB each
-constexpr int ATT_SMEM = 2 * ATT_TILE_BYTES /*Q_A,Q_B*/ + 2 * ATT_STAGES * ATT_KV_BYTES /*K,V*/ + 2 * ATT_TILE_BYTES /*P_A,P_B*/ + 512;
+// two CTAs per SM (4 softmax warps per SM sub-partition): 96.5 KB each
+constexpr int ATT_SMEM = 2 * ATT_TILE_BYTES /*Q_A,Q_B*/ + 2 * ATT_STAGES * ATT_KV_BYTES /*K,V*/ + 512;
 constexpr int ATT_TMEM_COLS = 256;                // S_A,S_B (64 each) + O_A,O_B (64 each)
 
 // exp2 on the FMA/ALU pipes for part of the elements (the MUFU unit, 16 ex2/clk/SM, is the binding resource at d = 64):
@@ -69,19 +71,16 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   uint8_t* sQ = smem;                                   // [2 sub-tiles][128][64]
   uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;                // [stages][64][64]
   uint8_t* sV = sK + ATT_STAGES * ATT_KV_BYTES;         // [stages][64][64]
-  uint8_t* sP = sV + ATT_STAGES * ATT_KV_BYTES;         // [2 sub-tiles][128 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_STAGES * ATT_KV_BYTES);
   uint64_t* q_full = bars;                       // 1
   uint64_t* k_full = bars + 1;                   // [ST]
   uint64_t* k_empty = k_full + ATT_STAGES;       // [ST]
   uint64_t* v_full = k_empty + ATT_STAGES;       // [ST]
   uint64_t* v_empty = v_full + ATT_STAGES;       // [ST]
-  uint64_t* s_full = v_empty + ATT_STAGES;       // [2]  per sub-tile
-  uint64_t* s_empty = s_full + 2;                // [2]
-  uint64_t* p_full = s_empty + 2;                // [2]
-  uint64_t* o_full = p_full + 2;                 // [2]
-  uint64_t* o_empty = o_full + 2;                // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_empty + 2);
+  uint64_t* s_full = v_empty + ATT_STAGES;       // [2]  per sub-tile: S_x(j) = Q K^T ready (and every earlier MMA retired)
+  uint64_t* p_full = s_full + 2;                 // [2]  P_x(j) written to TMEM (and any rescale of O_x done)
+  uint64_t* o_full = p_full + 2;                 // [2]  final O_x complete
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -102,9 +101,9 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], n_sub);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+      mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
-      mbar_init(&o_full[i], 1); mbar_init(&o_empty[i], 4);
+      mbar_init(&o_full[i], 1);
     }
     fence_barrier_init();
   }
@@ -113,7 +112,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tS = tmem_base;         // S_A / S_B at columns 0 / 64
+  const uint32_t tS = tmem_base;         // S_A / S_B at columns 0 / 64 (P_x aliases the first 32 columns of S_x)
   const uint32_t tO = tmem_base + 128;   // O_A / O_B at columns 128 / 192
 
   if (warp >= 8) {
@@ -140,22 +139,20 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       // softmax groups decoupled (a shared in-order issuer forces them into lockstep, i.e. into the same pipe at the same time).
       // The whole warp walks the loop (warp-uniform state -> uniform registers feed UTCHMMA), one elected lane issues.
       constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);  // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);   // P (K-major) x V (MN-major)
+      constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);   // P (TMEM) x V (MN-major)
       const int x = warp - 9;
       const uint32_t q_addr = smem_u32(sQ) + x * ATT_TILE_BYTES, sK_addr = smem_u32(sK), sV_addr = smem_u32(sV);
-      const uint32_t p_addr = smem_u32(sP) + x * ATT_TILE_BYTES;
+      const uint32_t tSx = tS + x * ATT_BN, tOx = tO + x * ATT_D;
       auto issue_qk = [&](int j) {
         const int st = j % ATT_STAGES;
         mbar_wait(&k_full[st], (j / ATT_STAGES) & 1, 0x50);
-        mbar_wait(&s_empty[x], (j & 1) ^ 1, 0x51);   // softmax has pulled S_x(j-1) into registers
         tc_fence_after();
         const uint32_t k_addr = sK_addr + st * ATT_KV_BYTES;
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < ATT_D / 16; ++k)
-            umma_bf16(tS + x * ATT_BN, desc_kmajor_sw128(q_addr + k * 32), desc_kmajor_sw128(k_addr + k * 32), idesc_s,
-                      k != 0 ? 1u : 0u);
-          umma_commit(&s_full[x]);
+            umma_bf16(tSx, desc_kmajor_sw128(q_addr + k * 32), desc_kmajor_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(&s_full[x]);      // also certifies that PV(j-1) has retired: O_x is quiescent, P_x is dead
           umma_commit(&k_empty[st]);
         }
         __syncwarp();
@@ -163,24 +160,23 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       mbar_wait(q_full, 0, 0x52);
       issue_qk(0);
       for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) issue_qk(j + 1);
         const int st = j % ATT_STAGES;
         mbar_wait(&v_full[st], (j / ATT_STAGES) & 1, 0x53);
-        mbar_wait(&p_full[x], j & 1, 0x54);   // P(j) in smem (and any rescale of O_x done)
+        mbar_wait(&p_full[x], j & 1, 0x54);   // P_x(j) is in TMEM (and any rescale of O_x done)
         tc_fence_after();
         const uint32_t v_addr = sV_addr + st * ATT_KV_BYTES;
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < ATT_BN / 16; ++k) {
-            // P: one 64-wide K atom, 32 B per K=16 step.  V (MN-major): 16 kv rows = 2048 B per step.
-            const uint64_t da = desc_kmajor_sw128(p_addr + k * 32);
+            // A = P from TMEM: 16 bf16 of K per step = 8 columns.  B = V (MN-major): 16 kv rows = 2048 B per step.
             const uint64_t db = desc_mnmajor_sw128(v_addr + k * 2048, ATT_KV_BYTES);
-            umma_bf16(tO + x * ATT_D, da, db, idesc_o, (j | k) != 0 ? 1u : 0u);   // O_x accumulates across KV tiles
+            umma_bf16_ts(tOx, tSx + k * 8, db, idesc_o, (j | k) != 0 ? 1u : 0u);   // O_x accumulates across KV tiles
           }
-          umma_commit(&o_full[x]);
           umma_commit(&v_empty[st]);
+          if (j == n_tiles - 1) umma_commit(&o_full[x]);
         }
         __syncwarp();
+        if (j + 1 < n_tiles) issue_qk(j + 1);   // overwrites S_x / P_x: in issue order after PV(j)
       }
     }
   } else {
@@ -193,7 +189,6 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
       const uint32_t tSx = tS + lane_off + x * ATT_BN;
       const uint32_t tOx = tO + lane_off + x * ATT_D;
-      const uint32_t prow = smem_u32(sP) + x * ATT_TILE_BYTES + r * 128;   // 32-bit shared address of this row of P
       const float sc = p.scale_log2;
       float m_run = -INFINITY, l_run = 0.f;
       const long long pc0 = prof_begin();
@@ -207,9 +202,6 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         tmem_ld32(tSx + 0, s0);
         tmem_ld32(tSx + 32, s1);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[x]);     // S_x is free for QK^T of tile j+1
         prof_lap(&lap, 0x62);                          // TMEM load of S
 
         const int kv_valid = S - j * ATT_BN;  // >= 1
@@ -271,43 +263,30 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         l_run = l_run * alpha + ((sa + sb) + (sc_ + sd));
         prof_lap(&lap, 0x64);                          // exp2 + sum + pack
 
-        // PV(j-1) retired <=> the tensor core no longer reads P smem and O_x holds tiles < j
-        if (j > 0) {
-#ifndef ATT_EXP_NO_OWAIT
-          mbar_wait(&o_full[x], (j - 1) & 1, 0x61);
-#endif
-          if (rescale) {                                 // rare: O_x *= alpha in TMEM
-            tc_fence_after();
-            uint32_t o0[32], o1[32];
-            tmem_ld32(tOx, o0);
-            tmem_ld32(tOx + 32, o1);
-            tmem_ld_wait();
+        // s_full(j) also certified that PV(j-1) has retired: O_x holds tiles < j and nobody reads P_x any more
+        if (j > 0 && rescale) {                          // rare: O_x *= alpha in TMEM
+          uint32_t o0[32], o1[32];
+          tmem_ld32(tOx, o0);
+          tmem_ld32(tOx + 32, o1);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
-              o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
-            }
-            tmem_st32(tOx, o0);
-            tmem_st32(tOx + 32, o1);
-            tmem_st_wait();
-            tc_fence_before();
+          for (int i = 0; i < 32; ++i) {
+            o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
+            o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
           }
+          tmem_st32(tOx, o0);
+          tmem_st32(tOx + 32, o1);
         }
-        prof_lap(&lap, 0x65);                          // wait PV(j-1) (+ rare O rescale)
-#pragma unroll
-#ifndef ATT_EXP_NO_STORE
-        for (int cc = 0; cc < 8; ++cc)                 // 16-byte chunks of 8 kv columns
-          st_shared_v4(prow + ((cc ^ (r & 7)) << 4), pk[cc * 4 + 0], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
-        fence_proxy_async_smem();
-#else
-        if (pk[0] == 0x12345678u && pk[31] == 0x9abcdefu) st_shared_v4(prow, pk[0], pk[5], pk[17], pk[31]);   // keep pk alive
-#endif   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        prof_lap(&lap, 0x65);                          // rare O rescale
+        tmem_st32(tSx, pk);                            // P_x(j): 64 bf16 per row = 32 columns, over the consumed S_x
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[x]);
-        prof_lap(&lap, 0x66);                          // P -> smem, proxy fence, arrive
+        prof_lap(&lap, 0x66);                          // P -> TMEM, arrive
       }
       // final output: O_x / l
-      mbar_wait(&o_full[x], (n_tiles - 1) & 1, 0x61);
+      mbar_wait(&o_full[x], 0, 0x61);
       tc_fence_after();
       float o_acc[ATT_D];
       {
