@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4, help="prompts per rank per rollout")
+    ap.add_argument("--batch", type=int, default=8, help="prompts per rank per rollout (reference example default: per_device_batch_size 8)")
     ap.add_argument("--height", type=int, default=1024)
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--num-inference-steps", type=int, default=30)

@@ -218,11 +218,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
 #pragma unroll
           for (int c = 0; c < 32; c += 2) mxs[(c >> 1) & 7] = fmax3(mxs[(c >> 1) & 7], __uint_as_float(a[c]), __uint_as_float(a[c + 1]));
         };
-#ifndef ATT_EXP_NO_MAX
         max32(s0, 0); max32(s1, 32);
-#else
-        mxs[0] = 8.0f;
-#endif
         const float mt = fmax3(fmax3(mxs[0], mxs[1], mxs[2]), fmax3(mxs[3], mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7]));
         // lazy rescale: adopt the new max only if some row of the warp grew by more than 2^8 (warp-uniform decision)
         const bool grow = (mt - m_run) * sc > 8.0f;           // true on the first tile (m_run = -inf)
@@ -242,9 +238,6 @@ attention_kernel(const __grid_constant__ AttnParams p) {
           for (int c = 0; c < 16; ++c) {
             const uint64_t x2 = ffma2(pack_f32x2(__uint_as_float(a[2 * c]), __uint_as_float(a[2 * c + 1])), sc2, mneg2);
             float e0, e1;
-#ifdef ATT_EXP_NO_EXP
-            if (true) { unpack_f32x2(x2, e0, e1); } else
-#endif
             if ((c % ATT_POLY_PERIOD) < ATT_POLY_NUM) {
               exp2_poly_pair(x2, e0, e1);
             } else {
