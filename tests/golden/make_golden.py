@@ -32,6 +32,12 @@ def golden_schedule():
         s = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0, num_sde_steps=None, dynamics_type="Flow-SDE")
         ts = set_scheduler_timesteps(s, T, seq_len=seq, device="cpu")
         out[f"T{T}"] = dict(timesteps=ts.clone(), sigmas=s.sigmas.clone(), sde=s.current_sde_steps.clone())
+    # dynamic shifting (FLUX-style: mu = calculate_shift(seq_len); diffusers time_shift 'exponential')
+    for T, seq in ((28, 4096), (10, 1024)):
+        s = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, use_dynamic_shifting=True, base_shift=0.5, max_shift=1.15,
+                                               base_image_seq_len=256, max_image_seq_len=4096)
+        ts = set_scheduler_timesteps(s, T, seq_len=seq, device="cpu")
+        out[f"dyn_T{T}"] = dict(timesteps=ts.clone(), sigmas=s.sigmas.clone())
     for seed in (0, 42, 43):
         for n in (1, 3):
             s = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0, num_sde_steps=n, seed=seed)

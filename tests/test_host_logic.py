@@ -34,6 +34,10 @@ def test_schedule_and_sde_window_match_reference(golden_dir):
             assert torch.equal(s.current_sde_steps, g[f"sde_seed{seed}_n{n}"])
             assert torch.equal(s.get_noise_levels(), g[f"noise_levels_seed{seed}_n{n}"])
             assert torch.equal(s.train_timesteps, s.current_sde_steps)
+    for T, seq in ((28, 4096), (10, 1024)):   # dynamic shifting (mu from calculate_shift; FLUX-style configs)
+        d = F.FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, use_dynamic_shifting=True)
+        ts = F.set_scheduler_timesteps(d, T, seq_len=seq)
+        assert torch.equal(ts, g[f"dyn_T{T}"]["timesteps"]) and torch.equal(d.sigmas, g[f"dyn_T{T}"]["sigmas"])
     s.set_seed(7); assert s.seed == 7
     s.eval(); assert s.is_eval
     s.rollout(); assert not s.is_eval
