@@ -126,10 +126,10 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         for (int j = 0; j < n_tiles; ++j) {
           const int st = j % ATT_STAGES;
           const uint32_t ph = (j / ATT_STAGES) & 1;
-          mbar_wait(&k_empty[st], ph ^ 1, 0x40);
+          mbar_wait_relaxed(&k_empty[st], ph ^ 1, 0x40);   // off the critical path: do not steal issue slots
           mbar_arrive_expect_tx(&k_full[st], ATT_KV_BYTES);
           tma_load_3d(sK + st * ATT_KV_BYTES, &p.tmKV, &k_full[st], ck, j * ATT_BN, b);
-          mbar_wait(&v_empty[st], ph ^ 1, 0x41);
+          mbar_wait_relaxed(&v_empty[st], ph ^ 1, 0x41);
           mbar_arrive_expect_tx(&v_full[st], ATT_KV_BYTES);
           tma_load_3d(sV + st * ATT_KV_BYTES, &p.tmKV, &v_full[st], cv, j * ATT_BN, b);
         }
@@ -143,28 +143,27 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       const int x = warp - 9;
       const uint32_t q_addr = smem_u32(sQ) + x * ATT_TILE_BYTES, sK_addr = smem_u32(sK), sV_addr = smem_u32(sV);
       const uint32_t tSx = tS + x * ATT_BN, tOx = tO + x * ATT_D;
-      auto issue_qk = [&](int j) {
-        const int st = j % ATT_STAGES;
-        mbar_wait(&k_full[st], (j / ATT_STAGES) & 1, 0x50);
-        tc_fence_after();
-        const uint32_t k_addr = sK_addr + st * ATT_KV_BYTES;
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < ATT_D / 16; ++k)
-            umma_bf16(tSx, desc_kmajor_sw128(q_addr + k * 32), desc_kmajor_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(&s_full[x]);      // also certifies that PV(j-1) has retired: O_x is quiescent, P_x is dead
-          umma_commit(&k_empty[st]);
-        }
-        __syncwarp();
-      };
+      // per tile ONE elected block issues PV(j) and QK(j+1) back to back (S_x / P_x are overwritten by QK(j+1) in issue order
+      // after PV(j) has read P_x): the softmax -> tensor core -> softmax round trip is on every warp's critical path
       mbar_wait(q_full, 0, 0x52);
-      issue_qk(0);
+      mbar_wait(&k_full[0], 0, 0x50);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_bf16(tSx, desc_kmajor_sw128(q_addr + k * 32), desc_kmajor_sw128(sK_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[x]);
+        umma_commit(&k_empty[0]);
+      }
+      __syncwarp();
       for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % ATT_STAGES;
+        const int st = j % ATT_STAGES, st1 = (j + 1) % ATT_STAGES;
+        const bool more = j + 1 < n_tiles;
         mbar_wait(&v_full[st], (j / ATT_STAGES) & 1, 0x53);
+        if (more) mbar_wait(&k_full[st1], ((j + 1) / ATT_STAGES) & 1, 0x50);   // prefetched long ago
         mbar_wait(&p_full[x], j & 1, 0x54);   // P_x(j) is in TMEM (and any rescale of O_x done)
         tc_fence_after();
-        const uint32_t v_addr = sV_addr + st * ATT_KV_BYTES;
+        const uint32_t v_addr = sV_addr + st * ATT_KV_BYTES, k_addr = sK_addr + st1 * ATT_KV_BYTES;
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < ATT_BN / 16; ++k) {
@@ -173,10 +172,17 @@ attention_kernel(const __grid_constant__ AttnParams p) {
             umma_bf16_ts(tOx, tSx + k * 8, db, idesc_o, (j | k) != 0 ? 1u : 0u);   // O_x accumulates across KV tiles
           }
           umma_commit(&v_empty[st]);
-          if (j == n_tiles - 1) umma_commit(&o_full[x]);
+          if (more) {
+#pragma unroll
+            for (int k = 0; k < ATT_D / 16; ++k)
+              umma_bf16(tSx, desc_kmajor_sw128(q_addr + k * 32), desc_kmajor_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
+            umma_commit(&s_full[x]);      // also certifies that PV(j) has retired: O_x is quiescent, P_x is dead
+            umma_commit(&k_empty[st1]);
+          } else {
+            umma_commit(&o_full[x]);
+          }
         }
         __syncwarp();
-        if (j + 1 < n_tiles) issue_qk(j + 1);   // overwrites S_x / P_x: in issue order after PV(j)
       }
     }
   } else {

@@ -65,6 +65,16 @@ __device__ __forceinline__ void mbar_wait_impl(uint64_t* bar, uint32_t parity, u
     if (globaltimer_ns() - t0 > 4000000000ull) mbar_timeout(tag);
   }
 }
+// Same bound, but backs off with nanosleep: for roles that are far off the critical path (TMA producers waiting for a free
+// slot) so that their polling does not take issue slots from the compute warps of the same SM sub-partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(128);
+    if (globaltimer_ns() - t0 > 4000000000ull) mbar_timeout(tag);
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag) {
 #ifdef FFB_PROFILE
   const long long c0 = clock64();
