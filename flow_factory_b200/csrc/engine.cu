@@ -113,6 +113,11 @@ static int build_gemm(const GemmSpec& s, GemmParams* p) {
   }
   p->rows_per_batch = s.rows_per_batch; p->num_batch = s.num_batch; p->N = s.N; p->K = s.K;
   p->tiles_m_per_batch = (s.rows_per_batch + 127) / 128;
+  {
+    const long band = (64l << 20) / (512l * s.K);   // A rows of one band <= 64 MB (half of the L2)
+    const int clusters = num_sms() / 2;
+    p->band = static_cast<int>(band < 1 ? 1 : (band > clusters ? clusters : band));
+  }
   p->epi = s.epi;
   p->bias = static_cast<const bf16*>(s.bias);
   p->out = static_cast<bf16*>(s.out);

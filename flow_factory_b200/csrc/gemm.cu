@@ -49,6 +49,19 @@ __device__ __forceinline__ void unpack8_bf16(const uint4& u, float* f) {
   f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
   f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
 }
+// Work unit -> (m-pair, n-tile).  Units are rasterised in bands of `band` m-pairs, m fastest inside a band, then n, then the
+// next band: a band's A rows (band*256*K*2 B, sized by the host to <= 64 MB) stay L2-resident for the whole sweep over N instead
+// of being streamed from HBM once per n-tile (at M = 65536 the activation matrix is 200 MB at K = 1536 and 805 MB at K = 6144,
+// far larger than the 126 MB L2).
+__device__ __forceinline__ void unit_to_tile(int unit, int pairs_m, int tiles_n, int band, int& mp, int& tn) {
+  const int per_band = band * tiles_n;
+  const int b = unit / per_band;
+  const int rem = unit - b * per_band;
+  const int pb = min(band, pairs_m - b * band);   // pairs in this band (the last band may be short)
+  tn = rem / pb;
+  mp = b * band + rem - tn * pb;
+}
+
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
@@ -102,7 +115,9 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
     const long long pc0 = prof_begin();
     int stage = 0; uint32_t phase = 0;
     for (int unit = cluster_id; unit < num_units; unit += num_clusters) {
-      const int tm = 2 * (unit % pairs_m) + static_cast<int>(cta_rank), tn = unit / pairs_m;
+      int mp, tn;
+      unit_to_tile(unit, pairs_m, tiles_n, p.band, mp, tn);
+      const int tm = 2 * mp + static_cast<int>(cta_rank);
       // a ghost tile (odd tile count) still feeds its half of W to the pair; its A rows are out of bounds -> zeros
       const int b = tm < tiles_m ? tm / p.tiles_m_per_batch : p.num_batch;
       const int row0 = tm < tiles_m ? (tm % p.tiles_m_per_batch) * GEMM_BM : 0;
@@ -171,7 +186,9 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
     for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int tm = 2 * (unit % pairs_m) + static_cast<int>(cta_rank), tn = unit / pairs_m;
+      int mp, tn;
+      unit_to_tile(unit, pairs_m, tiles_n, p.band, mp, tn);
+      const int tm = 2 * mp + static_cast<int>(cta_rank);
       const bool tile_ok = tm < tiles_m;
       const int b = tile_ok ? tm / p.tiles_m_per_batch : 0;
       const int row_base = (tm % p.tiles_m_per_batch) * GEMM_BM + ew * 32;   // first row (within the batch) of this warp

@@ -25,6 +25,7 @@ struct GemmParams {
   int rows_per_batch, num_batch, N, K;
   int tiles_m_per_batch;
   int bn;   // N tile: 256 / 128 / 64 (must divide N)
+  int band; // m-pairs per rasterisation band (L2 residency of the A rows)
   int epi;
   const bf16* bias;  // [N] or null
   bf16* out;         // out[b*out_batch_stride + (out_row_offset + row)*ldo + n]
