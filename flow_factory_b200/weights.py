@@ -124,3 +124,41 @@ class PackedWeights:
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self.tensors.values())
+
+
+def merge_lora_state_dict(state_dict: Dict[str, torch.Tensor], lora_alpha: float, lora_rank: int = 0,
+                          adapter: str = "default") -> Dict[str, torch.Tensor]:
+    """Fold PEFT LoRA pairs into the base weights: W' = W + (alpha / r) * B @ A (FF/models/abc.py:859-949 wraps the
+    transformer with `get_peft_model` / `add_adapter('default', LoraConfig(r, lora_alpha))`).
+
+    Accepts the state dict of a PEFT-wrapped SD3Transformer2DModel (keys like
+    `base_model.model.transformer_blocks.0.attn.to_q.base_layer.weight`, `...to_q.lora_A.default.weight`,
+    `...to_q.lora_B.default.weight`) or of a diffusers model with an added adapter (no `base_model.model.` prefix) and
+    returns a plain state dict with diffusers key names, ready for PackedWeights.pack / RolloutEngine.refresh_weights.
+    Cost: 2*r*out*in FLOP per adapted linear - negligible next to a rollout (SURVEY 7.2 #4)."""
+    strip = lambda k: k[len("base_model.model."):] if k.startswith("base_model.model.") else k
+    sd = {strip(k): v for k, v in state_dict.items()}
+    out: Dict[str, torch.Tensor] = {}
+    lora_a: Dict[str, torch.Tensor] = {}
+    lora_b: Dict[str, torch.Tensor] = {}
+    for k, v in sd.items():
+        if f".lora_A.{adapter}.weight" in k:
+            lora_a[k.replace(f".lora_A.{adapter}.weight", "")] = v
+        elif f".lora_B.{adapter}.weight" in k:
+            lora_b[k.replace(f".lora_B.{adapter}.weight", "")] = v
+        elif ".lora_" in k:
+            raise NotImplementedError(f"unsupported LoRA tensor {k} (DoRA / embedding LoRA are not merged)")
+        else:
+            out[k.replace(".base_layer.", ".")] = v
+    if set(lora_a) != set(lora_b):
+        raise ValueError("unpaired lora_A / lora_B tensors")
+    for mod, A in lora_a.items():
+        B = lora_b[mod]
+        r = lora_rank or A.shape[0]
+        key = mod + ".weight"
+        if key not in out:
+            raise KeyError(f"LoRA targets {mod} but the base weight {key} is missing")
+        W = out[key]
+        delta = (B.to(torch.float32) @ A.to(torch.float32)) * (float(lora_alpha) / r)
+        out[key] = (W.to(torch.float32) + delta.to(W.device)).to(W.dtype)
+    return out

@@ -187,3 +187,20 @@ def test_prompt_sharding_and_single_allgather_world2_gloo():
     res = sorted(q.get(timeout=120) for _ in range(2))
     [p.join(timeout=60) for p in ps]
     assert res == [(0, True, 0, 5), (1, True, 5, 10)]
+
+
+def test_merge_lora_state_dict_matches_explicit_lora_forward():
+    from flow_factory_b200.weights import merge_lora_state_dict
+    g = torch.Generator().manual_seed(0)
+    W = torch.randn(24, 16, generator=g); b = torch.randn(24, generator=g)
+    A = torch.randn(4, 16, generator=g) * 0.1; Bm = torch.randn(24, 4, generator=g) * 0.1
+    x = torch.randn(5, 16, generator=g)
+    sd = {"base_model.model.blk.to_q.base_layer.weight": W, "base_model.model.blk.to_q.base_layer.bias": b,
+          "base_model.model.blk.to_q.lora_A.default.weight": A, "base_model.model.blk.to_q.lora_B.default.weight": Bm,
+          "base_model.model.norm.weight": torch.ones(3)}
+    m = merge_lora_state_dict(sd, lora_alpha=8.0)
+    assert set(m) == {"blk.to_q.weight", "blk.to_q.bias", "norm.weight"}
+    ref = torch.nn.functional.linear(x, W, b) + (x @ A.t() @ Bm.t()) * (8.0 / 4)      # peft: base(x) + scale * B(A(x))
+    torch.testing.assert_close(torch.nn.functional.linear(x, m["blk.to_q.weight"], m["blk.to_q.bias"]), ref, rtol=1e-5, atol=1e-5)
+    with pytest.raises(ValueError):
+        merge_lora_state_dict({"a.lora_A.default.weight": A, "a.weight": W}, 8.0)
