@@ -51,18 +51,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must never hang the GPU box - after ~4 s record a tag and trap.
+// Debug build -DFFB_NO_TRAP: record the FIRST tag and let every later wait fall through, so the kernel ends (with garbage)
+// and the host can still read the error word (a trap poisons the context).
 __device__ __noinline__ void mbar_timeout(uint32_t tag) {
+#ifdef FFB_NO_TRAP
+  if (atomicCAS(&g_dev_error[0], 0u, 0xDEAD0000u | (tag & 0xFFFFu)) == 0u) {
+    g_dev_error[1] = blockIdx.x | (blockIdx.y << 12) | (blockIdx.z << 24);
+    g_dev_error[2] = threadIdx.x;
+  }
+  __threadfence();
+#else
   g_dev_error[0] = 0xDEAD0000u | (tag & 0xFFFFu);
   g_dev_error[1] = blockIdx.x;
   g_dev_error[2] = threadIdx.x;
   __threadfence_system();
   __trap();
+#endif
 }
+#ifdef FFB_NO_TRAP
+#define FFB_WAIT_BUDGET_NS (*reinterpret_cast<volatile unsigned int*>(&g_dev_error[0]) != 0u ? 0ull : 2000000000ull)
+#define FFB_AFTER_TIMEOUT break
+#else
+#define FFB_WAIT_BUDGET_NS 4000000000ull
+#define FFB_AFTER_TIMEOUT
+#endif
 __device__ __forceinline__ void mbar_wait_impl(uint64_t* bar, uint32_t parity, uint32_t tag) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = globaltimer_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > 4000000000ull) mbar_timeout(tag);
+    if (globaltimer_ns() - t0 > FFB_WAIT_BUDGET_NS) { mbar_timeout(tag); FFB_AFTER_TIMEOUT; }
   }
 }
 // Same bound, but backs off with nanosleep: for roles that are far off the critical path (TMA producers waiting for a free
@@ -72,7 +89,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   const uint64_t t0 = globaltimer_ns();
   while (!mbar_try_wait(bar, parity)) {
     __nanosleep(128);
-    if (globaltimer_ns() - t0 > 4000000000ull) mbar_timeout(tag);
+    if (globaltimer_ns() - t0 > FFB_WAIT_BUDGET_NS) { mbar_timeout(tag); FFB_AFTER_TIMEOUT; }
   }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag) {

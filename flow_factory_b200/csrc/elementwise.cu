@@ -95,14 +95,13 @@ cudaError_t launch_ln_modulate(const LnModParams& p, cudaStream_t stream) {
 // small_linear: out[b, n] = bf16(bf16(acc + bias) + addend), batch <= 32 handled 8 rows at a time;
 // one warp per output feature n; weights streamed once per batch chunk with 16-byte loads.
 // ------------------------------------------------------------------------------------------------
-constexpr int SL_BCHUNK = 8;
+constexpr int SL_BCHUNK = 16;  // batch rows per pass: the whole CFG batch of the bench (2 x 8) streams the weights once
 constexpr int SL_WARPS = 8;
 
 __global__ void __launch_bounds__(SL_WARPS * 32) small_linear_kernel(const SmallLinearParams p) {
   extern __shared__ __align__(16) uint8_t sl_smem[];
   bf16* xin = reinterpret_cast<bf16*>(sl_smem);  // [SL_BCHUNK][K]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x * SL_WARPS + warp;
   const int b0 = blockIdx.y * SL_BCHUNK;
   const int nb = min(SL_BCHUNK, p.batch - b0);
   const int kc = p.K >> 3;
@@ -119,32 +118,34 @@ __global__ void __launch_bounds__(SL_WARPS * 32) small_linear_kernel(const Small
     *reinterpret_cast<uint4*>(xin + bb * p.K + c * 8) = u;
   }
   __syncthreads();
-  if (n >= p.N) return;
-  float acc[SL_BCHUNK];
+  // persistent over groups of SL_WARPS output features: the staged inputs are reused for every group this CTA handles
+  for (int n = blockIdx.x * SL_WARPS + warp; n < p.N; n += gridDim.x * SL_WARPS) {
+    float acc[SL_BCHUNK];
 #pragma unroll
-  for (int i = 0; i < SL_BCHUNK; ++i) acc[i] = 0.f;
-  const bf16* wr = p.W + static_cast<long>(n) * p.K;
-  for (int c = lane; c < kc; c += 32) {
-    float wf[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(wr + c * 8)), wf);
+    for (int i = 0; i < SL_BCHUNK; ++i) acc[i] = 0.f;
+    const bf16* wr = p.W + static_cast<long>(n) * p.K;
+    for (int c = lane; c < kc; c += 32) {
+      float wf[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(wr + c * 8)), wf);
 #pragma unroll
-    for (int bb = 0; bb < SL_BCHUNK; ++bb) {
-      if (bb < nb) {
-        float xf[8];
-        unpack8(*reinterpret_cast<const uint4*>(xin + bb * p.K + c * 8), xf);
+      for (int bb = 0; bb < SL_BCHUNK; ++bb) {
+        if (bb < nb) {
+          float xf[8];
+          unpack8(*reinterpret_cast<const uint4*>(xin + bb * p.K + c * 8), xf);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[bb] = fmaf(wf[e], xf[e], acc[bb]);
+          for (int e = 0; e < 8; ++e) acc[bb] = fmaf(wf[e], xf[e], acc[bb]);
+        }
       }
     }
-  }
 #pragma unroll
-  for (int bb = 0; bb < SL_BCHUNK; ++bb) acc[bb] = warp_sum(acc[bb]);
-  if (lane == 0) {
-    const float bias = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
-    for (int bb = 0; bb < nb; ++bb) {
-      float y = bf16_round(acc[bb] + bias);
-      if (p.addend) y = y + __bfloat162float(p.addend[static_cast<long>(b0 + bb) * p.addend_stride + n]);
-      p.out[static_cast<long>(b0 + bb) * p.out_stride + n] = __float2bfloat16_rn(y);
+    for (int bb = 0; bb < SL_BCHUNK; ++bb) acc[bb] = warp_sum(acc[bb]);
+    if (lane == 0) {
+      const float bias = p.bias ? __bfloat162float(p.bias[n]) : 0.f;
+      for (int bb = 0; bb < nb; ++bb) {
+        float y = bf16_round(acc[bb] + bias);
+        if (p.addend) y = y + __bfloat162float(p.addend[static_cast<long>(b0 + bb) * p.addend_stride + n]);
+        p.out[static_cast<long>(b0 + bb) * p.out_stride + n] = __float2bfloat16_rn(y);
+      }
     }
   }
 }
@@ -158,7 +159,8 @@ cudaError_t launch_small_linear(const SmallLinearParams& p, cudaStream_t stream)
     if (e != cudaSuccess) return e;
     max_smem = smem;
   }
-  dim3 grid((p.N + SL_WARPS - 1) / SL_WARPS, (p.batch + SL_BCHUNK - 1) / SL_BCHUNK);
+  const int groups = (p.N + SL_WARPS - 1) / SL_WARPS;
+  dim3 grid(std::min(groups, 148 * 4), (p.batch + SL_BCHUNK - 1) / SL_BCHUNK);
   small_linear_kernel<<<grid, SL_WARPS * 32, smem, stream>>>(p);
   return cudaGetLastError();
 }

@@ -135,7 +135,7 @@ static int build_attn(const void* qkv, int batch, int seq, int heads, void* out,
   const uint32_t box[3] = {64, 128, 1};
   int r = make_tmap(&p->tmQKV, qkv, 3, dims, str, box);
   if (r) return r;
-  const uint32_t box_kv[3] = {64, 64, 1};
+  const uint32_t box_kv[3] = {64, ATT_BN, 1};   // kv rows per tile (attention.cu, same translation unit)
   r = make_tmap(&p->tmKV, qkv, 3, dims, str, box_kv);
   if (r) return r;
   p->seq_len = seq; p->num_heads = heads; p->inner_dim = D; p->batch = batch;

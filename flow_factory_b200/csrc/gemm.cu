@@ -202,22 +202,34 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
           st_shared_v4x(vec_gate + lane * 16, __ldg(reinterpret_cast<const uint4*>(p.gate + static_cast<long>(b) * p.gate_batch_stride + tn * BN) + lane));
       }
       __syncwarp();
+      // residual mode: the h chunk (whole-line loads, 8 lanes per 128-B row) is fetched one chunk AHEAD into registers - chunk 0
+      // before the accumulator wait, chunk c+1 while chunk c is processed - so its HBM latency never sits on the epilogue's
+      // critical path (at K = 1536 the epilogue, not the MMA, paces the attention out-projection).
+      uint4 hv[8];
+      auto load_residual = [&](int c) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + coop_row;
+          hv[i] = make_uint4(0, 0, 0, 0);
+          if (tile_ok && row_base + rr < p.rows_per_batch)
+            hv[i] = *reinterpret_cast<const uint4*>(out_base + static_cast<long>(rr) * p.ldo + c * 64 + coop_c * 8);
+        }
+      };
+      if (p.epi == EPI_GATE_RESIDUAL) load_residual(0);
       mbar_wait(&tmem_full[acc], acc_phase, 0x30);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 
       for (int c = 0; c < BN / 64; ++c) {
         const int n0 = tn * BN + c * 64;       // global column of this 64-wide chunk
-        // (1) residual mode: pull the h chunk in with whole-line loads -> staging tile (16-B chunks XOR-swizzled by row)
+        // (1) residual mode: prefetched h chunk -> staging tile (16-B chunks XOR-swizzled by row); start the next chunk's loads
         if (p.epi == EPI_GATE_RESIDUAL) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = i * 4 + coop_row;
-            if (tile_ok && row_base + rr < p.rows_per_batch) {
-              const uint4 hv = *reinterpret_cast<const uint4*>(out_base + static_cast<long>(rr) * p.ldo + c * 64 + coop_c * 8);
-              st_shared_v4x(stg + rr * 128 + ((coop_c ^ (rr & 7)) << 4), hv);
-            }
+            st_shared_v4x(stg + rr * 128 + ((coop_c ^ (rr & 7)) << 4), hv[i]);
           }
+          if (c + 1 < BN / 64) load_residual(c + 1);
           __syncwarp();
         }
         // (2) thread == row: accumulator chunk -> registers -> fused math -> bf16 -> own row of the staging tile

@@ -5,43 +5,37 @@
 // straight out of the fused-QKV GEMM's token-major [B, S, 3D] buffer with 3-D TMA boxes (one per head),
 // so there is no concat copy and no [B,H,S,d] transpose in HBM.
 //
-// One CTA per (384 query rows = three 128-row sub-tiles, head, batch), 16 warps, one CTA per SM:
-//   warps 0-3 / 4-7 / 8-11 : softmax of sub-tile 0 / 1 / 2; thread == query row == TMEM lane (no shuffles).  Three softmax warps
-//                            per SM sub-partition, each from a different sub-tile, cover each other's latencies.
-//   warp  12               : TMA producer (Q once; ring of 64x64 K and V tiles shared by the three sub-tiles)
-//   warps 13 / 14 / 15     : MMA issuers, one per sub-tile (S = Q K^T : M128 N64 K64 ; O += P V : M128 N64 K64, V as MN-major
-//                            operand).  One issuer per sub-tile keeps the softmax groups out of lockstep.
-//   setmaxnreg moves registers from warps 12-15 (24 each) to the softmax warps (152 each).
-// TMEM (all 512 columns): per sub-tile S (64 columns, fp32), P (32 columns, bf16 pairs) and the output accumulator O (64, fp32).
-//   * P has its OWN columns, so S is free again as soon as the softmax warps hold S(j) in registers: Q K^T of tile j+1 is issued
-//     right then and runs on the tensor core WHILE the softmax of tile j is computed - the softmax -> tensor core -> softmax
-//     round trip is off the critical path (with P aliased onto S it cost ~45 % of the tile time).
-//   * P is written with tcgen05.st and consumed by the P V MMA as its TMEM A operand (TS mode): no shared-memory round trip,
-//     no generic->async proxy fence.
+// One CTA per (256 query rows = two 128-row sub-tiles A/B, head, batch), 12 warps, TWO CTAs resident per SM:
+//   warps 0-3 / 4-7 : softmax of sub-tile A / B; thread == query row == TMEM lane (no shuffles).  Four softmax warps per SM
+//                     sub-partition (2 CTAs x 2 sub-tiles) hide each other's TMEM / barrier latencies.
+//   warp  8         : TMA producer (Q once; ring of 32x64 K and V tiles shared by both sub-tiles)
+//   warps 9 / 10    : MMA issuers for sub-tile A / B (S = Q K^T : M128 N32 K64 ; O += P V : M128 N64 K32, V as MN-major operand).
+//                     One issuer per sub-tile keeps the two softmax groups out of lockstep.
+//   setmaxnreg moves registers from warps 8-11 (24 each) to the softmax warps (104 each).
+// TMEM (256 columns per CTA): per sub-tile two S buffers of 32 columns + the output accumulator O (64 columns).
+//   * S is double-buffered: Q K^T of tile j+2 is issued right behind P V of tile j, so while the softmax warps work on tile j+1
+//     the tensor core refills the other buffer - the softmax -> tensor core -> softmax round trip is off the critical path.
+//   * P (bf16 pairs) is written back over the first 16 columns of the S buffer it came from (tcgen05.st) and consumed by the
+//     P V MMA as its TMEM A operand (TS mode): no shared-memory round trip, no generic->async proxy fence.
 //   * O accumulates in TMEM across KV tiles; the running row max is adopted lazily (only when some row of the warp grew by more
 //     than 2^8; otherwise the stale max is kept and P may exceed 1 - harmless in fp32/bf16), so O is rescaled in TMEM only in
 //     the first few tiles and read once at the end.
-// The MUFU unit (16 ex2/clk/SM) is the scarcest pipe at d = 64: 3 of every 8 element pairs go through a polynomial exp2 on the
-// FMA pipe; scale / sum use packed fp32x2 arithmetic; the row max uses 3-input max in independent chains.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace ffb {
 
 constexpr int ATT_BM = 128;     // query rows per sub-tile
-constexpr int ATT_NSUB = 3;     // sub-tiles per CTA
-constexpr int ATT_QB = ATT_NSUB * ATT_BM;   // query rows per CTA
-constexpr int ATT_BN = 64;      // kv rows per tile
+constexpr int ATT_QB = 256;     // query rows per CTA
+constexpr int ATT_BN = 32;      // kv rows per tile
 constexpr int ATT_D = 64;
 constexpr int ATT_STAGES = 6;
-constexpr int ATT_THREADS = 512;
+constexpr int ATT_THREADS = 384;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;      // 16 KB: a Q sub-tile (128 rows x 64 bf16)
-constexpr int ATT_KV_BYTES = ATT_BN * 64 * 2;     // 8 KB: a K or V tile
-constexpr int ATT_SMEM = ATT_NSUB * ATT_TILE_BYTES /*Q*/ + 2 * ATT_STAGES * ATT_KV_BYTES /*K,V*/ + 1024;   // 145 KB
-constexpr int ATT_TMEM_COLS = 512;
-constexpr int ATT_TMEM_S = 0;       // S_x at columns x*64
-constexpr int ATT_TMEM_P = 192;     // P_x at columns 192 + x*32
-constexpr int ATT_TMEM_O = 320;     // O_x at columns 320 + x*64 (last column used: 511)
+constexpr int ATT_KV_BYTES = ATT_BN * 64 * 2;     // 4 KB: a K or V tile
+// two CTAs per SM (4 softmax warps per SM sub-partition): 80.5 KB each
+constexpr int ATT_SMEM = 2 * ATT_TILE_BYTES /*Q_A,Q_B*/ + 2 * ATT_STAGES * ATT_KV_BYTES /*K,V*/ + 512;
+constexpr int ATT_TMEM_COLS = 256;                // per sub-tile S0,S1 (32 each) at columns x*64 ; O_A,O_B (64 each) above
 
 // exp2 on the FMA/ALU pipes for part of the elements (the MUFU unit, 16 ex2/clk/SM, is the binding resource at d = 64):
 // 2^x = 2^round(x) * p(x - round(x)), p = degree-3 minimax of 2^f on [-0.5, 0.5] (max rel. error 7.5e-5, far below the
@@ -72,24 +66,33 @@ constexpr int ATT_POLY_NUM = 3;      // ... this many go through exp2_poly_pair,
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+// 16 columns of registers -> TMEM (32x32b shape): the packed P row of one KV tile
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];    // SWIZZLE_128B tiles need 1024-byte alignment
-  uint8_t* sQ = smem;                                   // [3 sub-tiles][128][64]
-  uint8_t* sK = sQ + ATT_NSUB * ATT_TILE_BYTES;         // [stages][64][64]
-  uint8_t* sV = sK + ATT_STAGES * ATT_KV_BYTES;         // [stages][64][64]
+  uint8_t* sQ = smem;                                   // [2 sub-tiles][128][64]
+  uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;                // [stages][32][64]
+  uint8_t* sV = sK + ATT_STAGES * ATT_KV_BYTES;         // [stages][32][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_STAGES * ATT_KV_BYTES);
   uint64_t* q_full = bars;                       // 1
   uint64_t* k_full = bars + 1;                   // [ST]
   uint64_t* k_empty = k_full + ATT_STAGES;       // [ST]
   uint64_t* v_full = k_empty + ATT_STAGES;       // [ST]
   uint64_t* v_empty = v_full + ATT_STAGES;       // [ST]
-  uint64_t* s_full = v_empty + ATT_STAGES;       // [3]  S_x(j) = Q K_j^T is in TMEM
-  uint64_t* s_free = s_full + ATT_NSUB;          // [3]  the four softmax warps hold S_x(j) in registers: S_x may be overwritten
-  uint64_t* p_full = s_free + ATT_NSUB;          // [3]  P_x(j) written to TMEM (and any rescale of O_x done)
-  uint64_t* p_free = p_full + ATT_NSUB;          // [3]  P V of tile j retired: P_x may be overwritten, O_x is quiescent
-  uint64_t* o_full = p_free + ATT_NSUB;          // [3]  final O_x complete
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + ATT_NSUB);
+  uint64_t* s_full = v_empty + ATT_STAGES;       // [2 sub-tiles][2 buffers]  S_x[u] = Q K^T of a tile is ready
+  uint64_t* p_full = s_full + 4;                 // [2][2] P_x(j) written to buffer j & 1 (and any rescale of O_x done).  A softmax warp
+                                                 //        may run one tile ahead of its three siblings, hence one barrier per buffer
+  uint64_t* pv_done = p_full + 4;                // [2]  P V of tile j retired (O_x quiescent); only the rare rescale path waits on it
+  uint64_t* o_full = pv_done + 2;                // [2]  final O_x complete
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,9 +102,9 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   const int b = blockIdx.z;
   const int S = p.seq_len;
   const int n_tiles = (S + ATT_BN - 1) / ATT_BN;
-  const int n_sub = min(ATT_NSUB, (S - q0 + ATT_BM - 1) / ATT_BM);   // sub-tiles holding at least one valid row (>= 1)
+  const int n_sub = (q0 + ATT_BM < S) ? 2 : 1;   // sub-tile B exists only if it holds at least one valid row
 
-  if (warp == 12 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&p.tmQKV);
     tma_prefetch_desc(&p.tmKV);
     mbar_init(q_full, 1);
@@ -109,24 +112,24 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], n_sub);   // one MMA issuer warp per sub-tile releases the slot
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], n_sub);
     }
-    for (int i = 0; i < ATT_NSUB; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 4);
-      mbar_init(&p_full[i], 4);
-      mbar_init(&p_free[i], 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&pv_done[i], 1);
       mbar_init(&o_full[i], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 13) tmem_alloc(tmem_ptr_smem, ATT_TMEM_COLS);
+  if (warp == 9) tmem_alloc(tmem_ptr_smem, ATT_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tS = tmem_base;         // sub-tile x, buffer u at columns x*64 + u*32 (P aliases the first 16 columns of its buffer)
+  const uint32_t tO = tmem_base + 128;   // O_A / O_B at columns 128 / 192
 
-  if (warp >= 12) {
+  if (warp >= 8) {
     setmaxnreg_dec<24>();
-    if (warp == 12) {
+    if (warp == 8) {
       // ===================== TMA producer =====================
       if (lane == 0) {
         const int cq = head * ATT_D, ck = p.inner_dim + head * ATT_D, cv = 2 * p.inner_dim + head * ATT_D;
@@ -143,18 +146,16 @@ attention_kernel(const __grid_constant__ AttnParams p) {
           tma_load_3d(sV + st * ATT_KV_BYTES, &p.tmKV, &v_full[st], cv, j * ATT_BN, b);
         }
       }
-    } else if (warp - 13 < n_sub) {
-      // ===================== MMA issuers: warp 13 + x -> sub-tile x =====================
+    } else if (warp - 9 < n_sub) {
+      // ===================== MMA issuers: warp 9 -> sub-tile A, warp 10 -> sub-tile B.  One issuer per sub-tile keeps the two
+      // softmax groups decoupled (a shared in-order issuer forces them into lockstep, i.e. into the same pipe at the same time).
       // The whole warp walks the loop (warp-uniform state -> uniform registers feed UTCHMMA), one elected lane issues.
-      // Tensor-core order per sub-tile:  QK(0) ; { QK(j+1) ; PV(j) } for j = 0..  -  QK(j+1) starts when the softmax warps have
-      // S(j) in registers and runs during their exp2 work; PV(j) starts when they have written P(j).
       constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);  // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);   // P (TMEM) x V (MN-major)
-      const int x = warp - 13;
+      const int x = warp - 9;
       const uint32_t q_addr = smem_u32(sQ) + x * ATT_TILE_BYTES, sK_addr = smem_u32(sK), sV_addr = smem_u32(sV);
-      const uint32_t tSx = tmem_base + ATT_TMEM_S + x * ATT_BN, tPx = tmem_base + ATT_TMEM_P + x * (ATT_BN / 2),
-                     tOx = tmem_base + ATT_TMEM_O + x * ATT_D;
-      auto issue_qk = [&](int j) {
+      const uint32_t tSx = tS + x * 2 * ATT_BN, tOx = tO + x * ATT_D;
+      auto issue_qk = [&](int j) {   // S_x[j & 1] = Q K_j^T; the buffer is free: P V of tile j-2 was issued earlier (in-order pipe)
         const int st = j % ATT_STAGES;
         mbar_wait(&k_full[st], (j / ATT_STAGES) & 1, 0x50);
         tc_fence_after();
@@ -162,22 +163,20 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < ATT_D / 16; ++k)
-            umma_bf16(tSx, desc_kmajor_sw128(q_addr + k * 32), desc_kmajor_sw128(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(&s_full[x]);
+            umma_bf16(tSx + (j & 1) * ATT_BN, desc_kmajor_sw128(q_addr + k * 32), desc_kmajor_sw128(k_addr + k * 32), idesc_s,
+                      k != 0 ? 1u : 0u);
+          umma_commit(&s_full[x * 2 + (j & 1)]);
           umma_commit(&k_empty[st]);
         }
         __syncwarp();
       };
       mbar_wait(q_full, 0, 0x52);
       issue_qk(0);
+      if (n_tiles > 1) issue_qk(1);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % ATT_STAGES;
-        if (j + 1 < n_tiles) {
-          mbar_wait(&s_free[x], j & 1, 0x51);    // S_x(j) is in the softmax warps' registers
-          issue_qk(j + 1);
-        }
         mbar_wait(&v_full[st], (j / ATT_STAGES) & 1, 0x53);
-        mbar_wait(&p_full[x], j & 1, 0x54);      // P_x(j) is in TMEM (and any rescale of O_x done)
+        mbar_wait(&p_full[x * 2 + (j & 1)], (j >> 1) & 1, 0x54);   // P_x(j) is in TMEM (and any rescale of O_x done)
         tc_fence_after();
         const uint32_t v_addr = sV_addr + st * ATT_KV_BYTES;
         if (elect_one()) {
@@ -185,59 +184,53 @@ attention_kernel(const __grid_constant__ AttnParams p) {
           for (int k = 0; k < ATT_BN / 16; ++k) {
             // A = P from TMEM: 16 bf16 of K per step = 8 columns.  B = V (MN-major): 16 kv rows = 2048 B per step.
             const uint64_t db = desc_mnmajor_sw128(v_addr + k * 2048, ATT_KV_BYTES);
-            umma_bf16_ts(tOx, tPx + k * 8, db, idesc_o, (j | k) != 0 ? 1u : 0u);   // O_x accumulates across KV tiles
+            umma_bf16_ts(tOx, tSx + (j & 1) * ATT_BN + k * 8, db, idesc_o, (j | k) != 0 ? 1u : 0u);   // O_x accumulates across KV tiles
           }
           umma_commit(&v_empty[st]);
-          umma_commit(&p_free[x]);
+          umma_commit(&pv_done[x]);
           if (j == n_tiles - 1) umma_commit(&o_full[x]);
         }
         __syncwarp();
+        if (j + 2 < n_tiles) issue_qk(j + 2);   // refills buffer j & 1 while the softmax warps work on tile j+1
       }
     }
   } else {
-    // ===================== softmax: warps 4x .. 4x+3 -> sub-tile x =====================
-    setmaxnreg_inc<152>();   // pool: 512 x 128 regs at launch = 12 x 32 x 152 + 4 x 32 x 24 (+ 4096 spare)
+    // ===================== softmax / accumulate: warps 0-3 -> sub-tile A, warps 4-7 -> sub-tile B =====================
+    setmaxnreg_inc<104>();   // pool: 384 x 80 regs at launch = 8 x 32 x 104 + 4 x 32 x 24
     const int x = warp >> 2;                          // sub-tile
     if (x < n_sub) {
       const int wq = warp & 3;                        // TMEM lane quadrant
       const int r = wq * 32 + lane;                   // query row in the sub-tile == TMEM lane
       const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
-      const uint32_t tSx = tmem_base + lane_off + ATT_TMEM_S + x * ATT_BN;
-      const uint32_t tPx = tmem_base + lane_off + ATT_TMEM_P + x * (ATT_BN / 2);
-      const uint32_t tOx = tmem_base + lane_off + ATT_TMEM_O + x * ATT_D;
+      const uint32_t tSx = tS + lane_off + x * 2 * ATT_BN;
+      const uint32_t tOx = tO + lane_off + x * ATT_D;
       const float sc = p.scale_log2;
       float m_run = -INFINITY, l_run = 0.f;
       const long long pc0 = prof_begin();
       long long lap = prof_begin();
       for (int j = 0; j < n_tiles; ++j) {
+        const uint32_t tSb = tSx + (j & 1) * ATT_BN;
         prof_lap(&lap, 0x67);                          // loop overhead / previous arrive
-        mbar_wait(&s_full[x], j & 1, 0x60);
+        mbar_wait(&s_full[x * 2 + (j & 1)], (j >> 1) & 1, 0x60);
         tc_fence_after();
         prof_lap(&lap, 0x68);                          // wait s_full
-        uint32_t s0[32], s1[32];
-        tmem_ld32(tSx + 0, s0);
-        tmem_ld32(tSx + 32, s1);
+        uint32_t s0[32];
+        tmem_ld32(tSb, s0);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[x]);        // Q K^T of the next tile may overwrite S_x now
         prof_lap(&lap, 0x62);                          // TMEM load of S
 
         const int kv_valid = S - j * ATT_BN;  // >= 1
-        // row max of this tile: 8 independent chains (a single serial fmax chain is 128 x 4 cycles of pure latency)
+        if (kv_valid < ATT_BN) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c >= kv_valid) s0[c] = 0xFF800000u;    // -inf: key beyond the sequence
+        }
+        // row max of this tile: 8 independent chains (a single serial fmax chain is pure latency)
         float mxs[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mxs[i] = -INFINITY;
-        auto max32 = [&](uint32_t(&a)[32], int base) {
-          if (kv_valid < ATT_BN) {
+        for (int i = 0; i < 8; ++i) mxs[i] = fmaxf(__uint_as_float(s0[2 * i]), __uint_as_float(s0[2 * i + 1]));
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (base + c >= kv_valid) a[c] = 0xFF800000u;  // -inf: key beyond the sequence
-          }
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) mxs[(c >> 1) & 7] = fmax3(mxs[(c >> 1) & 7], __uint_as_float(a[c]), __uint_as_float(a[c + 1]));
-        };
-        max32(s0, 0); max32(s1, 32);
+        for (int i = 0; i < 8; ++i) mxs[i] = fmax3(mxs[i], __uint_as_float(s0[16 + 2 * i]), __uint_as_float(s0[17 + 2 * i]));
         const float mt = fmax3(fmax3(mxs[0], mxs[1], mxs[2]), fmax3(mxs[3], mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7]));
         // lazy rescale: adopt the new max only if some row of the warp grew by more than 2^8 (warp-uniform decision)
         const bool grow = (mt - m_run) * sc > 8.0f;           // true on the first tile (m_run = -inf)
@@ -251,35 +244,30 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         prof_lap(&lap, 0x63);                          // row max
         const uint64_t sc2 = pack_f32x2(sc, sc), mneg2 = pack_f32x2(-m_run * sc, -m_run * sc);
         uint64_t sums2[2] = {0ull, 0ull};              // 4 partial row sums as two packed pairs
-        uint32_t pk[32];                               // P(j) as packed bf16 pairs
-        auto exp32 = [&](uint32_t(&a)[32], int quarter) {
+        uint32_t pk[16];                               // P(j) as packed bf16 pairs
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const uint64_t x2 = ffma2(pack_f32x2(__uint_as_float(a[2 * c]), __uint_as_float(a[2 * c + 1])), sc2, mneg2);
-            float e0, e1;
-            if ((c % ATT_POLY_PERIOD) < ATT_POLY_NUM) {
-              exp2_poly_pair(x2, e0, e1);
-            } else {
-              float t0, t1;
-              unpack_f32x2(x2, t0, t1);
-              e0 = ex2_approx(t0); e1 = ex2_approx(t1);
-            }
-            sums2[c & 1] = fadd2(sums2[c & 1], pack_f32x2(e0, e1));
-            pk[quarter * 16 + c] = pack_bf16x2(e0, e1);
+        for (int c = 0; c < 16; ++c) {
+          const uint64_t x2 = ffma2(pack_f32x2(__uint_as_float(s0[2 * c]), __uint_as_float(s0[2 * c + 1])), sc2, mneg2);
+          float e0, e1;
+          if ((c % ATT_POLY_PERIOD) < ATT_POLY_NUM) {
+            exp2_poly_pair(x2, e0, e1);
+          } else {
+            float t0, t1;
+            unpack_f32x2(x2, t0, t1);
+            e0 = ex2_approx(t0); e1 = ex2_approx(t1);
           }
-        };
-        exp32(s0, 0); exp32(s1, 1);
+          sums2[c & 1] = fadd2(sums2[c & 1], pack_f32x2(e0, e1));
+          pk[c] = pack_bf16x2(e0, e1);
+        }
         float sa, sb, sc_, sd;
         unpack_f32x2(sums2[0], sa, sb);
         unpack_f32x2(sums2[1], sc_, sd);
         l_run = l_run * alpha + ((sa + sb) + (sc_ + sd));
         prof_lap(&lap, 0x64);                          // exp2 + sum + pack
 
-        if (j > 0) {                                   // P V of tile j-1 retired (issued a whole softmax ago): P_x free, O_x quiescent
-          mbar_wait(&p_free[x], (j - 1) & 1, 0x61);
+        if (j > 0 && rescale) {                          // rare: O_x *= alpha in TMEM, once P V of tile j-1 has retired
+          mbar_wait(&pv_done[x], (j - 1) & 1, 0x61);
           tc_fence_after();
-        }
-        if (j > 0 && rescale) {                          // rare: O_x *= alpha in TMEM
           uint32_t o0[32], o1[32];
           tmem_ld32(tOx, o0);
           tmem_ld32(tOx + 32, o1);
@@ -292,12 +280,12 @@ attention_kernel(const __grid_constant__ AttnParams p) {
           tmem_st32(tOx, o0);
           tmem_st32(tOx + 32, o1);
         }
-        prof_lap(&lap, 0x65);                          // wait p_free, rare O rescale
-        tmem_st32(tPx, pk);                            // P_x(j): 64 bf16 per row = 32 columns
+        prof_lap(&lap, 0x65);                          // rare O rescale
+        tmem_st16(tSb, pk);                            // P_x(j): 32 bf16 per row = 16 columns, over the consumed S buffer
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[x]);
+        if (lane == 0) mbar_arrive(&p_full[x * 2 + (j & 1)]);
         prof_lap(&lap, 0x66);                          // P -> TMEM, arrive
       }
       // final output: O_x / l
@@ -312,7 +300,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) { o_acc[i] = __uint_as_float(o0[i]); o_acc[32 + i] = __uint_as_float(o1[i]); }
       }
-      prof_end(pc0, 0x70 + warp);
+      prof_end(pc0, 0x78 + warp);
       // O_x and l_run are both relative to the final running max m_run.
       const int q = q0 + x * ATT_BM + r;
       if (q < S) {
@@ -333,7 +321,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT_TMEM_COLS);
   }
@@ -346,8 +334,7 @@ cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int qb = ATT_QB;
-  dim3 grid((p.seq_len + qb - 1) / qb, p.num_heads, p.batch);
+  dim3 grid((p.seq_len + ATT_QB - 1) / ATT_QB, p.num_heads, p.batch);
   attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(p);
   return cudaGetLastError();
 }

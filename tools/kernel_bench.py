@@ -26,7 +26,7 @@ def main():
     out = []
     for (M, N, K, epi, name) in [(8192, 4608, 1536, 3, "qkv"), (8192, 1536, 1536, 2, "attn_out"), (8192, 6144, 1536, 1, "mlp_up"),
                                  (8192, 1536, 6144, 2, "mlp_down"), (666, 1536, 4096, 0, "ctx_embed"), (32768, 4608, 1536, 3, "qkv_b8"),
-                                 (65536, 4608, 1536, 3, "qkv_b16"), (65536, 1536, 6144, 2, "mlp_down_b16"), (65536, 6144, 1536, 1, "mlp_up_b16")]:
+                                 (65536, 4608, 1536, 3, "qkv_b16"), (65536, 1536, 1536, 2, "attn_out_b16"), (65536, 1536, 6144, 2, "mlp_down_b16"), (65536, 6144, 1536, 1, "mlp_up_b16")]:
         A = torch.randn(M, K, device="cuda").bfloat16()
         W = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
         b = torch.randn(N, device="cuda").bfloat16()
