@@ -23,11 +23,13 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm + modulate.  One warp per token row, row kept in registers (D <= 2048, D % 8 == 0).
+// LayerNorm + modulate.  One warp per token row; the row stays in registers as the raw 16-byte bf16 chunks it was loaded as
+// (32 registers instead of 64 fp32 values: twice the resident warps, which is what hides the HBM latency of this pure
+// streaming kernel) and is unpacked on the fly in each of the three passes (mean, variance, output).  D <= 2048, D % 8 == 0.
 // ------------------------------------------------------------------------------------------------
 constexpr int LN_MAXC = 8;  // 16-byte chunks per lane
 
-__global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
+__global__ void __launch_bounds__(256, 4) ln_modulate_kernel(const LnModParams p) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int rows = p.rows_per_batch * p.num_batch;
@@ -35,26 +37,32 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
   const int b = warp / p.rows_per_batch;
   const int nchunk = p.D >> 3;
   const bf16* xr = p.x + static_cast<long>(warp) * p.D;
-  float v[LN_MAXC][8];
-  float sum = 0.f;
+  uint4 raw[LN_MAXC];
 #pragma unroll
   for (int i = 0; i < LN_MAXC; ++i) {
     const int c = lane + 32 * i;
-    if (c < nchunk) {
-      const uint4 u = *reinterpret_cast<const uint4*>(xr + c * 8);
-      unpack8(u, v[i]);
+    raw[i] = make_uint4(0, 0, 0, 0);
+    if (c < nchunk) raw[i] = *reinterpret_cast<const uint4*>(xr + c * 8);
+  }
+  float sum = 0.f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) sum += v[i][e];
+  for (int i = 0; i < LN_MAXC; ++i) {
+    if (lane + 32 * i < nchunk) {
+      float v[8];
+      unpack8(raw[i], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += v[e];
     }
   }
   const float mean = warp_sum(sum) / static_cast<float>(p.D);
   float sq = 0.f;
 #pragma unroll
   for (int i = 0; i < LN_MAXC; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nchunk) {
+    if (lane + 32 * i < nchunk) {
+      float v[8];
+      unpack8(raw[i], v);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; sq += d * d; }
+      for (int e = 0; e < 8; ++e) { const float d = v[e] - mean; sq += d * d; }
     }
   }
   const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(p.D) + p.eps);
@@ -64,8 +72,9 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
     const int c = lane + 32 * i;
     if (c < nchunk) {
       float y[8], sc[8], sh[8], o[8];
+      unpack8(raw[i], y);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] = (v[i][e] - mean) * rstd;
+      for (int e = 0; e < 8; ++e) y[e] = (y[e] - mean) * rstd;
       unpack8(__ldg(reinterpret_cast<const uint4*>(p.scale1 + mo + c * 8)), sc);
       unpack8(__ldg(reinterpret_cast<const uint4*>(p.shift1 + mo + c * 8)), sh);
 #pragma unroll
