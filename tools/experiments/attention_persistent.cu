@@ -1,0 +1,407 @@
+// tcgen05 / TMEM flash attention for the MMDiT joint (image+text) attention, head_dim 64, non-causal.
+//
+// Replaces F.scaled_dot_product_attention at DF/models/attention_processor.py:1484 together with the
+// torch.cat of image/text q,k,v (1480-1482) and the head transposes (1451-1452, 1485): q, k, v are read
+// straight out of the fused-QKV GEMM's token-major [B, S, 3D] buffer with 3-D TMA boxes (one per head),
+// so there is no concat copy and no [B,H,S,d] transpose in HBM.
+//
+// One CTA per (384 query rows = three 128-row sub-tiles, head, batch), 16 warps, one CTA per SM:
+//   warps 0-3 / 4-7 / 8-11 : softmax of sub-tile 0 / 1 / 2; thread == query row == TMEM lane (no shuffles).  Three softmax warps
+//                            per SM sub-partition, each from a different sub-tile, cover each other's latencies.
+//   warp  12               : TMA producer (Q once; ring of 64x64 K and V tiles shared by the three sub-tiles)
+//   warps 13 / 14 / 15     : MMA issuers, one per sub-tile (S = Q K^T : M128 N64 K64 ; O += P V : M128 N64 K64, V as MN-major
+//                            operand).  One issuer per sub-tile keeps the softmax groups out of lockstep.
+//   setmaxnreg moves registers from warps 12-15 (24 each) to the softmax warps (152 each).
+// TMEM (all 512 columns): per sub-tile S (64 columns, fp32), P (32 columns, bf16 pairs) and the output accumulator O (64, fp32).
+//   * P has its OWN columns, so S is free again as soon as the softmax warps hold S(j) in registers: Q K^T of tile j+1 is issued
+//     right then and runs on the tensor core WHILE the softmax of tile j is computed - the softmax -> tensor core -> softmax
+//     round trip is off the critical path (with P aliased onto S it cost ~45 % of the tile time).
+//   * P is written with tcgen05.st and consumed by the P V MMA as its TMEM A operand (TS mode): no shared-memory round trip,
+//     no generic->async proxy fence.
+//   * O accumulates in TMEM across KV tiles; the running row max is adopted lazily (only when some row of the warp grew by more
+//     than 2^8; otherwise the stale max is kept and P may exceed 1 - harmless in fp32/bf16), so O is rescaled in TMEM only in
+//     the first few tiles and read once at the end.
+// The MUFU unit (16 ex2/clk/SM) is the scarcest pipe at d = 64: 3 of every 8 element pairs go through a polynomial exp2 on the
+// FMA pipe; scale / sum use packed fp32x2 arithmetic; the row max uses 3-input max in independent chains.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ffb {
+
+constexpr int ATT_BM = 128;     // query rows per sub-tile
+constexpr int ATT_NSUB = 3;     // sub-tiles per CTA
+constexpr int ATT_QB = ATT_NSUB * ATT_BM;   // query rows per CTA
+constexpr int ATT_BN = 64;      // kv rows per tile
+constexpr int ATT_D = 64;
+constexpr int ATT_STAGES = 6;
+constexpr int ATT_THREADS = 512;
+constexpr int ATT_TILE_BYTES = 128 * 64 * 2;      // 16 KB: a Q sub-tile (128 rows x 64 bf16)
+constexpr int ATT_KV_BYTES = ATT_BN * 64 * 2;     // 8 KB: a K or V tile
+constexpr int ATT_SMEM = 2 * ATT_NSUB * ATT_TILE_BYTES /*Q x2*/ + 2 * ATT_STAGES * ATT_KV_BYTES /*K,V*/ + 1024;   // 193 KB
+constexpr int ATT_TMEM_COLS = 512;
+constexpr int ATT_TMEM_S = 0;       // S_x at columns x*64
+constexpr int ATT_TMEM_P = 192;     // P_x at columns 192 + x*32
+constexpr int ATT_TMEM_O = 320;     // O_x at columns 320 + x*64 (last column used: 511)
+
+// exp2 on the FMA/ALU pipes for part of the elements (the MUFU unit, 16 ex2/clk/SM, is the binding resource at d = 64):
+// 2^x = 2^round(x) * p(x - round(x)), p = degree-3 minimax of 2^f on [-0.5, 0.5] (max rel. error 7.5e-5, far below the
+// bf16 rounding of P); round() through the 1.5*2^23 magic-number add, exponent inserted with one shift-add.
+// Operates on a packed pair.  x must be <= ~+100; clamped below at -126.
+__device__ __forceinline__ void exp2_poly_pair(uint64_t x2, float& e0, float& e1) {
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const uint64_t xc = pack_f32x2(x0, x1);
+  const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);
+  const uint64_t xr = fadd2(xc, magic);                                   // round(x) sits in the low mantissa bits
+  const uint64_t r = fadd2(xr, pack_f32x2(-12582912.0f, -12582912.0f));   // round(x) as float
+  const uint64_t f = ffma2(r, pack_f32x2(-1.0f, -1.0f), xc);              // x - round(x) in [-0.5, 0.5]
+  uint64_t p = ffma2(f, pack_f32x2(0.05517132207751274f, 0.05517132207751274f), pack_f32x2(0.24261054396629333f, 0.24261054396629333f));
+  p = ffma2(p, f, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
+  p = ffma2(p, f, pack_f32x2(0.9999281167984009f, 0.9999281167984009f));
+  float p0, p1, r0, r1;
+  unpack_f32x2(p, p0, p1);
+  unpack_f32x2(xr, r0, r1);
+  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(r0) << 23));
+  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
+}
+constexpr int ATT_POLY_PERIOD = 8;   // of every ATT_POLY_PERIOD element pairs ...
+constexpr int ATT_POLY_NUM = 3;      // ... this many go through exp2_poly_pair, the rest through MUFU.EX2
+
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];    // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* sQ = smem;                                   // [2 buffers][3 sub-tiles][128][64]
+  uint8_t* sK = sQ + 2 * ATT_NSUB * ATT_TILE_BYTES;     // [stages][64][64]
+  uint8_t* sV = sK + ATT_STAGES * ATT_KV_BYTES;         // [stages][64][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_STAGES * ATT_KV_BYTES);
+  uint64_t* q_full = bars;                       // [2]  Q of a work item landed in buffer i
+  uint64_t* q_empty = q_full + 2;                // [2]  every Q K^T that reads buffer i has retired (3 MMA warps)
+  uint64_t* k_full = q_empty + 2;                // [ST]
+  uint64_t* k_empty = k_full + ATT_STAGES;       // [ST]
+  uint64_t* v_full = k_empty + ATT_STAGES;       // [ST]
+  uint64_t* v_empty = v_full + ATT_STAGES;       // [ST]
+  uint64_t* s_full = v_empty + ATT_STAGES;       // [3]  S_x(t) = Q K_t^T is in TMEM
+  uint64_t* s_free = s_full + ATT_NSUB;          // [3]  the four softmax warps hold S_x(t) in registers: S_x may be overwritten
+  uint64_t* p_full = s_free + ATT_NSUB;          // [3]  P_x(t) written to TMEM (and any rescale of O_x done)
+  uint64_t* p_free = p_full + ATT_NSUB;          // [3]  P V of tile t retired: P_x may be overwritten, O_x is quiescent
+  uint64_t* o_full = p_free + ATT_NSUB;          // [3]  final O_x of a work item complete
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + ATT_NSUB);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if ((smem_u32(smem) & 1023u) != 0) mbar_timeout(0xA11);   // swizzled tiles would be silently misread
+  const int S = p.seq_len;
+  const int n_tiles = (S + ATT_BN - 1) / ATT_BN;
+  // Persistent CTA: work item = (query tile of 384 rows, head, batch), query tile fastest so that the CTAs running at the same time
+  // share one head's K/V in L2.  All per-tile barriers run on counters that continue across items, so the TMA warp prefetches the
+  // next item's Q and K/V while the current item finishes and the first Q K^T of the next item is issued before the last P V.
+  const int n_qt = (S + ATT_QB - 1) / ATT_QB;
+  const int n_items = n_qt * p.num_heads * p.batch;
+  auto item_nsub = [&](int item) { return min(ATT_NSUB, (S - (item % n_qt) * ATT_QB + ATT_BM - 1) / ATT_BM); };   // sub-tiles with valid rows
+
+  if (warp == 12 && lane == 0) {
+    tma_prefetch_desc(&p.tmQKV);
+    tma_prefetch_desc(&p.tmKV);
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], ATT_NSUB); }
+    for (int i = 0; i < ATT_STAGES; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], ATT_NSUB);   // one MMA issuer warp per sub-tile releases the slot
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], ATT_NSUB);
+    }
+    for (int i = 0; i < ATT_NSUB; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_free[i], 1);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 13) tmem_alloc(tmem_ptr_smem, ATT_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp >= 12) {
+    setmaxnreg_dec<24>();
+    if (warp == 12) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        int kv_it = 0;
+        for (int item = blockIdx.x, k = 0; item < n_items; item += gridDim.x, ++k) {
+          const int qt = item % n_qt, head = (item / n_qt) % p.num_heads, b = item / (n_qt * p.num_heads);
+          const int n_sub = item_nsub(item);
+          const int cq = head * ATT_D, ck = p.inner_dim + head * ATT_D, cv = 2 * p.inner_dim + head * ATT_D;
+          const int qb = k & 1;
+          mbar_wait_relaxed(&q_empty[qb], ((k >> 1) & 1) ^ 1, 0x42);
+          mbar_arrive_expect_tx(&q_full[qb], n_sub * ATT_TILE_BYTES);
+          for (int x = 0; x < n_sub; ++x)
+            tma_load_3d(sQ + (qb * ATT_NSUB + x) * ATT_TILE_BYTES, &p.tmQKV, &q_full[qb], cq, qt * ATT_QB + x * ATT_BM, b);
+          for (int j = 0; j < n_tiles; ++j, ++kv_it) {
+            const int st = kv_it % ATT_STAGES;
+            const uint32_t ph = (kv_it / ATT_STAGES) & 1;
+            mbar_wait_relaxed(&k_empty[st], ph ^ 1, 0x40);   // off the critical path: do not steal issue slots
+            mbar_arrive_expect_tx(&k_full[st], ATT_KV_BYTES);
+            tma_load_3d(sK + st * ATT_KV_BYTES, &p.tmKV, &k_full[st], ck, j * ATT_BN, b);
+            mbar_wait_relaxed(&v_empty[st], ph ^ 1, 0x41);
+            mbar_arrive_expect_tx(&v_full[st], ATT_KV_BYTES);
+            tma_load_3d(sV + st * ATT_KV_BYTES, &p.tmKV, &v_full[st], cv, j * ATT_BN, b);
+          }
+        }
+      }
+    } else {
+      // ===================== MMA issuers: warp 13 + x -> sub-tile x =====================
+      // The whole warp walks the loop (warp-uniform state -> uniform registers feed UTCHMMA), one elected lane issues.
+      // Tensor-core order per sub-tile:  QK(0) ; { QK(t+1) ; PV(t) }  -  QK(t+1) starts when the softmax warps have S(t) in
+      // registers and runs during their exp2 work; PV(t) starts when they have written P(t).  t runs across work items.
+      constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);  // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);   // P (TMEM) x V (MN-major)
+      const int x = warp - 13;
+      const uint32_t sQ_addr = smem_u32(sQ), sK_addr = smem_u32(sK), sV_addr = smem_u32(sV);
+      const uint32_t tSx = tmem_base + ATT_TMEM_S + x * ATT_BN, tPx = tmem_base + ATT_TMEM_P + x * (ATT_BN / 2),
+                     tOx = tmem_base + ATT_TMEM_O + x * ATT_D;
+      int kv_it = 0;      // K/V tiles seen (all items: the ring is shared by the three sub-tiles)
+      int t = 0;          // tiles of THIS sub-tile issued so far (only items in which it holds valid rows)
+      bool qk0_issued = false;   // the first Q K^T of the current item was already issued at the end of the previous one
+      // S_x(t_s) = Q[k-th item] K^T of the K/V tile in ring slot position it; t_s is the sub-tile's running tile index
+      auto issue_qk = [&](int k, int it, int t_s, bool last_of_item) {
+        const int st = it % ATT_STAGES;
+        if (t_s > 0) mbar_wait(&s_free[x], (t_s - 1) & 1, 0x51);    // S_x(t_s - 1) is in the softmax warps' registers
+        mbar_wait(&k_full[st], (it / ATT_STAGES) & 1, 0x50);
+        tc_fence_after();
+        const uint32_t q_addr = sQ_addr + ((k & 1) * ATT_NSUB + x) * ATT_TILE_BYTES, k_addr = sK_addr + st * ATT_KV_BYTES;
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < ATT_D / 16; ++kk)
+            umma_bf16(tSx, desc_kmajor_sw128(q_addr + kk * 32), desc_kmajor_sw128(k_addr + kk * 32), idesc_s, kk != 0 ? 1u : 0u);
+          umma_commit(&s_full[x]);
+          umma_commit(&k_empty[st]);
+          if (last_of_item) umma_commit(&q_empty[k & 1]);           // the item's last read of this Q buffer
+        }
+        __syncwarp();
+      };
+      for (int item = blockIdx.x, k = 0; item < n_items; item += gridDim.x, ++k) {
+        if (x >= item_nsub(item)) {
+          // this sub-tile has no valid rows in the item: just pass the shared K/V tiles and the Q buffer on
+          if (lane == 0) {
+            for (int j = 0; j < n_tiles; ++j, ++kv_it) {
+              const int st = kv_it % ATT_STAGES;
+              mbar_wait(&k_full[st], (kv_it / ATT_STAGES) & 1, 0x50);
+              mbar_arrive(&k_empty[st]);
+              mbar_wait(&v_full[st], (kv_it / ATT_STAGES) & 1, 0x53);
+              mbar_arrive(&v_empty[st]);
+            }
+            mbar_arrive(&q_empty[k & 1]);
+          }
+          kv_it = __shfl_sync(0xffffffffu, kv_it, 0);
+          qk0_issued = false;
+          continue;
+        }
+        if (!qk0_issued) {
+          mbar_wait(&q_full[k & 1], (k >> 1) & 1, 0x52);
+          issue_qk(k, kv_it, t, n_tiles == 1);
+        }
+        qk0_issued = false;
+        for (int j = 0; j < n_tiles; ++j, ++kv_it, ++t) {
+          const int st = kv_it % ATT_STAGES;
+          if (j + 1 < n_tiles) {
+            issue_qk(k, kv_it + 1, t + 1, j + 2 == n_tiles);
+          } else {
+            // last tile of the item: start the next item's first Q K^T before this item's last P V (if this sub-tile is in it)
+            const int nitem = item + gridDim.x;
+            if (nitem < n_items && x < item_nsub(nitem)) {
+              mbar_wait(&q_full[(k + 1) & 1], ((k + 1) >> 1) & 1, 0x52);
+              issue_qk(k + 1, kv_it + 1, t + 1, n_tiles == 1);
+              qk0_issued = true;
+            }
+          }
+          mbar_wait(&v_full[st], (kv_it / ATT_STAGES) & 1, 0x53);
+          mbar_wait(&p_full[x], t & 1, 0x54);      // P_x(t) is in TMEM (and any rescale of O_x done)
+          tc_fence_after();
+          const uint32_t v_addr = sV_addr + st * ATT_KV_BYTES;
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+              // A = P from TMEM: 16 bf16 of K per step = 8 columns.  B = V (MN-major): 16 kv rows = 2048 B per step.
+              const uint64_t db = desc_mnmajor_sw128(v_addr + kk * 2048, ATT_KV_BYTES);
+              umma_bf16_ts(tOx, tPx + kk * 8, db, idesc_o, (j | kk) != 0 ? 1u : 0u);   // O_x accumulates across the item's KV tiles
+            }
+            umma_commit(&v_empty[st]);
+            umma_commit(&p_free[x]);
+            if (j == n_tiles - 1) umma_commit(&o_full[x]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===================== softmax: warps 4x .. 4x+3 -> sub-tile x =====================
+    setmaxnreg_inc<152>();   // pool: 512 x 128 regs at launch = 12 x 32 x 152 + 4 x 32 x 24 (+ 4096 spare)
+    const int x = warp >> 2;                          // sub-tile
+    const int wq = warp & 3;                          // TMEM lane quadrant
+    const int r = wq * 32 + lane;                     // query row in the sub-tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t tSx = tmem_base + lane_off + ATT_TMEM_S + x * ATT_BN;
+    const uint32_t tPx = tmem_base + lane_off + ATT_TMEM_P + x * (ATT_BN / 2);
+    const uint32_t tOx = tmem_base + lane_off + ATT_TMEM_O + x * ATT_D;
+    const float sc = p.scale_log2;
+    int t = 0;        // tiles of this sub-tile processed so far (all items)
+    int n_done = 0;   // items this sub-tile took part in
+    const long long pc0 = prof_begin();
+    long long lap = prof_begin();
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      if (x >= item_nsub(item)) continue;
+      const int qt = item % n_qt, head = (item / n_qt) % p.num_heads, b = item / (n_qt * p.num_heads);
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < n_tiles; ++j, ++t) {
+        prof_lap(&lap, 0x67);                          // loop overhead / previous arrive
+        mbar_wait(&s_full[x], t & 1, 0x60);
+        tc_fence_after();
+        prof_lap(&lap, 0x68);                          // wait s_full
+        uint32_t s0[32], s1[32];
+        tmem_ld32(tSx + 0, s0);
+        tmem_ld32(tSx + 32, s1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[x]);        // Q K^T of the next tile may overwrite S_x now
+        prof_lap(&lap, 0x62);                          // TMEM load of S
+
+        const int kv_valid = S - j * ATT_BN;  // >= 1
+        // row max of this tile: 8 independent chains (a single serial fmax chain is 128 x 4 cycles of pure latency)
+        float mxs[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mxs[i] = -INFINITY;
+        auto max32 = [&](uint32_t(&a)[32], int base) {
+          if (kv_valid < ATT_BN) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (base + c >= kv_valid) a[c] = 0xFF800000u;  // -inf: key beyond the sequence
+          }
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) mxs[(c >> 1) & 7] = fmax3(mxs[(c >> 1) & 7], __uint_as_float(a[c]), __uint_as_float(a[c + 1]));
+        };
+        max32(s0, 0); max32(s1, 32);
+        const float mt = fmax3(fmax3(mxs[0], mxs[1], mxs[2]), fmax3(mxs[3], mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7]));
+        // lazy rescale: adopt the new max only if some row of the warp grew by more than 2^8 (warp-uniform decision)
+        const bool grow = (mt - m_run) * sc > 8.0f;           // true on the first tile (m_run = -inf)
+        const bool rescale = __any_sync(0xffffffffu, grow);
+        float alpha = 1.0f;
+        if (rescale) {
+          const float mnew = fmaxf(m_run, mt);
+          alpha = ex2_approx((m_run - mnew) * sc);             // 0 on the first tile
+          m_run = mnew;
+        }
+        prof_lap(&lap, 0x63);                          // row max
+        const uint64_t sc2 = pack_f32x2(sc, sc), mneg2 = pack_f32x2(-m_run * sc, -m_run * sc);
+        uint64_t sums2[2] = {0ull, 0ull};              // 4 partial row sums as two packed pairs
+        uint32_t pk[32];                               // P(j) as packed bf16 pairs
+        auto exp32 = [&](uint32_t(&a)[32], int quarter) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const uint64_t x2 = ffma2(pack_f32x2(__uint_as_float(a[2 * c]), __uint_as_float(a[2 * c + 1])), sc2, mneg2);
+            float e0, e1;
+            if ((c % ATT_POLY_PERIOD) < ATT_POLY_NUM) {
+              exp2_poly_pair(x2, e0, e1);
+            } else {
+              float t0, t1;
+              unpack_f32x2(x2, t0, t1);
+              e0 = ex2_approx(t0); e1 = ex2_approx(t1);
+            }
+            sums2[c & 1] = fadd2(sums2[c & 1], pack_f32x2(e0, e1));
+            pk[quarter * 16 + c] = pack_bf16x2(e0, e1);
+          }
+        };
+        exp32(s0, 0); exp32(s1, 1);
+        float sa, sb, sc_, sd;
+        unpack_f32x2(sums2[0], sa, sb);
+        unpack_f32x2(sums2[1], sc_, sd);
+        l_run = l_run * alpha + ((sa + sb) + (sc_ + sd));
+        prof_lap(&lap, 0x64);                          // exp2 + sum + pack
+
+        if (t > 0) {                                   // P V of the previous tile retired (issued a whole softmax ago): P_x free, O_x quiescent
+          mbar_wait(&p_free[x], (t - 1) & 1, 0x61);
+          tc_fence_after();
+        }
+        if (j > 0 && rescale) {                          // rare: O_x *= alpha in TMEM
+          uint32_t o0[32], o1[32];
+          tmem_ld32(tOx, o0);
+          tmem_ld32(tOx + 32, o1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
+            o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
+          }
+          tmem_st32(tOx, o0);
+          tmem_st32(tOx + 32, o1);
+        }
+        prof_lap(&lap, 0x65);                          // wait p_free, rare O rescale
+        tmem_st32(tPx, pk);                            // P_x(j): 64 bf16 per row = 32 columns
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[x]);
+        prof_lap(&lap, 0x66);                          // P -> TMEM, arrive
+      }
+      // final output of the item: O_x / l  (the next item's first P V needs this sub-tile's P, i.e. comes after this read)
+      mbar_wait(&o_full[x], n_done & 1, 0x69);
+      ++n_done;
+      tc_fence_after();
+      float o_acc[ATT_D];
+      {
+        uint32_t o0[32], o1[32];
+        tmem_ld32(tOx, o0);
+        tmem_ld32(tOx + 32, o1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { o_acc[i] = __uint_as_float(o0[i]); o_acc[32 + i] = __uint_as_float(o1[i]); }
+      }
+      tc_fence_before();
+      // O_x and l_run are both relative to the final running max m_run.
+      const int q = qt * ATT_QB + x * ATT_BM + r;
+      if (q < S) {
+        const float inv = 1.0f / l_run;
+        bf16* dst = p.out + static_cast<long>(b) * p.out_batch_stride + static_cast<long>(q) * p.inner_dim + head * ATT_D;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 o;
+          o.x = pack_bf16x2(o_acc[c * 8 + 0] * inv, o_acc[c * 8 + 1] * inv);
+          o.y = pack_bf16x2(o_acc[c * 8 + 2] * inv, o_acc[c * 8 + 3] * inv);
+          o.z = pack_bf16x2(o_acc[c * 8 + 4] * inv, o_acc[c * 8 + 5] * inv);
+          o.w = pack_bf16x2(o_acc[c * 8 + 6] * inv, o_acc[c * 8 + 7] * inv);
+          reinterpret_cast<uint4*>(dst)[c] = o;
+        }
+      }
+    }
+    prof_end(pc0, 0x70 + warp);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+  }
+}
+
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  }
+  const int n_items = ((p.seq_len + ATT_QB - 1) / ATT_QB) * p.num_heads * p.batch;
+  attention_kernel<<<n_items < num_sms ? n_items : num_sms, ATT_THREADS, ATT_SMEM, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace ffb
