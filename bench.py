@@ -303,8 +303,13 @@ def run_b200(args):
     gemm_tf = 2.0 * M * N * K / gemm_ms / 1e9
     fl_latent = flops_per_latent(cfg, ni, args.n_text, T, cfg_on)
     step_tf = value * fl_latent / 1e12
+    # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture (profiles/r01_ncu_full_summaries.md,
+    # dram__bytes_read.sum + dram__bytes_write.sum at M=65536 N=6144 K=1536): only valid for that shape, else null.
+    # Algorithmic bytes of the launch: A + W + out = 2 * (M*K + N*K + M*N).
+    traffic = 1139.5e6 if (M, N, K) == (65536, 6144, 1536) else None
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel<256> (MLP up, bias+GELU epilogue)", "achieved": gemm_tf,
-                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["bf16_tflops"], "traffic": None,
+                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["bf16_tflops"], "traffic": traffic,
+                "traffic_unit": "bytes/launch (ncu dram read+write)", "algorithmic_bytes_per_launch": 2.0 * (M * K + N * K + M * N),
                 "peak_source": f"{peak_kind} cuBLAS bf16 burst", "flops_per_launch": 2.0 * M * N * K, "launch_ms": gemm_ms,
                 "whole_step_achieved_per_gpu": step_tf / world, "whole_step_frac_of_sustained": step_tf / world / peaks["bf16_tflops_sustained"],
                 "flops_per_latent": fl_latent}

@@ -14,7 +14,8 @@ if which == "attn":
     for _ in range(n):
         ops.attention(qkv, H, out)
 else:
-    shapes = {"gemm": (8192, 4608, 1536, 3), "gemm_up": (8192, 6144, 1536, 1), "gemm_out": (8192, 1536, 1536, 2)}
+    shapes = {"gemm": (8192, 4608, 1536, 3), "gemm_up": (8192, 6144, 1536, 1), "gemm_out": (8192, 1536, 1536, 2),
+              "gemm_b16": (65536, 4608, 1536, 3), "gemm_up_b16": (65536, 6144, 1536, 1), "gemm_out_b16": (65536, 1536, 1536, 2)}
     M, N, K, epi = shapes[which]
     A = torch.randn(M, K, device="cuda").bfloat16()
     W = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
