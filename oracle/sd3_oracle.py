@@ -333,7 +333,7 @@ def sde_step(noise_pred: torch.Tensor, latents: torch.Tensor, sigma: float, sigm
     v = noise_pred.float()
     x = latents.float()
     nl = next_latents.float() if next_latents is not None else None
-    f32 = lambda s: torch.tensor(s, dtype=torch.float32, device=x.device).view(1, 1, 1, 1)
+    f32 = lambda s: torch.tensor(s, dtype=torch.float32, device=x.device).view(*([1] * x.ndim))   # to_broadcast_tensor
     sigma_t, sigma_p, eta = f32(sigma), f32(sigma_prev), f32(noise_level)
     dt = sigma_p - sigma_t
     log_prob = None

@@ -198,7 +198,60 @@ def golden_advantage():
     return out
 
 
+def golden_flux():
+    """FLUX.1: the REAL FluxTransformer2DModel on tiny configs (fp32 truth + bf16 CPU autocast), and the loop
+    body of Flux1Adapter.inference/forward (FF/models/flux/flux1.py:211-250, 310-349) with the real scheduler (dynamic shift)."""
+    from diffusers.models.transformers.transformer_flux import FluxTransformer2DModel
+    from oracle import flux_oracle as FO
+    out = {}
+    for name, cfg, (B, lh, lw, nt), seed in (("tiny", FO.tiny_flux_config(), (2, 8, 8, 7), 0),
+                                              ("tiny3", FO.tiny_flux_config(num_layers=2, num_single_layers=1, heads=3, joint_dim=96, pooled_dim=48), (1, 12, 8, 21), 5)):
+        w32 = FO.make_flux_weights(cfg, seed=seed)
+        lat, pe, pooled, img_ids, txt_ids = FO.make_flux_inputs(cfg, B, lh, lw, nt, seed=seed + 1)
+        t = torch.tensor([0.9885, 0.25][:B])
+        gd = torch.full((B,), 3.5)
+        m = FluxTransformer2DModel(**cfg.ref_kwargs())
+        m.load_state_dict(w32, strict=True)
+        m = m.eval()
+        with torch.no_grad():
+            y32 = m(hidden_states=lat, timestep=t, guidance=gd, pooled_projections=pooled, encoder_hidden_states=pe,
+                    txt_ids=txt_ids, img_ids=img_ids, return_dict=False)[0]
+            mb = FluxTransformer2DModel(**cfg.ref_kwargs()); mb.load_state_dict(w32, strict=True); mb = mb.to(torch.bfloat16).eval()
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                yb = mb(hidden_states=lat.bfloat16(), timestep=t.bfloat16(), guidance=gd.bfloat16(), pooled_projections=pooled.bfloat16(),
+                        encoder_hidden_states=pe.bfloat16(), txt_ids=txt_ids.bfloat16(), img_ids=img_ids.bfloat16(), return_dict=False)[0]
+        out[name] = dict(t=t, guidance=gd, y32=y32, y_bf16_cpu_autocast=yb, keys=sorted(m.state_dict().keys()),
+                         shape=(B, lh, lw, nt), seed=seed)
+    # rollout: T=4, Flow-SDE, dynamic shift, packed fp32 latents round-tripped through the storage dtype like cast_latents
+    cfg = FO.tiny_flux_config()
+    w32 = FO.make_flux_weights(cfg, seed=0)
+    lat, pe, pooled, img_ids, txt_ids = FO.make_flux_inputs(cfg, 2, 8, 8, 7, seed=1)
+    m = FluxTransformer2DModel(**cfg.ref_kwargs()); m.load_state_dict(w32, strict=True); m = m.eval()
+    s = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, use_dynamic_shifting=True, base_shift=0.5, max_shift=1.15,
+                                           base_image_seq_len=256, max_image_seq_len=4096, num_sde_steps=None, dynamics_type="Flow-SDE")
+    ts = set_scheduler_timesteps(s, 4, seq_len=lat.shape[1], device="cpu")
+    s.rollout()
+    latents = lat.half()
+    lats, lps, vps = [latents], {}, []
+    torch.manual_seed(123)
+    with torch.no_grad():
+        for i, t in enumerate(ts):
+            nl = s.get_noise_level_for_timestep(t)
+            tn = ts[i + 1] if i + 1 < len(ts) else torch.tensor(0.0)
+            guidance = torch.as_tensor(3.5, dtype=latents.dtype).expand(2)
+            v = m(hidden_states=latents.float(), timestep=t.expand(2) / 1000, guidance=guidance.float(), pooled_projections=pooled,
+                  encoder_hidden_states=pe, txt_ids=torch.zeros(pe.shape[1], 3), img_ids=img_ids, return_dict=False)[0]
+            r = s.step(noise_pred=v, timestep=t, latents=latents, timestep_next=tn, noise_level=nl, compute_log_prob=nl > 0)
+            latents = r.next_latents.half()
+            lats.append(latents); vps.append(v)
+            if nl > 0:
+                lps[i] = r.log_prob
+    out["rollout_fp32"] = dict(latents=lats, log_probs=lps, noise_preds=vps, timesteps=ts.clone(), sigmas=s.sigmas.clone())
+    return out
+
+
 if __name__ == "__main__":
+    torch.save(golden_flux(), os.path.join(HERE, "flux_tiny.pt"))
     torch.save(golden_schedule(), os.path.join(HERE, "schedule.pt"))
     torch.save(golden_step(), os.path.join(HERE, "sde_step.pt"))
     torch.save(golden_forward(), os.path.join(HERE, "forward_tiny.pt"))
