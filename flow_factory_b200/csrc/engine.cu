@@ -127,20 +127,22 @@ static int build_gemm(const GemmSpec& s, GemmParams* p) {
   p->qk_dim = s.qk_dim; p->eps = s.eps; p->row_table = s.row_table;
   return 0;
 }
-static int build_attn(const void* qkv, int batch, int seq, int heads, void* out, AttnParams* p) {
+static int build_attn(const void* qkv, int batch, int seq, int heads, void* out, AttnParams* p, int head_dim = 64,
+                      int out_row_stride = 0) {
   memset(p, 0, sizeof(*p));
-  const int D = heads * 64;
+  const int D = heads * head_dim;
   const uint64_t dims[3] = {static_cast<uint64_t>(3 * D), static_cast<uint64_t>(seq), static_cast<uint64_t>(batch)};
   const uint64_t str[2] = {static_cast<uint64_t>(3 * D), static_cast<uint64_t>(seq) * 3 * D};
-  const uint32_t box[3] = {64, 128, 1};
+  const uint32_t box[3] = {64, 128, 1};      // one 64-column (= 128-byte swizzle span) panel of a 128-row Q sub-tile
   int r = make_tmap(&p->tmQKV, qkv, 3, dims, str, box);
   if (r) return r;
-  const uint32_t box_kv[3] = {64, ATT_BN, 1};   // kv rows per tile (attention.cu, same translation unit)
+  const uint32_t box_kv[3] = {64, ATT_BN, 1};   // kv rows per tile (attention.cu / attention_d128.cu, same translation unit)
   r = make_tmap(&p->tmKV, qkv, 3, dims, str, box_kv);
   if (r) return r;
   p->seq_len = seq; p->num_heads = heads; p->inner_dim = D; p->batch = batch;
-  p->out = static_cast<bf16*>(out); p->out_batch_stride = static_cast<long>(seq) * D;
-  p->scale_log2 = 0.125f * 1.4426950408889634f;
+  p->out_row_stride = out_row_stride > 0 ? out_row_stride : D;
+  p->out = static_cast<bf16*>(out); p->out_batch_stride = static_cast<long>(seq) * p->out_row_stride;
+  p->scale_log2 = (1.0f / sqrtf(static_cast<float>(head_dim))) * 1.4426950408889634f;
   return 0;
 }
 
@@ -694,6 +696,20 @@ int ffb200_attention(const void* qkv, int batch, int seq_len, int num_heads, voi
   if (r) return r;
   g_launch_count = 1;
   FFB_CUDA(launch_attention(ap, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int ffb200_attention_ex(const void* qkv, int batch, int seq_len, int num_heads, int head_dim, void* out, int out_row_stride,
+                        void* stream) {
+  FFB_CHECK(qkv && out && batch > 0 && seq_len > 0 && num_heads > 0, "bad argument");
+  if (head_dim != 64 && head_dim != 128) return fail(-2, "ffb200_attention_ex: head_dim must be 64 or 128");
+  if (out_row_stride != 0 && out_row_stride < num_heads * head_dim) return fail(-2, "ffb200_attention_ex: out_row_stride < inner dim");
+  AttnParams ap;
+  int r = build_attn(qkv, batch, seq_len, num_heads, out, &ap, head_dim, out_row_stride);
+  if (r) return r;
+  if (head_dim == 64 && ap.out_row_stride != ap.inner_dim) return fail(-2, "ffb200_attention_ex: head_dim 64 writes dense rows only");
+  g_launch_count = 1;
+  FFB_CUDA(head_dim == 64 ? launch_attention(ap, static_cast<cudaStream_t>(stream)) : launch_attention_d128(ap, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -52,11 +52,13 @@ struct AttnParams {
   int num_heads;      // H
   int inner_dim;      // D = 64*H
   int batch;
-  bf16* out;          // [B, S, D]
+  bf16* out;          // [B, S, out_row_stride >= D]
   long out_batch_stride;
-  float scale_log2;   // (1/sqrt(64)) * log2(e)
+  int out_row_stride; // elements between consecutive token rows of `out` (D, or wider when the output is a column block)
+  float scale_log2;   // (1/sqrt(head_dim)) * log2(e)
 };
-cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);        // head_dim 64  (SD3.x)
+cudaError_t launch_attention_d128(const AttnParams& p, cudaStream_t stream);   // head_dim 128 (FLUX.1)
 
 // ------------------------------------------------------------------ per-step scalars
 enum Dynamics : int { DYN_FLOW_SDE = 0, DYN_DANCE_SDE = 1, DYN_CPS = 2, DYN_ODE = 3 };

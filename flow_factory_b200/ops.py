@@ -30,12 +30,18 @@ def linear(A, W, bias, out, *, num_batch=1, rows_per_batch=None, a_batch_stride=
     _lib.check(code, "ffb200_linear")
 
 
-def attention(qkv: torch.Tensor, num_heads: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Joint attention over a fused token-major qkv buffer bf16 [B, S, 3*64*H] -> bf16 [B, S, 64*H]."""
+def attention(qkv: torch.Tensor, num_heads: int, out: Optional[torch.Tensor] = None, head_dim: int = 64,
+              out_row_stride: int = 0) -> torch.Tensor:
+    """Joint attention over a fused token-major qkv buffer bf16 [B, S, 3*head_dim*H] -> bf16 [B, S, head_dim*H].
+    head_dim 128 (FLUX.1) may write into a wider row (`out` [B, S, out_row_stride], columns [0, head_dim*H))."""
     B, S, _ = qkv.shape
     if out is None:
-        out = torch.empty((B, S, 64 * num_heads), dtype=torch.bfloat16, device=qkv.device)
-    _lib.check(_lib.lib().ffb200_attention(_ptr(qkv), B, S, num_heads, _ptr(out), _stream(qkv)), "ffb200_attention")
+        out = torch.empty((B, S, out_row_stride or head_dim * num_heads), dtype=torch.bfloat16, device=qkv.device)
+    if head_dim == 64 and out_row_stride == 0:
+        _lib.check(_lib.lib().ffb200_attention(_ptr(qkv), B, S, num_heads, _ptr(out), _stream(qkv)), "ffb200_attention")
+    else:
+        _lib.check(_lib.lib().ffb200_attention_ex(_ptr(qkv), B, S, num_heads, head_dim, _ptr(out), out_row_stride, _stream(qkv)),
+                   "ffb200_attention_ex")
     return out
 
 

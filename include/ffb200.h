@@ -155,6 +155,12 @@ int ffb200_linear(const void* A, int num_batch, int rows_per_batch, long long a_
 /* F.scaled_dot_product_attention over a fused token-major qkv buffer bf16 [B, S, 3*64*H] -> out bf16 [B, S, 64*H]
  * (DF/models/attention_processor.py:1480-1486). */
 int ffb200_attention(const void* qkv, int batch, int seq_len, int num_heads, void* out, void* stream);
+/* Same with head_dim 64 or 128 and an output row stride (elements; 0 = dense 64/128*H): head_dim 128 is the FLUX.1 joint
+ * [text ; image] attention, dispatch_attention_fn at DF/models/transformers/transformer_flux.py:118-125 (q, k already RMS-normed
+ * and rotated); a wider row stride lets FluxSingleTransformerBlock's torch.cat([attn_output, mlp_hidden_states], dim=2)
+ * (transformer_flux.py:400) be the attention kernel's own store.  head_dim 64 accepts dense rows only. */
+int ffb200_attention_ex(const void* qkv, int batch, int seq_len, int num_heads, int head_dim, void* out, int out_row_stride,
+                        void* stream);
 /* LayerNorm(no affine) * (1 + scale) + shift  (DF/models/normalization.py:120-126). vectors: [num_batch, *] with stride. */
 int ffb200_ln_modulate(const void* x, int num_batch, int rows_per_batch, int D, float eps, const void* shift1,
                        const void* scale1, void* out1, const void* shift2, const void* scale2, void* out2,

@@ -52,5 +52,20 @@ def main():
         print(json.dumps(out[-1]), flush=True)
 
 
+def flux_attention():
+    """head_dim 128 at the FLUX.1 1024^2 shape: S = 512 text + 4096 image tokens, 24 heads."""
+    from flow_factory_b200 import ops
+    for (B, S, H) in [(1, 4608, 24), (4, 4608, 24)]:
+        qkv = torch.randn(B, S, 3 * 128 * H, device="cuda").bfloat16()
+        o = torch.empty(B, S, 128 * H, device="cuda", dtype=torch.bfloat16)
+        ms = timeit(lambda: ops.attention(qkv, H, o, head_dim=128))
+        q, k, v = [t.reshape(B, S, H, 128).transpose(1, 2) for t in qkv.split(128 * H, dim=2)]
+        ms_lib = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))
+        fl = 4.0 * B * H * S * S * 128
+        print(json.dumps(dict(kernel="attention_d128", B=B, S=S, H=H, ms=ms, tflops=fl / ms / 1e9, sdpa_ms=ms_lib, sdpa_tflops=fl / ms_lib / 1e9)), flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "flux":
+        flux_attention(); sys.exit(0)
     main()
