@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
     L.ffb200_rollout.argtypes = [vp, C.POINTER(RolloutArgs), vp]
     L.ffb200_rollout_host.argtypes = [vp, C.POINTER(RolloutArgs), vp, vp, vp]
     L.ffb200_linear.argtypes = [vp, ci, ci, cll, ci, ci, vp, ci, vp, vp, cll, ci, ci, ci, vp, cll, vp, vp, ci, cf, vp, vp]
+    L.ffb200_linear_qkv_rope.argtypes = [vp, ci, ci, cll, ci, ci, vp, ci, vp, vp, cll, ci, ci, vp, vp, ci, cf, vp, vp, ci, vp]
     L.ffb200_attention.argtypes = [vp, ci, ci, ci, vp, vp]
     L.ffb200_attention_ex.argtypes = [vp, ci, ci, ci, ci, vp, ci, vp]
     L.ffb200_ln_modulate.argtypes = [vp, ci, ci, ci, cf, vp, vp, vp, vp, vp, vp, cll, vp]
@@ -95,7 +96,7 @@ EXPORTED_SYMBOLS = (
     "ffb200_engine_set_weights", "ffb200_engine_destroy", "ffb200_engine_mod_rows", "ffb200_plan_create",
     "ffb200_plan_destroy", "ffb200_plan_workspace_bytes", "ffb200_plan_set_prompts", "ffb200_transformer_forward",
     "ffb200_step", "ffb200_rollout", "ffb200_rollout_host", "ffb200_last_launch_count", "ffb200_linear",
-    "ffb200_attention", "ffb200_attention_ex", "ffb200_ln_modulate", "ffb200_small_linear", "ffb200_sde_step")
+    "ffb200_linear_qkv_rope", "ffb200_attention", "ffb200_attention_ex", "ffb200_ln_modulate", "ffb200_small_linear", "ffb200_sde_step")
 
 
 def check(code: int, what: str = "ffb200") -> None:

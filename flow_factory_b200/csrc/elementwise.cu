@@ -24,10 +24,10 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm + modulate.  One warp per token row; the row stays in registers as the raw 16-byte bf16 chunks it was loaded as
-// (32 registers instead of 64 fp32 values: twice the resident warps, which is what hides the HBM latency of this pure
-// streaming kernel) and is unpacked on the fly in each of the three passes (mean, variance, output).  D <= 2048, D % 8 == 0.
+// (<= 48 registers instead of 96 fp32 values: twice the resident warps, which is what hides the HBM latency of this pure
+// streaming kernel) and is unpacked on the fly in each of the three passes (mean, variance, output).  D <= 3072, D % 8 == 0.
 // ------------------------------------------------------------------------------------------------
-constexpr int LN_MAXC = 8;  // 16-byte chunks per lane
+constexpr int LN_MAXC = 12;  // 16-byte chunks per lane (D = 1536: 6, D = 3072: 12)
 
 __global__ void __launch_bounds__(256, 4) ln_modulate_kernel(const LnModParams p) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

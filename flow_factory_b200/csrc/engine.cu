@@ -90,6 +90,7 @@ struct GemmSpec {
   void* out; long out_batch_stride; int out_row_offset, ldo;
   int epi; const void* gate; long gate_batch_stride; const void* norm_q; const void* norm_k; int qk_dim; float eps;
   const float* row_table;
+  const float* rope_cos; const float* rope_sin; int rope_row_offset;   // EPI_QKV_RMSNORM_ROPE128
 };
 static int build_gemm(const GemmSpec& s, GemmParams* p) {
   memset(p, 0, sizeof(*p));
@@ -97,6 +98,9 @@ static int build_gemm(const GemmSpec& s, GemmParams* p) {
   FFB_CHECK(s.K % 8 == 0 && s.lda % 8 == 0 && s.ldo % 8 == 0, "GEMM K / lda / ldo must be multiples of 8");
   p->bn = gemm_pick_bn(s.N);
   if (s.epi == EPI_QKV_RMSNORM) FFB_CHECK(s.qk_dim % 64 == 0, "qk_dim must be a multiple of 64");
+  if (s.epi == EPI_QKV_RMSNORM_ROPE128)
+    FFB_CHECK(s.qk_dim % 128 == 0 && p->bn >= 128 && s.rope_cos && s.rope_sin && s.norm_q && s.norm_k,
+              "qkv+rope epilogue: head_dim 128 blocks, N multiple of 128, rope tables and norm weights required");
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(s.K), static_cast<uint64_t>(s.rows_per_batch), static_cast<uint64_t>(s.num_batch)};
     const uint64_t str[2] = {static_cast<uint64_t>(s.lda), static_cast<uint64_t>(s.a_batch_stride > 0 ? s.a_batch_stride : static_cast<long>(s.rows_per_batch) * s.lda)};
@@ -125,6 +129,7 @@ static int build_gemm(const GemmSpec& s, GemmParams* p) {
   p->gate = static_cast<const bf16*>(s.gate); p->gate_batch_stride = s.gate_batch_stride;
   p->norm_q = static_cast<const bf16*>(s.norm_q); p->norm_k = static_cast<const bf16*>(s.norm_k);
   p->qk_dim = s.qk_dim; p->eps = s.eps; p->row_table = s.row_table;
+  p->rope_cos = s.rope_cos; p->rope_sin = s.rope_sin; p->rope_row_offset = s.rope_row_offset;
   return 0;
 }
 static int build_attn(const void* qkv, int batch, int seq, int heads, void* out, AttnParams* p, int head_dim = 64,
@@ -681,6 +686,22 @@ int ffb200_linear(const void* A, int num_batch, int rows_per_batch, long long a_
   GemmSpec s = {A, num_batch, rows_per_batch, static_cast<long>(a_batch_stride), lda, K, W, N, bias, out,
                 static_cast<long>(out_batch_stride), out_row_offset, ldo, epilogue, gate, static_cast<long>(gate_batch_stride),
                 norm_q, norm_k, qk_dim, eps, row_table};
+  GemmParams gp;
+  int r = build_gemm(s, &gp);
+  if (r) return r;
+  g_launch_count = 1;
+  FFB_CUDA(launch_gemm(gp, num_sms(), static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int ffb200_linear_qkv_rope(const void* A, int num_batch, int rows_per_batch, long long a_batch_stride, int lda, int K, const void* W,
+                           int N, const void* bias, void* out, long long out_batch_stride, int out_row_offset, int ldo,
+                           const void* norm_q, const void* norm_k, int qk_dim, float eps, const float* rope_cos,
+                           const float* rope_sin, int rope_row_offset, void* stream) {
+  FFB_CHECK(A && W && out, "null argument");
+  GemmSpec s = {A, num_batch, rows_per_batch, static_cast<long>(a_batch_stride), lda, K, W, N, bias, out,
+                static_cast<long>(out_batch_stride), out_row_offset, ldo, EPI_QKV_RMSNORM_ROPE128, nullptr, 0, norm_q, norm_k, qk_dim, eps,
+                nullptr, rope_cos, rope_sin, rope_row_offset};
   GemmParams gp;
   int r = build_gemm(s, &gp);
   if (r) return r;

@@ -35,7 +35,7 @@ template <int BN> struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
   static constexpr int kStagingBytes = 4 * 32 * 128;        // per epilogue warp: 32 rows x 64 bf16
-  static constexpr int kVecBytes = 4 * (2 * BN * 2 + 2 * 64 * 2);  // per warp: bias[BN], gate[BN], norm_q[64], norm_k[64]
+  static constexpr int kVecBytes = 4 * (2 * BN * 2 + 2 * 128 * 2);  // per warp: bias[BN], gate[BN], norm_q[<=128], norm_k[<=128]
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kVecBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -172,14 +172,18 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
     // ===================== epilogue =====================
     const int ew = warp - 4;                 // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
     const uint32_t stg = smem_stage + ew * (32 * 128);                    // this warp's 32 x 128 B staging tile
-    const uint32_t vec_bias = smem_vec + ew * (2 * BN * 2 + 256);         // bias[BN] | gate[BN] | norm_q[64] | norm_k[64]
+    const uint32_t vec_bias = smem_vec + ew * (2 * BN * 2 + 512);         // bias[BN] | gate[BN] | norm_q[<=128] | norm_k[<=128]
     const uint32_t vec_gate = vec_bias + BN * 2;
-    const uint32_t vec_nq = vec_gate + BN * 2, vec_nk = vec_nq + 128;
+    const uint32_t vec_nq = vec_gate + BN * 2, vec_nk = vec_nq + 256;
     const int coop_row = lane >> 3, coop_c = lane & 7;                    // cooperative (coalesced) access: 8 lanes per 128-B row
     const long long pc0 = prof_begin();
     if (p.epi == EPI_QKV_RMSNORM) {
       if (lane < 8) st_shared_v4x(vec_nq + lane * 16, __ldg(reinterpret_cast<const uint4*>(p.norm_q) + lane));
       else if (lane < 16) st_shared_v4x(vec_nk + (lane - 8) * 16, __ldg(reinterpret_cast<const uint4*>(p.norm_k) + (lane - 8)));
+      __syncwarp();
+    } else if (p.epi == EPI_QKV_RMSNORM_ROPE128) {
+      if (lane < 16) st_shared_v4x(vec_nq + lane * 16, __ldg(reinterpret_cast<const uint4*>(p.norm_q) + lane));
+      else st_shared_v4x(vec_nk + (lane - 16) * 16, __ldg(reinterpret_cast<const uint4*>(p.norm_k) + (lane - 16)));
       __syncwarp();
     }
     int it = 0;
@@ -220,6 +224,106 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
 
+      // bf16 chunk of 64 columns -> own row of the swizzled staging tile -> whole-line stores (8 lanes per 128-B row, 4 rows per instruction)
+      auto flush_chunk = [&](int c, const float (&v)[64]) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st_shared_v4(stg + lane * 128 + ((q ^ (lane & 7)) << 4), pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]),
+                       pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]), pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]),
+                       pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
+        __syncwarp();
+        // (3) whole-line stores: 8 lanes per 128-B row, 4 rows per instruction
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + coop_row;
+          if (tile_ok && row_base + rr < p.rows_per_batch)
+            *reinterpret_cast<uint4*>(out_base + static_cast<long>(rr) * p.ldo + c * 64 + coop_c * 8) =
+                ld_shared_v4(stg + rr * 128 + ((coop_c ^ (rr & 7)) << 4));
+        }
+        __syncwarp();
+          };
+      if (p.epi == EPI_QKV_RMSNORM_ROPE128) {
+        // fused q|k|v projection, head_dim 128 (FLUX.1): torch.nn.RMSNorm on the q / k heads (transformer_flux.py:96-97, 104-105:
+        // bf16((x * rsqrt(mean x^2 + eps)) * w), fp32 inside) then apply_rotary_emb with interleaved pairs (embeddings.py:1222-1231:
+        // bf16(x * cos + [-x1, x0] * sin), fp32 inside).  A head is two 64-column chunks: pass 1 re-reads the accumulator for the
+        // sum of squares (TMEM reads are cheap), pass 2 normalises, rotates and stores.  thread == token row.
+        const bool row_ok = tile_ok && row_base + lane < p.rows_per_batch;
+        const long token = static_cast<long>(p.rope_row_offset + row_base + lane);
+        for (int hc = 0; hc < BN / 128; ++hc) {
+          const int which = (tn * BN + hc * 128) / p.qk_dim;   // 0 = q, 1 = k, 2 = v
+          float rs = 1.0f;
+          if (which < 2) {
+            float ss = 0.f;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+              uint32_t r0[32], r1[32];
+              tmem_ld32(t_row + hc * 128 + half * 64, r0);
+              tmem_ld32(t_row + hc * 128 + half * 64 + 32, r1);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float bf[8];
+                unpack8_bf16(ld_shared_v4(vec_bias + (hc * 128 + half * 64 + q * 8) * 2), bf);
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                  const int j = q * 8 + e;
+                  float a = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]) + bf[e];
+                  float b2 = __uint_as_float(j + 1 < 32 ? r0[j + 1] : r1[j + 1 - 32]) + bf[e + 1];
+                  bf16_round2(a, b2);
+                  ss += a * a + b2 * b2;
+                }
+              }
+            }
+            rs = rsqrtf(ss * (1.0f / 128.0f) + p.eps);
+          }
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            const int c = hc * 2 + half;
+            uint32_t r0[32], r1[32];
+            tmem_ld32(t_row + c * 64, r0);
+            tmem_ld32(t_row + c * 64 + 32, r1);
+            tmem_ld_wait();
+            float v[64];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float bf[8];
+              unpack8_bf16(ld_shared_v4(vec_bias + (c * 64 + q * 8) * 2), bf);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int j = q * 8 + e;
+                v[j] = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]) + bf[e];
+              }
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) bf16_round2(v[q * 8 + e], v[q * 8 + e + 1]);   // nn.Linear output is a bf16 tensor
+            }
+            if (which < 2) {
+              const uint32_t wn = (which == 0 ? vec_nq : vec_nk) + half * 128;
+              const float* cs = p.rope_cos + token * 128 + half * 64;
+              const float* sn = p.rope_sin + token * 128 + half * 64;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                float wf[8];
+                unpack8_bf16(ld_shared_v4(wn + q * 16), wf);
+                float4 c0 = make_float4(1.f, 1.f, 1.f, 1.f), c1 = c0, s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+                if (row_ok) {
+                  c0 = *reinterpret_cast<const float4*>(cs + q * 8); c1 = *reinterpret_cast<const float4*>(cs + q * 8 + 4);
+                  s0 = *reinterpret_cast<const float4*>(sn + q * 8); s1 = *reinterpret_cast<const float4*>(sn + q * 8 + 4);
+                }
+                const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                  float a = __fmul_rn(__fmul_rn(v[q * 8 + e], rs), wf[e]), b2 = __fmul_rn(__fmul_rn(v[q * 8 + e + 1], rs), wf[e + 1]);
+                  bf16_round2(a, b2);                                            // RMSNorm output is a bf16 tensor
+                  v[q * 8 + e] = __fadd_rn(__fmul_rn(a, cc[e]), __fmul_rn(-b2, sv[e]));
+                  v[q * 8 + e + 1] = __fadd_rn(__fmul_rn(b2, cc[e + 1]), __fmul_rn(a, sv[e + 1]));
+                }
+              }
+            }
+            flush_chunk(c, v);
+          }
+        }
+      } else
       for (int c = 0; c < BN / 64; ++c) {
         const int n0 = tn * BN + c * 64;       // global column of this 64-wide chunk
         // (1) residual mode: prefetched h chunk -> staging tile (16-B chunks XOR-swizzled by row); start the next chunk's loads
@@ -301,21 +405,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
             }
           }
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          st_shared_v4(stg + lane * 128 + ((q ^ (lane & 7)) << 4), pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]),
-                       pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]), pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]),
-                       pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]));
-        __syncwarp();
-        // (3) whole-line stores: 8 lanes per 128-B row, 4 rows per instruction
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + coop_row;
-          if (tile_ok && row_base + rr < p.rows_per_batch)
-            *reinterpret_cast<uint4*>(out_base + static_cast<long>(rr) * p.ldo + c * 64 + coop_c * 8) =
-                ld_shared_v4(stg + rr * 128 + ((coop_c ^ (rr & 7)) << 4));
-        }
-        __syncwarp();
+        flush_chunk(c, v);
       }
       tc_fence_before();
       __syncwarp();

@@ -17,6 +17,7 @@ enum GemmEpilogue : int {
   EPI_GATE_RESIDUAL = 2,      // out = bf16(out + bf16(gate[b,:] * bf16(acc + bias)))      (in place on the residual stream)
   EPI_QKV_RMSNORM = 3,        // fused q|k|v projection: per-head RMSNorm on the q and k column blocks
   EPI_BIAS_ADD_ROWTABLE = 4,  // out = bf16(bf16(acc + bias) + table[row, :])             (patch-embed + pos-embed)
+  EPI_QKV_RMSNORM_ROPE128 = 5,  // fused q|k|v projection, head_dim 128: RMSNorm + interleaved-pair RoPE on the q and k heads (FLUX.1)
 };
 
 struct GemmParams {
@@ -39,6 +40,9 @@ struct GemmParams {
   int qk_dim;        // width of each of the q|k|v column blocks (= inner_dim)
   float eps;
   const float* row_table;  // EPI_BIAS_ADD_ROWTABLE: fp32 [rows_per_batch, N]
+  const float* rope_cos;   // EPI_QKV_RMSNORM_ROPE128: fp32 [tokens, 128] (values repeated pairwise, FluxPosEmbed), row = rope_row_offset + row
+  const float* rope_sin;
+  int rope_row_offset;
 };
 
 int gemm_pick_bn(int N);

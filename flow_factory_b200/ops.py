@@ -30,6 +30,18 @@ def linear(A, W, bias, out, *, num_batch=1, rows_per_batch=None, a_batch_stride=
     _lib.check(code, "ffb200_linear")
 
 
+def linear_qkv_rope(A, W, bias, out, norm_q, norm_k, rope_cos, rope_sin, *, num_batch=1, rows_per_batch=None, a_batch_stride=0,
+                    out_batch_stride=0, out_row_offset=0, rope_row_offset=0, eps=1e-6) -> None:
+    """FLUX.1 fused q|k|v projection (head_dim 128): Linear + RMSNorm(q, k heads) + interleaved-pair RoPE, token-major into `out`
+    [.., S, 3*D] at row `out_row_offset`; rope tables fp32 [tokens, 128], GEMM row r uses table row rope_row_offset + r."""
+    K, N = W.shape[1], W.shape[0]
+    rows_per_batch = rows_per_batch if rows_per_batch is not None else A.numel() // K // num_batch
+    code = _lib.lib().ffb200_linear_qkv_rope(_ptr(A), num_batch, rows_per_batch, a_batch_stride, A.stride(-2), K, _ptr(W), N,
+                                             _ptr(bias), _ptr(out), out_batch_stride, out_row_offset, out.stride(-2), _ptr(norm_q),
+                                             _ptr(norm_k), N // 3, eps, _ptr(rope_cos), _ptr(rope_sin), rope_row_offset, _stream(A))
+    _lib.check(code, "ffb200_linear_qkv_rope")
+
+
 def attention(qkv: torch.Tensor, num_heads: int, out: Optional[torch.Tensor] = None, head_dim: int = 64,
               out_row_stride: int = 0) -> torch.Tensor:
     """Joint attention over a fused token-major qkv buffer bf16 [B, S, 3*head_dim*H] -> bf16 [B, S, head_dim*H].

@@ -152,6 +152,14 @@ int ffb200_linear(const void* A, int num_batch, int rows_per_batch, long long a_
                   const void* W, int N, const void* bias, void* out, long long out_batch_stride, int out_row_offset,
                   int ldo, int epilogue, const void* gate, long long gate_batch_stride, const void* norm_q,
                   const void* norm_k, int qk_dim, float eps, const float* row_table, void* stream);
+/* FLUX.1 fused q|k|v projection (head_dim 128): nn.Linear + torch.nn.RMSNorm on the q and k heads + apply_rotary_emb with
+ * interleaved pairs, written token-major into a joint [B, S, 3*qk_dim] buffer at row `out_row_offset` (text rows first, then image:
+ * DF/models/transformers/transformer_flux.py:87-117; DF/models/embeddings.py:1207-1233).  rope_cos / rope_sin: fp32 [tokens, 128]
+ * as FluxPosEmbed returns them (transformer_flux.py:500-522); the table row of GEMM row r is rope_row_offset + r. */
+int ffb200_linear_qkv_rope(const void* A, int num_batch, int rows_per_batch, long long a_batch_stride, int lda, int K,
+                           const void* W, int N, const void* bias, void* out, long long out_batch_stride, int out_row_offset,
+                           int ldo, const void* norm_q, const void* norm_k, int qk_dim, float eps, const float* rope_cos,
+                           const float* rope_sin, int rope_row_offset, void* stream);
 /* F.scaled_dot_product_attention over a fused token-major qkv buffer bf16 [B, S, 3*64*H] -> out bf16 [B, S, 64*H]
  * (DF/models/attention_processor.py:1480-1486). */
 int ffb200_attention(const void* qkv, int batch, int seq_len, int num_heads, void* out, void* stream);
