@@ -36,7 +36,10 @@ __global__ void __launch_bounds__(256, 4) ln_modulate_kernel(const LnModParams p
   if (warp >= rows) return;
   const int b = warp / p.rows_per_batch;
   const int nchunk = p.D >> 3;
-  const bf16* xr = p.x + static_cast<long>(warp) * p.D;
+  const int rib = warp - b * p.rows_per_batch;   // row inside the batch
+  const long dense = static_cast<long>(p.rows_per_batch) * p.D;
+  const bf16* xr = p.x + static_cast<long>(b) * (p.x_batch_stride ? p.x_batch_stride : dense) + static_cast<long>(rib) * p.D;
+  const long orow = static_cast<long>(b) * (p.out_batch_stride ? p.out_batch_stride : dense) + static_cast<long>(rib) * p.D;
   uint4 raw[LN_MAXC];
 #pragma unroll
   for (int i = 0; i < LN_MAXC; ++i) {
@@ -79,13 +82,13 @@ __global__ void __launch_bounds__(256, 4) ln_modulate_kernel(const LnModParams p
       unpack8(__ldg(reinterpret_cast<const uint4*>(p.shift1 + mo + c * 8)), sh);
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = __fadd_rn(__fmul_rn(y[e], bf16_round(1.0f + sc[e])), sh[e]);
-      *reinterpret_cast<uint4*>(p.out1 + static_cast<long>(warp) * p.D + c * 8) = pack8(o);
+      *reinterpret_cast<uint4*>(p.out1 + orow + c * 8) = pack8(o);
       if (p.out2 != nullptr) {
         unpack8(__ldg(reinterpret_cast<const uint4*>(p.scale2 + mo + c * 8)), sc);
         unpack8(__ldg(reinterpret_cast<const uint4*>(p.shift2 + mo + c * 8)), sh);
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = __fadd_rn(__fmul_rn(y[e], bf16_round(1.0f + sc[e])), sh[e]);
-        *reinterpret_cast<uint4*>(p.out2 + static_cast<long>(warp) * p.D + c * 8) = pack8(o);
+        *reinterpret_cast<uint4*>(p.out2 + orow + c * 8) = pack8(o);
       }
     }
   }
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(SL_WARPS * 32) small_linear_kernel(const Small
       for (int bb = 0; bb < nb; ++bb) {
         float y = bf16_round(acc[bb] + bias);
         if (p.addend) y = y + __bfloat162float(p.addend[static_cast<long>(b0 + bb) * p.addend_stride + n]);
+        if (p.addend2) y = bf16_round(y) + __bfloat162float(p.addend2[static_cast<long>(b0 + bb) * p.addend_stride + n]);
         p.out[static_cast<long>(b0 + bb) * p.out_stride + n] = __float2bfloat16_rn(y);
       }
     }
@@ -225,6 +229,15 @@ cudaError_t launch_patchify(const __half* x, int B, int reps, int C, int H, int 
 __global__ void cast_f32_bf16_kernel(const float* in, bf16* out, long n) {
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
     out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void cast_f16_bf16_kernel(const __half* in, bf16* out, long n) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
+    out[i] = __float2bfloat16_rn(__half2float(in[i]));
+}
+cudaError_t launch_cast_f16_to_bf16(const __half* in, bf16* out, long n, cudaStream_t stream) {
+  const int grid = static_cast<int>(std::min<long>((n + 255) / 256, 148 * 16));
+  cast_f16_bf16_kernel<<<grid, 256, 0, stream>>>(in, out, n);
+  return cudaGetLastError();
 }
 cudaError_t launch_cast_f32_to_bf16(const float* in, bf16* out, long n, cudaStream_t stream) {
   const int grid = static_cast<int>(std::min<long>((n + 255) / 256, 148 * 16));

@@ -290,7 +290,7 @@ static int add_attn(ffb200_plan* p, const void* qkv, int seq, void* out) {
 }
 static void add_lnmod(ffb200_plan* p, const bf16* x, int rows_per_batch, const bf16* shift1, const bf16* scale1, bf16* out1,
                       const bf16* shift2, const bf16* scale2, bf16* out2) {
-  LnModParams lp;
+  LnModParams lp{};
   lp.x = x; lp.rows_per_batch = rows_per_batch; lp.num_batch = p->Bp; lp.D = p->D; lp.eps = 1e-6f;
   lp.shift1 = shift1; lp.scale1 = scale1; lp.out1 = out1; lp.shift2 = shift2; lp.scale2 = scale2; lp.out2 = out2;
   lp.mod_batch_stride = p->e->mod_rows;
@@ -298,7 +298,7 @@ static void add_lnmod(ffb200_plan* p, const bf16* x, int rows_per_batch, const b
 }
 static void add_small(ffb200_plan* p, std::vector<Op>& ops, const bf16* in, int K, const void* W, const void* bias, int N,
                       bf16* out, const bf16* addend, int silu) {
-  SmallLinearParams sp;
+  SmallLinearParams sp{};
   sp.in = in; sp.batch = p->Bp; sp.K = K; sp.in_stride = K; sp.W = static_cast<const bf16*>(W);
   sp.bias = static_cast<const bf16*>(bias); sp.N = N; sp.out = out; sp.out_stride = N;
   sp.addend = addend; sp.addend_stride = N; sp.silu_input = silu;
@@ -737,7 +737,7 @@ int ffb200_attention_ex(const void* qkv, int batch, int seq_len, int num_heads, 
 int ffb200_ln_modulate(const void* x, int num_batch, int rows_per_batch, int D, float eps, const void* shift1, const void* scale1,
                        void* out1, const void* shift2, const void* scale2, void* out2, long long mod_batch_stride, void* stream) {
   FFB_CHECK(x && shift1 && scale1 && out1, "null argument");
-  LnModParams lp;
+  LnModParams lp{};
   lp.x = static_cast<const bf16*>(x); lp.rows_per_batch = rows_per_batch; lp.num_batch = num_batch; lp.D = D; lp.eps = eps;
   lp.shift1 = static_cast<const bf16*>(shift1); lp.scale1 = static_cast<const bf16*>(scale1); lp.out1 = static_cast<bf16*>(out1);
   lp.shift2 = static_cast<const bf16*>(shift2); lp.scale2 = static_cast<const bf16*>(scale2); lp.out2 = static_cast<bf16*>(out2);
@@ -750,7 +750,7 @@ int ffb200_ln_modulate(const void* x, int num_batch, int rows_per_batch, int D, 
 int ffb200_small_linear(const void* in, int batch, int K, long long in_stride, const void* W, const void* bias, int N, void* out,
                         long long out_stride, const void* addend, long long addend_stride, int silu_input, void* stream) {
   FFB_CHECK(in && W && out, "null argument");
-  SmallLinearParams sp;
+  SmallLinearParams sp{};
   sp.in = static_cast<const bf16*>(in); sp.batch = batch; sp.K = K; sp.in_stride = static_cast<long>(in_stride);
   sp.W = static_cast<const bf16*>(W); sp.bias = static_cast<const bf16*>(bias); sp.N = N; sp.out = static_cast<bf16*>(out);
   sp.out_stride = static_cast<long>(out_stride); sp.addend = static_cast<const bf16*>(addend);

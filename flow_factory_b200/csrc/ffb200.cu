@@ -5,3 +5,4 @@
 #include "elementwise.cu"
 #include "final_step.cu"
 #include "engine.cu"
+#include "flux_engine.cu"

@@ -92,6 +92,8 @@ struct LnModParams {
   const bf16* shift1; const bf16* scale1; bf16* out1;  // vectors: ptr + b*mod_batch_stride
   const bf16* shift2; const bf16* scale2; bf16* out2;  // optional second modulation (SD35AdaLayerNormZeroX)
   long mod_batch_stride;
+  long x_batch_stride;    // elements between batches of x (0 = rows_per_batch * D): row ranges of a joint [B, S, D] buffer
+  long out_batch_stride;  // same for out1 / out2
 };
 cudaError_t launch_ln_modulate(const LnModParams& p, cudaStream_t stream);
 
@@ -102,6 +104,7 @@ struct SmallLinearParams {
   bf16* out; long out_stride;
   const bf16* addend; long addend_stride;  // optional
   int silu_input;
+  const bf16* addend2;   // optional second bf16 addend, added after the first with its own rounding (same stride)
 };
 cudaError_t launch_small_linear(const SmallLinearParams& p, cudaStream_t stream);
 
@@ -113,6 +116,7 @@ cudaError_t launch_patchify(const __half* x, int B, int reps, int C, int H, int 
 
 // cast helpers
 cudaError_t launch_cast_f32_to_bf16(const float* in, bf16* out, long n, cudaStream_t stream);
+cudaError_t launch_cast_f16_to_bf16(const __half* in, bf16* out, long n, cudaStream_t stream);
 
 // ------------------------------------------------------------------ fused Euler/SDE step + log-prob (K14)
 

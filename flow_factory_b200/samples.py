@@ -67,3 +67,11 @@ class SD3_5Sample:
             else:
                 out[f.name] = vals
         return out
+
+
+@dataclass
+class Flux1Sample(SD3_5Sample):
+    """Mirror of FF/models/flux/flux1.py:53-59 (T2ISample + pooled_prompt_embeds, img_ids; img_ids is a shared field).
+    all_latents rows are PACKED latents (T', Ni, 64)."""
+    _shared_fields: ClassVar[frozenset] = frozenset({"img_ids"})
+    img_ids: Optional[torch.Tensor] = None

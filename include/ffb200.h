@@ -183,6 +183,72 @@ int ffb200_sde_step(const void* noise_pred_bf16, const void* latents_fp16, int B
                     const void* next_latents_fp16, void* out_next_fp16, float* out_mean, float* out_log_prob,
                     int* overflow_flag, void* stream);
 
+/* ================================================================ FLUX.1 (BASELINE config 3)
+ * Same boundary for the FLUX.1 rollout path: FluxTransformer2DModel.forward (DF/models/transformers/transformer_flux.py:676-778)
+ * behind Flux1Adapter.inference / forward (FF/models/flux/flux1.py:152-292, 296-349).  No CFG batch: guidance is an embedded
+ * scalar.  Latents are the PACKED [B, Ni, 64] tensors of the reference (FluxPipeline._pack_latents), stored fp16. */
+typedef struct ffb200_flux_config {
+  int num_layers;            /* dual-stream FluxTransformerBlocks (19) */
+  int num_single_layers;     /* FluxSingleTransformerBlocks (38) */
+  int num_heads;             /* inner_dim D = 128 * num_heads (head_dim is 128) */
+  int in_channels;           /* 64 */
+  int joint_attention_dim;   /* 4096 */
+  int pooled_projection_dim; /* 768 */
+  int guidance_embeds;       /* 1 for FLUX.1-dev */
+} ffb200_flux_config;
+
+/* bf16, nn.Linear layout [out, in]; q|k|v concatenated along out_features by the host packer */
+typedef struct ffb200_flux_dual_weights {
+  const void *qkv_w, *qkv_b, *norm_q, *norm_k;                     /* attn.to_{q,k,v}, attn.norm_{q,k} [128]              */
+  const void *add_qkv_w, *add_qkv_b, *norm_added_q, *norm_added_k; /* attn.add_{q,k,v}_proj, attn.norm_added_{q,k}        */
+  const void *out_w, *out_b, *add_out_w, *add_out_b;               /* attn.to_out.0, attn.to_add_out                      */
+  const void *ff1_w, *ff1_b, *ff2_w, *ff2_b;                       /* ff.net.0.proj, ff.net.2                             */
+  const void *cff1_w, *cff1_b, *cff2_w, *cff2_b;                   /* ff_context.*                                        */
+} ffb200_flux_dual_weights;
+typedef struct ffb200_flux_single_weights {
+  const void *qkv_w, *qkv_b, *norm_q, *norm_k;   /* attn.to_{q,k,v}, attn.norm_{q,k}   */
+  const void *mlp_w, *mlp_b;                     /* proj_mlp [4D, D]                   */
+  const void *out_w, *out_b;                     /* proj_out [D, 5D] over [attn | mlp] */
+} ffb200_flux_single_weights;
+typedef struct ffb200_flux_weights {
+  const void *x_w, *x_b;                 /* x_embedder [D, 64]                                                       */
+  const void *ctx_w, *ctx_b;             /* context_embedder                                                         */
+  const void *t1_w, *t1_b, *t2_w, *t2_b; /* time_text_embed.timestep_embedder.linear_{1,2}                           */
+  const void *g1_w, *g1_b, *g2_w, *g2_b; /* time_text_embed.guidance_embedder.linear_{1,2} (NULL unless guidance_embeds) */
+  const void *p1_w, *p1_b, *p2_w, *p2_b; /* time_text_embed.text_embedder.linear_{1,2}                               */
+  /* all adaLN projections stacked row-wise: per dual block [norm1.linear (6D) ; norm1_context.linear (6D)], then per single
+   * block norm.linear (3D), then norm_out.linear (2D) */
+  const void *mod_w, *mod_b;
+  const void *proj_w, *proj_b;           /* proj_out [64, D]                                                         */
+  const ffb200_flux_dual_weights* dual;     /* [num_layers]        */
+  const ffb200_flux_single_weights* single; /* [num_single_layers] */
+} ffb200_flux_weights;
+
+typedef struct ffb200_flux_engine ffb200_flux_engine;
+typedef struct ffb200_flux_plan ffb200_flux_plan;
+
+int ffb200_flux_engine_create(const ffb200_flux_config* cfg, const ffb200_flux_weights* w, ffb200_flux_engine** out);
+int ffb200_flux_engine_set_weights(ffb200_flux_engine* e, const ffb200_flux_weights* w);
+void ffb200_flux_engine_destroy(ffb200_flux_engine* e);
+int ffb200_flux_engine_mod_rows(const ffb200_flux_engine* e);
+/* Geometry: batch, image tokens Ni = (h/16)(w/16), text tokens; rope_cos / rope_sin: fp32 [Nt + Ni, 128] for ids = cat(txt_ids,
+ * img_ids) exactly as FluxPosEmbed returns them (transformer_flux.py:500-522, float64 frequencies) - host or device memory, copied. */
+int ffb200_flux_plan_create(ffb200_flux_engine* e, int batch, int n_img_tokens, int n_text, const float* rope_cos,
+                            const float* rope_sin, ffb200_flux_plan** out);
+void ffb200_flux_plan_destroy(ffb200_flux_plan* p);
+long long ffb200_flux_plan_workspace_bytes(const ffb200_flux_plan* p);
+/* prompt_embeds bf16 [B, Nt, joint_dim], pooled bf16 [B, pooled_dim]; guidance_model = float(bf16(bf16(guidance_scale) * 1000)),
+ * the value transformer_flux.py:681-682 feeds to the sinusoid (flux1.py:318-319 builds the tensor in the latents' dtype). */
+int ffb200_flux_set_prompts(ffb200_flux_plan* p, const void* prompt_embeds_bf16, const void* pooled_bf16, float guidance_model,
+                            void* stream);
+/* FluxTransformer2DModel.forward: packed latents fp16 [B, Ni, 64] -> noise prediction bf16 [B, Ni, 64].
+ * t_model = float(bf16(bf16(t / 1000) * 1000)) (flux1.py:325 ; transformer_flux.py:679). */
+int ffb200_flux_forward(ffb200_flux_plan* p, const void* latents_fp16, float t_model, void* noise_pred_bf16, void* stream);
+/* Flux1Adapter.forward under no_grad / the denoise loop of Flux1Adapter.inference: same argument blocks as ffb200_step /
+ * ffb200_rollout with [C,H,W] := [Ni*64] packed elements per sample; guidance_scale in the blocks is ignored (set_prompts). */
+int ffb200_flux_step(ffb200_flux_plan* p, const ffb200_step_args* a, void* stream);
+int ffb200_flux_rollout(ffb200_flux_plan* p, const ffb200_rollout_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
