@@ -1,0 +1,76 @@
+"""CPU tests of the FLUX.1 host-side logic (no GPU): index / table helpers against the oracle (itself pinned against the reference),
+the dynamic-shift schedule against the golden fixture, the adapter's keyword ABI and the C struct layouts."""
+import ctypes as C
+import inspect
+import os
+
+import pytest
+import torch
+
+from flow_factory_b200 import flux as F
+from flow_factory_b200.scheduler import FlowMatchEulerDiscreteSDEScheduler, set_scheduler_timesteps
+from oracle import flux_oracle as FO
+
+
+def test_pack_ids_and_rope_tables_match_the_oracle():
+    lat = torch.randn(2, 16, 12, 8)
+    assert torch.equal(F.pack_latents(lat), FO.pack_latents(lat))
+    assert torch.equal(F.latent_image_ids(6, 4), FO.latent_image_ids(12, 8))
+    ids = torch.cat([torch.zeros(7, 3), F.latent_image_ids(6, 4)])
+    c1, s1 = F.rope_tables(ids, (16, 56, 56))
+    c2, s2 = FO.rope_tables(ids, (16, 56, 56))
+    assert torch.equal(c1, c2) and torch.equal(s1, s2) and c1.shape == (31, 128) and c1.dtype == torch.float32
+    # interleaved repetition: column 2i == column 2i+1 (get_1d_rotary_pos_embed, repeat_interleave_real)
+    assert torch.equal(c1[:, 0::2], c1[:, 1::2]) and torch.equal(s1[:, 0::2], s1[:, 1::2])
+
+
+def test_dynamic_shift_schedule_matches_the_golden_fixture(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "flux_tiny.pt"), weights_only=False)["rollout_fp32"]
+    ts, sig = F.flux_make_schedule(4, 16)
+    assert torch.equal(ts, g["timesteps"]) and torch.equal(sig, g["sigmas"])
+    sch = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, use_dynamic_shifting=True)
+    ts2 = set_scheduler_timesteps(sch, 4, seq_len=16)
+    assert torch.equal(ts2, g["timesteps"]) and torch.equal(sch.sigmas, g["sigmas"])
+    gs = torch.load(os.path.join(golden_dir, "schedule.pt"), weights_only=False)
+    ts3, sig3 = F.flux_make_schedule(28, 4096)
+    assert torch.equal(ts3, gs["dyn_T28"]["timesteps"]) and torch.equal(sig3, gs["dyn_T28"]["sigmas"])
+
+
+def test_model_scalar_follows_the_bf16_casts():
+    # transformer_flux.py:679: timestep.to(bf16) * 1000 in bf16
+    assert F.model_scalar(0.5) == 500.0
+    t = 0.98863
+    expect = float((torch.tensor(t).to(torch.bfloat16) * 1000).float())
+    assert F.model_scalar(t) == expect
+    # guidance 3.5 is exact in fp16 and bf16 -> 3500 rounds to the bf16 grid (ulp 16 at 2048..4096)
+    assert F.model_scalar(3.5, torch.float16) == float((torch.tensor(3.5).bfloat16() * 1000).float()) == 3504.0
+
+
+def test_flux_adapter_keywords_are_the_reference_abi():
+    from flow_factory_b200.flux_adapter import B200Flux1Adapter
+    # FF/models/flux/flux1.py:153-172 and 296-312
+    ref_inf = ["prompt", "height", "width", "num_inference_steps", "guidance_scale", "generator", "prompt_ids", "prompt_embeds",
+               "pooled_prompt_embeds", "joint_attention_kwargs", "compute_log_prob", "extra_call_back_kwargs", "trajectory_indices"]
+    ref_fwd = ["t", "latents", "prompt_embeds", "pooled_prompt_embeds", "img_ids", "t_next", "next_latents", "guidance_scale",
+               "noise_level", "joint_attention_kwargs", "compute_log_prob", "return_kwargs"]
+    assert set(ref_inf) <= set(inspect.signature(B200Flux1Adapter.inference).parameters)
+    assert set(ref_fwd) <= set(inspect.signature(B200Flux1Adapter.forward).parameters)
+
+
+def test_flux_struct_layouts_and_config():
+    assert C.sizeof(F.FluxConfigC) == 7 * 4
+    assert C.sizeof(F.FluxDualWeights) == 20 * 8 and C.sizeof(F.FluxSingleWeights) == 8 * 8
+    assert C.sizeof(F.FluxWeights) == 20 * 8 + 2 * 8
+    cfg = F.FluxEngineConfig.from_model_config(FO.flux1_dev())
+    assert (cfg.num_layers, cfg.num_single_layers, cfg.inner_dim, cfg.guidance_embeds) == (19, 38, 3072, True)
+    with pytest.raises(ValueError):
+        F.FluxEngineConfig.from_model_config(dict(FO.flux1_dev().ref_kwargs(), attention_head_dim=64))
+
+
+def test_flux_sample_collate_shares_img_ids():
+    from flow_factory_b200.samples import Flux1Sample
+    ids = torch.zeros(4, 3)
+    a = Flux1Sample(all_latents=torch.zeros(3, 4, 64), img_ids=ids, height=32, width=32)
+    b = Flux1Sample(all_latents=torch.ones(3, 4, 64), img_ids=ids, height=32, width=32)
+    out = Flux1Sample.stack([a, b])
+    assert out["img_ids"] is ids and tuple(out["all_latents"].shape) == (2, 3, 4, 64)
