@@ -1,20 +1,42 @@
-"""FLUX.1-dev (BASELINE config 3 model, 19 dual + 38 single blocks, D = 3072) rollout on ONE B200: random-init weights created
-on the device, 1024^2 (4096 image + 512 text tokens), T denoise steps.  Developer measurement for the 'next' row, not bench.py."""
-import argparse, json, math, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+#!/usr/bin/env python
+"""FLUX.1-dev rollout bench (BASELINE config 3: FLUX.1-dev 1024^2 28-step GRPO rollout, prompt-sharded over the GPUs of a node).
+
+  python tools/flux_bench.py --gpus 1 --steps 2 --warmup 1
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P tools/flux_bench.py --gpus 8
+
+Same contract as bench.py (one rank per GPU, device-timed with CUDA events, max over ranks, rank 0 prints one JSON line), for the
+"next" row of SURVEY 8f: FLUX.1-dev architecture (19 dual + 38 single blocks, D = 3072, head_dim 128), random-init weights created
+on the device (no checkpoints offline), 4096 image + 512 text tokens, embedded guidance 3.5 (no CFG batch), Flow-SDE with the
+resolution-dependent shift.  A "step" is ONE ROLLOUT of `batch` prompts per rank through `B200Flux1Adapter.inference`.
+`value`: inputs resident in HBM; `e2e`: pinned host prompt embeddings in, host results out, copies inside the timed region.
+bench.py stays the driver's bench (config C2); this is the measurement tool of the FLUX.1 row."""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import torch
-from flow_factory_b200.flux import FluxEngineConfig, FluxRolloutEngine
 
 
 def rand_state_dict(cfg, device, seed=0):
+    """Random FluxTransformer2DModel.state_dict() (diffusers key names), bf16, drawn on the device."""
     g = torch.Generator(device=device).manual_seed(seed)
     D, d = cfg.inner_dim, 128
     sd = {}
+
     def lin(name, o, i, scale=1.0):
-        sd[name + ".weight"] = (torch.randn(o, i, generator=g, device=device, dtype=torch.bfloat16) * (scale / math.sqrt(i)))
+        sd[name + ".weight"] = torch.randn(o, i, generator=g, device=device, dtype=torch.bfloat16) * (scale / math.sqrt(i))
         sd[name + ".bias"] = torch.randn(o, generator=g, device=device, dtype=torch.bfloat16) * 0.02
+
     def rms(name):
         sd[name + ".weight"] = (1.0 + 0.1 * torch.randn(d, generator=g, device=device)).bfloat16()
+
     lin("x_embedder", D, 64); lin("context_embedder", D, cfg.joint_attention_dim)
     for n, i in (("timestep_embedder", 256), ("guidance_embedder", 256), ("text_embedder", cfg.pooled_projection_dim)):
         lin(f"time_text_embed.{n}.linear_1", D, i); lin(f"time_text_embed.{n}.linear_2", D, D)
@@ -39,43 +61,113 @@ def rand_state_dict(cfg, device, seed=0):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=2); ap.add_argument("--steps", type=int, default=28)
-    ap.add_argument("--res", type=int, default=1024); ap.add_argument("--n-text", type=int, default=512)
-    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--batch", type=int, default=2, help="prompts per rank per rollout")
+    ap.add_argument("--res", type=int, default=1024)
+    ap.add_argument("--n-text", type=int, default=512)
+    ap.add_argument("--num-inference-steps", type=int, default=28)
+    ap.add_argument("--guidance", type=float, default=3.5)
+    ap.add_argument("--num-sde-steps", type=int, default=1)
+    ap.add_argument("--no-graph", action="store_true")
     a = ap.parse_args()
-    dev = torch.device("cuda")
+    import torch.distributed as dist
+    from flow_factory_b200.dist import all_gather_rollout
+    from flow_factory_b200.flux import FluxEngineConfig, FluxRolloutEngine
+    from flow_factory_b200.flux_adapter import B200Flux1Adapter
+    from flow_factory_b200.scheduler import FlowMatchEulerDiscreteSDEScheduler
+    from flow_factory_b200.trajectory import compute_trajectory_indices
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     cfg = FluxEngineConfig()
-    t0 = time.time()
+    T, B = a.num_inference_steps, a.batch
+    sched = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, use_dynamic_shifting=True, num_sde_steps=a.num_sde_steps, seed=42)
     sd = rand_state_dict(cfg, dev)
-    eng = FluxRolloutEngine(cfg, sd, dev)
+    adapter = B200Flux1Adapter(cfg, sd, device=dev, scheduler=sched, rng="philox", use_graph=not a.no_graph)
+    adapter.rollout()
     del sd
-    h2 = w2 = a.res // 16
-    plan = eng.plan(a.batch, h2, w2, a.n_text)
-    g = torch.Generator(device=dev).manual_seed(1)
-    pe = torch.randn(a.batch, a.n_text, cfg.joint_attention_dim, generator=g, device=dev).bfloat16()
-    pooled = torch.randn(a.batch, cfg.pooled_projection_dim, generator=g, device=dev).bfloat16()
-    x0 = torch.randn(a.batch, h2 * w2, 64, generator=g, device=dev).half()
-    eng.set_prompts(plan, pe, pooled, 3.5)
-    T = a.steps
-    ts, sig, coefs = eng.make_coefs(plan, T, 0.7, [1], store_slots=[(0 if i == T - 1 else -1) for i in range(T)], logp_slots=[(0 if i == 1 else -1) for i in range(T)])
-    setup_s = time.time() - t0
-    r = eng.rollout(plan, x0, coefs, 1, -1, 1, seed=3)          # warm-up (captures the graph)
-    torch.cuda.synchronize()
-    times = []
-    for _ in range(a.reps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); r = eng.rollout(plan, x0, coefs, 1, -1, 1, seed=3); e1.record(); torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
-    ms = sorted(times)[len(times) // 2]
-    S, D, Ni = h2 * w2 + a.n_text, cfg.inner_dim, h2 * w2
-    lin = cfg.num_layers * (2 * S * D * 12 * D) + cfg.num_single_layers * (2 * S * D * 7 * D + 2 * S * 5 * D * D)
-    att = (cfg.num_layers + cfg.num_single_layers) * 4.0 * S * S * D
-    fl = (lin + att) * T * a.batch
-    print(json.dumps({"model": "FLUX.1-dev (random init)", "res": a.res, "batch": a.batch, "steps": T, "ms_per_rollout": ms,
-                      "latents_per_s": a.batch / (ms / 1e3), "tflops": fl / ms / 1e9, "flops_per_latent_T": (lin + att) * T / 1e12,
-                      "finite": bool(torch.isfinite(r["final_latents"].float()).all()), "log_prob": r["log_probs"].flatten().tolist(),
-                      "launches": eng.last_launch_count(), "weights_GB": eng.weights.nbytes() / 1e9,
-                      "workspace_GB": plan.workspace_bytes / 1e9, "setup_s": setup_s}))
+    ni = (a.res // 16) ** 2
+    sched.set_timesteps(T, seq_len=ni)
+    traj_idx = compute_trajectory_indices(sched.train_timesteps, T)
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    pe = torch.randn(B, a.n_text, cfg.joint_attention_dim, generator=g, device=dev).bfloat16()
+    pooled = torch.randn(B, cfg.pooled_projection_dim, generator=g, device=dev).bfloat16()
+    x0 = torch.randn(B, ni, 64, generator=g, device=dev).half()
+    kw = dict(height=a.res, width=a.res, num_inference_steps=T, guidance_scale=a.guidance, compute_log_prob=True, trajectory_indices=traj_idx)
+
+    def rollout_device():
+        s = adapter.inference(prompt_embeds=pe, pooled_prompt_embeds=pooled, latents=x0, **kw)
+        if world > 1:
+            all_gather_rollout(torch.stack([x.all_latents for x in s]), torch.stack([x.log_probs for x in s]))
+        return s
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        s = rollout_device()
+    barrier()
+    launches = FluxRolloutEngine.last_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        s = rollout_device()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    value = world * B * a.steps / (float(ms) / 1e3)
+
+    host_pe, host_pooled = pe.cpu().pin_memory(), pooled.cpu().pin_memory()
+
+    def rollout_e2e():
+        ss = adapter.inference(prompt_embeds=host_pe.to(dev, non_blocking=True), pooled_prompt_embeds=host_pooled.to(dev, non_blocking=True), **kw)
+        lat = torch.stack([x.all_latents for x in ss]); lp = torch.stack([x.log_probs for x in ss])
+        fin = torch.stack([x.extra_kwargs["final_latents"] for x in ss])
+        if world > 1:
+            lat, lp = all_gather_rollout(lat, lp)
+        out = (lat.cpu(), lp.cpu(), fin.cpu())
+        return sum(t.numel() * t.element_size() for t in out)
+
+    d2h = rollout_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        rollout_e2e()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        S, D = ni + a.n_text, cfg.inner_dim
+        lin = cfg.num_layers * (2 * S * D * 12 * D) + cfg.num_single_layers * (2 * S * D * 7 * D + 2 * S * 5 * D * D)
+        att = (cfg.num_layers + cfg.num_single_layers) * 4.0 * S * S * D
+        fl_latent = (lin + att) * T
+        lp0 = s[0].log_probs
+        print(json.dumps({
+            "metric": f"rollout latents/sec FLUX.1-dev {a.res}^2 {T}-step", "value": value, "unit": "latents/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(ms) / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "b200",
+            "config": {"workload": f"FLUX.1-dev architecture {a.res}x{a.res} {T}-step GRPO rollout (Flow-SDE, noise 0.7, num_sde_steps {a.num_sde_steps}, dynamic shift), "
+                                   f"embedded guidance {a.guidance}, {a.n_text} text tokens, random-init weights",
+                       "per_rank_batch": B, "global_batch": B * world, "parallelism": f"dp{world} (prompt-sharded, 1 all-gather/rollout)",
+                       "cuda_graph": not a.no_graph, "rng": "in-kernel Philox4x32-10"},
+            "e2e": {"value": world * B * a.steps / float(e2e_s), "unit": "latents/s",
+                    "h2d_bytes_per_step": host_pe.numel() * 2 + host_pooled.numel() * 2, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches * a.steps),
+            "whole_step_achieved_tflops_per_gpu": value * fl_latent / 1e12 / world, "flops_per_latent": fl_latent,
+            "finite": bool(torch.isfinite(s[0].all_latents.float()).all() and torch.isfinite(lp0).all()),
+            "log_probs_sample0": lp0.flatten().tolist(), "weights_GB": adapter.engine.weights.nbytes() / 1e9}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
