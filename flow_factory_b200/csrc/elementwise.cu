@@ -163,8 +163,95 @@ __global__ void __launch_bounds__(SL_WARPS * 32) small_linear_kernel(const Small
   }
 }
 
+// Tensor-core variant (mma.sync m16n8k16, bf16 -> fp32): the batch (<= 16 rows per pass, zero padded) is the M dimension, eight
+// output features the N dimension.  The stacked adaLN matrix is 1.5 GB (SD3.5-medium) / 6.5 GB (FLUX.1-dev) per denoise step and
+// the SIMT kernel above spends ~20 instructions per 16 weight bytes and batch row (0.9 TB/s); here a warp issues one 16-byte
+// weight load, two 16-byte shared-memory loads and two MMAs per 32 k, so the kernel streams the weights at HBM speed.
+// The k index inside a 32-wide block is permuted identically for A and B (a dot product does not care): lane q = lane % 4 owns
+// k = kb + 8q .. 8q+7 of its weight row (one 16-byte load) and feeds k-slots {2q, 2q+1, 2q+8, 2q+9} of two consecutive MMAs.
+constexpr int SLM_WARPS = 8;
+// staged input rows are padded so that the row stride is 64 bytes modulo 128: the 16-byte A loads of a quarter warp (two batch rows x
+// four k-chunks) then cover all 32 banks exactly once
+__host__ __device__ constexpr int slm_ld(int K) { return K + ((K & 63) == 0 ? 32 : 0); }
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(SLM_WARPS * 32) small_linear_mma_kernel(const SmallLinearParams p) {
+  extern __shared__ __align__(16) uint8_t sl_smem[];
+  bf16* xin = reinterpret_cast<bf16*>(sl_smem);  // [16][slm_ld(K)], rows >= nb are zero
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b0 = blockIdx.y * 16;
+  const int nb = min(16, p.batch - b0);
+  const int kc = p.K >> 3, ldx = slm_ld(p.K);
+  for (int i = threadIdx.x; i < 16 * kc; i += blockDim.x) {
+    const int bb = i / kc, c = i % kc;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (bb < nb) {
+      u = *reinterpret_cast<const uint4*>(p.in + static_cast<long>(b0 + bb) * p.in_stride + c * 8);
+      if (p.silu_input) {
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __fdividef(f[e], 1.0f + __expf(-f[e]));  // F.silu, then bf16
+        u = pack8(f);
+      }
+    }
+    *reinterpret_cast<uint4*>(xin + bb * ldx + c * 8) = u;
+  }
+  __syncthreads();
+  const int g = lane >> 2, q = lane & 3;
+  const bf16* xa = xin + g * ldx + q * 8;          // batch row g
+  const bf16* xb = xin + (g + 8) * ldx + q * 8;    // batch row g + 8
+  const int tiles = (p.N + 7) >> 3;
+  for (int t = blockIdx.x * SLM_WARPS + warp; t < tiles; t += gridDim.x * SLM_WARPS) {
+    const int n = t * 8 + g;                                            // this lane's weight row (B-fragment column)
+    const bf16* wr = p.W + static_cast<long>(n < p.N ? n : p.N - 1) * p.K + q * 8;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int kb = 0; kb < p.K; kb += 32) {
+      const uint4 w = __ldg(reinterpret_cast<const uint4*>(wr + kb));
+      const uint4 a = *reinterpret_cast<const uint4*>(xa + kb);
+      const uint4 b = *reinterpret_cast<const uint4*>(xb + kb);
+      mma_bf16_16816(c, a.x, b.x, a.y, b.y, w.x, w.y);
+      mma_bf16_16816(c, a.z, b.z, a.w, b.w, w.z, w.w);
+    }
+    // c[0], c[1]: batch row g, features t*8 + 2q, +1 ; c[2], c[3]: batch row g + 8
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int bb = g + 8 * h;
+      if (bb >= nb) continue;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int nn = t * 8 + 2 * q + e;
+        if (nn >= p.N) continue;
+        float y = bf16_round(c[2 * h + e] + (p.bias ? __bfloat162float(p.bias[nn]) : 0.f));
+        if (p.addend) y = y + __bfloat162float(p.addend[static_cast<long>(b0 + bb) * p.addend_stride + nn]);
+        if (p.addend2) y = bf16_round(y) + __bfloat162float(p.addend2[static_cast<long>(b0 + bb) * p.addend_stride + nn]);
+        p.out[static_cast<long>(b0 + bb) * p.out_stride + nn] = __float2bfloat16_rn(y);
+      }
+    }
+  }
+}
+
 cudaError_t launch_small_linear(const SmallLinearParams& p, cudaStream_t stream) {
   if (p.K % 8 != 0) return cudaErrorInvalidValue;
+  if (p.K % 32 == 0 && p.in_stride % 8 == 0) {
+    const int smem = 16 * slm_ld(p.K) * 2;
+    static int max_smem_mma = 48 * 1024;
+    if (smem > max_smem_mma) {
+      cudaError_t e = cudaFuncSetAttribute(small_linear_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      max_smem_mma = smem;
+    }
+    const int groups = ((p.N + 7) / 8 + SLM_WARPS - 1) / SLM_WARPS;
+    dim3 grid(std::min(groups, 148 * 4), (p.batch + 15) / 16);
+    small_linear_mma_kernel<<<grid, SLM_WARPS * 32, smem, stream>>>(p);
+    return cudaGetLastError();
+  }
   const int smem = SL_BCHUNK * p.K * 2;
   static int max_smem = 48 * 1024;
   if (smem > max_smem) {

@@ -84,7 +84,8 @@ def test_small_linear_matches_torch():
     from tests.gpu_util import ptr, stream
     from flow_factory_b200 import _lib
     torch.manual_seed(2)
-    for (B, K, N, silu, add) in ((2, 256, 128, 0, 0), (16, 1536, 4000, 1, 1), (3, 2048, 1536, 0, 0), (9, 32, 128, 1, 0)):
+    for (B, K, N, silu, add) in ((2, 256, 128, 0, 0), (16, 1536, 4000, 1, 1), (3, 2048, 1536, 0, 0), (9, 32, 128, 1, 0), (20, 3072, 1003, 1, 1), (5, 48, 64, 0, 0),
+                                 (16, 96, 4099, 1, 0)):
         x = torch.randn(B, K, device="cuda").bfloat16()
         W = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
         b = (torch.randn(N, device="cuda") * 0.1).bfloat16()
