@@ -250,7 +250,35 @@ def golden_flux():
     return out
 
 
+def golden_qwen():
+    """Qwen-Image (groundwork): the REAL QwenImageTransformer2DModel on a tiny config, fp32 + bf16 CPU autocast,
+    with and without a text padding mask, and the norm-rescaled true-CFG combine of FF/models/qwen_image/qwen_image.py:580-587."""
+    from diffusers.models.transformers.transformer_qwenimage import QwenImageTransformer2DModel
+    from oracle import qwen_oracle as QO
+    out = {}
+    cfg = QO.tiny_qwen_config()
+    w32 = QO.make_qwen_weights(cfg, seed=0)
+    B, h2, w2, nt = 2, 6, 4, 9
+    lat, pe = QO.make_qwen_inputs(cfg, B, h2, w2, nt, seed=1)
+    t = torch.tensor([0.9885, 0.25])
+    m = QwenImageTransformer2DModel(**cfg.ref_kwargs()); m.load_state_dict(w32, strict=True); m = m.eval()
+    mask = torch.ones(B, nt); mask[1, 6:] = 0
+    with torch.no_grad():
+        y32 = m(hidden_states=lat, timestep=t, encoder_hidden_states=pe, encoder_hidden_states_mask=None, img_shapes=[[(1, h2, w2)]] * B, return_dict=False)[0]
+        y32m = m(hidden_states=lat, timestep=t, encoder_hidden_states=pe, encoder_hidden_states_mask=mask, img_shapes=[[(1, h2, w2)]] * B, return_dict=False)[0]
+        mb = QwenImageTransformer2DModel(**cfg.ref_kwargs()); mb.load_state_dict(w32, strict=True); mb = mb.to(torch.bfloat16).eval()
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            yb = mb(hidden_states=lat.bfloat16(), timestep=t.bfloat16(), encoder_hidden_states=pe.bfloat16(), encoder_hidden_states_mask=None,
+                    img_shapes=[[(1, h2, w2)]] * B, return_dict=False)[0]
+    out["tiny"] = dict(t=t, y32=y32, y32_masked=y32m, mask=mask, y_bf16_cpu_autocast=yb, keys=sorted(m.state_dict().keys()), shape=(B, h2, w2, nt))
+    # true CFG with norm rescale (qwen_image.py:580-587) on the two predictions above
+    comb = y32m + 4.0 * (y32 - y32m)
+    out["cfg"] = dict(gs=4.0, pred=comb * (torch.norm(y32, dim=-1, keepdim=True) / torch.norm(comb, dim=-1, keepdim=True)))
+    return out
+
+
 if __name__ == "__main__":
+    torch.save(golden_qwen(), os.path.join(HERE, "qwen_tiny.pt"))
     torch.save(golden_flux(), os.path.join(HERE, "flux_tiny.pt"))
     torch.save(golden_schedule(), os.path.join(HERE, "schedule.pt"))
     torch.save(golden_step(), os.path.join(HERE, "sde_step.pt"))
