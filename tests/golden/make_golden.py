@@ -277,7 +277,26 @@ def golden_qwen():
     return out
 
 
+def golden_wan():
+    """Wan2.1 T2V (groundwork): the REAL WanTransformer3DModel on a tiny config, fp32 + bf16 CPU autocast."""
+    from diffusers.models.transformers.transformer_wan import WanTransformer3DModel
+    from oracle import wan_oracle as WO
+    cfg = WO.tiny_wan_config()
+    w32 = WO.make_wan_weights(cfg, seed=0)
+    B, fr, lh, lw, nt = 2, 3, 8, 12, 11
+    lat, pe = WO.make_wan_inputs(cfg, B, fr, lh, lw, nt, seed=1)
+    t = torch.tensor([988.5, 250.0])
+    m = WanTransformer3DModel(**cfg.ref_kwargs()); m.load_state_dict(w32, strict=True); m = m.eval()
+    with torch.no_grad():
+        y32 = m(hidden_states=lat, timestep=t, encoder_hidden_states=pe, return_dict=False)[0]
+        mb = WanTransformer3DModel(**cfg.ref_kwargs()); mb.load_state_dict(w32, strict=True); mb = mb.to(torch.bfloat16).eval()
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            yb = mb(hidden_states=lat.bfloat16(), timestep=t, encoder_hidden_states=pe.bfloat16(), return_dict=False)[0]
+    return {"tiny": dict(t=t, y32=y32, y_bf16_cpu_autocast=yb, keys=sorted(m.state_dict().keys()), shape=(B, fr, lh, lw, nt))}
+
+
 if __name__ == "__main__":
+    torch.save(golden_wan(), os.path.join(HERE, "wan_tiny.pt"))
     torch.save(golden_qwen(), os.path.join(HERE, "qwen_tiny.pt"))
     torch.save(golden_flux(), os.path.join(HERE, "flux_tiny.pt"))
     torch.save(golden_schedule(), os.path.join(HERE, "schedule.pt"))
