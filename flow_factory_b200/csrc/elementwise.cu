@@ -268,20 +268,21 @@ cudaError_t launch_small_linear(const SmallLinearParams& p, cudaStream_t stream)
 // ------------------------------------------------------------------------------------------------
 // timestep sinusoid: out[b, 0:128] = cos(t * f_i), out[b, 128:256] = sin(t * f_i), f_i = exp(-ln(1e4) * i / 128)
 // ------------------------------------------------------------------------------------------------
-__global__ void timestep_proj_kernel(const StepCoef* table, const int* step_ptr, int index, int batch, bf16* out) {
+__global__ void timestep_proj_kernel(const StepCoef* table, const int* step_ptr, int index, int batch, bf16* out, float post_scale) {
   const int i = threadIdx.x;  // 0..127
   const float t = table[step_ptr ? *step_ptr : index].t_model;
   const float exponent = (-9.210340371976184f * static_cast<float>(i)) / 128.0f;
   const float f = expf(exponent);
-  const float a = t * f;
+  const float a = __fmul_rn(post_scale, __fmul_rn(t, f));   // get_timestep_embedding: emb = scale * (t * f)  (embeddings.py:62-65)
   const bf16 c = __float2bfloat16_rn(cosf(a)), s = __float2bfloat16_rn(sinf(a));
   for (int b = 0; b < batch; ++b) {
     out[b * 256 + i] = c;
     out[b * 256 + 128 + i] = s;
   }
 }
-cudaError_t launch_timestep_proj(const StepCoef* table, const int* step_ptr, int index, int batch, bf16* out, cudaStream_t stream) {
-  timestep_proj_kernel<<<1, 128, 0, stream>>>(table, step_ptr, index, batch, out);
+cudaError_t launch_timestep_proj(const StepCoef* table, const int* step_ptr, int index, int batch, bf16* out, cudaStream_t stream,
+                                 float post_scale) {
+  timestep_proj_kernel<<<1, 128, 0, stream>>>(table, step_ptr, index, batch, out, post_scale);
   return cudaGetLastError();
 }
 
@@ -317,6 +318,83 @@ __global__ void cast_f32_bf16_kernel(const float* in, bf16* out, long n) {
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
     out[i] = __float2bfloat16_rn(in[i]);
 }
+// ------------------------------------------------------------------------------------------------
+// diffusers RMSNorm over whole rows (QwenImage txt_norm, DF/models/normalization.py:553-567): variance in fp32, x * rsqrt(var + eps)
+// in fp32 -> bf16 -> x bf16 weight.  One warp per row, two passes over the (L1-resident) row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rms_norm_rows_kernel(const bf16* x, const bf16* weight, bf16* out, long rows, int K, float eps) {
+  const long row = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bf16* xr = x + row * K;
+  const int nchunk = K >> 3;
+  float ss = 0.f;
+  for (int c = lane; c < nchunk; c += 32) {
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + c * 8), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss += v[e] * v[e];
+  }
+  const float rs = rsqrtf(warp_sum(ss) / static_cast<float>(K) + eps);
+  for (int c = lane; c < nchunk; c += 32) {
+    float v[8], wv[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + c * 8), v);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(weight + c * 8)), wv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = __fmul_rn(bf16_round(__fmul_rn(v[e], rs)), wv[e]);
+    *reinterpret_cast<uint4*>(out + row * K + c * 8) = pack8(o);
+  }
+}
+cudaError_t launch_rms_norm_rows(const bf16* x, const bf16* weight, bf16* out, long rows, int K, float eps, cudaStream_t stream) {
+  if (K % 8 != 0) return cudaErrorInvalidValue;
+  const int grid = static_cast<int>((rows + 7) / 8);
+  rms_norm_rows_kernel<<<grid, 256, 0, stream>>>(x, weight, out, rows, K, eps);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Qwen-Image true CFG with per-token norm rescale (FF/models/qwen_image/qwen_image.py:580-587), all in bf16 tensor steps:
+//   comb = neg + g * (pos - neg) ; pred = comb * (||pos|| / ||comb||)   with the norms over the last (64-wide) dim.
+// v: bf16 [2B, Ni, 64] (negative half first); out: bf16 [B, Ni, 64].  One thread per token (a 128-byte row).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) cfg_norm_rescale_kernel(const bf16* v, bf16* out, long tokens_per_half, float g) {
+  const long tok = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x;
+  if (tok >= tokens_per_half) return;
+  const uint4* neg = reinterpret_cast<const uint4*>(v + tok * 64);
+  const uint4* pos = reinterpret_cast<const uint4*>(v + (tokens_per_half + tok) * 64);
+  float comb[64];
+  float sp = 0.f, sc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float n[8], p[8];
+    unpack8(neg[c], n);
+    unpack8(pos[c], p);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float d = bf16_round(p[e] - n[e]);
+      const float gd = bf16_round(g * d);          // python scalar x bf16 tensor: fp32 math, bf16 result
+      const float cb = bf16_round(n[e] + gd);
+      comb[c * 8 + e] = cb;
+      sp += p[e] * p[e];
+      sc += cb * cb;
+    }
+  }
+  const float ratio = bf16_round(bf16_round(sqrtf(sp)) / bf16_round(sqrtf(sc)));
+  uint4* o = reinterpret_cast<uint4*>(out + tok * 64);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float r[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) r[e] = comb[c * 8 + e] * ratio;
+    o[c] = pack8(r);
+  }
+}
+cudaError_t launch_cfg_norm_rescale(const bf16* v, bf16* out, long tokens_per_half, float g, cudaStream_t stream) {
+  const int grid = static_cast<int>((tokens_per_half + 127) / 128);
+  cfg_norm_rescale_kernel<<<grid, 128, 0, stream>>>(v, out, tokens_per_half, g);
+  return cudaGetLastError();
+}
+
 __global__ void cast_f16_bf16_kernel(const __half* in, bf16* out, long n) {
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
     out[i] = __float2bfloat16_rn(__half2float(in[i]));

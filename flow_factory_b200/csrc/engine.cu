@@ -91,6 +91,7 @@ struct GemmSpec {
   int epi; const void* gate; long gate_batch_stride; const void* norm_q; const void* norm_k; int qk_dim; float eps;
   const float* row_table;
   const float* rope_cos; const float* rope_sin; int rope_row_offset;   // EPI_QKV_RMSNORM_ROPE128
+  int rms_round_first;
 };
 static int build_gemm(const GemmSpec& s, GemmParams* p) {
   memset(p, 0, sizeof(*p));
@@ -129,7 +130,7 @@ static int build_gemm(const GemmSpec& s, GemmParams* p) {
   p->gate = static_cast<const bf16*>(s.gate); p->gate_batch_stride = s.gate_batch_stride;
   p->norm_q = static_cast<const bf16*>(s.norm_q); p->norm_k = static_cast<const bf16*>(s.norm_k);
   p->qk_dim = s.qk_dim; p->eps = s.eps; p->row_table = s.row_table;
-  p->rope_cos = s.rope_cos; p->rope_sin = s.rope_sin; p->rope_row_offset = s.rope_row_offset;
+  p->rope_cos = s.rope_cos; p->rope_sin = s.rope_sin; p->rope_row_offset = s.rope_row_offset; p->rms_round_first = s.rms_round_first;
   return 0;
 }
 static int build_attn(const void* qkv, int batch, int seq, int heads, void* out, AttnParams* p, int head_dim = 64,
@@ -364,7 +365,6 @@ int ffb200_plan_create(ffb200_engine* e, int batch, int cfg, int lat_h, int lat_
   std::vector<Op>& ops = p->fwd_ops;
   const ffb200_weights& w = e->w;
   {  // timestep embedding + all-layer adaLN GEMV (embeddings.py:1592-1600; normalization.py:120,167,348)
-    const StepCoef* tbl_dummy = nullptr; (void)tbl_dummy;
     ffb200_plan* pp = p;
     ops.push_back([pp](cudaStream_t st) { ++g_launch_count; return launch_timestep_proj(pp->d_coefs, pp->d_step, 0, pp->Bp, pp->tproj, st); });
     add_small(p, ops, p->tproj, 256, w.t1_w, w.t1_b, D, p->ta, nullptr, 0);

@@ -29,10 +29,11 @@ struct ffb200_flux_engine {
 
 struct ffb200_flux_plan {
   ffb200_flux_engine* e;
-  int B, Ni, Nt, S, D;
+  int B, Bp, cfg, Ni, Nt, S, D;   // Bp = forward batch (2B with Qwen-Image's true CFG, negative half first)
+  float cfg_scale;
   std::vector<void*> allocs;
   long long ws_bytes;
-  bf16 *xin, *c0, *tproj, *gproj, *ta, *ga, *gemb, *pa, *pemb, *temb, *mod, *h, *a1, *qkv, *att, *ff, *cat, *vout;
+  bf16 *xin, *c0, *ctxn, *tproj, *gproj, *ta, *ga, *gemb, *pa, *pemb, *temb, *mod, *h, *a1, *qkv, *att, *ff, *cat, *vout, *vcfg;
   float *rope_cos, *rope_sin;
   __half* x_cur;
   float* logp_partial;
@@ -63,7 +64,7 @@ static int fadd_gemm(ffb200_flux_plan* p, const GemmSpec& s) {
 static void fadd_lnmod(ffb200_flux_plan* p, const bf16* x, long x_bs, int rows_per_batch, const bf16* shift, const bf16* scale, bf16* out,
                        long out_bs) {
   LnModParams lp{};
-  lp.x = x; lp.rows_per_batch = rows_per_batch; lp.num_batch = p->B; lp.D = p->D; lp.eps = 1e-6f;
+  lp.x = x; lp.rows_per_batch = rows_per_batch; lp.num_batch = p->Bp; lp.D = p->D; lp.eps = 1e-6f;
   lp.shift1 = shift; lp.scale1 = scale; lp.out1 = out;
   lp.mod_batch_stride = p->e->off.rows; lp.x_batch_stride = x_bs; lp.out_batch_stride = out_bs;
   p->fwd_ops.push_back([lp](cudaStream_t st) { ++g_launch_count; return launch_ln_modulate(lp, st); });
@@ -92,7 +93,9 @@ int ffb200_flux_engine_set_weights(ffb200_flux_engine* e, const ffb200_flux_weig
 int ffb200_flux_engine_create(const ffb200_flux_config* cfg, const ffb200_flux_weights* w, ffb200_flux_engine** out) {
   FFB_CHECK(cfg && w && out, "null argument");
   FFB_CHECK(cfg->num_layers >= 0 && cfg->num_single_layers >= 0 && cfg->num_heads > 0, "bad config");
-  FFB_CHECK(cfg->in_channels == 64, "FLUX.1 packed latents: in_channels must be 64");
+  FFB_CHECK(cfg->in_channels == 64, "packed latents: in_channels must be 64");
+  FFB_CHECK(cfg->variant == 0 || cfg->variant == 1, "variant: 0 = FLUX.1, 1 = Qwen-Image");
+  if (cfg->variant == 1) FFB_CHECK(cfg->num_single_layers == 0 && cfg->guidance_embeds == 0 && w->ctxn_w, "Qwen-Image: dual blocks only, no guidance embedding, txt_norm weight required");
   FFB_CHECK(cfg->joint_attention_dim % 8 == 0 && cfg->pooled_projection_dim % 8 == 0, "joint/pooled dims must be multiples of 8");
   int dev = 0, major = 0;
   FFB_CUDA(cudaGetDevice(&dev));
@@ -126,20 +129,23 @@ void ffb200_flux_plan_destroy(ffb200_flux_plan* p) {
 }
 long long ffb200_flux_plan_workspace_bytes(const ffb200_flux_plan* p) { return p ? p->ws_bytes : 0; }
 
-int ffb200_flux_plan_create(ffb200_flux_engine* e, int batch, int n_img_tokens, int n_text, const float* rope_cos,
-                            const float* rope_sin, ffb200_flux_plan** out) {
+int ffb200_flux_plan_create_ex(ffb200_flux_engine* e, int batch, int cfg, int n_img_tokens, int n_text, const float* rope_cos,
+                               const float* rope_sin, ffb200_flux_plan** out) {
   FFB_CHECK(e && out && rope_cos && rope_sin, "null argument");
-  FFB_CHECK(batch > 0 && batch <= 64 && n_img_tokens > 0 && n_text > 0, "batch / token counts out of range");
+  FFB_CHECK(batch > 0 && batch * (cfg ? 2 : 1) <= 64 && n_img_tokens > 0 && n_text > 0, "batch / token counts out of range");
+  FFB_CHECK(!cfg || e->cfg.variant == 1, "a CFG batch exists only for Qwen-Image (FLUX.1 embeds the guidance scale)");
   const ffb200_flux_config& mc = e->cfg;
   ffb200_flux_plan* p = new ffb200_flux_plan();
-  p->e = e; p->B = batch; p->Ni = n_img_tokens; p->Nt = n_text; p->S = n_img_tokens + n_text; p->D = e->D;
+  p->e = e; p->B = batch; p->cfg = cfg ? 1 : 0; p->Bp = batch * (cfg ? 2 : 1); p->cfg_scale = 1.0f;
+  p->Ni = n_img_tokens; p->Nt = n_text; p->S = n_img_tokens + n_text; p->D = e->D;
   p->ws_bytes = 0; p->graph_exec = nullptr; p->graph_valid = false; p->prompts_set = false; p->coef_cap = 0; p->d_coefs = nullptr;
-  const int D = p->D, B = p->B, Ni = p->Ni, Nt = p->Nt, S = p->S, R = e->off.rows;
+  const int D = p->D, B = p->Bp, Ni = p->Ni, Nt = p->Nt, S = p->S, R = e->off.rows;   // B: FORWARD batch from here on
   const size_t BS = static_cast<size_t>(B) * S;
   int r = 0;
 #define ALLOC(field, count, type) if (!r) r = fplan_alloc(p, reinterpret_cast<void**>(&p->field), static_cast<size_t>(count) * sizeof(type))
   ALLOC(xin, static_cast<size_t>(B) * Ni * 64, bf16);
   ALLOC(c0, static_cast<size_t>(B) * Nt * D, bf16);
+  if (mc.variant == 1) ALLOC(ctxn, static_cast<size_t>(B) * Nt * mc.joint_attention_dim, bf16);
   ALLOC(tproj, B * 256, bf16); ALLOC(gproj, B * 256, bf16);
   ALLOC(ta, B * D, bf16); ALLOC(ga, B * D, bf16); ALLOC(gemb, B * D, bf16); ALLOC(pa, B * D, bf16); ALLOC(pemb, B * D, bf16);
   ALLOC(temb, B * D, bf16);
@@ -151,10 +157,11 @@ int ffb200_flux_plan_create(ffb200_flux_engine* e, int batch, int n_img_tokens, 
   ALLOC(ff, BS * 4 * D, bf16);
   if (mc.num_single_layers > 0) ALLOC(cat, BS * 5 * D, bf16);
   ALLOC(vout, static_cast<size_t>(B) * Ni * 64, bf16);
+  if (p->cfg) ALLOC(vcfg, static_cast<size_t>(p->B) * Ni * 64, bf16);
   ALLOC(rope_cos, static_cast<size_t>(S) * 128, float);
   ALLOC(rope_sin, static_cast<size_t>(S) * 128, float);
-  ALLOC(x_cur, static_cast<size_t>(B) * Ni * 64, __half);
-  ALLOC(logp_partial, static_cast<size_t>(B) * 64, float);
+  ALLOC(x_cur, static_cast<size_t>(p->B) * Ni * 64, __half);
+  ALLOC(logp_partial, static_cast<size_t>(p->B) * 64, float);
   ALLOC(d_step, 1, int);
   ALLOC(d_gcoef, 1, StepCoef);
 #undef ALLOC
@@ -167,20 +174,29 @@ int ffb200_flux_plan_create(ffb200_flux_engine* e, int batch, int n_img_tokens, 
   ffb200_flux_plan* pp = p;
   // ---- timestep embedding: temb = bf16(bf16(t_emb + g_emb) + pooled_emb) (embeddings.py:1612-1624), then every adaLN projection of
   //      the model in one GEMV over the stacked matrix (normalization.py:167, 199, 348)
-  ops.push_back([pp](cudaStream_t st) { ++g_launch_count; return launch_timestep_proj(pp->d_coefs, pp->d_step, 0, pp->B, pp->tproj, st); });
+  const float t_post = mc.variant == 1 ? 1000.0f : 1.0f;   // Qwen-Image: Timesteps(scale=1000) on t/1000 (transformer_qwenimage.py:180)
+  ops.push_back([pp, B, t_post](cudaStream_t st) { ++g_launch_count; return launch_timestep_proj(pp->d_coefs, pp->d_step, 0, B, pp->tproj, st, t_post); });
   ops.push_back(small_op(B, p->tproj, 256, w.t1_w, w.t1_b, D, p->ta, nullptr, nullptr, 0));
-  ops.push_back(small_op(B, p->ta, D, w.t2_w, w.t2_b, D, p->temb, mc.guidance_embeds ? p->gemb : p->pemb,
-                         mc.guidance_embeds ? p->pemb : nullptr, 1));
+  if (mc.variant == 1)   // QwenTimestepProjEmbeddings: the timestep embedding alone (176-193)
+    ops.push_back(small_op(B, p->ta, D, w.t2_w, w.t2_b, D, p->temb, nullptr, nullptr, 1));
+  else
+    ops.push_back(small_op(B, p->ta, D, w.t2_w, w.t2_b, D, p->temb, mc.guidance_embeds ? p->gemb : p->pemb,
+                           mc.guidance_embeds ? p->pemb : nullptr, 1));
   ops.push_back(small_op(B, p->temb, D, w.mod_w, w.mod_b, R, p->mod, nullptr, nullptr, 1));
   // ---- x_embedder on the packed latents (676), context rows copied from the cached context_embedder output
   {
-    const long n = static_cast<long>(B) * Ni * 64;
-    ops.push_back([pp, n](cudaStream_t st) { ++g_launch_count; return launch_cast_f16_to_bf16(pp->x_cur, pp->xin, n, st); });
+    const long n = static_cast<long>(p->B) * Ni * 64;
+    const int reps = p->cfg ? 2 : 1;   // CFG: both halves of the forward batch see the same latents
+    ops.push_back([pp, n, reps](cudaStream_t st) {
+      cudaError_t ce = cudaSuccess;
+      for (int r2 = 0; r2 < reps && ce == cudaSuccess; ++r2) { ++g_launch_count; ce = launch_cast_f16_to_bf16(pp->x_cur, pp->xin + r2 * n, n, st); }
+      return ce;
+    });
     GemmSpec s = {p->xin, B, Ni, 0, 64, 64, w.x_w, D, w.x_b, p->h, static_cast<long>(S) * D, Nt, D, EPI_BIAS};
     if ((r = fadd_gemm(p, s))) { ffb200_flux_plan_destroy(p); return r; }
     const size_t row_bytes = static_cast<size_t>(Nt) * D * 2;
     ops.push_back([pp, row_bytes](cudaStream_t st) {
-      return cudaMemcpy2DAsync(pp->h, static_cast<size_t>(pp->S) * pp->D * 2, pp->c0, row_bytes, row_bytes, pp->B, cudaMemcpyDeviceToDevice, st);
+      return cudaMemcpy2DAsync(pp->h, static_cast<size_t>(pp->S) * pp->D * 2, pp->c0, row_bytes, row_bytes, pp->Bp, cudaMemcpyDeviceToDevice, st);
     });
   }
   const long hS = static_cast<long>(S) * D;            // batch stride of the joint buffers
@@ -193,10 +209,10 @@ int ffb200_flux_plan_create(ffb200_flux_engine* e, int batch, int n_img_tokens, 
     fadd_lnmod(p, h_img, hS, Ni, m1 + 0 * D, m1 + 1 * D, a_img, hS);
     fadd_lnmod(p, h_ctx, hS, Nt, mc1 + 0 * D, mc1 + 1 * D, a_ctx, hS);
     GemmSpec sc = {a_ctx, B, Nt, hS, D, D, L.add_qkv_w, 3 * D, L.add_qkv_b, p->qkv, 3 * hS, 0, 3 * D, EPI_QKV_RMSNORM_ROPE128,
-                   nullptr, 0, L.norm_added_q, L.norm_added_k, D, 1e-6f, nullptr, p->rope_cos, p->rope_sin, 0};
+                   nullptr, 0, L.norm_added_q, L.norm_added_k, D, 1e-6f, nullptr, p->rope_cos, p->rope_sin, 0, mc.variant == 1};
     if ((r = fadd_gemm(p, sc))) break;
     GemmSpec sq = {a_img, B, Ni, hS, D, D, L.qkv_w, 3 * D, L.qkv_b, p->qkv, 3 * hS, Nt, 3 * D, EPI_QKV_RMSNORM_ROPE128,
-                   nullptr, 0, L.norm_q, L.norm_k, D, 1e-6f, nullptr, p->rope_cos, p->rope_sin, Nt};
+                   nullptr, 0, L.norm_q, L.norm_k, D, 1e-6f, nullptr, p->rope_cos, p->rope_sin, Nt, mc.variant == 1};
     if ((r = fadd_gemm(p, sq))) break;
     {
       AttnParams ap;
@@ -244,10 +260,19 @@ int ffb200_flux_plan_create(ffb200_flux_engine* e, int batch, int n_img_tokens, 
     fadd_lnmod(p, h_img, hS, Ni, mo + 1 * D, mo + 0 * D, p->a1, 0);
     GemmSpec po = {p->a1, B, Ni, 0, D, D, w.proj_w, 64, w.proj_b, p->vout, static_cast<long>(Ni) * 64, 0, 64, EPI_BIAS};
     r = fadd_gemm(p, po);
+    if (!r && p->cfg) {   // true CFG + per-token norm rescale (FF/models/qwen_image/qwen_image.py:580-587)
+      const long toks = static_cast<long>(p->B) * Ni;
+      ops.push_back([pp, toks](cudaStream_t st) { ++g_launch_count; return launch_cfg_norm_rescale(pp->vout, pp->vcfg, toks, pp->cfg_scale, st); });
+    }
   }
   if (r) { ffb200_flux_plan_destroy(p); return r; }
   *out = p;
   return 0;
+}
+
+int ffb200_flux_plan_create(ffb200_flux_engine* e, int batch, int n_img_tokens, int n_text, const float* rope_cos,
+                            const float* rope_sin, ffb200_flux_plan** out) {
+  return ffb200_flux_plan_create_ex(e, batch, 0, n_img_tokens, n_text, rope_cos, rope_sin, out);
 }
 
 static int fensure_coefs(ffb200_flux_plan* p, int n) {
@@ -262,30 +287,42 @@ static int fensure_coefs(ffb200_flux_plan* p, int n) {
 
 int ffb200_flux_set_prompts(ffb200_flux_plan* p, const void* prompt_embeds_bf16, const void* pooled_bf16, float guidance_model,
                             void* stream) {
-  FFB_CHECK(p && prompt_embeds_bf16 && pooled_bf16, "null argument");
+  FFB_CHECK(p && prompt_embeds_bf16, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const ffb200_flux_engine* e = p->e;
-  const int J = e->cfg.joint_attention_dim, P = e->cfg.pooled_projection_dim, D = p->D, B = p->B;
+  const int J = e->cfg.joint_attention_dim, P = e->cfg.pooled_projection_dim, D = p->D, B = p->Bp;
   g_launch_count = 0;
-  // context_embedder (transformer_flux.py:686) - timestep independent, cached for the whole rollout
-  GemmSpec s = {prompt_embeds_bf16, B, p->Nt, 0, J, J, e->w.ctx_w, D, e->w.ctx_b, p->c0, static_cast<long>(p->Nt) * D, 0, D, EPI_BIAS};
+  const void* ctx_in = prompt_embeds_bf16;
+  if (e->cfg.variant == 1) {   // Qwen-Image: txt_norm (diffusers RMSNorm, eps 1e-6) before txt_in (transformer_qwenimage.py:936-937)
+    ++g_launch_count;
+    FFB_CUDA(launch_rms_norm_rows(static_cast<const bf16*>(prompt_embeds_bf16), static_cast<const bf16*>(e->w.ctxn_w), p->ctxn,
+                                  static_cast<long>(B) * p->Nt, J, 1e-6f, st));
+    ctx_in = p->ctxn;
+    p->cfg_scale = guidance_model;   // the true-CFG scale of the rollout (no embedded guidance in this model)
+  }
+  // context_embedder / txt_in (transformer_flux.py:686) - timestep independent, cached for the whole rollout
+  GemmSpec s = {ctx_in, B, p->Nt, 0, J, J, e->w.ctx_w, D, e->w.ctx_b, p->c0, static_cast<long>(p->Nt) * D, 0, D, EPI_BIAS};
   GemmParams gp;
   int r = build_gemm(s, &gp);
   if (r) return r;
   ++g_launch_count;
   FFB_CUDA(launch_gemm(gp, num_sms(), st));
-  // pooled-text MLP and (dev checkpoints) the guidance embedding: both constant over the rollout (embeddings.py:1616-1621)
-  FFB_CUDA(small_op(B, static_cast<const bf16*>(pooled_bf16), P, e->w.p1_w, e->w.p1_b, D, p->pa, nullptr, nullptr, 0)(st));
-  FFB_CUDA(small_op(B, p->pa, D, e->w.p2_w, e->w.p2_b, D, p->pemb, nullptr, nullptr, 1)(st));
-  if (e->cfg.guidance_embeds) {
-    StepCoef c; memset(&c, 0, sizeof(c)); c.t_model = guidance_model;   // bf16(guidance) * 1000 in bf16, computed by the host
-    FFB_CUDA(cudaMemcpyAsync(p->d_gcoef, &c, sizeof(c), cudaMemcpyHostToDevice, st));
-    ++g_launch_count;
-    FFB_CUDA(launch_timestep_proj(p->d_gcoef, nullptr, 0, B, p->gproj, st));
-    FFB_CUDA(small_op(B, p->gproj, 256, e->w.g1_w, e->w.g1_b, D, p->ga, nullptr, nullptr, 0)(st));
-    FFB_CUDA(small_op(B, p->ga, D, e->w.g2_w, e->w.g2_b, D, p->gemb, nullptr, nullptr, 1)(st));
+  if (e->cfg.variant == 0) {
+    FFB_CHECK(pooled_bf16, "FLUX.1 needs the pooled prompt embedding");
+    // pooled-text MLP and (dev checkpoints) the guidance embedding: both constant over the rollout (embeddings.py:1616-1621)
+    FFB_CUDA(small_op(B, static_cast<const bf16*>(pooled_bf16), P, e->w.p1_w, e->w.p1_b, D, p->pa, nullptr, nullptr, 0)(st));
+    FFB_CUDA(small_op(B, p->pa, D, e->w.p2_w, e->w.p2_b, D, p->pemb, nullptr, nullptr, 1)(st));
+    if (e->cfg.guidance_embeds) {
+      StepCoef c; memset(&c, 0, sizeof(c)); c.t_model = guidance_model;   // bf16(guidance) * 1000 in bf16, computed by the host
+      FFB_CUDA(cudaMemcpyAsync(p->d_gcoef, &c, sizeof(c), cudaMemcpyHostToDevice, st));
+      ++g_launch_count;
+      FFB_CUDA(launch_timestep_proj(p->d_gcoef, nullptr, 0, B, p->gproj, st));
+      FFB_CUDA(small_op(B, p->gproj, 256, e->w.g1_w, e->w.g1_b, D, p->ga, nullptr, nullptr, 0)(st));
+      FFB_CUDA(small_op(B, p->ga, D, e->w.g2_w, e->w.g2_b, D, p->gemb, nullptr, nullptr, 1)(st));
+    }
   }
   p->prompts_set = true;
+  p->graph_valid = p->graph_valid && e->cfg.variant == 0;   // the CFG scale is baked into the captured graph
   return 0;
 }
 
@@ -301,7 +338,7 @@ static void ffill_sde(const ffb200_flux_plan* p, SdeStepParams* sp) {
   memset(sp, 0, sizeof(*sp));
   // the packed latents [B, Ni, 64] are one flat "image" per sample for the elementwise scheduler step
   sp->B = p->B; sp->C = 1; sp->H = p->Ni; sp->W = 64; sp->patch = 1; sp->cfg = 0; sp->guidance = 1.0f;
-  sp->v_direct = p->vout; sp->x = p->x_cur; sp->logp_partial = p->logp_partial; sp->coef_table = p->d_coefs;
+  sp->v_direct = p->cfg ? p->vcfg : p->vout; sp->x = p->x_cur; sp->logp_partial = p->logp_partial; sp->coef_table = p->d_coefs;
 }
 
 int ffb200_flux_forward(ffb200_flux_plan* p, const void* latents_fp16, float t_model, void* noise_pred_bf16, void* stream) {
@@ -317,7 +354,7 @@ int ffb200_flux_forward(ffb200_flux_plan* p, const void* latents_fp16, float t_m
   FFB_CUDA(cudaMemsetAsync(p->d_step, 0, sizeof(int), st));
   FFB_CUDA(cudaMemcpyAsync(p->x_cur, latents_fp16, lat_bytes, cudaMemcpyDeviceToDevice, st));
   if ((r = frun_forward(p, st))) return r;
-  if (noise_pred_bf16) FFB_CUDA(cudaMemcpyAsync(noise_pred_bf16, p->vout, lat_bytes, cudaMemcpyDeviceToDevice, st));
+  if (noise_pred_bf16) FFB_CUDA(cudaMemcpyAsync(noise_pred_bf16, p->cfg ? p->vcfg : p->vout, lat_bytes, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 

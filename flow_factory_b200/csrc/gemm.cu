@@ -313,7 +313,9 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
                 const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) {
-                  float a = __fmul_rn(__fmul_rn(v[q * 8 + e], rs), wf[e]), b2 = __fmul_rn(__fmul_rn(v[q * 8 + e + 1], rs), wf[e + 1]);
+                  float a = __fmul_rn(v[q * 8 + e], rs), b2 = __fmul_rn(v[q * 8 + e + 1], rs);
+                  if (p.rms_round_first) bf16_round2(a, b2);                     // diffusers RMSNorm: .to(weight.dtype) before the weight multiply
+                  a = __fmul_rn(a, wf[e]); b2 = __fmul_rn(b2, wf[e + 1]);
                   bf16_round2(a, b2);                                            // RMSNorm output is a bf16 tensor
                   v[q * 8 + e] = __fadd_rn(__fmul_rn(a, cc[e]), __fmul_rn(-b2, sv[e]));
                   v[q * 8 + e + 1] = __fadd_rn(__fmul_rn(b2, cc[e + 1]), __fmul_rn(a, sv[e + 1]));

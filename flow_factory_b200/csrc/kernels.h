@@ -43,6 +43,7 @@ struct GemmParams {
   const float* rope_cos;   // EPI_QKV_RMSNORM_ROPE128: fp32 [tokens, 128] (values repeated pairwise, FluxPosEmbed), row = rope_row_offset + row
   const float* rope_sin;
   int rope_row_offset;
+  int rms_round_first;     // 0: torch.nn.RMSNorm bf16((x*rs)*w) (FLUX.1) ; 1: diffusers RMSNorm bf16(bf16(x*rs)*w) (Qwen-Image)
 };
 
 int gemm_pick_bn(int N);
@@ -109,7 +110,8 @@ struct SmallLinearParams {
 cudaError_t launch_small_linear(const SmallLinearParams& p, cudaStream_t stream);
 
 // sinusoidal timestep projection (embeddings.py:26-77, flip_sin_to_cos, shift 0) -> bf16 [batch, 256]
-cudaError_t launch_timestep_proj(const StepCoef* table, const int* step_ptr, int index, int batch, bf16* out, cudaStream_t stream);
+cudaError_t launch_timestep_proj(const StepCoef* table, const int* step_ptr, int index, int batch, bf16* out, cudaStream_t stream,
+                                 float post_scale = 1.0f);   // post_scale: Timesteps(scale=...) of Qwen-Image (1000)
 
 // im2col for the 2x2/stride-2 patch-embed conv: fp16 latents [B,C,H,W] -> bf16 [Bp*Ni, C*p*p] (Bp = B*reps)
 cudaError_t launch_patchify(const __half* x, int B, int reps, int C, int H, int W, int patch, bf16* out, cudaStream_t stream);
@@ -117,6 +119,10 @@ cudaError_t launch_patchify(const __half* x, int B, int reps, int C, int H, int 
 // cast helpers
 cudaError_t launch_cast_f32_to_bf16(const float* in, bf16* out, long n, cudaStream_t stream);
 cudaError_t launch_cast_f16_to_bf16(const __half* in, bf16* out, long n, cudaStream_t stream);
+// diffusers RMSNorm over rows of width K (text-stream input norm of Qwen-Image)
+cudaError_t launch_rms_norm_rows(const bf16* x, const bf16* weight, bf16* out, long rows, int K, float eps, cudaStream_t stream);
+// Qwen-Image true CFG + per-token norm rescale: v bf16 [2B, Ni, 64] (negative half first) -> out bf16 [B, Ni, 64]
+cudaError_t launch_cfg_norm_rescale(const bf16* v, bf16* out, long tokens_per_half, float guidance, cudaStream_t stream);
 
 // ------------------------------------------------------------------ fused Euler/SDE step + log-prob (K14)
 

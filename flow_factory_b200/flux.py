@@ -28,6 +28,7 @@ class FluxEngineConfig:
     pooled_projection_dim: int = 768
     guidance_embeds: bool = True
     axes_dims_rope: Tuple[int, int, int] = (16, 56, 56)
+    variant: int = 0     # 0 = FLUX.1 ; 1 = Qwen-Image (flow_factory_b200/qwen.py)
 
     @property
     def inner_dim(self) -> int:
@@ -100,12 +101,12 @@ DUAL_FIELDS = ("qkv_w", "qkv_b", "norm_q", "norm_k", "add_qkv_w", "add_qkv_b", "
                "add_out_w", "add_out_b", "ff1_w", "ff1_b", "ff2_w", "ff2_b", "cff1_w", "cff1_b", "cff2_w", "cff2_b")
 SINGLE_FIELDS = ("qkv_w", "qkv_b", "norm_q", "norm_k", "mlp_w", "mlp_b", "out_w", "out_b")
 GLOBAL_FIELDS = ("x_w", "x_b", "ctx_w", "ctx_b", "t1_w", "t1_b", "t2_w", "t2_b", "g1_w", "g1_b", "g2_w", "g2_b",
-                 "p1_w", "p1_b", "p2_w", "p2_b", "mod_w", "mod_b", "proj_w", "proj_b")
+                 "p1_w", "p1_b", "p2_w", "p2_b", "mod_w", "mod_b", "proj_w", "proj_b", "ctxn_w")
 
 
 class FluxConfigC(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("num_layers", "num_single_layers", "num_heads", "in_channels", "joint_attention_dim",
-                                       "pooled_projection_dim", "guidance_embeds")]
+                                       "pooled_projection_dim", "guidance_embeds", "variant")]
 
 
 class FluxDualWeights(C.Structure):
@@ -133,6 +134,7 @@ def _L() -> C.CDLL:
         L.ffb200_flux_engine_destroy.argtypes = [vp]; L.ffb200_flux_engine_destroy.restype = None
         L.ffb200_flux_engine_mod_rows.argtypes = [vp]
         L.ffb200_flux_plan_create.argtypes = [vp, ci, ci, ci, vp, vp, C.POINTER(vp)]
+        L.ffb200_flux_plan_create_ex.argtypes = [vp, ci, ci, ci, ci, vp, vp, C.POINTER(vp)]
         L.ffb200_flux_plan_destroy.argtypes = [vp]; L.ffb200_flux_plan_destroy.restype = None
         L.ffb200_flux_plan_workspace_bytes.argtypes = [vp]; L.ffb200_flux_plan_workspace_bytes.restype = C.c_longlong
         L.ffb200_flux_set_prompts.argtypes = [vp, vp, vp, cf, vp]
@@ -173,9 +175,17 @@ class FluxPackedWeights:
         W = self.struct
         for f in GLOBAL_FIELDS:
             setattr(W, f, None)
-        names = [("x", "x_embedder"), ("ctx", "context_embedder"), ("t1", "time_text_embed.timestep_embedder.linear_1"),
-                 ("t2", "time_text_embed.timestep_embedder.linear_2"), ("p1", "time_text_embed.text_embedder.linear_1"),
-                 ("p2", "time_text_embed.text_embedder.linear_2"), ("proj", "proj_out")]
+        qwen = cfg.variant == 1
+        # Qwen-Image module names (transformer_qwenimage.py:829-846, 622-650) for the same roles
+        k_norm1, k_norm1c, k_ff, k_ffc = (("img_mod.1", "txt_mod.1", "img_mlp", "txt_mlp") if qwen else
+                                          ("norm1.linear", "norm1_context.linear", "ff", "ff_context"))
+        names = [("x", "img_in" if qwen else "x_embedder"), ("ctx", "txt_in" if qwen else "context_embedder"),
+                 ("t1", "time_text_embed.timestep_embedder.linear_1"), ("t2", "time_text_embed.timestep_embedder.linear_2"),
+                 ("proj", "proj_out")]
+        if qwen:
+            W.ctxn_w = self._put("ctxn_w", sd["txt_norm.weight"])
+        else:
+            names += [("p1", "time_text_embed.text_embedder.linear_1"), ("p2", "time_text_embed.text_embedder.linear_2")]
         if cfg.guidance_embeds:
             names += [("g1", "time_text_embed.guidance_embedder.linear_1"), ("g2", "time_text_embed.guidance_embedder.linear_2")]
         for short, key in names:
@@ -185,8 +195,8 @@ class FluxPackedWeights:
         mod_b: List[torch.Tensor] = []
         for i in range(cfg.num_layers):
             pre, a = f"transformer_blocks.{i}.", f"transformer_blocks.{i}.attn."
-            mod_w += [sd[pre + "norm1.linear.weight"], sd[pre + "norm1_context.linear.weight"]]
-            mod_b += [sd[pre + "norm1.linear.bias"], sd[pre + "norm1_context.linear.bias"]]
+            mod_w += [sd[pre + k_norm1 + ".weight"], sd[pre + k_norm1c + ".weight"]]
+            mod_b += [sd[pre + k_norm1 + ".bias"], sd[pre + k_norm1c + ".bias"]]
             L = self.dual_structs[i]
             put = lambda field, t: setattr(L, field, self._put(f"D{i}.{field}", t))
             put("qkv_w", cat([a + "to_q.weight", a + "to_k.weight", a + "to_v.weight"]))
@@ -197,10 +207,10 @@ class FluxPackedWeights:
             put("norm_added_q", sd[a + "norm_added_q.weight"]); put("norm_added_k", sd[a + "norm_added_k.weight"])
             put("out_w", sd[a + "to_out.0.weight"]); put("out_b", sd[a + "to_out.0.bias"])
             put("add_out_w", sd[a + "to_add_out.weight"]); put("add_out_b", sd[a + "to_add_out.bias"])
-            put("ff1_w", sd[pre + "ff.net.0.proj.weight"]); put("ff1_b", sd[pre + "ff.net.0.proj.bias"])
-            put("ff2_w", sd[pre + "ff.net.2.weight"]); put("ff2_b", sd[pre + "ff.net.2.bias"])
-            put("cff1_w", sd[pre + "ff_context.net.0.proj.weight"]); put("cff1_b", sd[pre + "ff_context.net.0.proj.bias"])
-            put("cff2_w", sd[pre + "ff_context.net.2.weight"]); put("cff2_b", sd[pre + "ff_context.net.2.bias"])
+            put("ff1_w", sd[pre + k_ff + ".net.0.proj.weight"]); put("ff1_b", sd[pre + k_ff + ".net.0.proj.bias"])
+            put("ff2_w", sd[pre + k_ff + ".net.2.weight"]); put("ff2_b", sd[pre + k_ff + ".net.2.bias"])
+            put("cff1_w", sd[pre + k_ffc + ".net.0.proj.weight"]); put("cff1_b", sd[pre + k_ffc + ".net.0.proj.bias"])
+            put("cff2_w", sd[pre + k_ffc + ".net.2.weight"]); put("cff2_b", sd[pre + k_ffc + ".net.2.bias"])
         for i in range(cfg.num_single_layers):
             pre, a = f"single_transformer_blocks.{i}.", f"single_transformer_blocks.{i}.attn."
             mod_w.append(sd[pre + "norm.linear.weight"]); mod_b.append(sd[pre + "norm.linear.bias"])
@@ -223,15 +233,14 @@ class FluxPackedWeights:
 
 
 class FluxPlan:
-    def __init__(self, engine: "FluxRolloutEngine", batch: int, h2: int, w2: int, n_text: int):
-        self.engine, self.batch, self.h2, self.w2, self.n_text = engine, batch, h2, w2, n_text
+    def __init__(self, engine: "FluxRolloutEngine", batch: int, h2: int, w2: int, n_text: int, cfg: bool = False):
+        self.engine, self.batch, self.h2, self.w2, self.n_text, self.cfg = engine, batch, h2, w2, n_text, bool(cfg)
         self.n_img = h2 * w2
         self.img_ids = latent_image_ids(h2, w2)
-        ids = torch.cat([torch.zeros(n_text, 3), self.img_ids], dim=0)       # txt_ids are zeros (flux1.py:330)
-        cos, sin = rope_tables(ids, engine.cfg.axes_dims_rope)
+        cos, sin = engine.rope_tables(h2, w2, n_text)                        # fp32 [n_text + n_img, 128], text rows first
         self.handle = C.c_void_p()
-        _lib.check(_L().ffb200_flux_plan_create(engine.handle, batch, self.n_img, n_text, cos.data_ptr(), sin.data_ptr(),
-                                                C.byref(self.handle)), "ffb200_flux_plan_create")
+        _lib.check(_L().ffb200_flux_plan_create_ex(engine.handle, batch, int(self.cfg), self.n_img, n_text, cos.data_ptr(), sin.data_ptr(),
+                                                   C.byref(self.handle)), "ffb200_flux_plan_create_ex")
         self._keep: List[torch.Tensor] = []
 
     @property
@@ -260,7 +269,7 @@ class FluxRolloutEngine:
         self.cfg = model_config if isinstance(model_config, FluxEngineConfig) else FluxEngineConfig.from_model_config(model_config)
         self.weights = FluxPackedWeights(self.cfg, state_dict, self.device)
         mc = FluxConfigC(self.cfg.num_layers, self.cfg.num_single_layers, self.cfg.num_heads, self.cfg.in_channels,
-                         self.cfg.joint_attention_dim, self.cfg.pooled_projection_dim, int(self.cfg.guidance_embeds))
+                         self.cfg.joint_attention_dim, self.cfg.pooled_projection_dim, int(self.cfg.guidance_embeds), int(self.cfg.variant))
         self.handle = C.c_void_p()
         _lib.check(_L().ffb200_flux_engine_create(C.byref(mc), C.byref(self.weights.struct), C.byref(self.handle)),
                    "ffb200_flux_engine_create")
@@ -272,10 +281,15 @@ class FluxRolloutEngine:
         self.weights.pack(state_dict)
         _lib.check(_L().ffb200_flux_engine_set_weights(self.handle, C.byref(self.weights.struct)), "ffb200_flux_engine_set_weights")
 
-    def plan(self, batch: int, h2: int, w2: int, n_text: int) -> FluxPlan:
-        key = (batch, h2, w2, n_text)
+    def rope_tables(self, h2: int, w2: int, n_text: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """cos / sin fp32 [n_text + h2*w2, 128] for ids = cat(txt_ids = 0 (flux1.py:330), img_ids)."""
+        ids = torch.cat([torch.zeros(n_text, 3), latent_image_ids(h2, w2)], dim=0)
+        return rope_tables(ids, self.cfg.axes_dims_rope)
+
+    def plan(self, batch: int, h2: int, w2: int, n_text: int, cfg: bool = False) -> FluxPlan:
+        key = (batch, h2, w2, n_text, bool(cfg))
         if key not in self._plans:
-            self._plans[key] = FluxPlan(self, batch, h2, w2, n_text)
+            self._plans[key] = FluxPlan(self, batch, h2, w2, n_text, cfg)
         return self._plans[key]
 
     def stream(self) -> torch.cuda.Stream:

@@ -195,6 +195,7 @@ typedef struct ffb200_flux_config {
   int joint_attention_dim;   /* 4096 */
   int pooled_projection_dim; /* 768 */
   int guidance_embeds;       /* 1 for FLUX.1-dev */
+  int variant;               /* 0 = FLUX.1 ; 1 = Qwen-Image (dual blocks only, see below) */
 } ffb200_flux_config;
 
 /* bf16, nn.Linear layout [out, in]; q|k|v concatenated along out_features by the host packer */
@@ -220,6 +221,7 @@ typedef struct ffb200_flux_weights {
    * block norm.linear (3D), then norm_out.linear (2D) */
   const void *mod_w, *mod_b;
   const void *proj_w, *proj_b;           /* proj_out [64, D]                                                         */
+  const void *ctxn_w;                    /* Qwen-Image only: txt_norm.weight [joint_dim] (NULL for FLUX.1)           */
   const ffb200_flux_dual_weights* dual;     /* [num_layers]        */
   const ffb200_flux_single_weights* single; /* [num_single_layers] */
 } ffb200_flux_weights;
@@ -235,6 +237,15 @@ int ffb200_flux_engine_mod_rows(const ffb200_flux_engine* e);
  * img_ids) exactly as FluxPosEmbed returns them (transformer_flux.py:500-522, float64 frequencies) - host or device memory, copied. */
 int ffb200_flux_plan_create(ffb200_flux_engine* e, int batch, int n_img_tokens, int n_text, const float* rope_cos,
                             const float* rope_sin, ffb200_flux_plan** out);
+/* variant 1 = Qwen-Image (QwenImageTransformer2DModel.forward, DF/models/transformers/transformer_qwenimage.py:878-993,
+ * behind QwenImageAdapter.forward, FF/models/qwen_image/qwen_image.py:476-600): the same dual-stream engine with
+ * x_w/ctx_w := img_in/txt_in, norm1(.context).linear := img_mod.1/txt_mod.1, ff(.context) := img_mlp/txt_mlp, the text RMSNorm, the
+ * timestep-only conditioning (t1/t2; p*, g* unused), diffusers-style q/k RMSNorm, rope tables that also rotate the text rows, and
+ * - with cfg = 1 - a forward batch of 2B (negative prompts first) combined by the per-token norm-rescaled true CFG
+ * (qwen_image.py:580-587); the CFG scale is the `guidance_model` argument of ffb200_flux_set_prompts, `pooled_bf16` is NULL.
+ * Prompts of one call must share one (unpadded) length: key-padding masks are not implemented. */
+int ffb200_flux_plan_create_ex(ffb200_flux_engine* e, int batch, int cfg, int n_img_tokens, int n_text, const float* rope_cos,
+                               const float* rope_sin, ffb200_flux_plan** out);
 void ffb200_flux_plan_destroy(ffb200_flux_plan* p);
 long long ffb200_flux_plan_workspace_bytes(const ffb200_flux_plan* p);
 /* prompt_embeds bf16 [B, Nt, joint_dim], pooled bf16 [B, pooled_dim]; guidance_model = float(bf16(bf16(guidance_scale) * 1000)),

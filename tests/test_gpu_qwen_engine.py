@@ -1,0 +1,117 @@
+"""-m gpu parity of the Qwen-Image path: the dual-stream engine in variant-1 mode vs the oracle
+(oracle/qwen_oracle.py, pinned bit-exact against the reference's QwenImageTransformer2DModel on CPU)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tests.gpu_util import dump
+from flow_factory_b200.qwen import QwenRolloutEngine, qwen_rope_tables
+from oracle import qwen_oracle as QO
+from oracle import sd3_oracle as O
+
+
+def test_qwen_rope_tables_match_the_oracle():
+    cos, sin = qwen_rope_tables(6, 4, 9, (16, 56, 56))
+    vid, txt = QO.qwen_rope(1, 6, 4, 9, (16, 56, 56))
+    f = torch.cat([txt, vid])
+    assert torch.equal(cos[:, 0::2], f.real) and torch.equal(cos[:, 1::2], f.real)
+    assert torch.equal(sin[:, 0::2], f.imag) and torch.equal(sin[:, 1::2], f.imag)
+
+
+def _truth(cfg, wt, lat, pe, t_eff, h2, w2):
+    with torch.no_grad():
+        return QO.qwen_forward(wt, cfg, lat.float(), pe.float(), torch.full((lat.shape[0],), t_eff), (1, h2, w2))
+
+
+@pytest.mark.parametrize("name", ["tiny", "mid"])
+def test_qwen_forward_and_true_cfg_match_oracle(name):
+    cfg, (B, h2, w2, nt), seed = {"tiny": (QO.tiny_qwen_config(), (2, 6, 4, 9), 0),
+                                  "mid": (QO.tiny_qwen_config(num_layers=3, heads=4, joint_dim=256), (2, 24, 16, 37), 4)}[name]
+    w32 = QO.make_qwen_weights(cfg, seed=seed)
+    wb = {k: v.bfloat16() for k, v in w32.items()}
+    wt = {k: v.float() for k, v in wb.items()}
+    lat, pe = QO.make_qwen_inputs(cfg, B, h2, w2, nt, seed=seed + 1)
+    _, npe = QO.make_qwen_inputs(cfg, B, h2, w2, nt, seed=seed + 7)
+    lat, pe, npe = lat.half(), pe.bfloat16(), npe.bfloat16()
+    eng = QwenRolloutEngine(cfg, wb)
+    t = 612.0
+    t_eff = eng.t_model(t)
+    # --- plain forward
+    plan = eng.plan(B, h2, w2, nt)
+    eng.set_prompts(plan, pe)
+    got = eng.transformer_forward(plan, lat, t).float().cpu()
+    torch.cuda.synchronize()
+    truth = _truth(cfg, wt, lat, pe, t_eff, h2, w2)
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        ref_bf16 = QO.qwen_forward(wb, cfg, lat.bfloat16(), pe, torch.full((B,), t / 1000), (1, h2, w2)).float()
+    e_eng, e_ref, scale = float((got - truth).abs().max()), float((ref_bf16 - truth).abs().max()), float(truth.abs().max())
+    rep = dict(tag=f"qwen_fwd_{name}", e_engine=e_eng, e_ref_bf16=e_ref, truth_absmax=scale,
+               mean_engine=float((got - truth).abs().mean()), mean_ref=float((ref_bf16 - truth).abs().mean()))
+    dump(f"qwen_fwd_{name}.json", rep)
+    assert torch.isfinite(got).all()
+    assert e_eng <= max(3.0 * e_ref, 0.02 * scale), rep
+    assert rep["mean_engine"] <= max(3.0 * rep["mean_ref"], 0.004 * scale), rep
+    # --- true CFG with per-token norm rescale (qwen_image.py:580-587)
+    gs = 4.0
+    planc = eng.plan(B, h2, w2, nt, cfg=True)
+    eng.set_prompts(planc, pe, npe, gs)
+    gotc = eng.transformer_forward(planc, lat, t).float().cpu()
+    torch.cuda.synchronize()
+    truth_neg = _truth(cfg, wt, lat, npe, t_eff, h2, w2)
+    truth_c = QO.true_cfg_combine(truth, truth_neg, gs)
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        ref_neg = QO.qwen_forward(wb, cfg, lat.bfloat16(), npe, torch.full((B,), t / 1000), (1, h2, w2))
+        ref_c = QO.true_cfg_combine(ref_bf16.bfloat16(), ref_neg, gs).float()
+    e_eng_c, e_ref_c = float((gotc - truth_c).abs().max()), float((ref_c - truth_c).abs().max())
+    repc = dict(tag=f"qwen_cfg_{name}", e_engine=e_eng_c, e_ref_bf16=e_ref_c, truth_absmax=float(truth_c.abs().max()))
+    dump(f"qwen_cfg_{name}.json", repc)
+    assert e_eng_c <= max(3.0 * e_ref_c, 0.03 * repc["truth_absmax"]), repc
+
+
+def test_qwen_ode_rollout_matches_oracle_loop():
+    """DGPO-style rollout (ODE, no log-prob, true CFG): engine vs the oracle loop (fp32 truth and bf16 CPU autocast), graph == eager."""
+    cfg = QO.tiny_qwen_config()
+    w32 = QO.make_qwen_weights(cfg, seed=0)
+    wb = {k: v.bfloat16() for k, v in w32.items()}
+    B, h2, w2, nt, T, gs = 2, 6, 4, 9, 4, 4.0
+    lat, pe = QO.make_qwen_inputs(cfg, B, h2, w2, nt, seed=1)
+    _, npe = QO.make_qwen_inputs(cfg, B, h2, w2, nt, seed=8)
+    lat, pe, npe = lat.half(), pe.bfloat16(), npe.bfloat16()
+    eng = QwenRolloutEngine(cfg, wb)
+    plan = eng.plan(B, h2, w2, nt, cfg=True)
+    eng.set_prompts(plan, pe, npe, gs)
+    ts, sig, coefs = eng.make_coefs(plan, T, 0.0, [], dynamics="ODE", store_slots=[1, 2, 3, 4])
+    outs = {}
+    for graph in (False, True):
+        r = eng.rollout(plan, lat, coefs, n_latent_slots=T + 1, store_initial_slot=0, n_logp_slots=0, use_graph=graph)
+        torch.cuda.synchronize()
+        outs[graph] = r["all_latents"].cpu()
+    assert torch.equal(outs[False], outs[True])
+
+    def oracle_loop(w, autocast):
+        x = lat
+        xs = [x]
+        for i in range(T):
+            tm = torch.full((B,), float(ts[i]) / 1000)
+            if autocast:
+                with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+                    vp = QO.qwen_forward(w, cfg, x.bfloat16(), pe, tm, (1, h2, w2))
+                    vn = QO.qwen_forward(w, cfg, x.bfloat16(), npe, tm, (1, h2, w2))
+                    v = QO.true_cfg_combine(vp, vn, gs)
+            else:
+                with torch.no_grad():
+                    tme = torch.full((B,), eng.t_model(float(ts[i])))
+                    vp = QO.qwen_forward(w, cfg, x.float(), pe.float(), tme, (1, h2, w2))
+                    vn = QO.qwen_forward(w, cfg, x.float(), npe.float(), tme, (1, h2, w2))
+                    v = QO.true_cfg_combine(vp, vn, gs)
+            r = O.sde_step(v, x, float(sig[i]), float(sig[i + 1]), 0.0, float(sig[1]), "ODE", compute_log_prob=False)
+            x = O.cast_latents(r["next_latents"], torch.float16)
+            xs.append(x)
+        return xs
+    truth = oracle_loop({k: v.float() for k, v in wb.items()}, False)
+    refb = oracle_loop(wb, True)
+    for i in range(T + 1):
+        d = float((outs[True][:, i].float() - truth[i].float()).abs().max())
+        d_ref = float((refb[i].float() - truth[i].float()).abs().max())
+        assert d <= max(3.0 * d_ref, 0.05), (i, d, d_ref)

@@ -58,9 +58,9 @@ def test_flux_adapter_keywords_are_the_reference_abi():
 
 
 def test_flux_struct_layouts_and_config():
-    assert C.sizeof(F.FluxConfigC) == 7 * 4
+    assert C.sizeof(F.FluxConfigC) == 8 * 4
     assert C.sizeof(F.FluxDualWeights) == 20 * 8 and C.sizeof(F.FluxSingleWeights) == 8 * 8
-    assert C.sizeof(F.FluxWeights) == 20 * 8 + 2 * 8
+    assert C.sizeof(F.FluxWeights) == 21 * 8 + 2 * 8
     cfg = F.FluxEngineConfig.from_model_config(FO.flux1_dev())
     assert (cfg.num_layers, cfg.num_single_layers, cfg.inner_dim, cfg.guidance_embeds) == (19, 38, 3072, True)
     with pytest.raises(ValueError):
@@ -74,3 +74,17 @@ def test_flux_sample_collate_shares_img_ids():
     b = Flux1Sample(all_latents=torch.ones(3, 4, 64), img_ids=ids, height=32, width=32)
     out = Flux1Sample.stack([a, b])
     assert out["img_ids"] is ids and tuple(out["all_latents"].shape) == (2, 3, 4, 64)
+
+
+def test_qwen_config_and_rope_tables():
+    from flow_factory_b200.qwen import qwen_engine_config, qwen_rope_tables
+    from oracle import qwen_oracle as QO
+    cfg = qwen_engine_config(QO.qwen_image_20b())
+    assert (cfg.variant, cfg.num_layers, cfg.num_single_layers, cfg.inner_dim, cfg.joint_attention_dim) == (1, 60, 0, 3072, 3584)
+    with pytest.raises(NotImplementedError):
+        qwen_engine_config(dict(QO.qwen_image_20b().ref_kwargs(), zero_cond_t=True))
+    cos, sin = qwen_rope_tables(6, 4, 9, (16, 56, 56))
+    vid, txt = QO.qwen_rope(1, 6, 4, 9, (16, 56, 56))
+    f = torch.cat([txt, vid])
+    assert torch.equal(cos[:, 0::2], f.real) and torch.equal(cos[:, 1::2], f.real)
+    assert torch.equal(sin[:, 0::2], f.imag) and torch.equal(sin[:, 1::2], f.imag)
