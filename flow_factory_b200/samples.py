@@ -75,3 +75,13 @@ class Flux1Sample(SD3_5Sample):
     all_latents rows are PACKED latents (T', Ni, 64)."""
     _shared_fields: ClassVar[frozenset] = frozenset({"img_ids"})
     img_ids: Optional[torch.Tensor] = None
+
+
+@dataclass
+class QwenImageSample(SD3_5Sample):
+    """Mirror of the reference's QwenImageSample (FF/models/qwen_image/qwen_image.py): T2I sample + embedding masks + img_shapes.
+    all_latents rows are PACKED latents (T', Ni, 64)."""
+    _shared_fields: ClassVar[frozenset] = frozenset({"img_shapes"})
+    prompt_embeds_mask: Optional[torch.Tensor] = None
+    negative_prompt_embeds_mask: Optional[torch.Tensor] = None
+    img_shapes: Optional[List] = None

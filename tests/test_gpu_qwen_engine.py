@@ -115,3 +115,36 @@ def test_qwen_ode_rollout_matches_oracle_loop():
         d = float((outs[True][:, i].float() - truth[i].float()).abs().max())
         d_ref = float((refb[i].float() - truth[i].float()).abs().max())
         assert d <= max(3.0 * d_ref, 0.05), (i, d, d_ref)
+
+
+def test_qwen_adapter_inference_api():
+    """B200QwenImageAdapter mirrors QwenImageAdapter.inference / forward (qwen_image.py:290-600): DGPO-style ODE rollout with true CFG,
+    sample fields, refusal of padded prompts, and forward() reproducing a rollout step."""
+    from flow_factory_b200.qwen_adapter import B200QwenImageAdapter
+    cfg = QO.tiny_qwen_config()
+    wb = {k: v.bfloat16() for k, v in QO.make_qwen_weights(cfg, seed=0).items()}
+    ad = B200QwenImageAdapter(cfg, wb)
+    g = torch.Generator().manual_seed(5)
+    B, nt, T = 2, 9, 5
+    pe = torch.randn(B, nt, cfg.joint_attention_dim, generator=g).bfloat16().cuda()
+    npe = torch.randn(B, nt, cfg.joint_attention_dim, generator=g).bfloat16().cuda()
+    mask = torch.ones(B, nt, dtype=torch.long).cuda()
+    torch.manual_seed(3)
+    samples = ad.inference(prompt=["a"] * B, negative_prompt=[""] * B, height=96, width=64, num_inference_steps=T, guidance_scale=4.0,
+                           prompt_embeds=pe, prompt_embeds_mask=mask, negative_prompt_embeds=npe, negative_prompt_embeds_mask=mask,
+                           compute_log_prob=False, trajectory_indices="all")
+    torch.cuda.synchronize()
+    s0 = samples[0]
+    Ni = (96 // 16) * (64 // 16)
+    assert tuple(s0.all_latents.shape) == (T + 1, Ni, 64) and s0.log_probs is None and s0.img_shapes == [(1, 6, 4)]
+    assert torch.isfinite(s0.all_latents.float()).all()
+    lat = torch.stack([s.all_latents for s in samples])
+    out = ad.forward(t=s0.timesteps[2], t_next=s0.timesteps[3], latents=lat[:, 2], prompt_embeds=pe, prompt_embeds_mask=mask,
+                     img_shapes=[[(1, 6, 4)]] * B, negative_prompt_embeds=npe, negative_prompt_embeds_mask=mask, guidance_scale=4.0,
+                     compute_log_prob=False)
+    torch.cuda.synchronize()
+    # ODE: next_latents is the un-rounded mean; its fp16 storage cast is what the rollout kept
+    assert torch.equal(out.next_latents.half(), lat[:, 3])
+    bad = mask.clone(); bad[1, -2:] = 0
+    with pytest.raises(NotImplementedError):
+        ad.inference(height=96, width=64, num_inference_steps=2, prompt_embeds=pe, prompt_embeds_mask=bad)

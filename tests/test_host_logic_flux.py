@@ -88,3 +88,15 @@ def test_qwen_config_and_rope_tables():
     f = torch.cat([txt, vid])
     assert torch.equal(cos[:, 0::2], f.real) and torch.equal(cos[:, 1::2], f.real)
     assert torch.equal(sin[:, 0::2], f.imag) and torch.equal(sin[:, 1::2], f.imag)
+
+
+def test_qwen_adapter_keywords_are_the_reference_abi():
+    from flow_factory_b200.qwen_adapter import B200QwenImageAdapter
+    # FF/models/qwen_image/qwen_image.py:290-314 and 476-496
+    ref_inf = ["prompt", "negative_prompt", "num_inference_steps", "guidance_scale", "height", "width", "generator", "prompt_ids",
+               "prompt_embeds", "prompt_embeds_mask", "negative_prompt_ids", "negative_prompt_embeds", "negative_prompt_embeds_mask",
+               "attention_kwargs", "max_sequence_length", "compute_log_prob", "extra_call_back_kwargs", "trajectory_indices"]
+    ref_fwd = ["t", "latents", "prompt_embeds", "prompt_embeds_mask", "img_shapes", "negative_prompt_embeds", "negative_prompt_embeds_mask",
+               "guidance_scale", "t_next", "next_latents", "noise_level", "attention_kwargs", "compute_log_prob", "return_kwargs"]
+    assert set(ref_inf) <= set(inspect.signature(B200QwenImageAdapter.inference).parameters)
+    assert set(ref_fwd) <= set(inspect.signature(B200QwenImageAdapter.forward).parameters)
