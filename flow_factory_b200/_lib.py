@@ -99,7 +99,7 @@ EXPORTED_SYMBOLS = (
     "ffb200_linear_qkv_rope", "ffb200_attention", "ffb200_attention_ex", "ffb200_ln_modulate", "ffb200_small_linear", "ffb200_sde_step",
     # FLUX.1: bound in flow_factory_b200/flux.py
     "ffb200_flux_engine_create", "ffb200_flux_engine_set_weights", "ffb200_flux_engine_destroy", "ffb200_flux_engine_mod_rows",
-    "ffb200_flux_plan_create", "ffb200_flux_plan_create_ex", "ffb200_flux_plan_destroy", "ffb200_flux_plan_workspace_bytes", "ffb200_flux_set_prompts",
+    "ffb200_flux_plan_create", "ffb200_flux_plan_create_ex", "ffb200_flux_set_text_lengths", "ffb200_flux_plan_destroy", "ffb200_flux_plan_workspace_bytes", "ffb200_flux_set_prompts",
     "ffb200_flux_forward", "ffb200_flux_step", "ffb200_flux_rollout")
 
 

@@ -167,6 +167,8 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
       const uint32_t tOx = tmem_base + lane_off + A128_TMEM_O + x * A128_D;
       const float sc = p.scale_log2;
       float m_run = -INFINITY, l_run = 0.f;
+      const int mask_hi = p.kv_mask_lo ? p.kv_mask_hi : 0;
+      const int mask_lo = p.kv_mask_lo ? max(__ldg(p.kv_mask_lo + b), 1) : 0;   // key 0 always stays (keeps the running max finite)
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(&s_full[x], j & 1, 0x60);
         tc_fence_after();
@@ -177,6 +179,16 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_free[x]);
+        if (mask_lo < mask_hi) {                        // key-padding mask: only the first few KV tiles overlap the text rows
+          const int k0 = j * A128_BN;
+          if (k0 < mask_hi && k0 + A128_BN > mask_lo) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              if (k0 + c >= mask_lo && k0 + c < mask_hi) s0[c] = 0xFF800000u;
+              if (k0 + 32 + c >= mask_lo && k0 + 32 + c < mask_hi) s1[c] = 0xFF800000u;
+            }
+          }
+        }
         uint32_t pk[32];
         float alpha;
         const bool rescale = softmax_block64(s0, s1, S - j * A128_BN, sc, m_run, l_run, pk, alpha);

@@ -40,6 +40,7 @@ struct ffb200_flux_plan {
   int* d_step;
   StepCoef* d_coefs; int coef_cap;
   StepCoef* d_gcoef;
+  int* d_txt_len;   // [Bp] valid text tokens per forward-batch row (Qwen-Image key-padding mask); Nt = no padding
   std::vector<Op> fwd_ops;
   bool prompts_set;
   cudaGraphExec_t graph_exec; SdeStepParams graph_sde; bool graph_valid; long long graph_launches;
@@ -164,8 +165,13 @@ int ffb200_flux_plan_create_ex(ffb200_flux_engine* e, int batch, int cfg, int n_
   ALLOC(logp_partial, static_cast<size_t>(p->B) * 64, float);
   ALLOC(d_step, 1, int);
   ALLOC(d_gcoef, 1, StepCoef);
+  ALLOC(d_txt_len, B, int);
 #undef ALLOC
   if (r) { ffb200_flux_plan_destroy(p); return r; }
+  {
+    std::vector<int> full(B, Nt);
+    cudaMemcpy(p->d_txt_len, full.data(), sizeof(int) * B, cudaMemcpyHostToDevice);
+  }
   cudaMemcpy(p->rope_cos, rope_cos, static_cast<size_t>(S) * 128 * 4, cudaMemcpyDefault);
   cudaMemcpy(p->rope_sin, rope_sin, static_cast<size_t>(S) * 128 * 4, cudaMemcpyDefault);
 
@@ -217,6 +223,7 @@ int ffb200_flux_plan_create_ex(ffb200_flux_engine* e, int batch, int cfg, int n_
     {
       AttnParams ap;
       if ((r = build_attn(p->qkv, B, S, mc.num_heads, p->att, &ap, 128, 0))) break;
+      if (mc.variant == 1) { ap.kv_mask_lo = p->d_txt_len; ap.kv_mask_hi = Nt; }   // padded text keys (set_text_lengths; default: none)
       ops.push_back([ap](cudaStream_t st) { ++g_launch_count; return launch_attention_d128(ap, st); });
     }
     GemmSpec so = {p->att + static_cast<size_t>(Nt) * D, B, Ni, hS, D, D, L.out_w, D, L.out_b, p->h, hS, Nt, D, EPI_GATE_RESIDUAL,
@@ -323,6 +330,15 @@ int ffb200_flux_set_prompts(ffb200_flux_plan* p, const void* prompt_embeds_bf16,
   }
   p->prompts_set = true;
   p->graph_valid = p->graph_valid && e->cfg.variant == 0;   // the CFG scale is baked into the captured graph
+  return 0;
+}
+
+int ffb200_flux_set_text_lengths(ffb200_flux_plan* p, const int* lengths_host, void* stream) {
+  FFB_CHECK(p && lengths_host, "null argument");
+  FFB_CHECK(p->e->cfg.variant == 1, "key-padding masks exist only on the Qwen-Image path");
+  for (int i = 0; i < p->Bp; ++i) FFB_CHECK(lengths_host[i] >= 1 && lengths_host[i] <= p->Nt, "text length out of range");
+  FFB_CUDA(cudaMemcpyAsync(p->d_txt_len, lengths_host, sizeof(int) * p->Bp, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  FFB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));   // lengths_host may be a temporary
   return 0;
 }
 

@@ -61,6 +61,10 @@ struct AttnParams {
   long out_batch_stride;
   int out_row_stride; // elements between consecutive token rows of `out` (D, or wider when the output is a column block)
   float scale_log2;   // (1/sqrt(head_dim)) * log2(e)
+  // optional key-padding mask (head_dim 128 kernel only): keys [kv_mask_lo[b], kv_mask_hi) of batch b are excluded - the padded tail
+  // of the text rows of a joint [text ; image] sequence (Qwen-Image attention_mask, transformer_qwenimage.py:952-958); null = none
+  const int* kv_mask_lo;
+  int kv_mask_hi;
 };
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);        // head_dim 64  (SD3.x)
 cudaError_t launch_attention_d128(const AttnParams& p, cudaStream_t stream);   // head_dim 128 (FLUX.1)

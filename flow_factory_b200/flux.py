@@ -135,6 +135,7 @@ def _L() -> C.CDLL:
         L.ffb200_flux_engine_mod_rows.argtypes = [vp]
         L.ffb200_flux_plan_create.argtypes = [vp, ci, ci, ci, vp, vp, C.POINTER(vp)]
         L.ffb200_flux_plan_create_ex.argtypes = [vp, ci, ci, ci, ci, vp, vp, C.POINTER(vp)]
+        L.ffb200_flux_set_text_lengths.argtypes = [vp, C.POINTER(ci), vp]
         L.ffb200_flux_plan_destroy.argtypes = [vp]; L.ffb200_flux_plan_destroy.restype = None
         L.ffb200_flux_plan_workspace_bytes.argtypes = [vp]; L.ffb200_flux_plan_workspace_bytes.restype = C.c_longlong
         L.ffb200_flux_set_prompts.argtypes = [vp, vp, vp, cf, vp]

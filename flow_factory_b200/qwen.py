@@ -67,8 +67,11 @@ class QwenRolloutEngine(FluxRolloutEngine):
         return qwen_rope_tables(h2, w2, n_text, self.cfg.axes_dims_rope)
 
     def set_prompts(self, plan: FluxPlan, prompt_embeds: torch.Tensor, negative_prompt_embeds: Optional[torch.Tensor] = None,
-                    guidance_scale: float = 1.0) -> None:
-        """prompt_embeds [B, Nt, joint_dim]; with plan.cfg the negative embeddings (same Nt) form the first half of the batch."""
+                    guidance_scale: float = 1.0, prompt_lengths: Optional[Sequence[int]] = None,
+                    negative_lengths: Optional[Sequence[int]] = None) -> None:
+        """prompt_embeds [B, Nt, joint_dim] (right-padded to the plan's Nt); with plan.cfg the negative embeddings (same Nt) form the
+        first half of the batch.  `*_lengths`: valid leading tokens per sample (encoder_hidden_states_mask of the reference); the padded
+        tail is masked as attention keys."""
         if plan.cfg:
             if negative_prompt_embeds is None or negative_prompt_embeds.shape != prompt_embeds.shape:
                 raise ValueError("true CFG needs negative_prompt_embeds of the same (unpadded) shape as prompt_embeds")
@@ -80,6 +83,11 @@ class QwenRolloutEngine(FluxRolloutEngine):
         plan._keep = [pe]
         st = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(_L().ffb200_flux_set_prompts(plan.handle, pe.data_ptr(), None, float(guidance_scale), st), "ffb200_flux_set_prompts")
+        full = [plan.n_text] * plan.batch
+        lens = (list(negative_lengths or full) if plan.cfg else []) + list(prompt_lengths or full)
+        import ctypes as C
+        arr = (C.c_int * len(lens))(*[int(v) for v in lens])
+        _lib.check(_L().ffb200_flux_set_text_lengths(plan.handle, arr, st), "ffb200_flux_set_text_lengths")
 
     @staticmethod
     def t_model(timestep: float, latents_dtype: torch.dtype = torch.float16) -> float:

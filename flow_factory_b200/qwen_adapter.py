@@ -1,9 +1,9 @@
 """B200QwenImageAdapter - drop-in for Flow-Factory's QwenImageAdapter on the rollout path (first cut).
 
 Mirrors FF/models/qwen_image/qwen_image.py: `inference()` (290-470) and `forward()` (476-600); parameter names are the ABI.
-True CFG (two prompt sets, per-token norm rescale) runs as one forward batch of 2B.  Restrictions of this first cut, all enforced
-loudly: every prompt of a call must have the same UNPADDED length (masks all ones) for both the positive and the negative set -
-the attention kernel has no key masks yet; text encoding, VAE decode and the autograd replay stay on the reference."""
+True CFG (two prompt sets, per-token norm rescale) runs as one forward batch of 2B; prompts of different lengths are right-padded
+to one length and the padding is masked as attention keys (the reference's encoder_hidden_states_mask).  Only prefix masks are
+accepted; text encoding, VAE decode and the autograd replay stay on the reference."""
 from __future__ import annotations
 
 from typing import Any, Callable, Dict, List, Optional, Union
@@ -16,17 +16,31 @@ from .scheduler import FlowMatchEulerDiscreteSDEScheduler, SDESchedulerOutput, s
 from .trajectory import TrajectoryIndicesType, plan_slots
 
 
-def _dense(embeds, mask, what: str) -> torch.Tensor:
-    """List / padded tensor + mask -> dense [B, Nt, J]; refuses ragged or padded prompts."""
+def _dense(embeds, mask, what: str):
+    """List / padded tensor + mask -> (right-padded dense [B, Nt, J], valid lengths).  The reference's masks are prefix masks
+    (tokenizer padding on the right, `_pad_batch_prompt`); anything else is refused."""
     if isinstance(embeds, (list, tuple)):
-        if len({tuple(e.shape) for e in embeds}) != 1:
-            raise NotImplementedError(f"{what}: prompts of different lengths need key masks (not on the accelerated path yet)")
-        embeds = torch.stack(list(embeds), dim=0)
+        nt = max(e.shape[0] for e in embeds)
+        lens = [int(e.shape[0]) for e in embeds]
+        embeds = torch.stack([torch.nn.functional.pad(e, (0, 0, 0, nt - e.shape[0])) for e in embeds], dim=0)
+        if mask is not None:
+            lens = [min(l, int(torch.as_tensor(m).sum())) for l, m in zip(lens, mask)]
+            mask = None
+    else:
+        lens = [int(embeds.shape[1])] * len(embeds)
     if mask is not None:
-        m = torch.stack(list(mask), dim=0) if isinstance(mask, (list, tuple)) else mask
-        if not bool(m.to(torch.bool).all()):
-            raise NotImplementedError(f"{what}: padded prompts need key masks (not on the accelerated path yet)")
-    return embeds
+        m = (torch.stack(list(mask), dim=0) if isinstance(mask, (list, tuple)) else mask).to(torch.bool)
+        lens = [int(v) for v in m.sum(dim=1).tolist()]
+        ar = torch.arange(m.shape[1], device=m.device)[None, :]
+        if not bool((m == (ar < torch.as_tensor(lens, device=m.device)[:, None])).all()):
+            raise NotImplementedError(f"{what}: only right-padded (prefix) masks are on the accelerated path")
+    if min(lens) < 1:
+        raise ValueError(f"{what}: empty prompt")
+    return embeds, lens
+
+
+def _pad_to(embeds: torch.Tensor, nt: int) -> torch.Tensor:
+    return embeds if embeds.shape[1] == nt else torch.nn.functional.pad(embeds, (0, 0, 0, nt - embeds.shape[1]))
 
 
 class B200QwenImageAdapter:
@@ -56,12 +70,16 @@ class B200QwenImageAdapter:
     def cast_latents(self, latents: torch.Tensor, default_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
         return latents if latents.dtype == torch.float16 else latents.clamp(-65504.0, 65504.0).to(torch.float16)
 
-    def _plan(self, B: int, h2: int, w2: int, pe: torch.Tensor, npe: Optional[torch.Tensor], guidance_scale: float):
-        do_cfg = guidance_scale > 1.0 and npe is not None
-        if do_cfg and npe.shape != pe.shape:
-            raise NotImplementedError("positive and negative prompts of different lengths need key masks (not on the accelerated path yet)")
-        plan = self.engine.plan(B, h2, w2, pe.shape[1], cfg=do_cfg)
-        self.engine.set_prompts(plan, pe, npe if do_cfg else None, float(guidance_scale) if do_cfg else 1.0)
+    def _plan(self, B: int, h2: int, w2: int, pos, neg, guidance_scale: float):
+        """pos / neg: (dense embeds, lengths).  Both sets are right-padded to one common text length (multiple of 8 rows keeps the
+        plan cache small); the padded keys are masked in the attention kernel."""
+        (pe, plens), do_cfg = pos, guidance_scale > 1.0 and neg is not None
+        npe, nlens = neg if do_cfg else (None, None)
+        nt = max(pe.shape[1], npe.shape[1] if do_cfg else 0)
+        nt = (nt + 7) // 8 * 8
+        plan = self.engine.plan(B, h2, w2, nt, cfg=do_cfg)
+        self.engine.set_prompts(plan, _pad_to(pe, nt), _pad_to(npe, nt) if do_cfg else None, float(guidance_scale) if do_cfg else 1.0,
+                                prompt_lengths=plens, negative_lengths=nlens)
         return plan
 
     @torch.no_grad()
@@ -95,11 +113,12 @@ class B200QwenImageAdapter:
         if extra_call_back_kwargs:
             raise NotImplementedError("per-step callbacks need the step-by-step path: call forward() in a loop")
         dev, T = self.device, int(num_inference_steps)
-        pe = _dense(prompt_embeds, prompt_embeds_mask, "prompt_embeds")
-        npe = _dense(negative_prompt_embeds, negative_prompt_embeds_mask, "negative_prompt_embeds") if negative_prompt_embeds is not None else None
+        pos = _dense(prompt_embeds, prompt_embeds_mask, "prompt_embeds")
+        neg = _dense(negative_prompt_embeds, negative_prompt_embeds_mask, "negative_prompt_embeds") if negative_prompt_embeds is not None else None
+        pe, npe = pos[0], (neg[0] if neg is not None else None)
         B = len(pe)
         h2, w2 = int(height) // self.vae_scale_factor // 2, int(width) // self.vae_scale_factor // 2
-        plan = self._plan(B, h2, w2, pe, npe, guidance_scale)
+        plan = self._plan(B, h2, w2, pos, neg, guidance_scale)
         if latents is None:   # prepare_latents: randn (B, 1, 16, 2*h2, 2*w2) packed 2x2 -> (B, h2*w2, 64)
             z = torch.randn((B, 16, 2 * h2, 2 * w2), generator=generator, device=dev, dtype=torch.bfloat16)
             latents = z.view(B, 16, h2, 2, w2, 2).permute(0, 2, 4, 1, 3, 5).reshape(B, h2 * w2, 64)
@@ -123,7 +142,7 @@ class B200QwenImageAdapter:
         r = self.engine.rollout(plan, x0, coefs, n_lat, lat_slot[0], n_lp, noise=noise, seed=seed, use_graph=self.use_graph)
         final = r["final_latents"]
         images = self.decode_fn(final, height, width) if self.decode_fn is not None else None
-        ones = lambda e: torch.ones(e.shape[0], dtype=torch.long, device=e.device)
+        mk = lambda e, n: (torch.arange(e.shape[0], device=e.device) < n).long()
         samples = []
         for b in range(B):
             samples.append(QwenImageSample(
@@ -134,11 +153,11 @@ class B200QwenImageAdapter:
                 height=height, width=width, image=images[b] if images is not None else None, img_shapes=[(1, h2, w2)],
                 prompt=prompt[b] if isinstance(prompt, list) else prompt,
                 prompt_ids=prompt_ids[b] if prompt_ids is not None else None,
-                prompt_embeds=pe[b], prompt_embeds_mask=ones(pe[b]),
+                prompt_embeds=pe[b], prompt_embeds_mask=mk(pe[b], pos[1][b]),
                 negative_prompt=negative_prompt[b] if isinstance(negative_prompt, list) else negative_prompt,
                 negative_prompt_ids=negative_prompt_ids[b] if negative_prompt_ids is not None else None,
                 negative_prompt_embeds=npe[b] if npe is not None else None,
-                negative_prompt_embeds_mask=ones(npe[b]) if npe is not None else None,
+                negative_prompt_embeds_mask=mk(npe[b], neg[1][b]) if npe is not None else None,
                 extra_kwargs={"callback_index_map": None, "final_latents": final[b]},
             ))
         self._last_overflow = r["overflow"]
@@ -166,14 +185,14 @@ class B200QwenImageAdapter:
             raise RuntimeError("B200QwenImageAdapter.forward serves the no-grad path; keep the autograd replay on the reference adapter")
         if attention_kwargs:
             raise NotImplementedError("attention_kwargs are not on the accelerated path")
-        pe = _dense(prompt_embeds, prompt_embeds_mask, "prompt_embeds")
-        npe = _dense(negative_prompt_embeds, negative_prompt_embeds_mask, "negative_prompt_embeds") if negative_prompt_embeds is not None else None
+        pos = _dense(prompt_embeds, prompt_embeds_mask, "prompt_embeds")
+        neg = _dense(negative_prompt_embeds, negative_prompt_embeds_mask, "negative_prompt_embeds") if negative_prompt_embeds is not None else None
         B, Ni, _ = latents.shape
         shp = img_shapes[0]
         shp = shp[0] if isinstance(shp, (list, tuple)) and isinstance(shp[0], (list, tuple)) else shp
         _, h2, w2 = shp
         assert h2 * w2 == Ni, (h2, w2, Ni)
-        plan = self._plan(B, int(h2), int(w2), pe, npe, guidance_scale)
+        plan = self._plan(B, int(h2), int(w2), pos, neg, guidance_scale)
         sch = self.scheduler
         t0 = (t if isinstance(t, torch.Tensor) else torch.tensor(float(t))).flatten()[0].detach().cpu().float()
         if t_next is None:

@@ -246,6 +246,10 @@ int ffb200_flux_plan_create(ffb200_flux_engine* e, int batch, int n_img_tokens, 
  * Prompts of one call must share one (unpadded) length: key-padding masks are not implemented. */
 int ffb200_flux_plan_create_ex(ffb200_flux_engine* e, int batch, int cfg, int n_img_tokens, int n_text, const float* rope_cos,
                                const float* rope_sin, ffb200_flux_plan** out);
+/* Qwen-Image key-padding mask (encoder_hidden_states_mask -> attention_mask, transformer_qwenimage.py:941-958): lengths[i] = number of
+ * valid (leading) text tokens of forward-batch row i (2B rows with cfg, negative prompts first); keys [lengths[i], n_text) are masked.
+ * Default after plan creation: no padding. */
+int ffb200_flux_set_text_lengths(ffb200_flux_plan* p, const int* lengths_host, void* stream);
 void ffb200_flux_plan_destroy(ffb200_flux_plan* p);
 long long ffb200_flux_plan_workspace_bytes(const ffb200_flux_plan* p);
 /* prompt_embeds bf16 [B, Nt, joint_dim], pooled bf16 [B, pooled_dim]; guidance_model = float(bf16(bf16(guidance_scale) * 1000)),
