@@ -145,6 +145,46 @@ def test_qwen_adapter_inference_api():
     torch.cuda.synchronize()
     # ODE: next_latents is the un-rounded mean; its fp16 storage cast is what the rollout kept
     assert torch.equal(out.next_latents.half(), lat[:, 3])
-    bad = mask.clone(); bad[1, -2:] = 0
+    # ragged prompts (list form) are right-padded and masked; a non-prefix mask is refused
+    rag = ad.inference(height=96, width=64, num_inference_steps=2, guidance_scale=1.0, prompt_embeds=[pe[0], pe[1, :6]],
+                       prompt_embeds_mask=[mask[0], mask[1, :6]])
+    torch.cuda.synchronize()
+    assert rag[1].prompt_embeds_mask.sum() == 6 and torch.isfinite(rag[1].all_latents.float()).all()
+    bad = mask.clone(); bad[1, 2] = 0
     with pytest.raises(NotImplementedError):
         ad.inference(height=96, width=64, num_inference_steps=2, prompt_embeds=pe, prompt_embeds_mask=bad)
+
+
+def test_qwen_key_padding_mask_matches_oracle():
+    """encoder_hidden_states_mask -> joint attention mask (transformer_qwenimage.py:941-958): right-padded prompts, padded keys masked.
+    Engine vs the oracle's masked forward (itself pinned against the reference with a mask, tests/golden/qwen_tiny.pt)."""
+    cfg = QO.tiny_qwen_config(num_layers=2, heads=2, joint_dim=64)
+    w32 = QO.make_qwen_weights(cfg, seed=2)
+    wb = {k: v.bfloat16() for k, v in w32.items()}
+    wt = {k: v.float() for k, v in wb.items()}
+    B, h2, w2, nt = 3, 10, 12, 150          # text rows span three 64-wide KV tiles: partially and fully masked tiles
+    lat, pe = QO.make_qwen_inputs(cfg, B, h2, w2, nt, seed=3)
+    lat, pe = lat.half(), pe.bfloat16()
+    lens = [150, 70, 5]
+    mask = (torch.arange(nt)[None, :] < torch.tensor(lens)[:, None]).float()
+    eng = QwenRolloutEngine(cfg, wb)
+    plan = eng.plan(B, h2, w2, nt)
+    eng.set_prompts(plan, pe, prompt_lengths=lens)
+    t = 431.0
+    got = eng.transformer_forward(plan, lat, t).float().cpu()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        te = torch.full((B,), eng.t_model(t))
+        truth = QO.qwen_forward(wt, cfg, lat.float(), pe.float(), te, (1, h2, w2), encoder_hidden_states_mask=mask)
+        unmasked = QO.qwen_forward(wt, cfg, lat.float(), pe.float(), te, (1, h2, w2))
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        ref_bf16 = QO.qwen_forward(wb, cfg, lat.bfloat16(), pe, torch.full((B,), t / 1000), (1, h2, w2), encoder_hidden_states_mask=mask).float()
+    e_eng, e_ref = float((got - truth).abs().max()), float((ref_bf16 - truth).abs().max())
+    effect = float((unmasked - truth).abs().max())
+    rep = dict(tag="qwen_masked", e_engine=e_eng, e_ref_bf16=e_ref, mask_effect=effect, truth_absmax=float(truth.abs().max()))
+    dump("qwen_masked.json", rep)
+    assert effect > 10 * e_ref, rep                                      # the mask matters on this input ...
+    assert e_eng <= max(3.0 * e_ref, 0.02 * rep["truth_absmax"]), rep    # ... and the engine applies it
+    eng.set_prompts(plan, pe)                                            # resetting the lengths restores the unmasked result
+    got2 = eng.transformer_forward(plan, lat, t).float().cpu()
+    assert float((got2 - unmasked).abs().max()) <= max(3.0 * e_ref, 0.02 * rep["truth_absmax"])
