@@ -295,7 +295,27 @@ def golden_wan():
     return {"tiny": dict(t=t, y32=y32, y_bf16_cpu_autocast=yb, keys=sorted(m.state_dict().keys()), shape=(B, fr, lh, lw, nt))}
 
 
+def golden_vae():
+    """VAE decode (groundwork): the REAL AutoencoderKL.decode on a tiny decoder, through the latent rescale of
+    SD3_5Adapter.decode_latents (sd3_5.py:166-169)."""
+    from diffusers.models.autoencoders.autoencoder_kl import AutoencoderKL
+    from oracle import vae_oracle as VO
+    cfg = VO.tiny_vae_config()
+    w = VO.make_vae_decoder_weights(cfg, seed=0)
+    m = AutoencoderKL(**cfg.ref_kwargs())
+    missing, unexpected = m.load_state_dict(w, strict=False)
+    assert not unexpected and all(k.startswith("encoder.") for k in missing), (missing, unexpected)
+    m = m.eval()
+    lat = torch.randn(2, cfg.latent_channels, 6, 10, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        z = (lat / m.config.scaling_factor) + m.config.shift_factor
+        img = m.decode(z, return_dict=False)[0]
+    dec_keys = sorted(k for k in m.state_dict().keys() if k.startswith("decoder."))
+    return {"tiny": dict(lat=lat, img=img, keys=dec_keys)}
+
+
 if __name__ == "__main__":
+    torch.save(golden_vae(), os.path.join(HERE, "vae_tiny.pt"))
     torch.save(golden_wan(), os.path.join(HERE, "wan_tiny.pt"))
     torch.save(golden_qwen(), os.path.join(HERE, "qwen_tiny.pt"))
     torch.save(golden_flux(), os.path.join(HERE, "flux_tiny.pt"))
