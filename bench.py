@@ -9,6 +9,8 @@ Euler/SDE + log-prob step, synthetic inputs of the BASELINE shape, random-init w
 (no checkpoints offline).  `value` = whole-job latents/s with inputs resident in HBM, device-timed (CUDA events, max over
 ranks); `e2e` = the same metric through the public adapter API with HOST (pinned) inputs and host outputs, copies inside
 the timed region.  Working set (4.5 GB of weights + GBs of activations per step) is far larger than the 126 MB L2.
+`roofline`: the kernel with the largest time share of a step (joint attention), `roofline_gemm`: the kernel with the largest FLOP
+share (MLP-up GEMM); both timed live here, DRAM traffic from the committed ncu captures.
 """
 from __future__ import annotations
 
@@ -26,6 +28,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "rollout latents/sec SD3.5-medium 1024^2 30-step"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE attention launch, keyed by (forward batch, joint tokens, heads), from the committed
+# `ncu --set full` captures (profiles/r01_ncu_full_summaries.md)
+ATTENTION_NCU_TRAFFIC = {(4, 4429, 24): 90.3e6}
 
 
 def parse():
@@ -283,7 +288,7 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    # ---------------- roofline of the dominant kernel (tcgen05 GEMM, MLP-up shape of this batch), timed live ----------------
+    # ---------------- rooflines, timed live: the tcgen05 GEMM (MLP-up shape of this batch) and the joint attention ----------------
     peaks, peak_kind = load_peaks()
     from flow_factory_b200.ops import linear as op_linear
     Bp = B * (2 if cfg_on else 1)
@@ -307,10 +312,36 @@ def run_b200(args):
     # dram__bytes_read.sum + dram__bytes_write.sum at M=65536 N=6144 K=1536): only valid for that shape, else null.
     # Algorithmic bytes of the launch: A + W + out = 2 * (M*K + N*K + M*N).
     traffic = 1139.5e6 if (M, N, K) == (65536, 6144, 1536) else None
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel<256> (MLP up, bias+GELU epilogue)", "achieved": gemm_tf,
-                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["bf16_tflops"], "traffic": traffic,
-                "traffic_unit": "bytes/launch (ncu dram read+write)", "algorithmic_bytes_per_launch": 2.0 * (M * K + N * K + M * N),
-                "peak_source": f"{peak_kind} cuBLAS bf16 burst", "flops_per_launch": 2.0 * M * N * K, "launch_ms": gemm_ms,
+    roofline_gemm = {"bound": "tensor", "kernel": "gemm_bf16_kernel<256> (MLP up, bias+GELU epilogue)", "achieved": gemm_tf,
+                     "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["bf16_tflops"], "traffic": traffic,
+                     "traffic_unit": "bytes/launch (ncu dram read+write)", "algorithmic_bytes_per_launch": 2.0 * (M * K + N * K + M * N),
+                     "peak_source": f"{peak_kind} cuBLAS bf16 burst", "flops_per_launch": 2.0 * M * N * K, "launch_ms": gemm_ms,
+                     "time_share_of_step": "43.9 % (profiles/r01_launch_list_one_step_b8.md)"}
+    # The kernel with the largest TIME share of the step is the joint attention (51 %, profiles/r01_launch_list_one_step_b8.md): it is
+    # the `roofline` entry; the GEMM that carries most of the FLOPs is reported beside it as `roofline_gemm`.
+    from flow_factory_b200.ops import attention as op_attention
+    S_joint, Hh = ni + args.n_text, cfg.num_attention_heads
+    qkv = torch.randn(Bp, S_joint, 3 * cfg.inner_dim, device=dev).bfloat16()
+    ao = torch.empty(Bp, S_joint, cfg.inner_dim, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        op_attention(qkv, Hh, ao)
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); op_attention(qkv, Hh, ao); b_.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b_))
+    att_ms = sorted(ts)[len(ts) // 2]
+    att_fl = 4.0 * Bp * Hh * S_joint * S_joint * 64
+    att_tf = att_fl / att_ms / 1e9
+    # DRAM bytes of one launch at this shape from the committed ncu capture (profiles/r01_ncu_full_summaries.md); else null
+    att_traffic = ATTENTION_NCU_TRAFFIC.get((Bp, S_joint, Hh))
+    roofline = {"bound": "tensor", "kernel": "attention_kernel (joint image+text attention, head_dim 64)", "achieved": att_tf,
+                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": att_tf / peaks["bf16_tflops"], "traffic": att_traffic,
+                "traffic_unit": "bytes/launch (ncu dram read+write)",
+                "algorithmic_bytes_per_launch": 2.0 * Bp * S_joint * 4 * cfg.inner_dim, "peak_source": f"{peak_kind} cuBLAS bf16 burst",
+                "flops_per_launch": att_fl, "launch_ms": att_ms, "time_share_of_step": "51.2 % (profiles/r01_launch_list_one_step_b8.md)",
+                "note": "SIMT-softmax-limited at head_dim 64 (cuDNN SDPA on the same box: 0.53 of this peak), see DESIGN.md section 5",
                 "whole_step_achieved_per_gpu": step_tf / world, "whole_step_frac_of_sustained": step_tf / world / peaks["bf16_tflops_sustained"],
                 "flops_per_latent": fl_latent}
 
@@ -335,7 +366,7 @@ def run_b200(args):
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "latents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_per_rollout * args.steps),
-            "roofline": roofline, "cpu_baseline": cpu, "wall_s_timed_region": wall}
+            "roofline": roofline, "roofline_gemm": roofline_gemm, "cpu_baseline": cpu, "wall_s_timed_region": wall}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -7,8 +7,8 @@ from flow_factory_b200 import ops
 which = sys.argv[1] if len(sys.argv) > 1 else "gemm"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 torch.manual_seed(0)
-if which == "attn":
-    B, S, H = 2, 4429, 24
+if which in ("attn", "attn_b16"):
+    B, S, H = (16 if which == "attn_b16" else 2), 4429, 24
     qkv = torch.randn(B, S, 3 * 64 * H, device="cuda").bfloat16()
     out = torch.empty(B, S, 64 * H, device="cuda", dtype=torch.bfloat16)
     for _ in range(n):
