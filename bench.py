@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 METRIC = "rollout latents/sec SD3.5-medium 1024^2 30-step"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE attention launch, keyed by (forward batch, joint tokens, heads), from the committed
 # `ncu --set full` captures (profiles/r01_ncu_full_summaries.md)
-ATTENTION_NCU_TRAFFIC = {(4, 4429, 24): 90.3e6}
+ATTENTION_NCU_TRAFFIC = {(4, 4429, 24): 90.3e6, (16, 4429, 24): 854.0e6}
 
 
 def parse():
