@@ -100,3 +100,22 @@ def test_qwen_adapter_keywords_are_the_reference_abi():
                "guidance_scale", "t_next", "next_latents", "noise_level", "attention_kwargs", "compute_log_prob", "return_kwargs"]
     assert set(ref_inf) <= set(inspect.signature(B200QwenImageAdapter.inference).parameters)
     assert set(ref_fwd) <= set(inspect.signature(B200QwenImageAdapter.forward).parameters)
+
+
+def test_qwen_prompt_densify_and_mask_rules():
+    """qwen_adapter._dense: ragged lists are right-padded with their lengths, prefix masks become lengths, anything else is refused."""
+    from flow_factory_b200.qwen_adapter import _dense, _pad_to
+    a, b = torch.randn(5, 8), torch.randn(3, 8)
+    e, lens = _dense([a, b], None, "p")
+    assert tuple(e.shape) == (2, 5, 8) and lens == [5, 3] and torch.equal(e[1, :3], b) and bool((e[1, 3:] == 0).all())
+    e2, lens2 = _dense([a, b], [torch.ones(5), torch.tensor([1.0, 1.0, 0.0])], "p")
+    assert lens2 == [5, 2]
+    x = torch.randn(2, 6, 8)
+    m = torch.tensor([[1, 1, 1, 1, 1, 1], [1, 1, 1, 0, 0, 0]])
+    e3, lens3 = _dense(x, m, "p")
+    assert e3 is x and lens3 == [6, 3]
+    with pytest.raises(NotImplementedError):
+        _dense(x, torch.tensor([[1, 1, 1, 1, 1, 1], [1, 0, 1, 0, 0, 0]]), "p")
+    with pytest.raises(ValueError):
+        _dense(x, torch.tensor([[1, 1, 1, 1, 1, 1], [0, 0, 0, 0, 0, 0]]), "p")
+    assert tuple(_pad_to(x, 8).shape) == (2, 8, 8) and _pad_to(x, 6) is x
