@@ -13,6 +13,7 @@
 //     panels (leading-dimension byte offset = the panel stride).
 #include "common.cuh"
 #include "kernels.h"
+#include "softmax.cuh"
 
 namespace ffb {
 

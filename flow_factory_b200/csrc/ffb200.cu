@@ -1,6 +1,10 @@
 // Single translation unit of libffb200.so (keeps the device error word and helper templates in one module).
 #include "gemm.cu"
+#ifdef FFB_ATT_BN128
+#include "experimental/attention_bn128.cu"   // measured alternative (tools/gpu_variants.sh); not the product kernel
+#else
 #include "attention.cu"
+#endif
 #include "attention_d128.cu"
 #include "elementwise.cu"
 #include "final_step.cu"
