@@ -1,11 +1,13 @@
-// EXPERIMENT, NOT VALIDATED ON A GPU YET - compiled only with -DFFB_ATT_BN128 (see ffb200.cu); the product kernel is ../attention.cu.
+// EXPERIMENT - compiled only with -DFFB_ATT_BN128 (see ffb200.cu); the product kernel is ../attention.cu.
+// Result (r01, tools/gpu_bn128.sh): passes the attention + engine parity tests, but B=8 S=4429 H=24 takes 1.357 ms against 1.236 ms for
+// the product kernel (+10 %): losing the third softmax warp per SM sub-partition costs more than the halved skeleton saves.
 //
 // Head-dim-64 flash attention with a KV tile of 128 (one Q K^T MMA of N = 128 and one P V of K = 128 per tile) whose two 64-column
 // halves are processed back to back by the same softmax warp: the per-tile synchronisation skeleton (s_full wait, s_free / p_full
 // arrives, p_free wait, loop) is paid once per 128 columns instead of once per 64.  Price: S 128 + P 64 + O 64 TMEM columns per
 // sub-tile, i.e. only TWO 128-row sub-tiles per CTA (two softmax warps per SM sub-partition instead of three).
 // profiles/r01_attention_whatif.md (T(n) ~ 940 + 400 n cycles per 64-column tile for n softmax warps per sub-partition) says
-// this only wins if halving the skeleton outweighs losing the third warp - to be measured (tools/gpu_variants.sh).
+// this only wins if halving the skeleton outweighs losing the third warp - it does not.
 #include "../common.cuh"
 #include "../kernels.h"
 #include "../softmax.cuh"
