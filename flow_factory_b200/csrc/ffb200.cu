@@ -10,3 +10,6 @@
 #include "final_step.cu"
 #include "engine.cu"
 #include "flux_engine.cu"
+#include "vae_conv.cu"          // VAE decode: first GPU run pending, see the file headers
+#include "vae_elementwise.cu"
+#include "vae_engine.cu"

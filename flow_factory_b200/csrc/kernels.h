@@ -128,6 +128,53 @@ cudaError_t launch_rms_norm_rows(const bf16* x, const bf16* weight, bf16* out, l
 // Qwen-Image true CFG + per-token norm rescale: v bf16 [2B, Ni, 64] (negative half first) -> out bf16 [B, Ni, 64]
 cudaError_t launch_cfg_norm_rescale(const bf16* v, bf16* out, long tokens_per_half, float guidance, cudaStream_t stream);
 
+// ------------------------------------------------------------------ VAE decode: NHWC bf16 convolutions
+enum ConvEpilogue : int {
+  EPI_CONV_BIAS = 0,      // out = bf16(acc + bias)                                  NHWC
+  EPI_CONV_RESIDUAL = 1,  // out = bf16(bf16(acc + bias) + residual)                 NHWC   (ResnetBlock2D: x + h, resnet.py:375)
+  EPI_CONV_NCHW = 2,      // first n_store channels of bf16(acc + bias) as planar [B, n_store, H, W]   (conv_out -> image)
+  EPI_CONV_F32 = 3,       // out_f32 = acc * out_scale, row pitch ldo_f32                              (attention scores of the mid block)
+};
+
+// Stride-1 "same" convolution (3x3 pad 1, or 1x1 == plain GEMM over pixel rows) as an implicit GEMM on the tensor cores:
+//   out[b, h, w, n] = sum_{tap, c} x[b, h + dy(tap), w + dx(tap), c] * Wp[n, tap * kc * 64 + c]
+// The A operand of tap (dy, dx) is the SAME 4-D TMA box of x moved by (dy, dx): out-of-range pixels (the padding) and channels beyond
+// Cin are zero-filled by the TMA unit, so there is no im2col buffer and no halo logic in the kernel.
+struct ConvParams {
+  CUtensorMap tmA;  // 4-D {Cin, W, H, B} over NHWC x (pixel pitch lda), box {64, tw, th, 1}, SWIZZLE_128B
+  CUtensorMap tmB;  // 2-D {taps * kc * 64, N} packed weights [N][tap][Cin padded to 64], box {64, bn/2}
+  int B, H, W;
+  int tw_log2;      // pixel tile = th x tw with tw = 1 << tw_log2, th = 128 / tw
+  int tiles_w, tiles_h;
+  int kc, taps;     // 64-channel blocks per tap; 9 or 1
+  int N, bn, band;
+  int epi;
+  const bf16* bias;      // [N] or null
+  bf16* out; int ldo;    // NHWC (pixel pitch ldo) or planar (EPI_CONV_NCHW)
+  int n_store;           // output channels actually stored (<= N; multiple of 8 for the NHWC modes)
+  const bf16* residual; int ldr;
+  float* out_f32; long ldo_f32; float out_scale;
+};
+cudaError_t launch_conv(const ConvParams& p, int num_sms, cudaStream_t stream);
+
+// GroupNorm over NHWC bf16 [B, P pixels, C]: fp32 statistics (CUDA autocast keeps group_norm in fp32), affine, optional SiLU, bf16 out.
+// stats: double [B][C][2] (sum, sum of squares), zeroed by the caller; one pass accumulates, the apply pass finishes per group.
+struct GroupNormParams {
+  const bf16* x; bf16* out;
+  int B; long P; int C, groups;
+  float eps; int silu;
+  const bf16* gamma; const bf16* beta;
+  double* stats;
+};
+cudaError_t launch_group_norm_stats(const GroupNormParams& p, cudaStream_t stream);
+cudaError_t launch_group_norm_apply(const GroupNormParams& p, cudaStream_t stream);
+// nearest-neighbour 2x upsample, NHWC bf16 [B, H, W, C] -> [B, 2H, 2W, C]   (Upsample2D, upsampling.py)
+cudaError_t launch_upsample2x_nhwc(const bf16* x, bf16* out, int B, int H, int W, int C, cudaStream_t stream);
+// decode_latents prologue (sd3_5.py:166-167): fp16 NCHW latents -> bf16 NHWC z = bf16(bf16(bf16(x) / scaling) + shift), channels padded to Cp
+cudaError_t launch_vae_prep_latents(const __half* x, bf16* out, int B, int C, int H, int W, int Cp, float scaling, float shift, cudaStream_t stream);
+// row softmax of fp32 scores [rows][pitch] (first n columns) -> bf16 probabilities written IN PLACE at the start of each row
+cudaError_t launch_softmax_rows_inplace(float* scores, long rows, int n, long pitch, cudaStream_t stream);
+
 // ------------------------------------------------------------------ fused Euler/SDE step + log-prob (K14)
 
 struct SdeStepParams {

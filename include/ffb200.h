@@ -264,6 +264,50 @@ int ffb200_flux_forward(ffb200_flux_plan* p, const void* latents_fp16, float t_m
 int ffb200_flux_step(ffb200_flux_plan* p, const ffb200_step_args* a, void* stream);
 int ffb200_flux_rollout(ffb200_flux_plan* p, const ffb200_rollout_args* a, void* stream);
 
+/* ================================================================ VAE decode
+ * STATUS: added at the end of round 1 after the GPU budget was spent: compiles for sm_100a, host logic unit-tested on CPU, first GPU
+ * run pending (tests/test_gpu_vae.py, gated on FFB200_PENDING=1).
+ *
+ * Replaces SD3_5Adapter.decode_latents (FF/models/stable_diffusion/sd3_5.py:161-172) = AutoencoderKL.decode ->
+ * Decoder.forward (DF/models/autoencoders/vae.py:279-316) under the trainer's bf16 autocast: conv_in, UNetMidBlock2D
+ * (ResnetBlock2D, single-head attention, ResnetBlock2D), UpDecoderBlock2D x n (ResnetBlock2D x (layers_per_block + 1), nearest 2x
+ * upsample + conv), GroupNorm, SiLU, conv_out.  Activations are NHWC bf16; every convolution / linear runs on the tensor cores. */
+typedef struct ffb200_vae_config {
+  int latent_channels;        /* 16 */
+  int out_channels;           /* 3 */
+  int num_blocks;             /* len(block_out_channels), <= 8 */
+  int block_out_channels[8];  /* encoder order, e.g. 128 256 512 512 (the decoder walks it reversed); multiples of 8, the last one of 64 */
+  int layers_per_block;       /* 2 (the decoder uses layers_per_block + 1 resnets per up block) */
+  int norm_num_groups;        /* 32 */
+  float scaling_factor;       /* 1.5305 */
+  float shift_factor;         /* 0.0609 */
+} ffb200_vae_config;
+
+typedef struct ffb200_vae_decoder ffb200_vae_decoder;
+
+/* Number of weight pointers ffb200_vae_decoder_create expects for `cfg` (the order is documented in flow_factory_b200/vae.py:
+ * conv_in, mid resnet 0, mid attention, mid resnet 1, up blocks, conv_norm_out, conv_out; bf16; 3x3 kernels packed [Cout][tap][Cin
+ * padded to 64]; biases padded to a multiple of 8).  Negative on an invalid config. */
+int ffb200_vae_weight_count(const ffb200_vae_config* cfg);
+/* Builds the launch list and the workspace for decoding `batch` latents of lat_h x lat_w at a time.  Weight pointers are borrowed
+ * and must stay valid while the decoder lives. */
+int ffb200_vae_decoder_create(const ffb200_vae_config* cfg, const void* const* weights, int n_weights, int batch, int lat_h, int lat_w,
+                              ffb200_vae_decoder** out);
+void ffb200_vae_decoder_destroy(ffb200_vae_decoder* d);
+long long ffb200_vae_decoder_workspace_bytes(const ffb200_vae_decoder* d);
+/* latents: fp16 [batch, latent_channels, lat_h, lat_w] (the rollout's final latents); image: bf16 [batch, out_channels, 8 lat_h, 8 lat_w]
+ * (AutoencoderKL.decode(...)[0], before image_processor.postprocess). */
+int ffb200_vae_decode(ffb200_vae_decoder* d, const void* latents_f16, void* image_bf16, void* stream);
+
+/* Op-level entries (one per reference call site), used by the parity tests:
+ * nn.Conv2d(k=3, p=1) / nn.Conv2d(k=1) on NHWC bf16 x [B, H, W, Cin] -> out [B, H, W, Cout]; w packed as above (taps = 9) or the plain
+ * [Cout, Cin] matrix (taps = 1); residual (optional, NHWC [B, H, W, Cout]) is added after the bias with its own bf16 rounding. */
+int ffb200_conv2d_nhwc(const void* x, const void* w_packed, const void* bias, const void* residual, void* out, int B, int H, int W,
+                       int Cin, int Cout, int taps, void* stream);
+/* nn.GroupNorm(groups, C, eps, affine) (+ SiLU) on NHWC bf16 [B, P, C]; workspace: >= B * C * 16 bytes (zeroed by the call). */
+int ffb200_group_norm_nhwc(const void* x, const void* gamma, const void* beta, void* out, int B, long long P, int C, int groups,
+                           float eps, int silu, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
