@@ -92,6 +92,22 @@ class B200SD3_5Adapter:
             return None
         return self.decode_fn(latents)
 
+    def use_native_vae(self, vae_config, vae_state_dict: Dict[str, torch.Tensor], batch: int = 4) -> None:
+        """Route `decode_latents` (sd3_5.py:161-172) through the native decoder (vae.py) instead of a callback into
+        the reference's AutoencoderKL; one decoder per latent geometry, built on first use.  (First GPU run of that decoder is
+        pending - see flow_factory_b200/vae.py.)"""
+        from .vae import B200VaeDecoder, VaeDecoderConfig
+        cfg = vae_config if isinstance(vae_config, VaeDecoderConfig) else VaeDecoderConfig.from_config(vae_config)
+        cache: Dict[tuple, B200VaeDecoder] = {}
+
+        def decode(lat: torch.Tensor) -> torch.Tensor:
+            key = (int(lat.shape[2]), int(lat.shape[3]))
+            if key not in cache:
+                cache[key] = B200VaeDecoder(cfg, vae_state_dict, key[0], key[1], batch=batch, device=self.device)
+            return cache[key].decode_latents(lat, output_type="pt")
+
+        self.decode_fn = decode
+
     # -------------------------------------------------------------- the trajectory sampler
     @torch.no_grad()
     def inference(
