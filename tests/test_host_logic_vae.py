@@ -163,3 +163,83 @@ def test_decoder_needs_cuda():
         pytest.skip("CPU-only check")
     with pytest.raises(RuntimeError, match="no CPU path"):
         V.B200VaeDecoder(V.VaeDecoderConfig(), {}, 8, 8)
+
+
+# ------------------------------------------------------------------------------------------------ tile-level model of csrc/vae_conv.cu
+def _pick_tw_log2(H, W):
+    """vae_pick_tw_log2 (csrc/vae_engine.cu)."""
+    best, best_area = 7, None
+    for l in range(7, 2, -1):
+        tw, th = 1 << l, 128 >> l
+        area = -(-W // tw) * tw * (-(-H // th)) * th
+        if best_area is None or area < best_area:
+            best, best_area = l, area
+    return best
+
+
+def _tma_box(x, b, h0, w0, c0, th, tw):
+    """cp.async.bulk.tensor.4d tile mode on NHWC x: box {64, tw, th, 1} at (c0, w0, h0, b), zero fill outside the tensor; rows in
+    box order (w fastest, then h) = the rows of the 128 x 64 A tile."""
+    B, H, W, Cc = x.shape
+    box = torch.zeros(th, tw, 64)
+    if 0 <= b < B:
+        for i in range(th):
+            for j in range(tw):
+                h, w = h0 + i, w0 + j
+                if 0 <= h < H and 0 <= w < W:
+                    n = max(0, min(64, Cc - c0))
+                    box[i, j, :n] = x[b, h, w, c0:c0 + n]
+    return box.reshape(th * tw, 64)
+
+
+def _conv_tiled(x, wp, bias, cout, taps):
+    """Walks m tiles in CTA pairs exactly like conv_bf16_kernel: conv_tile_origin, the tap / channel-block K loop, pixel_of, n_store."""
+    B, H, W, cin = x.shape
+    l2 = _pick_tw_log2(H, W)
+    tw, th = 1 << l2, 128 >> l2
+    tiles_w, tiles_h = -(-W // tw), -(-H // th)
+    tiles_m = B * tiles_h * tiles_w
+    kc = -(-cin // 64)
+    N = -(-cout // 64) * 64
+    wfull = torch.zeros(N, taps * kc * 64)
+    wfull[:cout, :wp.shape[1]] = wp.float()                       # rows beyond Cout / columns beyond k_total: TMA zero fill
+    out = torch.full((B, H, W, cout), float("nan"))
+    writes = torch.zeros(B, H, W, dtype=torch.int32)
+    for mp in range((tiles_m + 1) // 2):
+        for rank in range(2):
+            tm = 2 * mp + rank
+            if tm >= tiles_m:
+                b, h0, w0 = B, 0, 0                                # ghost tile
+            else:
+                b, rem = divmod(tm, tiles_h * tiles_w)
+                ty, tx = divmod(rem, tiles_w)
+                h0, w0 = ty * th, tx * tw
+            acc = torch.zeros(128, N)
+            kb = 0
+            for tap in range(taps):
+                dy, dx = (tap // 3 - 1, tap % 3 - 1) if taps == 9 else (0, 0)
+                for kcb in range(kc):
+                    a = _tma_box(x, b, h0 + dy, w0 + dx, kcb * 64, th, tw)
+                    acc += a @ wfull[:, kb * 64:(kb + 1) * 64].t()
+                    kb += 1
+            for r in range(128):
+                h, w = h0 + (r >> l2), w0 + (r & (tw - 1))
+                if tm < tiles_m and h < H and w < W:
+                    out[b, h, w] = acc[r, :cout] + bias.float()[:cout]
+                    writes[b, h, w] += 1
+    assert int(writes.min()) == 1 and int(writes.max()) == 1       # every output pixel written exactly once
+    return out
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,taps", [(1, 5, 6, 8, 8, 9), (2, 3, 20, 16, 24, 9), (1, 1, 130, 72, 8, 1), (3, 9, 9, 8, 72, 9),
+                                                   (1, 16, 16, 8, 8, 9)])
+def test_conv_tile_walk_matches_conv2d(B, H, W, cin, cout, taps):
+    g = torch.Generator().manual_seed(B + H + W + cin + cout)
+    x = torch.randn(B, H, W, cin, generator=g).bfloat16().float()
+    k = 3 if taps == 9 else 1
+    w = (torch.randn(cout, cin, k, k, generator=g) / (k * cin ** 0.5)).bfloat16().float()
+    bias = torch.randn(cout, generator=g).bfloat16().float()
+    wp = V.pack_conv3x3(w) if taps == 9 else V.pack_conv1x1(w)
+    got = _conv_tiled(x, wp, V.pad_vec8(bias), cout, taps)
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, bias, padding=k // 2).permute(0, 2, 3, 1)
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
