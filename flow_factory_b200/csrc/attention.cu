@@ -241,6 +241,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       // O_x and l_run are both relative to the final running max m_run.
       const int q = q0 + x * ATT_BM + r;
       if (q < S) {
+        softmax_final_check(l_run);
         const float inv = 1.0f / l_run;
         bf16* dst = p.out + static_cast<long>(b) * p.out_batch_stride + static_cast<long>(q) * p.inner_dim + head * ATT_D;
 #pragma unroll

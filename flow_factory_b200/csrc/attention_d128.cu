@@ -217,6 +217,7 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
       mbar_wait(&o_full[x], 0, 0x69);
       tc_fence_after();
       const int q = q0 + x * A128_BM + r;
+      if (q < S) softmax_final_check(l_run);
       const float inv = 1.0f / l_run;
       bf16* dst = p.out + static_cast<long>(b) * p.out_batch_stride + static_cast<long>(q) * p.out_row_stride + head * A128_D;
 #pragma unroll 1

@@ -49,6 +49,41 @@ __device__ __forceinline__ bool softmax_block64(uint32_t (&s0)[32], uint32_t (&s
 #pragma unroll
     for (int c = 0; c < 32; c += 2) mxs[(c >> 1) & 7] = fmax3(mxs[(c >> 1) & 7], __uint_as_float(a[c]), __uint_as_float(a[c + 1]));
   };
+#ifdef FFB_ATT_MAXFREE
+  // EXPERIMENT (not the product build; tools/gpu_maxfree.sh): the row-max pass costs ~14 % of the kernel (profiles/
+  // r01_attention_whatif.md) and online softmax does not need the MAX as its reference, only A reference that keeps 2^((s - m) sc)
+  // inside the fp32 / bf16 exponent range (both have 8 exponent bits).  So only the first tile of a row takes its exact maximum;
+  // later tiles reuse the reference and move it by a power of two whenever the running sum - an upper bound of every P so far -
+  // has grown past 2^24.  P may exceed 1 (by at most the growth of one tile); a score more than 127 / sc above the reference within
+  // a single tile would overflow: that is detected (l_run = inf) and trapped by softmax_final_check / the next tile, never silent.
+  bool rescale;
+  alpha = 1.0f;
+  if (__any_sync(0xffffffffu, m_run == -INFINITY)) {     // first tile of the row block: exact maximum
+    max32(s0, 0); max32(s1, 32);
+    const float mt = fmax3(fmax3(mxs[0], mxs[1], mxs[2]), fmax3(mxs[3], mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7]));
+    alpha = 0.0f;
+    m_run = mt;
+    rescale = true;
+  } else {
+    if (kv_valid < 64) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        if (c >= kv_valid) s0[c] = 0xFF800000u;
+        if (32 + c >= kv_valid) s1[c] = 0xFF800000u;
+      }
+    }
+    const bool grow = !(l_run <= 16777216.0f);            // also true for inf / NaN
+    rescale = __any_sync(0xffffffffu, grow);
+    if (rescale) {
+      if (!(l_run < 3.0e38f)) mbar_timeout(0x6F);         // overflow inside one tile: fail loudly (tag 0x6F)
+      if (grow) {
+        const int e = static_cast<int>((__float_as_uint(l_run) >> 23) & 0xFF) - 127;   // floor(log2(l_run)) >= 24
+        alpha = __uint_as_float(static_cast<uint32_t>(127 - e) << 23);                 // 2^-e, exact
+        m_run += __fdividef(static_cast<float>(e), sc);                                 // reference up by e in exponent units
+      }
+    }
+  }
+#else
   max32(s0, 0); max32(s1, 32);
   const float mt = fmax3(fmax3(mxs[0], mxs[1], mxs[2]), fmax3(mxs[3], mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7]));
   // lazy rescale: adopt the new max only if some row of the warp grew by more than 2^8 (warp-uniform decision)
@@ -60,6 +95,7 @@ __device__ __forceinline__ bool softmax_block64(uint32_t (&s0)[32], uint32_t (&s
     alpha = ex2_approx((m_run - mnew) * sc);             // 0 on the first tile
     m_run = mnew;
   }
+#endif
   const uint64_t sc2 = pack_f32x2(sc, sc), mneg2 = pack_f32x2(-m_run * sc, -m_run * sc);
   uint64_t sums2[2] = {0ull, 0ull};              // 4 partial row sums as two packed pairs
   auto exp32 = [&](uint32_t(&a)[32], int quarter) {
@@ -84,6 +120,15 @@ __device__ __forceinline__ bool softmax_block64(uint32_t (&s0)[32], uint32_t (&s
   unpack_f32x2(sums2[1], sc_, sd);
   l_run = l_run * alpha + ((sa + sb) + (sc_ + sd));
   return rescale;
+}
+
+// End-of-row check of the max-free experiment (no code in the product build).
+__device__ __forceinline__ void softmax_final_check(float l_run) {
+#ifdef FFB_ATT_MAXFREE
+  if (!(l_run < 3.0e38f)) mbar_timeout(0x6F);
+#else
+  (void)l_run;
+#endif
 }
 
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
