@@ -61,8 +61,9 @@ __device__ __forceinline__ bool softmax_block64(uint32_t (&s0)[32], uint32_t (&s
   if (__any_sync(0xffffffffu, m_run == -INFINITY)) {     // first tile of the row block: exact maximum
     max32(s0, 0); max32(s1, 32);
     const float mt = fmax3(fmax3(mxs[0], mxs[1], mxs[2]), fmax3(mxs[3], mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7]));
-    alpha = 0.0f;
-    m_run = mt;
+    const float mnew = fmaxf(m_run, mt);                 // per lane: a row that already has state keeps it consistent
+    alpha = ex2_approx((m_run - mnew) * sc);             // 0 on the first tile
+    m_run = mnew;
     rescale = true;
   } else {
     if (kv_valid < 64) {
