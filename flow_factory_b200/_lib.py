@@ -101,6 +101,10 @@ EXPORTED_SYMBOLS = (
     "ffb200_flux_engine_create", "ffb200_flux_engine_set_weights", "ffb200_flux_engine_destroy", "ffb200_flux_engine_mod_rows",
     "ffb200_flux_plan_create", "ffb200_flux_plan_create_ex", "ffb200_flux_set_text_lengths", "ffb200_flux_plan_destroy", "ffb200_flux_plan_workspace_bytes", "ffb200_flux_set_prompts",
     "ffb200_flux_forward", "ffb200_flux_step", "ffb200_flux_rollout",
+    # Wan2.1 T2V: bound in flow_factory_b200/wan.py
+    "ffb200_wan_engine_create", "ffb200_wan_engine_set_weights", "ffb200_wan_engine_destroy", "ffb200_wan_plan_create",
+    "ffb200_wan_plan_destroy", "ffb200_wan_plan_workspace_bytes", "ffb200_wan_set_prompts", "ffb200_wan_forward", "ffb200_wan_step",
+    "ffb200_wan_rollout",
     # VAE decode: bound in flow_factory_b200/vae.py
     "ffb200_vae_weight_count", "ffb200_vae_decoder_create", "ffb200_vae_decoder_destroy", "ffb200_vae_decoder_workspace_bytes",
     "ffb200_vae_decode", "ffb200_conv2d_nhwc", "ffb200_group_norm_nhwc")

@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libffb200.so")
-SOURCES = ["ffb200.cu", "gemm.cu", "attention.cu", "attention_d128.cu", "elementwise.cu", "final_step.cu", "engine.cu", "flux_engine.cu", "vae_conv.cu", "vae_elementwise.cu", "vae_engine.cu", "common.cuh", "kernels.h", "softmax.cuh"]
+SOURCES = ["ffb200.cu", "gemm.cu", "attention.cu", "attention_d128.cu", "elementwise.cu", "final_step.cu", "engine.cu", "flux_engine.cu", "vae_conv.cu", "vae_elementwise.cu", "vae_engine.cu", "wan_elementwise.cu", "wan_engine.cu", "common.cuh", "kernels.h", "softmax.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 

@@ -32,6 +32,10 @@ constexpr int A128_TMEM_S = 0;        // S_x at columns x*64
 constexpr int A128_TMEM_P = 128;      // P_x at columns 128 + x*32
 constexpr int A128_TMEM_O = 256;      // O_x at columns 256 + x*128
 
+// CROSS = false: self / joint attention over one fused [B, S, 3D] buffer (the validated FLUX.1 / Qwen-Image kernel, unchanged).
+// CROSS = true : queries and keys / values come from different tensors with different lengths (Wan cross-attention to the text
+//                tokens, DF/models/transformers/transformer_wan.py:78-162 with encoder_hidden_states); first GPU run pending.
+template <bool CROSS>
 __global__ void __launch_bounds__(A128_THREADS, 1)
 attention_d128_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -58,7 +62,8 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   const int S = p.seq_len;
-  const int n_tiles = (S + A128_BN - 1) / A128_BN;
+  const int Skv = CROSS ? p.kv_len : S;
+  const int n_tiles = (Skv + A128_BN - 1) / A128_BN;
   const int n_sub = min(A128_NSUB, (S - q0 + A128_BM - 1) / A128_BM);
 
   if (warp == 8 && lane == 0) {
@@ -89,7 +94,8 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
     if (warp == 8) {
       // ===================== TMA producer =====================
       if (lane == 0) {
-        const int cq = head * A128_D, ck = p.inner_dim + head * A128_D, cv = 2 * p.inner_dim + head * A128_D;
+        const int cq = (CROSS ? p.q_col : 0) + head * A128_D, ck = (CROSS ? p.k_col : p.inner_dim) + head * A128_D,
+                  cv = (CROSS ? p.v_col : 2 * p.inner_dim) + head * A128_D;
         mbar_arrive_expect_tx(q_full, n_sub * 2 * A128_QPANEL);
         for (int x = 0; x < n_sub; ++x)
           for (int h = 0; h < 2; ++h)
@@ -192,7 +198,7 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
         }
         uint32_t pk[32];
         float alpha;
-        const bool rescale = softmax_block64(s0, s1, S - j * A128_BN, sc, m_run, l_run, pk, alpha);
+        const bool rescale = softmax_block64(s0, s1, Skv - j * A128_BN, sc, m_run, l_run, pk, alpha);
         if (j > 0) {
           mbar_wait(&p_free[x], (j - 1) & 1, 0x61);
           tc_fence_after();
@@ -251,12 +257,25 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
 cudaError_t launch_attention_d128(const AttnParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_d128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A128_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_d128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A128_SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   dim3 grid((p.seq_len + A128_QB - 1) / A128_QB, p.num_heads, p.batch);
-  attention_d128_kernel<<<grid, A128_THREADS, A128_SMEM, stream>>>(p);
+  attention_d128_kernel<false><<<grid, A128_THREADS, A128_SMEM, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_attention_d128_cross(const AttnParams& p, cudaStream_t stream) {
+  if (p.kv_len <= 0 || p.kv_mask_lo != nullptr) return cudaErrorInvalidValue;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_d128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A128_SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((p.seq_len + A128_QB - 1) / A128_QB, p.num_heads, p.batch);
+  attention_d128_kernel<true><<<grid, A128_THREADS, A128_SMEM, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -13,3 +13,5 @@
 #include "vae_conv.cu"          // VAE decode: first GPU run pending, see the file headers
 #include "vae_elementwise.cu"
 #include "vae_engine.cu"
+#include "wan_elementwise.cu"   // Wan2.1 T2V: first GPU run pending, see the file headers
+#include "wan_engine.cu"

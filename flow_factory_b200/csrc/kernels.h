@@ -65,9 +65,13 @@ struct AttnParams {
   // of the text rows of a joint [text ; image] sequence (Qwen-Image attention_mask, transformer_qwenimage.py:952-958); null = none
   const int* kv_mask_lo;
   int kv_mask_hi;
+  // cross-attention (head_dim 128 kernel, launch_attention_d128_cross only): tmQKV addresses the query tensor [B, seq_len, >= D]
+  // (head h at column q_col + 128 h), tmKV the key / value tensor [B, kv_len, ...] (columns k_col + 128 h / v_col + 128 h)
+  int kv_len, q_col, k_col, v_col;
 };
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);        // head_dim 64  (SD3.x)
 cudaError_t launch_attention_d128(const AttnParams& p, cudaStream_t stream);   // head_dim 128 (FLUX.1)
+cudaError_t launch_attention_d128_cross(const AttnParams& p, cudaStream_t stream);   // head_dim 128, separate q / kv tensors and lengths (Wan)
 
 // ------------------------------------------------------------------ per-step scalars
 enum Dynamics : int { DYN_FLOW_SDE = 0, DYN_DANCE_SDE = 1, DYN_CPS = 2, DYN_ODE = 3 };
@@ -174,6 +178,24 @@ cudaError_t launch_upsample2x_nhwc(const bf16* x, bf16* out, int B, int H, int W
 cudaError_t launch_vae_prep_latents(const __half* x, bf16* out, int B, int C, int H, int W, int Cp, float scaling, float shift, cudaStream_t stream);
 // row softmax of fp32 scores [rows][pitch] (first n columns) -> bf16 probabilities written IN PLACE at the start of each row
 cudaError_t launch_softmax_rows_inplace(float* scores, long rows, int n, long pitch, cudaStream_t stream);
+
+// ------------------------------------------------------------------ Wan2.1 T2V: elementwise pieces (wan_elementwise.cu)
+cudaError_t launch_wan_patchify(const __half* x, int B, int reps, int C, int F, int H, int W, int pt, int ph, int pw, bf16* out, cudaStream_t stream);
+cudaError_t launch_wan_mod_vectors(const bf16* const* tables, const bf16* temb6, float* mod, int L, int Bp, int n6, cudaStream_t stream);
+cudaError_t launch_wan_final_mod(const bf16* table, const bf16* temb, bf16* out, int Bp, int D, cudaStream_t stream);
+struct WanLnParams {
+  const bf16* x; bf16* out;          // [num_batch * rows_per_batch, D], dense
+  int rows_per_batch, num_batch, D;
+  float eps;
+  int mode;                          // 0: fp32 (1 + scale[b]) / shift[b] modulation   1: affine weight / bias (bf16 [D])
+  const float* scale; const float* shift; long mod_batch_stride;
+  const bf16* weight; const bf16* bias;
+};
+cudaError_t launch_wan_ln(const WanLnParams& p, cudaStream_t stream);
+cudaError_t launch_wan_gate_residual(bf16* h, const bf16* y, const float* gate, long gate_batch_stride, int num_batch, long rows_per_batch,
+                                     int D, cudaStream_t stream);
+cudaError_t launch_wan_rms_rope(bf16* x, long rows, int rows_per_batch, int ld, int D, const bf16* weight, float eps, const float* cos_t,
+                                const float* sin_t, cudaStream_t stream);
 
 // ------------------------------------------------------------------ fused Euler/SDE step + log-prob (K14)
 

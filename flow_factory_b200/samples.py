@@ -85,3 +85,10 @@ class QwenImageSample(SD3_5Sample):
     prompt_embeds_mask: Optional[torch.Tensor] = None
     negative_prompt_embeds_mask: Optional[torch.Tensor] = None
     img_shapes: Optional[List] = None
+
+
+@dataclass
+class WanT2VSample(SD3_5Sample):
+    """Mirror of FF/models/wan/wan2_t2v.py:47-50 (T2VSample, no shared fields): `video` instead of `image`;
+    all_latents rows are (T', C, F, H, W)."""
+    video: Optional[torch.Tensor] = None

@@ -277,3 +277,39 @@ def set_scheduler_timesteps(scheduler: FlowMatchEulerDiscreteSDEScheduler, num_i
                             seq_len: Optional[int] = None, sigmas=None, device=None, mu: Optional[float] = None):
     """FF/scheduler/flow_match_euler_discrete.py:49-77."""
     return scheduler.set_timesteps(num_inference_steps, seq_len=seq_len, device=device, sigmas=sigmas, mu=mu)
+
+
+class UniPCMultistepSDEScheduler(FlowMatchEulerDiscreteSDEScheduler):
+    """Host mirror of FF/scheduler/unipc_multistep.py (Wan2.x): the rollout uses the SAME Euler / SDE step arithmetic as
+    FlowMatchEulerDiscreteSDEScheduler.step (unipc_multistep.py:290-421); only the schedule differs - diffusers'
+    UniPCMultistepScheduler.set_timesteps with `use_flow_sigmas` (DF/schedulers/scheduling_unipc_multistep.py:428-466): INTEGER
+    timesteps (`sigmas * 1000` truncated to int64) next to fp32 sigmas, so the step's sigma = int_timestep / 1000 differs from
+    `sigmas[i]` while `sigma_max` stays `sigmas[1]`."""
+
+    def __init__(self, noise_level: float = 0.7, sde_steps=None, num_sde_steps=None, seed: int = 42, dynamics_type: str = "Flow-SDE",
+                 num_train_timesteps: int = 1000, flow_shift: float = 3.0, **kwargs):
+        kwargs.pop("shift", None)
+        if kwargs.get("use_dynamic_shifting") or kwargs.get("shift_terminal"):
+            raise NotImplementedError("UniPC mirror: only the static flow_shift schedule of the Wan configs is implemented")
+        super().__init__(noise_level=noise_level, sde_steps=sde_steps, num_sde_steps=num_sde_steps, seed=seed, dynamics_type=dynamics_type,
+                         num_train_timesteps=num_train_timesteps, shift=flow_shift, **kwargs)
+        self.config["flow_shift"] = flow_shift
+        self.order = 1
+
+    def set_timesteps(self, num_inference_steps: int, seq_len=None, device=None, sigmas=None, mu=None) -> torch.Tensor:
+        n = self.config["num_train_timesteps"]
+        sig = np.linspace(1, 1 / n, num_inference_steps + 1)[:-1] if sigmas is None else np.array(sigmas, dtype=np.float64)
+        shift = self.config["flow_shift"]
+        sig = shift * sig / (1 + (shift - 1) * sig)
+        if np.fabs(sig[0] - 1) < 1e-6:
+            sig[0] -= 1e-6
+        timesteps = (sig * n).copy()
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [0]]).astype(np.float32))
+        self.timesteps = torch.from_numpy(timesteps).to(dtype=torch.int64)
+        self.num_inference_steps = len(timesteps)
+        return self.timesteps
+
+    def get_noise_levels(self) -> torch.Tensor:
+        nl = torch.zeros(len(self.timesteps), dtype=torch.float32)
+        nl[self.current_sde_steps] = self.noise_level
+        return nl

@@ -264,6 +264,71 @@ int ffb200_flux_forward(ffb200_flux_plan* p, const void* latents_fp16, float t_m
 int ffb200_flux_step(ffb200_flux_plan* p, const ffb200_step_args* a, void* stream);
 int ffb200_flux_rollout(ffb200_flux_plan* p, const ffb200_rollout_args* a, void* stream);
 
+/* ================================================================ Wan2.1 T2V (SURVEY.md section 8f row 4 / BASELINE config 4)
+ * STATUS: added at the end of round 1 after the GPU budget was spent: compiles for sm_100a, host logic unit-tested on CPU, first GPU
+ * run pending (tests/test_gpu_wan.py, gated on FFB200_PENDING=1).
+ *
+ * WanTransformer3DModel.forward (DF/models/transformers/transformer_wan.py:629-740; blocks 462-505, attention processor 78-162, rotary
+ * embedding 354-417, condition embedder 330-351) behind Wan2_T2V_Adapter.forward / .inference (FF/models/wan/wan2_t2v.py:235-543):
+ * true CFG as a batch of 2B (negative prompts first), u + g (c - u) in bf16, then the Euler / SDE step of UniPCMultistepSDEScheduler
+ * (FF/scheduler/unipc_multistep.py:290-421 - the same arithmetic as FlowMatchEulerDiscreteSDEScheduler.step).
+ * Latents fp16 [B, 16, F, H, W]; patch (1, 2, 2); head_dim 128; T2V only (no image conditioning, one scalar timestep per sample). */
+typedef struct ffb200_wan_config {
+  int num_layers;     /* 30 (1.3 B) / 40 (14 B) */
+  int num_heads;      /* inner_dim D = 128 * num_heads: 12 / 40 */
+  int in_channels;    /* 16 (== out_channels) */
+  int text_dim;       /* 4096 */
+  int freq_dim;       /* 256 */
+  int ffn_dim;        /* 8960 / 13824 */
+  int patch_t, patch_h, patch_w; /* 1, 2, 2 (patch_t must be 1) */
+  float eps;          /* 1e-6 */
+} ffb200_wan_config;
+
+/* bf16, nn.Linear layout [out, in]; q|k|v (attn1) and k|v (attn2) concatenated along out_features by the host packer */
+typedef struct ffb200_wan_layer_weights {
+  const void *table;                                  /* scale_shift_table [6, D] (module dtype)            */
+  const void *qkv_w, *qkv_b, *norm_q, *norm_k;        /* attn1.to_{q,k,v}, attn1.norm_{q,k} [D]             */
+  const void *out_w, *out_b;                          /* attn1.to_out.0                                     */
+  const void *norm2_w, *norm2_b;                      /* norm2 (FP32LayerNorm, elementwise_affine) [D]      */
+  const void *q2_w, *q2_b, *kv2_w, *kv2_b;            /* attn2.to_q ; attn2.to_{k,v} [2D, D]                */
+  const void *norm_q2, *norm_k2;                      /* attn2.norm_{q,k} [D]                               */
+  const void *out2_w, *out2_b;                        /* attn2.to_out.0                                     */
+  const void *ff1_w, *ff1_b, *ff2_w, *ff2_b;          /* ffn.net.0.proj [ffn, D], ffn.net.2 [D, ffn]        */
+} ffb200_wan_layer_weights;
+typedef struct ffb200_wan_weights {
+  const void *pe_w, *pe_b;                 /* patch_embedding as [D, C*pt*ph*pw]                                  */
+  const void *t1_w, *t1_b, *t2_w, *t2_b;   /* condition_embedder.time_embedder.linear_{1,2}                       */
+  const void *tp_w, *tp_b;                 /* condition_embedder.time_proj [6D, D]                                */
+  const void *x1_w, *x1_b, *x2_w, *x2_b;   /* condition_embedder.text_embedder.linear_{1,2}                       */
+  const void *table;                       /* scale_shift_table [2, D]                                            */
+  const void *proj_w, *proj_b;             /* proj_out [C*pt*ph*pw, D]                                            */
+  const ffb200_wan_layer_weights* layers;  /* [num_layers]                                                        */
+} ffb200_wan_weights;
+
+typedef struct ffb200_wan_engine ffb200_wan_engine;
+typedef struct ffb200_wan_plan ffb200_wan_plan;
+
+int ffb200_wan_engine_create(const ffb200_wan_config* cfg, const ffb200_wan_weights* w, ffb200_wan_engine** out);
+int ffb200_wan_engine_set_weights(ffb200_wan_engine* e, const ffb200_wan_weights* w);
+void ffb200_wan_engine_destroy(ffb200_wan_engine* e);
+/* Geometry: batch, cfg (1 = forward batch 2B), latent frames / height / width, text tokens; rope_cos / rope_sin: fp32 [S, 128] with
+ * S = (F/pt)(H/ph)(W/pw), the values WanRotaryPosEmbed returns AFTER the cast to the module dtype (its buffers follow `.to(bf16)`) -
+ * host or device memory, copied. */
+int ffb200_wan_plan_create(ffb200_wan_engine* e, int batch, int cfg, int frames, int height, int width, int n_text, const float* rope_cos,
+                           const float* rope_sin, ffb200_wan_plan** out);
+void ffb200_wan_plan_destroy(ffb200_wan_plan* p);
+long long ffb200_wan_plan_workspace_bytes(const ffb200_wan_plan* p);
+/* prompt_embeds bf16 [Bp, Nt, text_dim] (Bp = 2B with cfg: negative prompts first): text embedder + the cross-attention keys / values
+ * of every block, cached for the whole rollout (they do not depend on the timestep). */
+int ffb200_wan_set_prompts(ffb200_wan_plan* p, const void* prompt_embeds_bf16, void* stream);
+/* WanTransformer3DModel.forward + CFG combine: latents fp16 [B, C, F, H, W] -> noise prediction bf16 [B, C, F, H, W].
+ * t_model = the fp32 timestep on the 0..1000 scale (wan2_t2v.py:499-506). */
+int ffb200_wan_forward(ffb200_wan_plan* p, const void* latents_fp16, float t_model, float guidance_scale, void* noise_pred_bf16, void* stream);
+/* Wan2_T2V_Adapter.forward under no_grad / the denoise loop of .inference: same argument blocks as ffb200_step / ffb200_rollout with
+ * [C, H, W] := [C, F*H, W]. */
+int ffb200_wan_step(ffb200_wan_plan* p, const ffb200_step_args* a, void* stream);
+int ffb200_wan_rollout(ffb200_wan_plan* p, const ffb200_rollout_args* a, void* stream);
+
 /* ================================================================ VAE decode
  * STATUS: added at the end of round 1 after the GPU budget was spent: compiles for sm_100a, host logic unit-tested on CPU, first GPU
  * run pending (tests/test_gpu_vae.py, gated on FFB200_PENDING=1).

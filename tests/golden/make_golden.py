@@ -314,7 +314,41 @@ def golden_vae():
     return {"tiny": dict(lat=lat, img=img, keys=dec_keys)}
 
 
+def golden_wan_schedule():
+    """UniPCMultistepSDEScheduler (FF/scheduler/unipc_multistep.py; diffusers use_flow_sigmas branch): integer timesteps, fp32 sigmas, SDE
+    step selection, and scheduler.step through the `timestep_next` path Wan2_T2V_Adapter uses (sigma = int timestep / 1000)."""
+    from flow_factory.scheduler import UniPCMultistepSDEScheduler
+    out = {}
+    for T, shift in ((10, 3.0), (50, 3.0), (20, 5.0)):
+        s = UniPCMultistepSDEScheduler(noise_level=0.7, num_sde_steps=2, seed=5, dynamics_type="Flow-SDE", prediction_type="flow_prediction",
+                                       use_flow_sigmas=True, flow_shift=shift, num_train_timesteps=1000)
+        s.set_timesteps(T, device="cpu")
+        out[f"T{T}_s{shift}"] = dict(timesteps=s.timesteps.clone(), sigmas=s.sigmas.clone(), sde=s.current_sde_steps.clone(),
+                                      noise_levels=s.get_noise_levels().clone())
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 16, 2, 4, 4, generator=g).half()
+    v = torch.randn(2, 16, 2, 4, 4, generator=g).bfloat16()
+    out["x"], out["v"] = x, v
+    for dyn in ("Flow-SDE", "Dance-SDE", "CPS", "ODE"):
+        s = UniPCMultistepSDEScheduler(noise_level=0.7, dynamics_type=dyn, prediction_type="flow_prediction", use_flow_sigmas=True,
+                                       flow_shift=3.0, num_train_timesteps=1000)
+        s.set_timesteps(10, device="cpu")
+        s.rollout()
+        for i in (0, 4, 9):
+            t = s.timesteps[i]
+            tn = s.timesteps[i + 1] if i + 1 < len(s.timesteps) else torch.tensor(0)
+            torch.manual_seed(100 + i)
+            o = s.step(noise_pred=v, timestep=t, latents=x, timestep_next=tn, noise_level=0.7, compute_log_prob=True, return_dict=True)
+            torch.manual_seed(100 + i)
+            noise = torch.randn(v.shape, dtype=torch.float32)
+            out[f"{dyn}_{i}"] = dict(t=t.clone(), tn=tn.clone(), next_latents=o.next_latents.clone(), mean=o.next_latents_mean.clone(),
+                                     log_prob=None if o.log_prob is None else o.log_prob.clone(), std_dev_t=o.std_dev_t.clone(),
+                                     dt=o.dt.clone(), noise=noise, sigma_max=float(s.sigmas[1]))
+    return out
+
+
 if __name__ == "__main__":
+    torch.save(golden_wan_schedule(), os.path.join(HERE, "wan_schedule.pt"))
     torch.save(golden_vae(), os.path.join(HERE, "vae_tiny.pt"))
     torch.save(golden_wan(), os.path.join(HERE, "wan_tiny.pt"))
     torch.save(golden_qwen(), os.path.join(HERE, "qwen_tiny.pt"))
