@@ -10,3 +10,4 @@ import ctypes as C
 buf = (C.c_uint * 4)()
 print("device error word:", _lib.lib().ffb200_device_error(C.byref(buf)), [hex(x) for x in buf])
 PY
+timeout 1500 python tools/wan_bench.py --steps 1 --warmup 1 --num-inference-steps 10 2>&1 | tail -3 | tee gpurun_out/wan_bench_10step.json
