@@ -57,3 +57,56 @@ def all_gather_rollout(all_latents: Optional[torch.Tensor], log_probs: Optional[
     out = torch.empty((world * buf.shape[0], buf.shape[1]), dtype=torch.uint8, device=buf.device)
     dist.all_gather_into_tensor(out, buf, group=group)
     return unpack_rollout(out, meta)
+
+
+# ------------------------------------------------------------------------------------------------ FSDP2-sharded weight intake
+def _local_shard(t: torch.Tensor):
+    """(local dim-0 shard, full shape) of a parameter: a DTensor sharded Shard(0) by FSDP2's fully_shard, or a plain (replicated) tensor."""
+    try:
+        from torch.distributed.tensor import DTensor, Shard
+    except Exception:                      # pragma: no cover - torch without DTensor
+        DTensor = None
+    if DTensor is not None and isinstance(t, DTensor):
+        if len(t.placements) != 1 or not isinstance(t.placements[0], Shard) or t.placements[0].dim != 0:
+            raise NotImplementedError(f"only 1-D meshes with Shard(0) placements (FSDP2 fully_shard) are handled, got {t.placements}")
+        return t.to_local(), tuple(t.shape)
+    return None, tuple(t.shape)
+
+
+def gather_sharded_state_dict(state_dict, group=None, dtype: Optional[torch.dtype] = torch.bfloat16):
+    """FSDP2 (`fully_shard`) keeps every parameter as a DTensor sharded along dim 0 (rank r owns rows [r c, (r+1) c), c = ceil(n / W),
+    the tail padded / empty - SURVEY.md section 8(e), BASELINE config 5).  The rollout engine wants replicated weights, and the path
+    wants ONE collective per rollout, not one per block: all local shards are packed into a single flat buffer, gathered with one
+    all_gather_into_tensor, and unpacked into full tensors (cast to `dtype` BEFORE the gather, so the payload is the bf16 model:
+    40 GB for Qwen-Image 20 B = ~50 ms over NVLink 5).  Plain tensors in the dict are passed through (already replicated)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("gather_sharded_state_dict needs an initialised process group")
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    plan, parts = [], []
+    out = {}
+    for name, t in state_dict.items():
+        local, full = _local_shard(t)
+        if local is None:
+            out[name] = t if dtype is None or not t.is_floating_point() else t.to(dtype)
+            continue
+        n0 = full[0]
+        chunk = -(-n0 // world)                                    # ceil: FSDP2's padded shard size along dim 0
+        rest = 1
+        for d in full[1:]:
+            rest *= d
+        buf = torch.zeros(chunk * rest, dtype=dtype or local.dtype, device=local.device)
+        buf[: local.numel()] = local.reshape(-1).to(buf.dtype)     # ranks past the tail hold fewer (or zero) rows
+        plan.append((name, full, chunk, rest))
+        parts.append(buf)
+    if not parts:
+        return out
+    flat = torch.cat(parts)
+    gathered = torch.empty(world * flat.numel(), dtype=flat.dtype, device=flat.device)
+    dist.all_gather_into_tensor(gathered, flat, group=group)       # the one collective
+    gathered = gathered.view(world, flat.numel())
+    off = 0
+    for name, full, chunk, rest in plan:
+        sz = chunk * rest
+        out[name] = gathered[:, off: off + sz].reshape(world * chunk, *full[1:])[: full[0]].contiguous()
+        off += sz
+    return out

@@ -204,3 +204,45 @@ def test_merge_lora_state_dict_matches_explicit_lora_forward():
     torch.testing.assert_close(torch.nn.functional.linear(x, m["blk.to_q.weight"], m["blk.to_q.bias"]), ref, rtol=1e-5, atol=1e-5)
     with pytest.raises(ValueError):
         merge_lora_state_dict({"a.lora_A.default.weight": A, "a.weight": W}, 8.0)
+
+
+def _fsdp_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from torch.distributed.device_mesh import init_device_mesh
+    from torch.distributed.tensor import Shard, distribute_tensor
+    from flow_factory_b200 import dist as D
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        mesh = init_device_mesh("cpu", (world,))
+        g = torch.Generator().manual_seed(0)
+        full = {"a.weight": torch.randn(7, 5, generator=g), "b.bias": torch.randn(3, generator=g), "c.weight": torch.randn(8, 2, 3, generator=g),
+                "d.weight": torch.randn(1, 4, generator=g)}                     # 7 and 3 rows: padded tails; 1 row: rank 1 holds nothing
+        sharded = {k: distribute_tensor(v, mesh, [Shard(0)]) for k, v in full.items()}
+        sharded["plain"] = torch.arange(4.0)                                    # replicated entries pass through
+        calls = []
+        orig = dist.all_gather_into_tensor
+        dist.all_gather_into_tensor = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+        out = D.gather_sharded_state_dict(sharded, dtype=torch.bfloat16)
+        dist.all_gather_into_tensor = orig
+        ok = len(calls) == 1 and set(out) == set(sharded)
+        for k, v in full.items():
+            ok &= out[k].dtype == torch.bfloat16 and torch.equal(out[k], v.bfloat16())
+        ok &= torch.equal(out["plain"], torch.arange(4.0).bfloat16())
+        out32 = D.gather_sharded_state_dict({"a.weight": sharded["a.weight"]}, dtype=None)
+        ok &= torch.equal(out32["a.weight"], full["a.weight"])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fsdp2_sharded_weight_intake_one_allgather_world2_gloo():
+    """SURVEY 8(e) / BASELINE config 5: DTensor Shard(0) parameters (what FSDP2's fully_shard holds) -> replicated bf16 tensors with ONE
+    collective, including padded and empty tail shards."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_fsdp_worker, args=(r, 2, 29613, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    [p.join(timeout=60) for p in ps]
+    assert res == [(0, True), (1, True)]
