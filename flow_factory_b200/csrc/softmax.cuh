@@ -29,7 +29,10 @@ __device__ __forceinline__ void exp2_poly_pair(uint64_t x2, float& e0, float& e1
   e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
 }
 constexpr int ATT_POLY_PERIOD = 8;   // of every ATT_POLY_PERIOD element pairs ...
-constexpr int ATT_POLY_NUM = 3;      // ... this many go through exp2_poly_pair, the rest through MUFU.EX2
+#ifndef FFB_ATT_POLY_NUM
+#define FFB_ATT_POLY_NUM 3           // product value; -DFFB_ATT_POLY_NUM=n only for the A/B builds of tools/gpu_maxfree.sh
+#endif
+constexpr int ATT_POLY_NUM = FFB_ATT_POLY_NUM;   // ... this many go through exp2_poly_pair, the rest through MUFU.EX2
 
 // Online-softmax step of one thread (= one query row) over a 128 x 64 block of scores held in registers (s0: columns 0-31,
 // s1: 32-63).  Updates the running max / sum, returns P as 32 packed bf16 pairs, the factor `alpha` by which the accumulator has
