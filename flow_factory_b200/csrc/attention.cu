@@ -141,6 +141,11 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         __syncwarp();
       };
       mbar_wait(q_full, 0, 0x52);
+#ifdef FFB_ATT_STAGGER
+      // EXPERIMENT (tools/gpu_maxfree.sh): start sub-tile x a fraction of a tile late, to test whether the three identical softmax
+      // groups of an SM sub-partition run in lockstep (synchronised stalls) - costs x * FFB_ATT_STAGGER cycles once per CTA.
+      if (x > 0) { const long long t0 = clock64(); while (clock64() - t0 < static_cast<long long>(x) * FFB_ATT_STAGGER) {} }
+#endif
       issue_qk(0);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % ATT_STAGES;
