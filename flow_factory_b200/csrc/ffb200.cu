@@ -1,7 +1,9 @@
 // Single translation unit of libffb200.so (keeps the device error word and helper templates in one module).
 #include "gemm.cu"
-#ifdef FFB_ATT_BN128
+#if defined(FFB_ATT_BN128)
 #include "experimental/attention_bn128.cu"   // measured alternative (tools/gpu_variants.sh); not the product kernel
+#elif defined(FFB_ATT_SUMMMA)
+#include "experimental/attention_summma.cu"  // row sum on the tensor core (tools/gpu_maxfree.sh); not the product kernel, not yet run
 #else
 #include "attention.cu"
 #endif

@@ -37,6 +37,9 @@ constexpr int ATT_POLY_NUM = FFB_ATT_POLY_NUM;   // ... this many go through exp
 // Online-softmax step of one thread (= one query row) over a 128 x 64 block of scores held in registers (s0: columns 0-31,
 // s1: 32-63).  Updates the running max / sum, returns P as 32 packed bf16 pairs, the factor `alpha` by which the accumulator has
 // to be scaled if the (warp-uniform) return value is true.  Shared by the d = 64 and d = 128 kernels.
+// kSum = false (experimental/attention_summma.cu only): the row sum is NOT accumulated here - the tensor core produces it as an extra
+// accumulator column (V extended by a panel of ones) - and l_run is left untouched.
+template <bool kSum = true>
 __device__ __forceinline__ bool softmax_block64(uint32_t (&s0)[32], uint32_t (&s1)[32], int kv_valid, float sc, float& m_run,
                                                 float& l_run, uint32_t (&pk)[32], float& alpha) {
   // row max of this tile: 8 independent chains (a single serial fmax chain is 128 x 4 cycles of pure latency)
@@ -114,15 +117,17 @@ __device__ __forceinline__ bool softmax_block64(uint32_t (&s0)[32], uint32_t (&s
         unpack_f32x2(x2, t0, t1);
         e0 = ex2_approx(t0); e1 = ex2_approx(t1);
       }
-      sums2[c & 1] = fadd2(sums2[c & 1], pack_f32x2(e0, e1));
+      if (kSum) sums2[c & 1] = fadd2(sums2[c & 1], pack_f32x2(e0, e1));
       pk[quarter * 16 + c] = pack_bf16x2(e0, e1);
     }
   };
   exp32(s0, 0); exp32(s1, 1);
-  float sa, sb, sc_, sd;
-  unpack_f32x2(sums2[0], sa, sb);
-  unpack_f32x2(sums2[1], sc_, sd);
-  l_run = l_run * alpha + ((sa + sb) + (sc_ + sd));
+  if (kSum) {
+    float sa, sb, sc_, sd;
+    unpack_f32x2(sums2[0], sa, sb);
+    unpack_f32x2(sums2[1], sc_, sd);
+    l_run = l_run * alpha + ((sa + sb) + (sc_ + sd));
+  }
   return rescale;
 }
 

@@ -1,16 +1,34 @@
 #!/bin/bash
-# A/B of the max-free online softmax experiment (softmax.cuh, -DFFB_ATT_MAXFREE) against the product kernels.
-# Build first (CPU):  for n in 2 3 4; do nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC \
-#                          -DFFB_ATT_MAXFREE -DFFB_ATT_POLY_NUM=$n -o flow_factory_b200/libffb200_exp_maxfree_p$n.so flow_factory_b200/csrc/ffb200.cu; done
-#                     cp flow_factory_b200/libffb200_exp_maxfree_p3.so flow_factory_b200/libffb200_exp_maxfree.so
-#                     nvcc ... -DFFB_ATT_STAGGER=700 -o flow_factory_b200/libffb200_exp_stagger700.so ...   (lockstep test, product softmax)
-#                     (with the row-max pass gone the ALU pipe has room: the best polynomial share of exp2 may move from 3 of 8)
-# Run:                /usr/local/graft/bin/gpurun --timeout 900 -- bash tools/gpu_maxfree.sh
-# Parity (attention, SD3.5 / FLUX / Qwen engines) with the experimental library, then isolated attention timings of both, then a bench.
-mkdir -p gpurun_out; : > gpurun_out/variants.log
-export V=$PWD/flow_factory_b200/libffb200_exp_maxfree.so
-FFB200_LIB=$V timeout 600 python -m pytest tests/test_gpu_attention.py tests/test_gpu_engine.py tests/test_gpu_flux_engine.py tests/test_gpu_qwen_engine.py \
-  -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/test_maxfree.log 2>&1; echo "maxfree tests exit $?"; tail -n 6 gpurun_out/test_maxfree.log
-for l in flow_factory_b200/libffb200.so flow_factory_b200/libffb200_exp_maxfree*.so flow_factory_b200/libffb200_exp_stagger*.so; do FFB200_LIB=$PWD/$l timeout 120 python tools/attn_variants.py >> gpurun_out/variants.log 2>&1; done
+# A/B of the attention experiments against the product kernels (none of them has run on a GPU yet):
+#   maxfree_p{2,3,4} : -DFFB_ATT_MAXFREE [-DFFB_ATT_POLY_NUM=n]  max-free online softmax (softmax.cuh), polynomial share n of 8
+#   summma           : -DFFB_ATT_SUMMMA       row sum on the tensor core, P aliased on S (experimental/attention_summma.cu)
+#   summma_nowait    : ... -DFFB_ATT_SUMMMA_NOWAIT  same, Q K^T (j+1) issued right behind P V (j)
+#   stagger700       : -DFFB_ATT_STAGGER=700  product kernel, sub-tiles started 700 / 1400 cycles late (lockstep test)
+# Build first (CPU), e.g.:
+#   B="nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC"; S=flow_factory_b200/csrc/ffb200.cu; O=flow_factory_b200/libffb200_exp
+#   for n in 2 3 4; do $B -DFFB_ATT_MAXFREE -DFFB_ATT_POLY_NUM=$n -o ${O}_maxfree_p$n.so $S; done
+#   $B -DFFB_ATT_SUMMMA -o ${O}_summma.so $S; $B -DFFB_ATT_SUMMMA -DFFB_ATT_SUMMMA_NOWAIT -o ${O}_summma_nowait.so $S; $B -DFFB_ATT_STAGGER=700 -o ${O}_stagger700.so $S
+# Run:  /usr/local/graft/bin/gpurun --timeout 1500 -- bash tools/gpu_maxfree.sh
+# Per variant: parity (attention + SD3.5 engine; the softmax.cuh variants also FLUX / Qwen), then isolated attention timing; then one bench
+# with the fastest passing variant is left to the caller (FFB200_LIB=... python bench.py --skip-cpu-baseline).
+mkdir -p gpurun_out; : > gpurun_out/variants.log; : > gpurun_out/variants_tests.log
+for V in flow_factory_b200/libffb200_exp_*.so; do
+  [ -f "$V" ] || continue
+  case "$V" in *bn128*) continue;; esac
+  T="tests/test_gpu_attention.py tests/test_gpu_engine.py"
+  case "$V" in *maxfree*) T="$T tests/test_gpu_flux_engine.py tests/test_gpu_qwen_engine.py";; esac
+  K=""; case "$V" in *summma*|*stagger*) K='-k not d128';; esac
+  FFB200_LIB=$PWD/$V timeout 600 python -m pytest $T -m gpu -q --tb=line -p no:cacheprovider ${K:+"$K"} > gpurun_out/test_$(basename $V .so).log 2>&1
+  echo "$(basename $V) tests exit $? : $(tail -n 1 gpurun_out/test_$(basename $V .so).log)" | tee -a gpurun_out/variants_tests.log
+done
+for l in flow_factory_b200/libffb200.so flow_factory_b200/libffb200_exp_*.so; do
+  case "$l" in *bn128*) continue;; esac
+  FFB200_LIB=$PWD/$l timeout 120 python tools/attn_variants.py >> gpurun_out/variants.log 2>&1
+done
 cat gpurun_out/variants.log
-FFB200_LIB=$V timeout 600 python bench.py --steps 2 --warmup 3 --skip-cpu-baseline > gpurun_out/bench_maxfree.json 2> gpurun_out/bench_maxfree.err; tail -c 600 gpurun_out/bench_maxfree.json
+python - <<'PY' 2>&1 | tee gpurun_out/variants_deverr.log
+from flow_factory_b200 import _lib
+import ctypes as C
+buf = (C.c_uint * 4)()
+print("device error word:", _lib.lib().ffb200_device_error(C.byref(buf)), [hex(x) for x in buf])
+PY
