@@ -13,9 +13,9 @@
 #include "../kernels.h"
 #include "../softmax.cuh"
 
-#ifdef FFB_ATT_MAXFREE
-#error "FFB_ATT_SUMMMA keeps no running sum in registers: the max-free reference shift (which triggers on it) cannot be combined yet"
-#endif
+// Combined with -DFFB_ATT_MAXFREE (softmax.cuh) the reference shift needs the running sum as its magnitude signal: the softmax warps
+// then read accumulator column 64 back once per tile, right after the wait that guarantees P V (j-1) has retired, and use it - two tiles
+// late - for the decision of tile j+1 (threshold 2^24 against an fp32 / bf16 range of 2^127: the lag is harmless, an overflow still traps).
 
 namespace ffb {
 
@@ -27,6 +27,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -227,6 +230,14 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         if (j > 0) {                                   // P V of tile j-1 retired (issued a whole softmax ago): P_x free, O_x quiescent
           mbar_wait(&p_free[x], (j - 1) & 1, 0x61);
           tc_fence_after();
+#ifdef FFB_ATT_MAXFREE
+          if (!rescale) {                              // running sum through tile j-1 (same reference as this tile: no shift pending)
+            uint32_t lr;
+            tmem_ld1(tOx + 64, lr);
+            tmem_ld_wait();
+            l_run = __uint_as_float(lr);
+          }
+#endif
         }
         if (j > 0 && rescale) {                          // rare: O_x *= alpha in TMEM
           uint32_t o0[32], o1[32];
@@ -246,6 +257,9 @@ attention_kernel(const __grid_constant__ AttnParams p) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) o2[i] = __float_as_uint(__uint_as_float(o2[i]) * alpha);
           tmem_st16(tOx + 64, o2);
+#ifdef FFB_ATT_MAXFREE
+          l_run = __uint_as_float(o2[0]);              // the rescaled running sum through tile j-1
+#endif
         }
         prof_lap(&lap, 0x65);                          // wait p_free, rare O rescale
         tmem_st32(tPx, pk);                            // P_x(j): 64 bf16 per row = 32 columns

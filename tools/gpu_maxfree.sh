@@ -3,11 +3,13 @@
 #   maxfree_p{2,3,4} : -DFFB_ATT_MAXFREE [-DFFB_ATT_POLY_NUM=n]  max-free online softmax (softmax.cuh), polynomial share n of 8
 #   summma           : -DFFB_ATT_SUMMMA       row sum on the tensor core, P aliased on S (experimental/attention_summma.cu)
 #   summma_nowait    : ... -DFFB_ATT_SUMMMA_NOWAIT  same, Q K^T (j+1) issued right behind P V (j)
+#   summma_maxfree[_nowait] : both (-DFFB_ATT_SUMMMA -DFFB_ATT_MAXFREE): the reference shift triggers on the row sum read back from TMEM
 #   stagger700       : -DFFB_ATT_STAGGER=700  product kernel, sub-tiles started 700 / 1400 cycles late (lockstep test)
 # Build first (CPU), e.g.:
 #   B="nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC"; S=flow_factory_b200/csrc/ffb200.cu; O=flow_factory_b200/libffb200_exp
 #   for n in 2 3 4; do $B -DFFB_ATT_MAXFREE -DFFB_ATT_POLY_NUM=$n -o ${O}_maxfree_p$n.so $S; done
 #   $B -DFFB_ATT_SUMMMA -o ${O}_summma.so $S; $B -DFFB_ATT_SUMMMA -DFFB_ATT_SUMMMA_NOWAIT -o ${O}_summma_nowait.so $S; $B -DFFB_ATT_STAGGER=700 -o ${O}_stagger700.so $S
+#   $B -DFFB_ATT_SUMMMA -DFFB_ATT_MAXFREE -o ${O}_summma_maxfree.so $S; $B -DFFB_ATT_SUMMMA -DFFB_ATT_MAXFREE -DFFB_ATT_SUMMMA_NOWAIT -o ${O}_summma_maxfree_nowait.so $S
 # Run:  /usr/local/graft/bin/gpurun --timeout 1500 -- bash tools/gpu_maxfree.sh
 # Per variant: parity (attention + SD3.5 engine; the softmax.cuh variants also FLUX / Qwen), then isolated attention timing; then one bench
 # with the fastest passing variant is left to the caller (FFB200_LIB=... python bench.py --skip-cpu-baseline).
@@ -16,7 +18,7 @@ for V in flow_factory_b200/libffb200_exp_*.so; do
   [ -f "$V" ] || continue
   case "$V" in *bn128*) continue;; esac
   T="tests/test_gpu_attention.py tests/test_gpu_engine.py"
-  case "$V" in *maxfree*) T="$T tests/test_gpu_flux_engine.py tests/test_gpu_qwen_engine.py";; esac
+  case "$V" in *maxfree_p*) T="$T tests/test_gpu_flux_engine.py tests/test_gpu_qwen_engine.py";; esac
   K=""; case "$V" in *summma*|*stagger*) K='-k not d128';; esac
   FFB200_LIB=$PWD/$V timeout 600 python -m pytest $T -m gpu -q --tb=line -p no:cacheprovider ${K:+"$K"} > gpurun_out/test_$(basename $V .so).log 2>&1
   echo "$(basename $V) tests exit $? : $(tail -n 1 gpurun_out/test_$(basename $V .so).log)" | tee -a gpurun_out/variants_tests.log
