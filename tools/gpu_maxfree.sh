@@ -5,7 +5,7 @@
 #   summma_nowait    : ... -DFFB_ATT_SUMMMA_NOWAIT  same, Q K^T (j+1) issued right behind P V (j)
 #   summma_maxfree[_nowait] : both (-DFFB_ATT_SUMMMA -DFFB_ATT_MAXFREE): the reference shift triggers on the row sum read back from TMEM
 #   stagger700       : -DFFB_ATT_STAGGER=700  product kernel, sub-tiles started 700 / 1400 cycles late (lockstep test)
-# Build first (CPU), e.g.:
+# Build first (CPU): bash tools/build_variants.sh   - i.e.:
 #   B="nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC"; S=flow_factory_b200/csrc/ffb200.cu; O=flow_factory_b200/libffb200_exp
 #   for n in 2 3 4; do $B -DFFB_ATT_MAXFREE -DFFB_ATT_POLY_NUM=$n -o ${O}_maxfree_p$n.so $S; done
 #   $B -DFFB_ATT_SUMMMA -o ${O}_summma.so $S; $B -DFFB_ATT_SUMMMA -DFFB_ATT_SUMMMA_NOWAIT -o ${O}_summma_nowait.so $S; $B -DFFB_ATT_STAGGER=700 -o ${O}_stagger700.so $S
