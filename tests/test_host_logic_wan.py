@@ -169,3 +169,83 @@ def test_config_guards_and_engine_needs_cuda():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             W.WanRolloutEngine(W.WanEngineConfig(), {})
+
+
+# ------------------------------------------------------------------------------------------------ adapter bookkeeping with a stub engine
+class _StubPlan:
+    def __init__(self, batch, frames, height, width, n_text, cfg):
+        self.batch, self.frames, self.height, self.width, self.n_text, self.cfg = batch, frames, height, width, n_text, cfg
+        self.latent_shape = (batch, 16, frames, height, width)
+
+
+class _StubEngine:
+    """Stands in for WanRolloutEngine (which needs a B200): records the calls, returns tensors of the contract's shapes."""
+
+    def __init__(self, model_config, state_dict, device):
+        self.device, self.cfg, self.calls = torch.device("cpu"), model_config, []
+
+    def plan(self, batch, frames, height, width, n_text, cfg=True):
+        return _StubPlan(batch, frames, height, width, n_text, cfg)
+
+    def set_prompts(self, plan, pe, neg=None):
+        self.calls.append(("set_prompts", tuple(pe.shape), None if neg is None else tuple(neg.shape)))
+
+    def rollout(self, plan, x0, coefs, guidance, n_lat, store_initial, n_lp, noise=None, seed=0, use_graph=True):
+        self.calls.append(("rollout", len(coefs), guidance, n_lat, store_initial, n_lp, None if noise is None else tuple(noise.shape)))
+        self.coefs = coefs
+        B = plan.batch
+        return dict(all_latents=torch.zeros(B, max(n_lat, 1), *plan.latent_shape[1:], dtype=torch.float16) if n_lat else None,
+                    log_probs=torch.zeros(B, max(n_lp, 1)) if n_lp else None, final_latents=torch.zeros(plan.latent_shape, dtype=torch.float16),
+                    overflow=torch.zeros(1, dtype=torch.int32))
+
+    def step(self, plan, latents, coef, guidance, noise=None, next_latents=None, seed=0):
+        self.calls.append(("step", coef.sigma, coef.sigma_prev, guidance))
+        z = torch.zeros(plan.latent_shape)
+        return dict(next_latents=z.half(), next_latents_mean=z, log_prob=torch.zeros(plan.batch), noise_pred=z.bfloat16(), overflow=torch.zeros(1))
+
+
+def test_adapter_bookkeeping_with_stub_engine(monkeypatch):
+    from flow_factory_b200 import wan_adapter as WA
+    from flow_factory_b200.trajectory import compute_trajectory_indices
+    monkeypatch.setattr(WA, "WanRolloutEngine", _StubEngine)
+    sch = UniPCMultistepSDEScheduler(noise_level=0.7, flow_shift=3.0, num_sde_steps=2, seed=5)
+    ad = WA.B200Wan21Adapter(W.WanEngineConfig(), {}, device="cpu", scheduler=sch, rng="torch")
+    ad.rollout()
+    assert ad.latent_shape(2, 480, 832, 81) == (2, 16, 21, 60, 104)
+    T = 10
+    sch.set_timesteps(T)
+    idx = compute_trajectory_indices(sch.train_timesteps, T)
+    pe, neg = torch.zeros(2, 12, 4096), torch.zeros(2, 12, 4096)
+    out = ad.inference(prompt=["a", "b"], height=64, width=96, num_frames=9, num_inference_steps=T, guidance_scale=5.0, prompt_embeds=pe,
+                       negative_prompt_embeds=neg, compute_log_prob=True, trajectory_indices=idx)
+    eng = ad.engine
+    assert eng.calls[0] == ("set_prompts", (2, 12, 4096), (2, 12, 4096))
+    kind, n_coef, g, n_lat, store0, n_lp, nshape = eng.calls[1]
+    assert (kind, n_coef, g) == ("rollout", T, 5.0) and nshape == (T, 2, 16, 3, 8, 12)
+    sde = sorted(sch.current_sde_steps.tolist())
+    assert n_lp == len(sde) == 2
+    # per-step scalars: integer timesteps feed the model, sigma = t / 1000, noise only on the selected SDE steps
+    ts = sch.timesteps
+    for i, c in enumerate(eng.coefs):
+        assert c.t_model == float(ts[i]) and c.sigma == pytest.approx(float(ts[i]) / 1000, rel=1e-7)
+        assert (c.noise_level > 0) == (i in sde) and bool(c.compute_log_prob) == (i in sde)
+        assert (c.logp_slot >= 0) == (i in sde)
+    assert len(out) == 2 and out[0].timesteps.dtype == torch.int64 and out[0].prompt == "a" and out[1].prompt == "b"
+    assert out[0].log_probs.shape == (n_lp,) and out[0].all_latents.shape == (n_lat, 16, 3, 8, 12)
+    lm, pm = out[0].latent_index_map, out[0].log_prob_index_map
+    assert lm.shape == (T + 1,) and int((lm >= 0).sum()) == n_lat and int((pm >= 0).sum()) == n_lp
+    # no CFG when the scale is <= 1 or there is no negative prompt (wan2_t2v.py:487-495)
+    eng.calls.clear()
+    ad.inference(height=64, width=96, num_frames=9, num_inference_steps=4, guidance_scale=1.0, prompt_embeds=pe, negative_prompt_embeds=neg)
+    assert eng.calls[0][2] is None and eng.calls[1][2] == 1.0
+    # forward(): one step on the integer timesteps
+    eng.calls.clear()
+    sch.set_timesteps(T)
+    o = ad.forward(t=sch.timesteps[3], latents=torch.zeros(2, 16, 3, 8, 12), prompt_embeds=pe, negative_prompt_embeds=neg, guidance_scale=5.0,
+                   noise_level=0.7, compute_log_prob=True)
+    st = [c for c in eng.calls if c[0] == "step"][0]
+    assert st[1] == pytest.approx(float(sch.timesteps[3]) / 1000) and st[2] == pytest.approx(float(sch.timesteps[4]) / 1000) and st[3] == 5.0
+    assert o.std_dev_t.shape == (2, 1, 1, 1, 1) and o.next_latents.dtype == torch.float32
+    for bad in (dict(guidance_scale_2=3.0), dict(attention_kwargs={"a": 1}), dict(extra_call_back_kwargs=["noise_pred"])):
+        with pytest.raises(NotImplementedError):
+            ad.inference(height=64, width=96, num_frames=9, num_inference_steps=4, prompt_embeds=pe, **bad)
