@@ -12,32 +12,13 @@
 #include "../common.cuh"
 #include "../kernels.h"
 #include "../softmax.cuh"
+#include "tmem_narrow.cuh"
 
 // Combined with -DFFB_ATT_MAXFREE (softmax.cuh) the reference shift needs the running sum as its magnitude signal: the softmax warps
 // then read accumulator column 64 back once per tile, right after the wait that guarantees P V (j-1) has retired, and use it - two tiles
 // late - for the decision of tile j+1 (threshold 2^24 against an fp32 / bf16 range of 2^127: the lag is harmless, an overflow still traps).
 
 namespace ffb {
-
-// 32 lanes x 16 consecutive fp32 columns (the row-sum block behind the 64 output columns)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
 
 constexpr int ATT_BM = 128;     // query rows per sub-tile
 constexpr int ATT_NSUB = 3;     // sub-tiles per CTA

@@ -7,7 +7,11 @@
 #else
 #include "attention.cu"
 #endif
+#if defined(FFB_ATT_SUMMMA)
+#include "experimental/attention_d128_summma.cu"   // not the product kernel, not yet run
+#else
 #include "attention_d128.cu"
+#endif
 #include "elementwise.cu"
 #include "final_step.cu"
 #include "engine.cu"

@@ -1,7 +1,8 @@
 #!/bin/bash
 # A/B of the attention experiments against the product kernels (none of them has run on a GPU yet):
 #   maxfree_p{2,3,4} : -DFFB_ATT_MAXFREE [-DFFB_ATT_POLY_NUM=n]  max-free online softmax (softmax.cuh), polynomial share n of 8
-#   summma           : -DFFB_ATT_SUMMMA       row sum on the tensor core, P aliased on S (experimental/attention_summma.cu)
+#   summma           : -DFFB_ATT_SUMMMA       row sum on the tensor core: head_dim 64 with P aliased on S (experimental/attention_summma.cu),
+#                                              head_dim 128 without aliasing (experimental/attention_d128_summma.cu)
 #   summma_nowait    : ... -DFFB_ATT_SUMMMA_NOWAIT  same, Q K^T (j+1) issued right behind P V (j)
 #   summma_maxfree[_nowait] : both (-DFFB_ATT_SUMMMA -DFFB_ATT_MAXFREE): the reference shift triggers on the row sum read back from TMEM
 #   stagger700       : -DFFB_ATT_STAGGER=700  product kernel, sub-tiles started 700 / 1400 cycles late (lockstep test)
@@ -16,11 +17,13 @@
 mkdir -p gpurun_out; : > gpurun_out/variants.log; : > gpurun_out/variants_tests.log
 for V in flow_factory_b200/libffb200_exp_*.so; do
   [ -f "$V" ] || continue
-  case "$V" in *bn128*) continue;; esac
   T="tests/test_gpu_attention.py tests/test_gpu_engine.py"
-  case "$V" in *maxfree_p*) T="$T tests/test_gpu_flux_engine.py tests/test_gpu_qwen_engine.py";; esac
-  K=""; case "$V" in *summma*|*stagger*) K='-k not d128';; esac
-  FFB200_LIB=$PWD/$V timeout 600 python -m pytest $T -m gpu -q --tb=line -p no:cacheprovider ${K:+"$K"} > gpurun_out/test_$(basename $V .so).log 2>&1
+  case "$V" in
+    *bn128*|*maxfree_p2*|*maxfree_p4*) continue;;                                   # p2 / p4 differ from p3 by one constant: timing only
+    *maxfree_p3*|*summma_maxfree.so) T="$T tests/test_gpu_flux_engine.py tests/test_gpu_qwen_engine.py";;   # softmax.cuh / d128 changes reach FLUX + Qwen
+    *stagger*) T="tests/test_gpu_attention.py";;
+  esac
+  FFB200_LIB=$PWD/$V timeout 600 python -m pytest $T -m gpu -q --tb=line -p no:cacheprovider > gpurun_out/test_$(basename $V .so).log 2>&1
   echo "$(basename $V) tests exit $? : $(tail -n 1 gpurun_out/test_$(basename $V .so).log)" | tee -a gpurun_out/variants_tests.log
 done
 for l in flow_factory_b200/libffb200.so flow_factory_b200/libffb200_exp_*.so; do
