@@ -1,18 +1,47 @@
-"""Times ffb200_attention (B=8 S=4429 H=24) for the library named by FFB200_LIB.  Developer experiment aid."""
+"""Times the attention entry points for the library named by FFB200_LIB: head_dim 64 at the SD3.5 bench shape (B=8 S=4429 H=24) and head_dim
+128 at the FLUX.1 shape (B=2 S=4608 H=24); L2 flushed between launches, median of 7.  Also reports the max relative error against torch
+SDPA on a strongly trending score pattern that forces the max-free variants through their reference shifts.  Developer experiment aid."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+import torch.nn.functional as F
 from flow_factory_b200 import ops
+
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-B, S, H = 8, 4429, 24
-torch.manual_seed(0)
-qkv = torch.randn(B, S, 3 * 64 * H, device="cuda").bfloat16()
-out = torch.empty(B, S, 64 * H, device="cuda", dtype=torch.bfloat16)
-ts = []
-for i in range(9):
-    flush.zero_()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); ops.attention(qkv, H, out); b.record(); torch.cuda.synchronize()
-    if i >= 2: ts.append(a.elapsed_time(b))
-ts.sort()
-print(json.dumps({"lib": os.path.basename(os.environ.get("FFB200_LIB", "libffb200.so")), "ms": ts[len(ts) // 2]}))
+
+
+def timed(B, S, H, d):
+    torch.manual_seed(0)
+    qkv = torch.randn(B, S, 3 * d * H, device="cuda").bfloat16()
+    out = torch.empty(B, S, d * H, device="cuda", dtype=torch.bfloat16)
+    ts = []
+    for i in range(9):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); ops.attention(qkv, H, out, head_dim=d); b.record(); torch.cuda.synchronize()
+        if i >= 2:
+            ts.append(a.elapsed_time(b))
+    ts.sort()
+    ms = ts[len(ts) // 2]
+    return ms, 4.0 * B * H * S * S * d / (ms * 1e-3) / 1e12
+
+
+def trend_error(d):
+    """keys whose scores rise steadily along the sequence: later tiles exceed the first tile's maximum by ~2^40"""
+    B, S, H = 1, 1536, 2
+    g = torch.Generator(device="cuda").manual_seed(1)
+    q = torch.randn(B, S, H, d, generator=g, device="cuda")
+    k = torch.randn(B, S, H, d, generator=g, device="cuda")
+    q[..., 0] = 8.0
+    k[..., 0] = torch.linspace(0, 4.0 * d ** 0.5, S, device="cuda")[None, :, None]      # adds up to ~32 nats along the sequence
+    v = torch.randn(B, S, H, d, generator=g, device="cuda")
+    qkv = torch.cat([q.reshape(B, S, H * d), k.reshape(B, S, H * d), v.reshape(B, S, H * d)], -1).bfloat16().contiguous()
+    out = ops.attention(qkv, H, head_dim=d)
+    qb, kb, vb = (t.reshape(B, S, H, d).transpose(1, 2).float() for t in qkv.split(H * d, dim=-1))
+    ref = F.scaled_dot_product_attention(qb, kb, vb).transpose(1, 2).reshape(B, S, H * d)
+    return float((out.float() - ref).norm() / ref.norm())
+
+
+r64, r128 = timed(8, 4429, 24, 64), timed(2, 4608, 24, 128)
+print(json.dumps({"lib": os.path.basename(os.environ.get("FFB200_LIB", "libffb200.so")), "ms": r64[0], "tflops": r64[1],
+                  "d128_ms": r128[0], "d128_tflops": r128[1], "trend_rel_err_d64": trend_error(64), "trend_rel_err_d128": trend_error(128)}))
