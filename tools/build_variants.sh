@@ -13,6 +13,7 @@ echo "-DFFB_ATT_SUMMMA|summma"
 echo "-DFFB_ATT_SUMMMA -DFFB_ATT_SUMMMA_NOWAIT|summma_nowait"
 echo "-DFFB_ATT_SUMMMA -DFFB_ATT_MAXFREE|summma_maxfree"
 echo "-DFFB_ATT_SUMMMA -DFFB_ATT_MAXFREE -DFFB_ATT_SUMMMA_NOWAIT|summma_maxfree_nowait"
+for n in 1 2; do echo "-DFFB_ATT_SUMMMA -DFFB_ATT_MAXFREE -DFFB_ATT_POLY_NUM=$n|summma_maxfree_p$n"; done   # less FMA-pipe work left: the best polynomial share moves down
 echo "-DFFB_ATT_STAGGER=700|stagger700"
 ) | xargs -P 4 -I{} bash -c 'IFS="|" read -r flags name <<< "{}"; '"$B"' $flags -o '"$O"'_$name.so '"$S"' && echo built $name'
 ls -la flow_factory_b200/libffb200_exp_*.so

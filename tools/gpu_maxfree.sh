@@ -19,7 +19,7 @@ for V in flow_factory_b200/libffb200_exp_*.so; do
   [ -f "$V" ] || continue
   T="tests/test_gpu_attention.py tests/test_gpu_engine.py"
   case "$V" in
-    *bn128*|*maxfree_p2*|*maxfree_p4*) continue;;                                   # p2 / p4 differ from p3 by one constant: timing only
+    *bn128*|*maxfree_p1*|*maxfree_p2*|*maxfree_p4*) continue;;                                   # p2 / p4 differ from p3 by one constant: timing only
     *maxfree_p3*|*summma_maxfree.so) T="$T tests/test_gpu_flux_engine.py tests/test_gpu_qwen_engine.py";;   # softmax.cuh / d128 changes reach FLUX + Qwen
     *stagger*) T="tests/test_gpu_attention.py";;
   esac
