@@ -16,7 +16,7 @@ from typing import Any, Dict, List, Mapping, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from .scheduler import UniPCMultistepSDEScheduler, make_step_coef
+from .scheduler import UniPCMultistepSDEScheduler
 
 vp, ci, cf = C.c_void_p, C.c_int, C.c_float
 
