@@ -7,7 +7,9 @@
 #else
 #include "attention.cu"
 #endif
-#if defined(FFB_ATT_SUMMMA)
+#if defined(FFB_ATT_SPLIT)
+#include "experimental/attention_d128_split.cu"    // column-split softmax on top of the two experiments below; not yet run
+#elif defined(FFB_ATT_SUMMMA)
 #include "experimental/attention_d128_summma.cu"   // not the product kernel, not yet run
 #else
 #include "attention_d128.cu"

@@ -6,6 +6,8 @@
 #   summma_nowait    : ... -DFFB_ATT_SUMMMA_NOWAIT  same, Q K^T (j+1) issued right behind P V (j)
 #   summma_maxfree[_nowait] : both (-DFFB_ATT_SUMMMA -DFFB_ATT_MAXFREE): the reference shift triggers on the row sum read back from TMEM
 #   stagger700       : -DFFB_ATT_STAGGER=700  product kernel, sub-tiles started 700 / 1400 cycles late (lockstep test)
+#   split128[_p2]    : -DFFB_ATT_SPLIT        head_dim 128 only (experimental/attention_d128_split.cu): score columns split between two warps per
+#                                              row, 16 softmax warps; max-free reference + tensor-core row sum built in
 # Build first (CPU): bash tools/build_variants.sh   - i.e.:
 #   B="nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC"; S=flow_factory_b200/csrc/ffb200.cu; O=flow_factory_b200/libffb200_exp
 #   for n in 2 3 4; do $B -DFFB_ATT_MAXFREE -DFFB_ATT_POLY_NUM=$n -o ${O}_maxfree_p$n.so $S; done
@@ -22,6 +24,8 @@ for V in flow_factory_b200/libffb200_exp_*.so; do
     *bn128*|*maxfree_p1*|*maxfree_p2*|*maxfree_p4*) continue;;                                   # p2 / p4 differ from p3 by one constant: timing only
     *maxfree_p3*|*summma_maxfree.so) T="$T tests/test_gpu_flux_engine.py tests/test_gpu_qwen_engine.py";;   # softmax.cuh / d128 changes reach FLUX + Qwen
     *stagger*) T="tests/test_gpu_attention.py";;
+    *split128_p2*) continue;;
+    *split128*) T="tests/test_gpu_attention.py tests/test_gpu_flux_engine.py tests/test_gpu_qwen_engine.py";;
   esac
   FFB200_LIB=$PWD/$V timeout 600 python -m pytest $T -m gpu -q --tb=line -p no:cacheprovider > gpurun_out/test_$(basename $V .so).log 2>&1
   echo "$(basename $V) tests exit $? : $(tail -n 1 gpurun_out/test_$(basename $V .so).log)" | tee -a gpurun_out/variants_tests.log
