@@ -311,7 +311,13 @@ def golden_vae():
         z = (lat / m.config.scaling_factor) + m.config.shift_factor
         img = m.decode(z, return_dict=False)[0]
     dec_keys = sorted(k for k in m.state_dict().keys() if k.startswith("decoder."))
-    return {"tiny": dict(lat=lat, img=img, keys=dec_keys)}
+    mb = AutoencoderKL(**cfg.ref_kwargs())
+    mb.load_state_dict(w, strict=False)
+    mb = mb.eval().to(torch.bfloat16)                       # the trainer's frozen-VAE dtype under mixed_precision bf16 (FF/models/abc.py:826-853)
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        lb = lat.to(torch.bfloat16)
+        img_bf16 = mb.decode((lb / mb.config.scaling_factor) + mb.config.shift_factor, return_dict=False)[0]
+    return {"tiny": dict(lat=lat, img=img, keys=dec_keys, img_bf16=img_bf16)}
 
 
 def golden_wan_schedule():
