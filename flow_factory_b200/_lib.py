@@ -104,7 +104,8 @@ EXPORTED_SYMBOLS = (
     # Wan2.1 T2V: bound in flow_factory_b200/wan.py
     "ffb200_wan_engine_create", "ffb200_wan_engine_set_weights", "ffb200_wan_engine_destroy", "ffb200_wan_plan_create",
     "ffb200_wan_plan_destroy", "ffb200_wan_plan_workspace_bytes", "ffb200_wan_set_prompts", "ffb200_wan_forward", "ffb200_wan_step",
-    "ffb200_wan_rollout",
+    "ffb200_wan_rollout", "ffb200_wan_rms_rope", "ffb200_wan_layer_norm", "ffb200_wan_gate_residual", "ffb200_wan_patchify",
+    "ffb200_attention_cross",
     # VAE decode: bound in flow_factory_b200/vae.py
     "ffb200_vae_weight_count", "ffb200_vae_decoder_create", "ffb200_vae_decoder_destroy", "ffb200_vae_decoder_workspace_bytes",
     "ffb200_vae_decode", "ffb200_conv2d_nhwc", "ffb200_group_norm_nhwc")

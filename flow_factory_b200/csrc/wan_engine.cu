@@ -455,4 +455,61 @@ int ffb200_wan_rollout(ffb200_wan_plan* p, const ffb200_rollout_args* a, void* s
   return 0;
 }
 
+// ---------------------------------------------------------------- op-level entries (parity tests)
+int ffb200_wan_rms_rope(void* x_bf16, long long rows, int rows_per_batch, int ld, int D, const void* weight_bf16, float eps,
+                        const float* cos, const float* sin, void* stream) {
+  FFB_CHECK(x_bf16 && weight_bf16 && rows > 0 && rows_per_batch > 0, "wan_rms_rope: bad argument");
+  FFB_CHECK((cos == nullptr) == (sin == nullptr), "wan_rms_rope: cos and sin come together");
+  g_launch_count = 1;
+  FFB_CUDA(launch_wan_rms_rope(static_cast<bf16*>(x_bf16), static_cast<long>(rows), rows_per_batch, ld, D, static_cast<const bf16*>(weight_bf16),
+                               eps, cos, sin, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int ffb200_wan_layer_norm(const void* x_bf16, void* out_bf16, int num_batch, int rows_per_batch, int D, float eps, int mode,
+                          const float* scale, const float* shift, long long mod_batch_stride, const void* weight_bf16,
+                          const void* bias_bf16, void* stream) {
+  FFB_CHECK(x_bf16 && out_bf16, "wan_layer_norm: null argument");
+  FFB_CHECK(mode == 0 ? (scale && shift) : (mode == 1 && weight_bf16 && bias_bf16), "wan_layer_norm: mode 0 needs scale / shift, mode 1 weight / bias");
+  WanLnParams lp{};
+  lp.x = static_cast<const bf16*>(x_bf16); lp.out = static_cast<bf16*>(out_bf16); lp.rows_per_batch = rows_per_batch; lp.num_batch = num_batch;
+  lp.D = D; lp.eps = eps; lp.mode = mode; lp.scale = scale; lp.shift = shift; lp.mod_batch_stride = static_cast<long>(mod_batch_stride);
+  lp.weight = static_cast<const bf16*>(weight_bf16); lp.bias = static_cast<const bf16*>(bias_bf16);
+  g_launch_count = 1;
+  FFB_CUDA(launch_wan_ln(lp, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int ffb200_wan_gate_residual(void* h_bf16, const void* y_bf16, const float* gate, long long gate_batch_stride, int num_batch,
+                             long long rows_per_batch, int D, void* stream) {
+  FFB_CHECK(h_bf16 && y_bf16 && gate, "wan_gate_residual: null argument");
+  g_launch_count = 1;
+  FFB_CUDA(launch_wan_gate_residual(static_cast<bf16*>(h_bf16), static_cast<const bf16*>(y_bf16), gate, static_cast<long>(gate_batch_stride),
+                                    num_batch, static_cast<long>(rows_per_batch), D, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int ffb200_wan_patchify(const void* x_f16, int B, int reps, int C, int F, int H, int W, int pt, int ph, int pw, void* out_bf16, void* stream) {
+  FFB_CHECK(x_f16 && out_bf16 && reps >= 1, "wan_patchify: bad argument");
+  g_launch_count = 1;
+  FFB_CUDA(launch_wan_patchify(static_cast<const __half*>(x_f16), B, reps, C, F, H, W, pt, ph, pw, static_cast<bf16*>(out_bf16),
+                               static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int ffb200_attention_cross(const void* q_bf16, int q_ld, const void* kv_bf16, int kv_ld, int v_col, int B, int Sq, int Skv, int num_heads,
+                           void* out_bf16, void* stream) {
+  FFB_CHECK(q_bf16 && kv_bf16 && out_bf16 && B > 0 && Sq > 0 && Skv > 0 && num_heads > 0, "attention_cross: bad argument");
+  FFB_CHECK(q_ld % 8 == 0 && kv_ld % 8 == 0 && v_col % 8 == 0, "attention_cross: pitches / column offsets must be multiples of 8");
+  ffb200_wan_plan geo{};                       // only the geometry fields wbuild_attn reads
+  geo.S = Sq; geo.Bp = B; geo.D = num_heads * 128;
+  AttnParams ap;
+  int r = wbuild_attn(&geo, static_cast<const bf16*>(q_bf16), q_ld, static_cast<const bf16*>(kv_bf16), kv_ld, Skv, static_cast<bf16*>(out_bf16), &ap);
+  if (r) return r;
+  ap.v_col = v_col;
+  g_launch_count = 1;
+  FFB_CUDA(launch_attention_d128_cross(ap, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 }  // extern "C"

@@ -116,6 +116,12 @@ def _L() -> C.CDLL:
         L.ffb200_wan_forward.argtypes = [vp, vp, cf, cf, vp, vp]
         L.ffb200_wan_step.argtypes = [vp, C.POINTER(_lib.StepArgs), vp]
         L.ffb200_wan_rollout.argtypes = [vp, C.POINTER(_lib.RolloutArgs), vp]
+        cll = C.c_longlong
+        L.ffb200_wan_rms_rope.argtypes = [vp, cll, ci, ci, ci, vp, cf, vp, vp, vp]
+        L.ffb200_wan_layer_norm.argtypes = [vp, vp, ci, ci, ci, cf, ci, vp, vp, cll, vp, vp, vp]
+        L.ffb200_wan_gate_residual.argtypes = [vp, vp, vp, cll, ci, cll, ci, vp]
+        L.ffb200_wan_patchify.argtypes = [vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, vp]
+        L.ffb200_attention_cross.argtypes = [vp, ci, vp, ci, ci, ci, ci, ci, ci, vp, vp]
         _bound = True
     return L
 
@@ -365,3 +371,61 @@ class WanRolloutEngine:
                 self.handle = None
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------------------------- op-level wrappers (parity tests)
+def _st(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def rms_rope_(x: torch.Tensor, width: int, weight: torch.Tensor, eps: float = 1e-6, cos: Optional[torch.Tensor] = None,
+              sin: Optional[torch.Tensor] = None, col: int = 0) -> torch.Tensor:
+    """In place on columns [col, col + width) of a bf16 [B, S, ld] tensor: RMSNorm across the width (+ RoPE with fp32 [S, 128] tables)."""
+    B, S, ld = x.shape
+    w = weight.to(device=x.device, dtype=torch.bfloat16).contiguous()
+    _lib.check(_L().ffb200_wan_rms_rope(x.data_ptr() + 2 * col, B * S, S, ld, width, w.data_ptr(), eps,
+                                        cos.data_ptr() if cos is not None else None, sin.data_ptr() if sin is not None else None, _st(x)),
+               "ffb200_wan_rms_rope")
+    return x
+
+
+def layer_norm(x: torch.Tensor, eps: float = 1e-6, scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
+               weight: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x bf16 [B, S, D]; (scale, shift) fp32 [B, D] -> FP32LayerNorm + fp32 modulate; (weight, bias) -> affine FP32LayerNorm."""
+    B, S, D = x.shape
+    out = torch.empty_like(x)
+    if scale is not None:
+        sc, sh = scale.float().contiguous(), shift.float().contiguous()
+        _lib.check(_L().ffb200_wan_layer_norm(x.data_ptr(), out.data_ptr(), B, S, D, eps, 0, sc.data_ptr(), sh.data_ptr(), D, None, None, _st(x)),
+                   "ffb200_wan_layer_norm")
+    else:
+        wb, bb = weight.to(x.device, torch.bfloat16).contiguous(), bias.to(x.device, torch.bfloat16).contiguous()
+        _lib.check(_L().ffb200_wan_layer_norm(x.data_ptr(), out.data_ptr(), B, S, D, eps, 1, None, None, 0, wb.data_ptr(), bb.data_ptr(), _st(x)),
+                   "ffb200_wan_layer_norm")
+    return out
+
+
+def gate_residual_(h: torch.Tensor, y: torch.Tensor, gate: torch.Tensor) -> torch.Tensor:
+    """In place: h = bf16(float(h) + float(y) * gate[b]); h, y bf16 [B, S, D], gate fp32 [B, D]."""
+    B, S, D = h.shape
+    g = gate.float().contiguous()
+    _lib.check(_L().ffb200_wan_gate_residual(h.data_ptr(), y.data_ptr(), g.data_ptr(), D, B, S, D, _st(h)), "ffb200_wan_gate_residual")
+    return h
+
+
+def patchify(x: torch.Tensor, patch: Tuple[int, int, int] = (1, 2, 2), reps: int = 1) -> torch.Tensor:
+    """fp16 [B, C, F, H, W] -> bf16 [reps * B * tokens, C * pt * ph * pw] (rows (b, f', h', w'), columns (c, dt, dh, dw))."""
+    B, Cc, Fr, H, Wd = x.shape
+    pt, ph, pw = patch
+    out = torch.empty(reps * B * (Fr // pt) * (H // ph) * (Wd // pw), Cc * pt * ph * pw, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_L().ffb200_wan_patchify(x.contiguous().data_ptr(), B, reps, Cc, Fr, H, Wd, pt, ph, pw, out.data_ptr(), _st(x)), "ffb200_wan_patchify")
+    return out
+
+
+def attention_cross(q: torch.Tensor, kv: torch.Tensor, num_heads: int) -> torch.Tensor:
+    """q bf16 [B, Sq, 128 H]; kv bf16 [B, Skv, 2 * 128 H] (k | v) -> bf16 [B, Sq, 128 H]."""
+    B, Sq, D = q.shape
+    out = torch.empty_like(q)
+    _lib.check(_L().ffb200_attention_cross(q.data_ptr(), q.shape[2], kv.data_ptr(), kv.shape[2], D, B, Sq, kv.shape[1], num_heads, out.data_ptr(), _st(q)),
+               "ffb200_attention_cross")
+    return out

@@ -329,6 +329,26 @@ int ffb200_wan_forward(ffb200_wan_plan* p, const void* latents_fp16, float t_mod
 int ffb200_wan_step(ffb200_wan_plan* p, const ffb200_step_args* a, void* stream);
 int ffb200_wan_rollout(ffb200_wan_plan* p, const ffb200_rollout_args* a, void* stream);
 
+/* Op-level entries (one per reference call site), used by the parity tests to isolate a kernel:
+ * torch.nn.RMSNorm over the full width D of rows with pitch ld, in place, + optional interleaved-pair RoPE per 128-wide head evaluated in
+ * bf16 like the reference's tensor arithmetic (transformer_wan.py:96-117); cos / sin: fp32 [rows_per_batch, 128] or NULL. */
+int ffb200_wan_rms_rope(void* x_bf16, long long rows, int rows_per_batch, int ld, int D, const void* weight_bf16, float eps,
+                        const float* cos, const float* sin, void* stream);
+/* FP32LayerNorm (no affine) + fp32 modulate: out = bf16(LN(x) * (1 + scale[b]) + shift[b]) with fp32 vectors `mod_batch_stride` apart
+ * (mode 0, transformer_wan.py:486, 500), or FP32LayerNorm with bf16 affine weight / bias [D] (mode 1, norm2, 493). */
+int ffb200_wan_layer_norm(const void* x_bf16, void* out_bf16, int num_batch, int rows_per_batch, int D, float eps, int mode,
+                          const float* scale, const float* shift, long long mod_batch_stride, const void* weight_bf16,
+                          const void* bias_bf16, void* stream);
+/* hs = (hs.float() + y * gate[b]).type_as(hs) (transformer_wan.py:489, 503); gate fp32, `gate_batch_stride` apart. */
+int ffb200_wan_gate_residual(void* h_bf16, const void* y_bf16, const float* gate, long long gate_batch_stride, int num_batch,
+                             long long rows_per_batch, int D, void* stream);
+/* im2col of the Conv3d patch embedding: fp16 [B, C, F, H, W] -> bf16 [reps * B * tokens, C*pt*ph*pw]. */
+int ffb200_wan_patchify(const void* x_f16, int B, int reps, int C, int F, int H, int W, int pt, int ph, int pw, void* out_bf16, void* stream);
+/* Cross-attention, head_dim 128: q bf16 [B, Sq, q_ld] (head h at column 128 h), kv bf16 [B, Skv, kv_ld] (k at column 128 h, v at
+ * v_col + 128 h) -> out bf16 [B, Sq, 128 H]   (WanAttnProcessor with encoder_hidden_states, transformer_wan.py:78-162). */
+int ffb200_attention_cross(const void* q_bf16, int q_ld, const void* kv_bf16, int kv_ld, int v_col, int B, int Sq, int Skv, int num_heads,
+                           void* out_bf16, void* stream);
+
 /* ================================================================ VAE decode
  * STATUS: added at the end of round 1 after the GPU budget was spent: compiles for sm_100a, host logic unit-tested on CPU, first GPU
  * run pending (tests/test_gpu_vae.py, gated on FFB200_PENDING=1).

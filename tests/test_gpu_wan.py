@@ -45,6 +45,72 @@ def _oracle_pred(w, ocfg, lat16, t, pe, dtype):
             return WO.wan_forward(wd, ocfg, x.bfloat16(), tt, pe.to(DEV))
 
 
+# ------------------------------------------------------------------------------------------------ kernel by kernel (isolates a failure)
+def test_op_patchify():
+    x = torch.randn(2, 16, 3, 8, 12, generator=torch.Generator().manual_seed(0)).half().to(DEV)
+    out = W.patchify(x, (1, 2, 2), reps=2)
+    B, C, Fr, H, Wd = x.shape
+    ref = x.reshape(B, C, Fr, 1, H // 2, 2, Wd // 2, 2).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(B * Fr * (H // 2) * (Wd // 2), C * 4).bfloat16()
+    assert torch.equal(out, torch.cat([ref, ref], 0))
+
+
+@pytest.mark.parametrize("D,rope", [(256, True), (1536, True), (384, False)])
+def test_op_rms_rope(D, rope):
+    g = torch.Generator(device=DEV).manual_seed(D)
+    B, S = 2, 77
+    qkv = torch.randn(B, S, 3 * D, generator=g, device=DEV).bfloat16()
+    w = (1 + 0.1 * torch.randn(D, generator=g, device=DEV)).bfloat16()
+    cos, sin = W.wan_rope_tables(W.WanEngineConfig(rope_max_seq_len=64), 7, 1, 11)     # 77 tokens, bf16-rounded values
+    cos, sin = cos.to(DEV), sin.to(DEV)
+    x = qkv.clone()
+    W.rms_rope_(x, D, w, 1e-6, cos if rope else None, sin if rope else None, col=D)     # the k block of a fused q|k|v row
+    k = qkv[..., D:2 * D]
+    ref = torch.nn.functional.rms_norm(k.float(), (D,), w.float(), 1e-6).bfloat16()
+    if rope:
+        rh = ref.reshape(B, S, D // 128, 128)
+        c, s_ = cos.bfloat16()[None, :, None, 0::2], sin.bfloat16()[None, :, None, 1::2]
+        x1, x2 = rh[..., 0::2], rh[..., 1::2]
+        o = torch.empty_like(rh)
+        o[..., 0::2] = x1 * c - x2 * s_                                                # bf16 tensor arithmetic, as the reference
+        o[..., 1::2] = x1 * s_ + x2 * c
+        ref = o.reshape(B, S, D)
+    assert torch.equal(x[..., :D], qkv[..., :D]) and torch.equal(x[..., 2 * D:], qkv[..., 2 * D:])   # neighbours untouched
+    torch.testing.assert_close(x[..., D:2 * D].float(), ref.float(), rtol=1.6e-2, atol=1e-2)
+    assert _rel(x[..., D:2 * D], ref) < 3e-3
+
+
+def test_op_layer_norm_and_gate_residual():
+    g = torch.Generator(device=DEV).manual_seed(3)
+    B, S, D = 2, 100, 1536
+    x = (torch.randn(B, S, D, generator=g, device=DEV) * 2 + 0.3).bfloat16()
+    scale, shift = torch.randn(B, D, generator=g, device=DEV) * 0.2, torch.randn(B, D, generator=g, device=DEV) * 0.2
+    ln = torch.nn.functional.layer_norm(x.float(), (D,), None, None, 1e-6)
+    out = W.layer_norm(x, 1e-6, scale=scale, shift=shift)
+    torch.testing.assert_close(out.float(), (ln * (1 + scale[:, None]) + shift[:, None]).bfloat16().float(), rtol=1.6e-2, atol=1e-2)
+    wt, bs = (1 + 0.1 * torch.randn(D, generator=g, device=DEV)).bfloat16(), (0.1 * torch.randn(D, generator=g, device=DEV)).bfloat16()
+    out = W.layer_norm(x, 1e-6, weight=wt, bias=bs)
+    torch.testing.assert_close(out.float(), (ln * wt.float() + bs.float()).bfloat16().float(), rtol=1.6e-2, atol=1e-2)
+    y = torch.randn(B, S, D, generator=g, device=DEV).bfloat16()
+    gate = torch.randn(B, D, generator=g, device=DEV)
+    h = x.clone()
+    W.gate_residual_(h, y, gate)
+    assert torch.equal(h, (x.float() + y.float() * gate[:, None]).bfloat16())           # one rounding, exactly the reference expression
+
+
+@pytest.mark.parametrize("Sq,Skv,H", [(300, 70, 2), (256, 512, 3), (1000, 64, 1)])
+def test_op_attention_cross(Sq, Skv, H):
+    g = torch.Generator(device=DEV).manual_seed(Sq + Skv)
+    B, D = 2, 128 * H
+    q = torch.randn(B, Sq, D, generator=g, device=DEV).bfloat16()
+    kv = torch.randn(B, Skv, 2 * D, generator=g, device=DEV).bfloat16()
+    out = W.attention_cross(q, kv, H)
+    sp = lambda t: t.reshape(B, t.shape[1], H, 128).transpose(1, 2).float()
+    ref = torch.nn.functional.scaled_dot_product_attention(sp(q), sp(kv[..., :D]), sp(kv[..., D:])).transpose(1, 2).reshape(B, Sq, D)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out, ref) < 8e-3
+
+
+# ------------------------------------------------------------------------------------------------ engine
 @pytest.mark.parametrize("geom", [dict(), dict(layers=3, heads=3, B=1, Fr=2, H=16, Wd=20, nt=512)])
 def test_forward_matches_oracle(geom):
     ocfg, cfg, w, lat, pe, neg = _setup(**geom)
