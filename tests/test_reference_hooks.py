@@ -1,0 +1,70 @@
+"""The drop-in boundary checked against the REAL reference, imported read-only in the build container:
+* the reference's own plug points resolve this repo's classes - `get_model_adapter_class(<python path>)` (FF/models/registry.py:73-79, what
+  `model.model_type: "<path>"` in the YAML goes through) and `register_scheduler` / `get_sde_scheduler_class` (FF/scheduler/registry.py);
+* "parameter names are the ABI" (`filter_kwargs`, FF/utils/base.py:38-63): every keyword the reference adapters' `inference()` /
+  `forward()` accept is accepted by the B200 adapters, so whatever a trainer passes through `filter_kwargs` arrives.
+Runs only where /root/reference exists (the build container; CPU suite) - the GPU box never reads the reference."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "flow_factory")), reason="reference tree not present (GPU box)")
+
+_SCRIPT = r'''
+import inspect, json, sys
+sys.path[:0] = [sys.argv[1] + "/tests/golden/ref_stubs", "/root/reference/diffusers/src", "/root/reference/src", sys.argv[1]]
+from flow_factory.models.registry import get_model_adapter_class
+from flow_factory.scheduler.registry import register_scheduler, get_sde_scheduler_class
+from flow_factory.utils.base import filter_kwargs
+out = {}
+pairs = {"sd3_5": ("flow_factory.models.stable_diffusion.sd3_5.SD3_5Adapter", "flow_factory_b200.adapter.B200SD3_5Adapter"),
+         "flux1": ("flow_factory.models.flux.flux1.Flux1Adapter", "flow_factory_b200.flux_adapter.B200Flux1Adapter"),
+         "qwen": ("flow_factory.models.qwen_image.qwen_image.QwenImageAdapter", "flow_factory_b200.qwen_adapter.B200QwenImageAdapter"),
+         "wan": ("flow_factory.models.wan.wan2_t2v.Wan2_T2V_Adapter", "flow_factory_b200.wan_adapter.B200Wan21Adapter")}
+for name, (ref_path, my_path) in pairs.items():
+    mine = get_model_adapter_class(my_path)                       # the registry's importlib fall-through
+    ref = get_model_adapter_class(ref_path)
+    rec = {"resolved": mine.__module__ + "." + mine.__name__}
+    for fn in ("inference", "forward"):
+        rp = [p for p in inspect.signature(getattr(ref, fn)).parameters if p != "self"]
+        mp = [p for p in inspect.signature(getattr(mine, fn)).parameters if p != "self"]
+        rec[fn + "_missing"] = [p for p in rp if p not in mp]
+        kw = {p: 0 for p in rp}
+        rec[fn + "_filtered"] = sorted(filter_kwargs(getattr(mine, fn), **kw)) == sorted(p for p in rp if p in mp)
+    out[name] = rec
+register_scheduler("FlowMatchEulerDiscreteScheduler", "flow_factory_b200.scheduler.FlowMatchEulerDiscreteSDEScheduler")
+register_scheduler("UniPCMultistepScheduler", "flow_factory_b200.scheduler.UniPCMultistepSDEScheduler")
+class FlowMatchEulerDiscreteScheduler: pass
+class UniPCMultistepScheduler: pass
+out["sched"] = [get_sde_scheduler_class(FlowMatchEulerDiscreteScheduler()).__module__, get_sde_scheduler_class(UniPCMultistepScheduler).__module__]
+print("RESULT " + json.dumps(out))
+'''
+
+
+@pytest.fixture(scope="module")
+def hooks():
+    r = subprocess.run([sys.executable, "-c", _SCRIPT, ROOT], capture_output=True, text=True, timeout=600)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+    assert lines, r.stdout[-2000:] + r.stderr[-4000:]
+    return json.loads(lines[-1][7:])
+
+
+def test_registry_resolves_b200_adapters_by_python_path(hooks):
+    assert hooks["sd3_5"]["resolved"] == "flow_factory_b200.adapter.B200SD3_5Adapter"
+    assert hooks["flux1"]["resolved"] == "flow_factory_b200.flux_adapter.B200Flux1Adapter"
+    assert hooks["qwen"]["resolved"] == "flow_factory_b200.qwen_adapter.B200QwenImageAdapter"
+    assert hooks["wan"]["resolved"] == "flow_factory_b200.wan_adapter.B200Wan21Adapter"
+    assert hooks["sched"] == ["flow_factory_b200.scheduler", "flow_factory_b200.scheduler"]
+
+
+@pytest.mark.parametrize("model", ["sd3_5", "flux1", "qwen", "wan"])
+def test_keyword_abi_is_a_superset_of_the_reference(hooks, model):
+    rec = hooks[model]
+    assert rec["inference_missing"] == [], rec
+    assert rec["forward_missing"] == [], rec
+    assert rec["inference_filtered"] and rec["forward_filtered"]
