@@ -22,6 +22,9 @@ class SD3_5Sample:
     height: Optional[int] = None
     width: Optional[int] = None
     image: Optional[torch.Tensor] = None
+    video: Optional[torch.Tensor] = None                 # (T, C, H, W); filled by the video adapters (FF/samples/samples.py:96-99)
+    audio: Optional[torch.Tensor] = None
+    audio_sample_rate: Optional[int] = None
     prompt: Optional[str] = None
     prompt_ids: Optional[torch.Tensor] = None
     prompt_embeds: Optional[torch.Tensor] = None
@@ -31,10 +34,13 @@ class SD3_5Sample:
     pooled_prompt_embeds: Optional[torch.Tensor] = None
     negative_pooled_prompt_embeds: Optional[torch.Tensor] = None
     extra_kwargs: Dict[str, Any] = field(default_factory=dict)
+    _unique_id: Optional[int] = field(default=None, repr=False, compare=False)
 
     @property
     def unique_id(self) -> int:
-        """sha256 over the prompt identity fields (FF/samples/samples.py:268-288)."""
+        """sha256 over the prompt identity fields (FF/samples/samples.py:268-288), cached like the reference's `_unique_id`."""
+        if self._unique_id is not None:
+            return self._unique_id
         h = hashlib.sha256()
         for name in sorted(self._id_fields):
             v = getattr(self, name)
@@ -42,7 +48,8 @@ class SD3_5Sample:
                 continue
             h.update(name.encode())
             h.update(v.detach().cpu().numpy().tobytes() if isinstance(v, torch.Tensor) else str(v).encode())
-        return int.from_bytes(h.digest()[:8], "big", signed=True)
+        self._unique_id = int.from_bytes(h.digest()[:8], "big", signed=True)
+        return self._unique_id
 
     def to(self, device) -> "SD3_5Sample":
         for f in fields(self):
@@ -79,9 +86,9 @@ class Flux1Sample(SD3_5Sample):
 
 @dataclass
 class QwenImageSample(SD3_5Sample):
-    """Mirror of the reference's QwenImageSample (FF/models/qwen_image/qwen_image.py): T2I sample + embedding masks + img_shapes.
-    all_latents rows are PACKED latents (T', Ni, 64)."""
-    _shared_fields: ClassVar[frozenset] = frozenset({"img_shapes"})
+    """Mirror of the reference's QwenImageSample (FF/models/qwen_image/qwen_image.py:54-61): T2I sample + embedding masks + img_shapes,
+    NO shared fields (img_shapes is collated per sample like any other list).  all_latents rows are PACKED latents (T', Ni, 64)."""
+    _shared_fields: ClassVar[frozenset] = frozenset({})
     prompt_embeds_mask: Optional[torch.Tensor] = None
     negative_prompt_embeds_mask: Optional[torch.Tensor] = None
     img_shapes: Optional[List] = None
@@ -89,6 +96,5 @@ class QwenImageSample(SD3_5Sample):
 
 @dataclass
 class WanT2VSample(SD3_5Sample):
-    """Mirror of FF/models/wan/wan2_t2v.py:47-50 (T2VSample, no shared fields): `video` instead of `image`;
+    """Mirror of FF/models/wan/wan2_t2v.py:47-50 (T2VSample, no shared fields): fills `video` instead of `image`;
     all_latents rows are (T', C, F, H, W)."""
-    video: Optional[torch.Tensor] = None

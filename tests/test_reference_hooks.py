@@ -37,6 +37,18 @@ for name, (ref_path, my_path) in pairs.items():
         kw = {p: 0 for p in rp}
         rec[fn + "_filtered"] = sorted(filter_kwargs(getattr(mine, fn), **kw)) == sorted(p for p in rp if p in mp)
     out[name] = rec
+import dataclasses
+samples = {"sd3_5": ("flow_factory.models.stable_diffusion.sd3_5", "SD3_5Sample", "SD3_5Sample"),
+           "flux1": ("flow_factory.models.flux.flux1", "Flux1Sample", "Flux1Sample"),
+           "qwen": ("flow_factory.models.qwen_image.qwen_image", "QwenImageSample", "QwenImageSample"),
+           "wan": ("flow_factory.models.wan.wan2_t2v", "WanT2VSample", "WanT2VSample")}
+import importlib
+mine_mod = importlib.import_module("flow_factory_b200.samples")
+for name, (mod, ref_cls, my_cls) in samples.items():
+    rf = {f.name for f in dataclasses.fields(getattr(importlib.import_module(mod), ref_cls))}
+    mf = {f.name for f in dataclasses.fields(getattr(mine_mod, my_cls))}
+    out[name]["sample_fields_missing"] = sorted(rf - mf)
+    out[name]["shared_fields"] = [sorted(getattr(importlib.import_module(mod), ref_cls)._shared_fields), sorted(getattr(mine_mod, my_cls)._shared_fields)]
 register_scheduler("FlowMatchEulerDiscreteScheduler", "flow_factory_b200.scheduler.FlowMatchEulerDiscreteSDEScheduler")
 register_scheduler("UniPCMultistepScheduler", "flow_factory_b200.scheduler.UniPCMultistepSDEScheduler")
 class FlowMatchEulerDiscreteScheduler: pass
@@ -68,3 +80,10 @@ def test_keyword_abi_is_a_superset_of_the_reference(hooks, model):
     assert rec["inference_missing"] == [], rec
     assert rec["forward_missing"] == [], rec
     assert rec["inference_filtered"] and rec["forward_filtered"]
+
+
+@pytest.mark.parametrize("model", ["sd3_5", "flux1", "qwen", "wan"])
+def test_sample_records_carry_the_reference_fields(hooks, model):
+    rec = hooks[model]
+    assert rec["shared_fields"][0] == rec["shared_fields"][1], rec["shared_fields"]      # what stack() collates as one value per batch
+    assert rec["sample_fields_missing"] == [], rec["sample_fields_missing"]            # every field of the reference record exists
