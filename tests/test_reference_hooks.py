@@ -47,8 +47,42 @@ mine_mod = importlib.import_module("flow_factory_b200.samples")
 for name, (mod, ref_cls, my_cls) in samples.items():
     rf = {f.name for f in dataclasses.fields(getattr(importlib.import_module(mod), ref_cls))}
     mf = {f.name for f in dataclasses.fields(getattr(mine_mod, my_cls))}
-    out[name]["sample_fields_missing"] = sorted(rf - mf)
-    out[name]["shared_fields"] = [sorted(getattr(importlib.import_module(mod), ref_cls)._shared_fields), sorted(getattr(mine_mod, my_cls)._shared_fields)]
+    out[name]["sample_fields_missing"] = sorted(rf ^ mf)          # symmetric difference: identical field sets
+    R, M = getattr(importlib.import_module(mod), ref_cls), getattr(mine_mod, my_cls)
+    out[name]["shared_fields"] = [sorted(R.shared_fields()), sorted(M.shared_fields())]
+    # behaviour on identical data: unique ids, dict views, attribute fall-through, collate - also the REFERENCE's stack() fed with B200 records
+    import torch
+    def mk(cls, i, prompt):
+        kw = dict(timesteps=torch.arange(4.0), all_latents=torch.full((2, 3, 4), float(i)), log_probs=torch.tensor([0.5 * i]),
+                  latent_index_map=torch.tensor([0, -1, 1, -1, -1]), log_prob_index_map=torch.tensor([-1, 0, -1, -1]), height=64, width=32,
+                  prompt=prompt, prompt_ids=torch.tensor([1, 2, i]), prompt_embeds=torch.ones(5, 2) * i,
+                  extra_kwargs={"final_latents": torch.full((3, 4), float(i)), "callback_index_map": None, "tag": {"a": torch.tensor([float(i)])}})
+        if "img_ids" in {f.name for f in dataclasses.fields(cls)}:
+            kw["img_ids"] = torch.arange(6.0).reshape(2, 3)
+        if "img_shapes" in {f.name for f in dataclasses.fields(cls)}:
+            kw["img_shapes"] = [(1, 4, 2)]
+        return cls(**kw)
+    def norm(v):
+        if isinstance(v, torch.Tensor): return ["T", list(v.shape), v.flatten().tolist()]
+        if isinstance(v, dict): return {k: norm(x) for k, x in v.items()}
+        if isinstance(v, (list, tuple)): return [norm(x) for x in v]
+        return v
+    rs = [mk(R, 1, "a cat"), mk(R, 2, "a dog")]
+    ms = [mk(M, 1, "a cat"), mk(M, 2, "a dog")]
+    beh = {}
+    beh["unique_id"] = [[int(x.unique_id) for x in rs], [int(x.unique_id) for x in ms]]
+    ids_only_r, ids_only_m = R(prompt_ids=torch.tensor([7, 8]), negative_prompt="n"), M(prompt_ids=torch.tensor([7, 8]), negative_prompt="n")
+    beh["unique_id_ids"] = [int(ids_only_r.unique_id), int(ids_only_m.unique_id)]
+    beh["to_dict_keys"] = [list(rs[0].to_dict().keys()), list(ms[0].to_dict().keys())]
+    beh["getattr_extra"] = [norm(rs[0].final_latents), norm(ms[0].final_latents), norm(rs[0]["tag"]), norm(ms[0]["tag"])]
+    beh["stack"] = [norm(R.stack(rs)), norm(M.stack(ms))]
+    from flow_factory.samples import BaseSample as RefBase
+    beh["ref_stack_on_mine"] = norm(RefBase.stack(ms)) == beh["stack"][0]
+    rt_r, rt_m = R.from_dict(rs[0].to_dict()), M.from_dict(ms[0].to_dict())
+    beh["from_dict"] = [norm(rt_r.to_dict()), norm(rt_m.to_dict())]
+    ms[0].prompt = "changed"; rs[0].prompt = "changed"
+    beh["reset_on_set"] = [int(rs[0].unique_id), int(ms[0].unique_id)]
+    out[name]["behaviour"] = beh
 register_scheduler("FlowMatchEulerDiscreteScheduler", "flow_factory_b200.scheduler.FlowMatchEulerDiscreteSDEScheduler")
 register_scheduler("UniPCMultistepScheduler", "flow_factory_b200.scheduler.UniPCMultistepSDEScheduler")
 class FlowMatchEulerDiscreteScheduler: pass
@@ -87,3 +121,18 @@ def test_sample_records_carry_the_reference_fields(hooks, model):
     rec = hooks[model]
     assert rec["shared_fields"][0] == rec["shared_fields"][1], rec["shared_fields"]      # what stack() collates as one value per batch
     assert rec["sample_fields_missing"] == [], rec["sample_fields_missing"]            # every field of the reference record exists
+
+
+@pytest.mark.parametrize("model", ["sd3_5", "flux1", "qwen", "wan"])
+def test_sample_records_behave_like_the_reference(hooks, model):
+    """Same data into the reference record and the B200 record: identical ids, dict views, extra_kwargs fall-through and collate; and the
+    reference's own `BaseSample.stack` (what the trainers call) accepts B200 records and returns the same batch."""
+    beh = hooks[model]["behaviour"]
+    assert beh["unique_id"][0] == beh["unique_id"][1] and beh["unique_id"][0][0] != beh["unique_id"][0][1]
+    assert beh["unique_id_ids"][0] == beh["unique_id_ids"][1]
+    assert beh["to_dict_keys"][0] == beh["to_dict_keys"][1]
+    assert beh["getattr_extra"][0] == beh["getattr_extra"][1] and beh["getattr_extra"][2] == beh["getattr_extra"][3]
+    assert beh["stack"][0] == beh["stack"][1]
+    assert beh["ref_stack_on_mine"] is True
+    assert beh["from_dict"][0] == beh["from_dict"][1]
+    assert beh["reset_on_set"][0] == beh["reset_on_set"][1]
