@@ -83,6 +83,46 @@ for name, (mod, ref_cls, my_cls) in samples.items():
     ms[0].prompt = "changed"; rs[0].prompt = "changed"
     beh["reset_on_set"] = [int(rs[0].unique_id), int(ms[0].unique_id)]
     out[name]["behaviour"] = beh
+# ---- trajectory bookkeeping: the reference's two collectors driven as in sd3_5.py:266-304 vs plan_slots, on randomised index specs
+import random, torch
+from flow_factory.utils.trajectory_collector import create_trajectory_collector as ref_collector, compute_trajectory_indices as ref_cti
+from flow_factory_b200.trajectory import plan_slots, compute_trajectory_indices as my_cti
+rng = random.Random(0)
+mism = []
+for case in range(300):
+    T = rng.choice([1, 2, 4, 7, 10, 30])
+    kind = rng.choice(["all", "none", "list", "neg", "dups", "cti"])
+    if kind == "all": idx = "all"
+    elif kind == "none": idx = None
+    elif kind == "list": idx = sorted(rng.sample(range(T + 1), rng.randint(1, T + 1)))
+    elif kind == "neg": idx = [rng.randint(-(T + 1), T) for _ in range(rng.randint(1, 5))]
+    elif kind == "dups": idx = [rng.randint(0, T) for _ in range(rng.randint(1, 8))]
+    else:
+        tr = sorted(rng.sample(range(T), rng.randint(1, T)))
+        inc = rng.random() < 0.5
+        idx = ref_cti(tr, T, include_initial=inc)
+        if idx != my_cti(tr, T, include_initial=inc): mism.append(("cti", T, tr, inc))
+    has_lp = [rng.random() < 0.5 for _ in range(T)]
+    try:
+        lc, pc = ref_collector(idx, T), ref_collector(idx, T)
+    except Exception as e:
+        try:
+            plan_slots(idx, T, has_lp); mism.append(("ref raised, mine did not", T, idx, repr(e)))
+        except Exception:
+            pass
+        continue
+    lc.collect(torch.zeros(1), step_idx=0)
+    for i in range(T):
+        lc.collect(torch.zeros(1), i + 1)
+        if has_lp[i]: pc.collect(torch.zeros(1), i)
+    lat_slot, lp_slot, lat_map, lp_map = plan_slots(idx, T, has_lp)
+    rl, rp = lc.get_result(), pc.get_result()
+    n_lat, n_lp = sum(1 for x in lat_slot if x >= 0), sum(1 for x in lp_slot if x >= 0)
+    ok = (0 if rl is None else len(rl)) == n_lat and (0 if rp is None else len(rp)) == n_lp
+    for mine, ref in ((lat_map, lc.get_index_map()), (lp_map, pc.get_index_map())):
+        ok = ok and ((mine is None) == (ref is None)) and (mine is None or torch.equal(mine, ref))
+    if not ok: mism.append((kind, T, idx, has_lp))
+out["trajectory_mismatches"] = [repr(m) for m in mism[:5]]
 register_scheduler("FlowMatchEulerDiscreteScheduler", "flow_factory_b200.scheduler.FlowMatchEulerDiscreteSDEScheduler")
 register_scheduler("UniPCMultistepScheduler", "flow_factory_b200.scheduler.UniPCMultistepSDEScheduler")
 class FlowMatchEulerDiscreteScheduler: pass
@@ -136,3 +176,9 @@ def test_sample_records_behave_like_the_reference(hooks, model):
     assert beh["ref_stack_on_mine"] is True
     assert beh["from_dict"][0] == beh["from_dict"][1]
     assert beh["reset_on_set"][0] == beh["reset_on_set"][1]
+
+
+def test_trajectory_bookkeeping_matches_the_reference_collectors(hooks):
+    """300 randomised (T, trajectory_indices, SDE-step) cases: stored-latent / log-prob counts and both index maps equal what the
+    reference's TrajectoryCollector pair produces when driven like SD3_5Adapter.inference."""
+    assert hooks["trajectory_mismatches"] == []
