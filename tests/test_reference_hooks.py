@@ -123,6 +123,46 @@ for case in range(300):
         ok = ok and ((mine is None) == (ref is None)) and (mine is None or torch.equal(mine, ref))
     if not ok: mism.append((kind, T, idx, has_lp))
 out["trajectory_mismatches"] = [repr(m) for m in mism[:5]]
+# ---- scheduler mirrors: schedule, SDE-step selection and per-step scalars vs the reference on randomised settings
+from flow_factory.scheduler import FlowMatchEulerDiscreteSDEScheduler as RefFM, UniPCMultistepSDEScheduler as RefUP, set_scheduler_timesteps as ref_set
+from flow_factory_b200.scheduler import FlowMatchEulerDiscreteSDEScheduler as MyFM, UniPCMultistepSDEScheduler as MyUP
+smis = []
+x = torch.randn(2, 4, 4, 4, generator=torch.Generator().manual_seed(0)).half()
+v = torch.randn(2, 4, 4, 4, generator=torch.Generator().manual_seed(1)).bfloat16()
+for case in range(60):
+    T = rng.choice([4, 10, 28, 30])
+    dyn = rng.choice(["Flow-SDE", "Dance-SDE", "CPS", "ODE"])
+    nsde = rng.choice([None, 1, 2, 3])
+    sde = rng.choice([None, sorted(rng.sample(range(T), rng.randint(1, T)))])
+    seed = rng.randint(0, 1000)
+    nl = rng.choice([0.3, 0.7, 1.0])
+    if rng.random() < 0.5:
+        dynshift = rng.random() < 0.5
+        kw = dict(use_dynamic_shifting=True) if dynshift else dict(shift=rng.choice([1.0, 3.0, 5.0]))
+        r = RefFM(noise_level=nl, sde_steps=sde, num_sde_steps=nsde, seed=seed, dynamics_type=dyn, **kw)
+        m = MyFM(noise_level=nl, sde_steps=sde, num_sde_steps=nsde, seed=seed, dynamics_type=dyn, **kw)
+        seq = rng.choice([256, 1024, 4096])
+        rt = ref_set(r, T, seq_len=seq, device="cpu"); mt = m.set_timesteps(T, seq_len=seq)
+    else:
+        fs = rng.choice([3.0, 5.0])
+        r = RefUP(noise_level=nl, sde_steps=sde, num_sde_steps=nsde, seed=seed, dynamics_type=dyn, prediction_type="flow_prediction",
+                  use_flow_sigmas=True, flow_shift=fs, num_train_timesteps=1000)
+        m = MyUP(noise_level=nl, sde_steps=sde, num_sde_steps=nsde, seed=seed, dynamics_type=dyn, flow_shift=fs)
+        r.set_timesteps(T, device="cpu"); rt = r.timesteps; mt = m.set_timesteps(T)
+    r.rollout(); m.rollout()
+    ok = torch.equal(rt.cpu(), mt) and torch.equal(r.sigmas.cpu(), m.sigmas)
+    ok = ok and torch.equal(r.sde_steps, m.sde_steps) and r.num_sde_steps == m.num_sde_steps and torch.equal(r.current_sde_steps, m.current_sde_steps)
+    ok = ok and torch.equal(r.get_noise_levels().float(), m.get_noise_levels().float()) and torch.equal(torch.as_tensor(r.train_timesteps), torch.as_tensor(m.train_timesteps))
+    i = rng.randrange(T)
+    t, tn = rt[i], (rt[i + 1] if i + 1 < T else torch.tensor(0, dtype=rt.dtype))
+    ok = ok and r.get_noise_level_for_timestep(t) == m.get_noise_level_for_timestep(t) and r.index_for_timestep(t) == m.index_for_timestep(t)
+    cur = r.get_noise_level_for_timestep(t)
+    import logging; logging.disable(logging.WARNING)
+    o = r.step(noise_pred=v, timestep=t, latents=x, timestep_next=tn, noise_level=cur, compute_log_prob=False, return_dict=True)
+    c = m.step_coef(t, tn, cur, compute_log_prob=False)
+    ok = ok and float(o.dt.flatten()[0]) == c.dt and float(torch.as_tensor(o.std_dev_t).flatten()[0]) == c.std_dev_t
+    if not ok: smis.append((case, T, dyn, nsde, sde, seed, type(r).__name__))
+out["scheduler_mismatches"] = [repr(m) for m in smis[:5]]
 register_scheduler("FlowMatchEulerDiscreteScheduler", "flow_factory_b200.scheduler.FlowMatchEulerDiscreteSDEScheduler")
 register_scheduler("UniPCMultistepScheduler", "flow_factory_b200.scheduler.UniPCMultistepSDEScheduler")
 class FlowMatchEulerDiscreteScheduler: pass
@@ -182,3 +222,9 @@ def test_trajectory_bookkeeping_matches_the_reference_collectors(hooks):
     """300 randomised (T, trajectory_indices, SDE-step) cases: stored-latent / log-prob counts and both index maps equal what the
     reference's TrajectoryCollector pair produces when driven like SD3_5Adapter.inference."""
     assert hooks["trajectory_mismatches"] == []
+
+
+def test_scheduler_mirrors_match_the_reference_on_random_settings(hooks):
+    """60 randomised settings of both scheduler mirrors: timesteps, sigmas, SDE-step selection under the seed, noise levels, index lookup
+    and the per-step scalars (dt, std_dev_t of the reference's step) - all bit-exact."""
+    assert hooks["scheduler_mismatches"] == []
