@@ -27,9 +27,11 @@ from .weights import EngineConfig
 
 
 def filter_kwargs(fn: Callable, **kwargs) -> Dict[str, Any]:
-    """FF/utils/base.py:38-63: keep only the keyword arguments `fn` names."""
-    names = set(inspect.signature(fn).parameters)
-    return {k: v for k, v in kwargs.items() if k in names}
+    """FF/utils/base.py:38-63: keep only the keyword arguments `fn` names - everything if `fn` itself takes **kwargs."""
+    params = inspect.signature(fn).parameters
+    if any(p.kind == inspect.Parameter.VAR_KEYWORD for p in params.values()):
+        return kwargs
+    return {k: v for k, v in kwargs.items() if k in params}
 
 
 class B200SD3_5Adapter:

@@ -163,6 +163,11 @@ for case in range(60):
     ok = ok and float(o.dt.flatten()[0]) == c.dt and float(torch.as_tensor(o.std_dev_t).flatten()[0]) == c.std_dev_t
     if not ok: smis.append((case, T, dyn, nsde, sde, seed, type(r).__name__))
 out["scheduler_mismatches"] = [repr(m) for m in smis[:5]]
+from flow_factory_b200.adapter import filter_kwargs as my_filter
+def f1(a, b=1): pass
+def f2(a, **kw): pass
+def f3(*args, c=3): pass
+out["filter_kwargs"] = [[sorted(filter_kwargs(f, a=1, b=2, c=3, z=4)) for f in (f1, f2, f3)], [sorted(my_filter(f, a=1, b=2, c=3, z=4)) for f in (f1, f2, f3)]]
 register_scheduler("FlowMatchEulerDiscreteScheduler", "flow_factory_b200.scheduler.FlowMatchEulerDiscreteSDEScheduler")
 register_scheduler("UniPCMultistepScheduler", "flow_factory_b200.scheduler.UniPCMultistepSDEScheduler")
 class FlowMatchEulerDiscreteScheduler: pass
@@ -228,3 +233,7 @@ def test_scheduler_mirrors_match_the_reference_on_random_settings(hooks):
     """60 randomised settings of both scheduler mirrors: timesteps, sigmas, SDE-step selection under the seed, noise levels, index lookup
     and the per-step scalars (dt, std_dev_t of the reference's step) - all bit-exact."""
     assert hooks["scheduler_mismatches"] == []
+
+
+def test_filter_kwargs_mirror(hooks):
+    assert hooks["filter_kwargs"][0] == hooks["filter_kwargs"][1]
