@@ -37,6 +37,36 @@ class SDESchedulerOutput:
         names = {f.name for f in fields(cls)}
         return cls(**{k: v for k, v in data.items() if k in names})
 
+    # The reference class derives from diffusers' BaseOutput (an ordered mapping over the non-None fields): the NFT / AWM / CRD trainers read
+    # the no-grad forward as `output['noise_pred']` (nft.py:375, awm.py:461, crd.py:699), pipelines as `output[0]`.
+    def keys(self):
+        return [f.name for f in fields(self) if getattr(self, f.name) is not None]
+
+    def values(self):
+        return [getattr(self, k) for k in self.keys()]
+
+    def items(self):
+        return [(k, getattr(self, k)) for k in self.keys()]
+
+    def to_tuple(self):
+        return tuple(self.values())
+
+    def __getitem__(self, k):
+        if isinstance(k, str):
+            if k not in self.keys():
+                raise KeyError(k)
+            return getattr(self, k)
+        return self.to_tuple()[k]
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self) -> int:
+        return len(self.keys())
+
+    def __contains__(self, k) -> bool:
+        return k in self.keys()
+
 
 def calculate_shift(image_seq_len: int, base_seq_len: int = 256, max_seq_len: int = 4096, base_shift: float = 0.5,
                     max_shift: float = 1.15) -> float:

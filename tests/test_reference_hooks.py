@@ -163,6 +163,18 @@ for case in range(60):
     ok = ok and float(o.dt.flatten()[0]) == c.dt and float(torch.as_tensor(o.std_dev_t).flatten()[0]) == c.std_dev_t
     if not ok: smis.append((case, T, dyn, nsde, sde, seed, type(r).__name__))
 out["scheduler_mismatches"] = [repr(m) for m in smis[:5]]
+from flow_factory.scheduler.abc import SDESchedulerOutput as RefOut
+from flow_factory_b200.scheduler import SDESchedulerOutput as MyOut
+def probe(cls):
+    o = cls.from_dict(dict(next_latents=torch.ones(2), log_prob=torch.zeros(2), noise_pred=torch.full((2,), 3.0), junk=1))
+    res = {"keys": list(o.keys()), "len": len(o), "by_key": o["noise_pred"].tolist(), "by_index": o[0].tolist(), "tuple_len": len(o.to_tuple()),
+           "iter": list(iter(o)), "contains": ["log_prob" in o, "dt" in o], "attr_none": o.dt is None}
+    try:
+        o["dt"]; res["missing_key"] = "no error"
+    except KeyError:
+        res["missing_key"] = "KeyError"
+    return res
+out["scheduler_output"] = [probe(RefOut), probe(MyOut)]
 from flow_factory_b200.adapter import filter_kwargs as my_filter
 def f1(a, b=1): pass
 def f2(a, **kw): pass
@@ -237,3 +249,8 @@ def test_scheduler_mirrors_match_the_reference_on_random_settings(hooks):
 
 def test_filter_kwargs_mirror(hooks):
     assert hooks["filter_kwargs"][0] == hooks["filter_kwargs"][1]
+
+
+def test_scheduler_output_mapping_protocol(hooks):
+    """`output['noise_pred']` (NFT / AWM / CRD trainers), `output[0]`, keys / iteration over the non-None fields - as diffusers' BaseOutput."""
+    assert hooks["scheduler_output"][0] == hooks["scheduler_output"][1]
