@@ -163,6 +163,35 @@ for case in range(60):
     ok = ok and float(o.dt.flatten()[0]) == c.dt and float(torch.as_tensor(o.std_dev_t).flatten()[0]) == c.std_dev_t
     if not ok: smis.append((case, T, dyn, nsde, sde, seed, type(r).__name__))
 out["scheduler_mismatches"] = [repr(m) for m in smis[:5]]
+# ---- GRPO / GDPO advantage arithmetic (FF/advantage/advantage_processor.py:314-481) on randomised groups, incl. constant-reward groups
+import numpy as np
+from flow_factory.advantage.advantage_processor import AdvantageProcessor
+from flow_factory_b200 import advantage as MyAdv
+nrng = np.random.default_rng(1)
+amis = []
+for case in range(40):
+    n_groups, k = int(nrng.integers(1, 7)), int(nrng.integers(1, 6))
+    gid = nrng.permutation(np.repeat(np.arange(n_groups), k))
+    keys = ["pick", "ocr", "aes"][: int(nrng.integers(1, 4))]
+    rewards = {kk: (nrng.normal(size=len(gid)) if nrng.random() < 0.8 else np.full(len(gid), 0.5)) for kk in keys}
+    if nrng.random() < 0.3:
+        rewards[keys[0]][gid == 0] = 1.25                       # one group with identical rewards: std clamps
+    weights = {kk: float(nrng.choice([1.0, 0.5, 2.0])) for kk in keys}
+    for global_std in (True, False):
+        ap = AdvantageProcessor.__new__(AdvantageProcessor)
+        ap.reward_weights, ap.global_std, ap.group_size, ap.group_on_same_rank = weights, global_std, k, False
+        ap.collect_group_rewards = lambda samples, rw, gid=gid: ({kk: np.asarray(v, dtype=np.float64) for kk, v in rw.items()}, gid)
+        ap._to_local = lambda a: a
+        ap._build_weighted_sum_log_data = lambda *a, **kw: {}
+        ap._build_gdpo_log_data = lambda *a, **kw: {}
+        r_sum = np.asarray(ap.compute_weighted_sum([], rewards, False))
+        m_sum = np.asarray(MyAdv.advantages_sum(rewards, weights, gid, global_std=global_std))
+        if not np.allclose(r_sum, m_sum, rtol=1e-12, atol=1e-12): amis.append(("sum", case, global_std))
+    ap.global_std = True
+    r_g = np.asarray(ap.compute_gdpo([], rewards, False))
+    m_g = np.asarray(MyAdv.advantages_gdpo(rewards, weights, gid))
+    if not np.allclose(r_g, m_g, rtol=1e-12, atol=1e-12): amis.append(("gdpo", case))
+out["advantage_mismatches"] = [repr(m) for m in amis[:5]]
 from flow_factory.scheduler.abc import SDESchedulerOutput as RefOut
 from flow_factory_b200.scheduler import SDESchedulerOutput as MyOut
 def probe(cls):
@@ -254,3 +283,7 @@ def test_filter_kwargs_mirror(hooks):
 def test_scheduler_output_mapping_protocol(hooks):
     """`output['noise_pred']` (NFT / AWM / CRD trainers), `output[0]`, keys / iteration over the non-None fields - as diffusers' BaseOutput."""
     assert hooks["scheduler_output"][0] == hooks["scheduler_output"][1]
+
+
+def test_advantage_arithmetic_matches_the_reference_on_random_groups(hooks):
+    assert hooks["advantage_mismatches"] == []
