@@ -163,6 +163,37 @@ for case in range(60):
     ok = ok and float(o.dt.flatten()[0]) == c.dt and float(torch.as_tensor(o.std_dev_t).flatten()[0]) == c.std_dev_t
     if not ok: smis.append((case, T, dyn, nsde, sde, seed, type(r).__name__))
 out["scheduler_mismatches"] = [repr(m) for m in smis[:5]]
+# ---- positional tables and latent packing vs the real diffusers modules
+from diffusers.models.transformers.transformer_flux import FluxPosEmbed
+from diffusers.models.transformers.transformer_qwenimage import QwenEmbedRope
+from diffusers.models.transformers.transformer_wan import WanRotaryPosEmbed
+from diffusers.pipelines.flux.pipeline_flux import FluxPipeline
+from flow_factory.scheduler.flow_match_euler_discrete import calculate_shift as ref_shift
+from flow_factory_b200 import flux as MF, qwen as MQ, wan as MW
+from flow_factory_b200.scheduler import calculate_shift as my_shift
+pos = {}
+h2, w2, nt = 6, 10, 7
+ids = torch.cat([torch.zeros(nt, 3), FluxPipeline._prepare_latent_image_ids(1, h2, w2, "cpu", torch.float32)], 0)
+rc, rs_ = FluxPosEmbed(theta=10000, axes_dim=[16, 56, 56])(ids)
+mc, ms_ = MF.rope_tables(torch.cat([torch.zeros(nt, 3), MF.latent_image_ids(h2, w2)], 0), (16, 56, 56))
+pos["flux_rope"] = bool(torch.equal(rc, mc) and torch.equal(rs_, ms_))
+lat = torch.randn(2, 16, 2 * h2, 2 * w2)
+pos["flux_pack"] = bool(torch.equal(FluxPipeline._pack_latents(lat, 2, 16, 2 * h2, 2 * w2), MF.pack_latents(lat)))
+pos["shift"] = [ref_shift(n) == my_shift(n) for n in (256, 1024, 4096, 4429)]
+qr = QwenEmbedRope(theta=10000, axes_dim=[16, 56, 56], scale_rope=True)
+vid, txt = qr([(1, h2, w2)], max_txt_seq_len=nt, device=torch.device("cpu"))
+qc, qs = MQ.qwen_rope_tables(h2, w2, nt, (16, 56, 56))
+ref_c = torch.cat([txt, vid], 0)
+pos["qwen_rope"] = bool(torch.equal(ref_c.real.float().repeat_interleave(2, 1), qc) and torch.equal(ref_c.imag.float().repeat_interleave(2, 1), qs))
+wr = WanRotaryPosEmbed(attention_head_dim=128, patch_size=(1, 2, 2), max_seq_len=64)
+wc, ws = wr(torch.zeros(1, 16, 3, 8, 10))
+mwc, mws = MW.wan_rope_tables(MW.WanEngineConfig(rope_max_seq_len=64), 3, 4, 5, table_dtype=torch.float32)
+pos["wan_rope"] = bool(torch.equal(wc.reshape(60, 128), mwc) and torch.equal(ws.reshape(60, 128), mws))
+wrb = wr.to(torch.bfloat16)                                    # the buffers follow the module dtype
+wcb, wsb = wrb(torch.zeros(1, 16, 3, 8, 10))
+mwcb, mwsb = MW.wan_rope_tables(MW.WanEngineConfig(rope_max_seq_len=64), 3, 4, 5)
+pos["wan_rope_bf16"] = bool(wcb.dtype == torch.bfloat16 and torch.equal(wcb.float().reshape(60, 128), mwcb) and torch.equal(wsb.float().reshape(60, 128), mwsb))
+out["positional"] = pos
 # ---- GRPO / GDPO advantage arithmetic (FF/advantage/advantage_processor.py:314-481) on randomised groups, incl. constant-reward groups
 import numpy as np
 from flow_factory.advantage.advantage_processor import AdvantageProcessor
@@ -287,3 +318,11 @@ def test_scheduler_output_mapping_protocol(hooks):
 
 def test_advantage_arithmetic_matches_the_reference_on_random_groups(hooks):
     assert hooks["advantage_mismatches"] == []
+
+
+def test_positional_tables_and_packing_match_diffusers(hooks):
+    """FluxPosEmbed / QwenEmbedRope (scale_rope) / WanRotaryPosEmbed (fp32 and bf16-cast buffers), FLUX latent packing + image ids and
+    calculate_shift: the host tables the kernels read are bit-identical to what the real modules produce."""
+    pos = hooks["positional"]
+    assert all(pos["shift"])
+    assert {k: v for k, v in pos.items() if k != "shift"} == {"flux_rope": True, "flux_pack": True, "qwen_rope": True, "wan_rope": True, "wan_rope_bf16": True}
