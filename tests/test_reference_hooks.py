@@ -194,6 +194,24 @@ wcb, wsb = wrb(torch.zeros(1, 16, 3, 8, 10))
 mwcb, mwsb = MW.wan_rope_tables(MW.WanEngineConfig(rope_max_seq_len=64), 3, 4, 5)
 pos["wan_rope_bf16"] = bool(wcb.dtype == torch.bfloat16 and torch.equal(wcb.float().reshape(60, 128), mwcb) and torch.equal(wsb.float().reshape(60, 128), mwsb))
 out["positional"] = pos
+# ---- VAE host side against the real AutoencoderKL / VaeImageProcessor
+from diffusers.models.autoencoders.autoencoder_kl import AutoencoderKL
+from diffusers.image_processor import VaeImageProcessor
+from flow_factory_b200 import vae as MV
+vm = AutoencoderKL(in_channels=3, out_channels=3, down_block_types=("DownEncoderBlock2D",) * 2, up_block_types=("UpDecoderBlock2D",) * 2,
+                   block_out_channels=(32, 64), layers_per_block=1, latent_channels=4, norm_num_groups=8, use_quant_conv=False,
+                   use_post_quant_conv=False, scaling_factor=1.5305, shift_factor=0.0609)
+vcfg = MV.VaeDecoderConfig.from_config(vm.config)
+packed = MV.pack_vae_decoder_weights(vm.state_dict(), vcfg)
+img = torch.randn(2, 3, 8, 8) * 2
+vae_rec = {"cfg": [vcfg.latent_channels, list(vcfg.block_out_channels), vcfg.layers_per_block, vcfg.norm_num_groups, vcfg.scaling_factor, vcfg.shift_factor],
+           "n_packed": [len(packed), MV.expected_weight_count(vcfg)],
+           "postprocess": bool(torch.equal(VaeImageProcessor(vae_scale_factor=8).postprocess(img, output_type="pt"), MV.postprocess_pt(img)))}
+try:
+    MV.VaeDecoderConfig.from_config(AutoencoderKL(block_out_channels=(32,), norm_num_groups=8).config); vae_rec["post_quant_guard"] = "no error"
+except NotImplementedError:
+    vae_rec["post_quant_guard"] = "NotImplementedError"
+out["vae_host"] = vae_rec
 # ---- GRPO / GDPO advantage arithmetic (FF/advantage/advantage_processor.py:314-481) on randomised groups, incl. constant-reward groups
 import numpy as np
 from flow_factory.advantage.advantage_processor import AdvantageProcessor
@@ -326,3 +344,12 @@ def test_positional_tables_and_packing_match_diffusers(hooks):
     pos = hooks["positional"]
     assert all(pos["shift"])
     assert {k: v for k, v in pos.items() if k != "shift"} == {"flux_rope": True, "flux_pack": True, "qwen_rope": True, "wan_rope": True, "wan_rope_bf16": True}
+
+
+def test_vae_host_side_against_the_real_autoencoder(hooks):
+    """Config intake from a real AutoencoderKL.config, packing of its real state_dict, the 'pt' postprocess, and the post_quant_conv guard
+    (diffusers' default AutoencoderKL has one)."""
+    v = hooks["vae_host"]
+    assert v["cfg"] == [4, [32, 64], 1, 8, 1.5305, 0.0609]
+    assert v["n_packed"][0] == v["n_packed"][1]
+    assert v["postprocess"] is True and v["post_quant_guard"] == "NotImplementedError"
