@@ -212,6 +212,37 @@ try:
 except NotImplementedError:
     vae_rec["post_quant_guard"] = "NotImplementedError"
 out["vae_host"] = vae_rec
+# ---- config intake + weight packing from REAL (tiny) diffusers transformers: every key the packers read exists in the real state dicts
+from diffusers.models.transformers.transformer_sd3 import SD3Transformer2DModel
+from diffusers.models.transformers.transformer_flux import FluxTransformer2DModel
+from diffusers.models.transformers.transformer_qwenimage import QwenImageTransformer2DModel
+from diffusers.models.transformers.transformer_wan import WanTransformer3DModel
+from flow_factory_b200.weights import EngineConfig, PackedWeights
+cpu = torch.device("cpu")
+intake = {}
+m = SD3Transformer2DModel(sample_size=16, patch_size=2, in_channels=16, num_layers=2, attention_head_dim=64, num_attention_heads=2,
+                          joint_attention_dim=64, caption_projection_dim=128, pooled_projection_dim=32, out_channels=16, pos_embed_max_size=16,
+                          dual_attention_layers=(0,), qk_norm="rms_norm")
+c = EngineConfig.from_model_config(m.config)
+pw = PackedWeights(c, m.state_dict(), cpu)
+intake["sd3"] = [c.num_layers, c.num_heads, c.num_dual_layers, len(pw.tensors) > 0]
+m = FluxTransformer2DModel(patch_size=1, in_channels=64, num_layers=1, num_single_layers=1, attention_head_dim=128, num_attention_heads=2,
+                           joint_attention_dim=64, pooled_projection_dim=32, guidance_embeds=True, axes_dims_rope=(16, 56, 56))
+c = MF.FluxEngineConfig.from_model_config(m.config)
+pw = MF.FluxPackedWeights(c, m.state_dict(), cpu)
+intake["flux"] = [c.num_layers, c.num_single_layers, c.num_heads, bool(c.guidance_embeds), pw.mod_rows == (12 + 3 + 2) * 256]
+m = QwenImageTransformer2DModel(patch_size=2, in_channels=64, out_channels=16, num_layers=1, attention_head_dim=128, num_attention_heads=2,
+                                joint_attention_dim=64, axes_dims_rope=(16, 56, 56))
+c = MQ.qwen_engine_config(m.config)
+pw = MF.FluxPackedWeights(c, m.state_dict(), cpu)
+intake["qwen"] = [c.num_layers, c.variant, c.num_heads, len(pw.tensors) > 0]
+m = WanTransformer3DModel(patch_size=(1, 2, 2), num_attention_heads=2, attention_head_dim=128, in_channels=16, out_channels=16, text_dim=64,
+                          freq_dim=256, ffn_dim=320, num_layers=1, cross_attn_norm=True, qk_norm="rms_norm_across_heads", eps=1e-6,
+                          rope_max_seq_len=64)
+c = MW.WanEngineConfig.from_model_config(m.config)
+g_, layers_ = MW.pack_wan_state_dict(c, m.state_dict())
+intake["wan"] = [c.num_layers, c.num_attention_heads, c.ffn_dim, list(g_["pe_w"].shape), len(layers_)]
+out["intake"] = intake
 # ---- GRPO / GDPO advantage arithmetic (FF/advantage/advantage_processor.py:314-481) on randomised groups, incl. constant-reward groups
 import numpy as np
 from flow_factory.advantage.advantage_processor import AdvantageProcessor
@@ -353,3 +384,13 @@ def test_vae_host_side_against_the_real_autoencoder(hooks):
     assert v["cfg"] == [4, [32, 64], 1, 8, 1.5305, 0.0609]
     assert v["n_packed"][0] == v["n_packed"][1]
     assert v["postprocess"] is True and v["post_quant_guard"] == "NotImplementedError"
+
+
+def test_config_intake_and_packing_from_real_models(hooks):
+    """`transformer.config` (FrozenDict) and `transformer.state_dict()` of real (tiny) diffusers models go through every engine's config
+    intake and weight packer - the key names the packers read are the real ones."""
+    it = hooks["intake"]
+    assert it["sd3"] == [2, 2, 1, True]
+    assert it["flux"] == [1, 1, 2, True, True]
+    assert it["qwen"] == [1, 1, 2, True]
+    assert it["wan"] == [1, 2, 320, [256, 64], 1]
