@@ -243,6 +243,28 @@ c = MW.WanEngineConfig.from_model_config(m.config)
 g_, layers_ = MW.pack_wan_state_dict(c, m.state_dict())
 intake["wan"] = [c.num_layers, c.num_attention_heads, c.ffn_dim, list(g_["pe_w"].shape), len(layers_)]
 out["intake"] = intake
+# ---- B200SD3_5Adapter.from_reference_adapter fed with real reference objects (engine stubbed: no GPU here)
+import flow_factory_b200.adapter as MA
+class _Eng:
+    def __init__(self, model_config, state_dict, device):
+        self.device, self.cfg, self.n_keys = torch.device("cpu"), EngineConfig.from_model_config(model_config), len(state_dict)
+MA.RolloutEngine = _Eng
+class _RefAdapter:                                   # the attributes from_reference_adapter reads off a flow_factory SD3_5Adapter
+    pass
+ra = _RefAdapter()
+ra.transformer = SD3Transformer2DModel(sample_size=16, patch_size=2, in_channels=16, num_layers=2, attention_head_dim=64, num_attention_heads=2,
+                                       joint_attention_dim=64, caption_projection_dim=128, pooled_projection_dim=32, out_channels=16,
+                                       pos_embed_max_size=16, dual_attention_layers=(0,), qk_norm="rms_norm")
+ra.scheduler = RefFM(noise_level=0.6, sde_steps=[1, 2, 5], num_sde_steps=2, seed=7, dynamics_type="Dance-SDE", shift=3.0)
+ra.device = "cpu"
+ra.decode_latents = lambda lat, output_type="pt": lat * 0 + 0.5
+b = MA.B200SD3_5Adapter.from_reference_adapter(ra, rng="torch")
+ref_set(ra.scheduler, 10, seq_len=64, device="cpu"); b.scheduler.set_timesteps(10, seq_len=64)
+out["from_reference"] = {"cfg": [b.model_config.num_layers, b.model_config.num_heads], "n_keys": b.engine.n_keys == len(ra.transformer.state_dict()),
+                         "sched": [b.scheduler.noise_level, b.scheduler.dynamics_type, b.scheduler.seed, b.scheduler.num_sde_steps, b.scheduler.sde_steps.tolist()],
+                         "timesteps_equal": bool(torch.equal(ra.scheduler.timesteps, b.scheduler.timesteps)),
+                         "sde_equal": bool(torch.equal(ra.scheduler.current_sde_steps, b.scheduler.current_sde_steps)),
+                         "decode": float(b.decode_latents(torch.zeros(1, 2)).mean())}
 # ---- GRPO / GDPO advantage arithmetic (FF/advantage/advantage_processor.py:314-481) on randomised groups, incl. constant-reward groups
 import numpy as np
 from flow_factory.advantage.advantage_processor import AdvantageProcessor
@@ -394,3 +416,12 @@ def test_config_intake_and_packing_from_real_models(hooks):
     assert it["flux"] == [1, 1, 2, True, True]
     assert it["qwen"] == [1, 1, 2, True]
     assert it["wan"] == [1, 2, 320, [256, 64], 1]
+
+
+def test_from_reference_adapter_reads_real_reference_objects(hooks):
+    """The constructor INTEGRATION.md's glue uses: a real SD3Transformer2DModel and a real reference scheduler instance in, the engine config,
+    every weight, the scheduler settings (incl. SDE-step list / seed / dynamics) and the decode callback out."""
+    r = hooks["from_reference"]
+    assert r["cfg"] == [2, 2] and r["n_keys"] is True
+    assert r["sched"] == [0.6, "Dance-SDE", 7, 2, [1, 2, 5]]
+    assert r["timesteps_equal"] and r["sde_equal"] and r["decode"] == 0.5
