@@ -101,6 +101,69 @@ def create_trajectory_collector(indices: TrajectoryIndicesType, num_steps: int) 
     return TrajectoryCollector(indices=indices, total_steps=num_steps)
 
 
+class CallbackCollector:
+    """Mirror of FF/utils/trajectory_collector.py:187-337: named per-step values (`extra_call_back_kwargs`, e.g. GRPO-Guard's
+    `next_latents_mean`, grpo.py:404) recorded at the gated steps; each key is resolved from `capturable` first, then from the step output."""
+
+    def __init__(self, indices: TrajectoryIndicesType = "all", total_steps: int = 0):
+        self._gate = TrajectoryCollector(indices=indices, total_steps=total_steps)
+        self._data: dict = {}
+        self._collected_indices: List[int] = []
+        self._collected_set: Set[int] = set()
+
+    @property
+    def is_disabled(self) -> bool:
+        return self._gate.is_disabled
+
+    def should_collect(self, step_idx: int) -> bool:
+        return self._gate.should_collect(step_idx)
+
+    def collect_step(self, step_idx: int, output, keys: Sequence[str], capturable: Optional[dict] = None) -> None:
+        if not keys or not self.should_collect(step_idx):
+            return
+        if step_idx not in self._collected_set:
+            self._collected_indices.append(step_idx)
+            self._collected_set.add(step_idx)
+        for key in keys:
+            val = None
+            if capturable and key in capturable and capturable[key] is not None:
+                val = capturable[key]
+            elif hasattr(output, key):
+                val = getattr(output, key)
+            if val is not None:
+                self._data.setdefault(key, []).append(val)
+
+    def get_result(self) -> dict:
+        """Tensor lists are stacked batch-first: list of (B, ...) -> (B, T', ...); other values stay lists."""
+        return {k: (torch.stack(v, dim=1) if v and isinstance(v[0], torch.Tensor) else v) for k, v in self._data.items()}
+
+    def get_index_map(self) -> Optional[torch.Tensor]:
+        if self.is_disabled:
+            return None
+        total = self._gate.total_steps
+        if self._gate.collect_all:
+            return torch.arange(total, dtype=torch.long)
+        m = torch.full((total,), -1, dtype=torch.long)
+        for compact, orig in enumerate(self._collected_indices):
+            if 0 <= orig < total:
+                m[orig] = compact
+        return m
+
+    @property
+    def collected_indices(self) -> List[int]:
+        return self._collected_indices
+
+    def reset(self) -> None:
+        self._data, self._collected_indices, self._collected_set = {}, [], set()
+
+    def __len__(self) -> int:
+        return len(self._collected_indices)
+
+
+def create_callback_collector(indices: TrajectoryIndicesType, num_steps: int) -> CallbackCollector:
+    return CallbackCollector(indices=indices, total_steps=num_steps)
+
+
 def plan_slots(indices: TrajectoryIndicesType, num_steps: int, step_has_logp: Sequence[bool]):
     """Slot assignment for a T-step rollout, identical to what the reference's two collectors would produce
     (sd3_5.py:266-304): latent position p in [0, T] and log-prob of step i are kept iff the index gate admits them.

@@ -246,3 +246,67 @@ def test_fsdp2_sharded_weight_intake_one_allgather_world2_gloo():
     res = sorted(q.get(timeout=180) for _ in range(2))
     [p.join(timeout=60) for p in ps]
     assert res == [(0, True), (1, True)]
+
+
+def test_callback_collector_and_stepwise_inference_with_stub_engine(monkeypatch):
+    """`extra_call_back_kwargs` (GRPO-Guard: next_latents_mean, grpo.py:404) routes inference() through the reference's step loop over
+    forward(); bookkeeping checked with a stub engine (the kernels behind forward() are the validated ones)."""
+    from flow_factory_b200 import adapter as A
+    from flow_factory_b200.trajectory import CallbackCollector, compute_trajectory_indices
+    from flow_factory_b200.weights import EngineConfig
+
+    class Plan:
+        pass
+
+    class Eng:
+        def __init__(self, model_config, state_dict, device):
+            self.device, self.steps = torch.device("cpu"), []
+            self.cfg = EngineConfig(num_layers=1, num_heads=1, patch_size=2, in_channels=16, joint_attention_dim=8, pooled_projection_dim=8,
+                                    pos_embed_max_size=8, num_dual_layers=0)
+
+        def plan(self, *a):
+            return Plan()
+
+        def set_prompts(self, *a):
+            pass
+
+        def step(self, plan, latents, coef, guidance, noise=None, next_latents=None, seed=0, want_mean=True):
+            self.steps.append((coef.sigma, coef.noise_level, bool(coef.compute_log_prob), want_mean))
+            B = latents.shape[0]
+            nxt = (latents.float() * 0.5).half()
+            return dict(next_latents=nxt, next_latents_mean=latents.float() * 0.5 if want_mean else None,
+                        log_prob=torch.full((B,), float(len(self.steps))) if coef.compute_log_prob else None,
+                        noise_pred=torch.zeros_like(latents, dtype=torch.bfloat16), overflow=torch.zeros(1))
+
+    monkeypatch.setattr(A, "RolloutEngine", Eng)
+    sch = A.FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0, num_sde_steps=2, seed=3)
+    ad = A.B200SD3_5Adapter(None, {}, device="cpu", scheduler=sch, rng="philox")
+    ad.rollout()
+    T = 6
+    sch.set_timesteps(T, seq_len=16)
+    sde = sorted(sch.current_sde_steps.tolist())
+    idx = compute_trajectory_indices(sde, T)
+    pe, pp = torch.zeros(2, 3, 8), torch.zeros(2, 8)
+    out = ad.inference(prompt=["a", "b"], height=64, width=64, num_inference_steps=T, guidance_scale=1.0, prompt_embeds=pe, pooled_prompt_embeds=pp,
+                       compute_log_prob=True, extra_call_back_kwargs=["next_latents_mean", "noise_level"], trajectory_indices=idx,
+                       latents=torch.ones(2, 16, 8, 8))
+    eng = ad.engine
+    assert len(eng.steps) == T and [s[2] for s in eng.steps] == [i in sde for i in range(T)] and all(s[3] for s in eng.steps)
+    s0 = out[0]
+    n_lat = len(idx)
+    gated = [i for i in range(T) if i in set(idx)]                         # callback steps use the same gate as the latents (step index)
+    assert s0.all_latents.shape == (n_lat, 16, 8, 8) and s0.log_probs.shape == (len([i for i in sde if i in set(idx)]),)
+    assert s0.next_latents_mean.shape == (len(gated), 16, 8, 8)            # extra_kwargs fall-through, (T', C, H, W) per sample
+    cmap = s0.callback_index_map
+    assert cmap.shape == (T,) and [int(i) for i in (cmap >= 0).nonzero().flatten()] == gated
+    # latents halve every step in the stub: position p holds 0.5 ** p
+    for pos in idx:
+        assert float(s0.all_latents[int(s0.latent_index_map[pos])].float().mean()) == pytest.approx(0.5 ** pos, rel=1e-3)
+    for step in gated:
+        assert float(s0.next_latents_mean[int(cmap[step])].mean()) == pytest.approx(0.5 ** (step + 1), rel=1e-3)
+    assert torch.equal(s0.final_latents, (torch.ones(16, 8, 8) * 0.5 ** T).half())
+    c = CallbackCollector(None, 4)
+    c.collect_step(0, object(), ["x"], {"x": 1})
+    assert c.is_disabled and c.get_result() == {} and c.get_index_map() is None
+    with pytest.raises(NotImplementedError):
+        ad.inference(height=64, width=64, num_inference_steps=2, prompt_embeds=pe, pooled_prompt_embeds=pp, extra_call_back_kwargs=["std_dev_t"])

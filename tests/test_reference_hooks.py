@@ -122,6 +122,25 @@ for case in range(300):
     for mine, ref in ((lat_map, lc.get_index_map()), (lp_map, pc.get_index_map())):
         ok = ok and ((mine is None) == (ref is None)) and (mine is None or torch.equal(mine, ref))
     if not ok: mism.append((kind, T, idx, has_lp))
+from flow_factory.utils.trajectory_collector import create_callback_collector as ref_cb
+from flow_factory_b200.trajectory import create_callback_collector as my_cb
+class _O:
+    def __init__(self, i): self.next_latents_mean = torch.full((2, 3), float(i)); self.log_prob = None; self.tag = "s%d" % i
+for case in range(120):
+    T = rng.choice([1, 3, 6, 10])
+    idx = rng.choice(["all", None, sorted(rng.sample(range(T + 1), rng.randint(1, T + 1))), [rng.randint(-(T + 1), T) for _ in range(3)]])
+    keys = rng.choice([[], ["next_latents_mean"], ["next_latents_mean", "noise_level", "tag", "log_prob", "missing"]])
+    a, b_ = ref_cb(idx, T), my_cb(idx, T)
+    for i in range(T):
+        cap = {"noise_level": 0.7 if i % 2 else None}
+        a.collect_step(i, _O(i), keys, cap); b_.collect_step(i, _O(i), keys, cap)
+    ra, rb = a.get_result(), b_.get_result()
+    ok = list(ra.keys()) == list(rb.keys()) and len(a) == len(b_) and a.collected_indices == b_.collected_indices and a.is_disabled == b_.is_disabled
+    for k in ra:
+        ok = ok and (torch.equal(ra[k], rb[k]) if isinstance(ra[k], torch.Tensor) else ra[k] == rb[k])
+    ma, mb = a.get_index_map(), b_.get_index_map()
+    ok = ok and ((ma is None) == (mb is None)) and (ma is None or torch.equal(ma, mb))
+    if not ok: mism.append(("callback", T, idx, keys))
 out["trajectory_mismatches"] = [repr(m) for m in mism[:5]]
 # ---- scheduler mirrors: schedule, SDE-step selection and per-step scalars vs the reference on randomised settings
 from flow_factory.scheduler import FlowMatchEulerDiscreteSDEScheduler as RefFM, UniPCMultistepSDEScheduler as RefUP, set_scheduler_timesteps as ref_set

@@ -4,6 +4,7 @@
 # The parity module is gated on FFB200_PENDING=1 until it has passed once.
 mkdir -p gpurun_out
 export FFB200_PENDING=1
+timeout 300 python -m pytest tests/test_gpu_stepwise.py -q 2>&1 | tail -5 | tee gpurun_out/stepwise_tests.log
 timeout 600 python -m pytest tests/test_gpu_vae.py -x -q 2>&1 | tail -40 | tee gpurun_out/vae_tests.log
 python - <<'PY' 2>&1 | tee gpurun_out/vae_deverr.log
 from flow_factory_b200 import _lib
