@@ -20,6 +20,7 @@ import torch
 
 from . import _lib
 from .engine import RolloutEngine
+from .rng import randn_tensor
 from .samples import SD3_5Sample
 from .scheduler import FlowMatchEulerDiscreteSDEScheduler, SDESchedulerOutput, set_scheduler_timesteps
 from .trajectory import (TrajectoryIndicesType, compute_trajectory_indices, create_callback_collector, create_trajectory_collector,
@@ -162,7 +163,7 @@ class B200SD3_5Adapter:
                                 negative_prompt_embeds if do_cfg else None, negative_pooled_prompt_embeds if do_cfg else None)
         # 3. initial latents: randn in the transformer dtype (pipeline_stable_diffusion_3.py:633-662), then cast_latents
         if latents is None:
-            latents = torch.randn((B, C, lh, lw), generator=generator, device=dev, dtype=torch.bfloat16)
+            latents = randn_tensor((B, C, lh, lw), generator=generator, device=dev, dtype=torch.bfloat16)
         x0 = self.cast_latents(latents.to(dev))
         # 5. schedule (host only, no device syncs)
         seq_len = (lh // self.model_config.patch_size) * (lw // self.model_config.patch_size)
@@ -221,7 +222,7 @@ class B200SD3_5Adapter:
         T, B, C = int(num_inference_steps), len(prompt_embeds), self.model_config.in_channels
         lh, lw = int(height) // self.vae_scale_factor, int(width) // self.vae_scale_factor
         if latents is None:
-            latents = torch.randn((B, C, lh, lw), generator=generator, device=dev, dtype=torch.bfloat16)
+            latents = randn_tensor((B, C, lh, lw), generator=generator, device=dev, dtype=torch.bfloat16)
         sch = self.scheduler
         seq_len = (lh // self.model_config.patch_size) * (lw // self.model_config.patch_size)
         timesteps = set_scheduler_timesteps(sch, T, seq_len=seq_len)

@@ -12,6 +12,7 @@ from typing import Any, Callable, Dict, List, Optional, Union
 import torch
 
 from .flux import FluxRolloutEngine, model_scalar, pack_latents
+from .rng import randn_tensor
 from .samples import Flux1Sample
 from .scheduler import FlowMatchEulerDiscreteSDEScheduler, SDESchedulerOutput, set_scheduler_timesteps
 from .trajectory import TrajectoryIndicesType, plan_slots
@@ -95,7 +96,7 @@ class B200Flux1Adapter:
         plan = self.engine.plan(B, h2, w2, prompt_embeds.shape[1])
         self.engine.set_prompts(plan, prompt_embeds, pooled_prompt_embeds, float(guidance_scale), latents_dtype=torch.float16)
         if latents is None:
-            latents = pack_latents(torch.randn((B, self.model_config.in_channels // 4, lh, lw), generator=generator, device=dev,
+            latents = pack_latents(randn_tensor((B, self.model_config.in_channels // 4, lh, lw), generator=generator, device=dev,
                                                dtype=torch.bfloat16))
         x0 = self.cast_latents(latents.to(dev))
         sch = self.scheduler

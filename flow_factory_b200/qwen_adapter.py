@@ -11,6 +11,7 @@ from typing import Any, Callable, Dict, List, Optional, Union
 import torch
 
 from .qwen import QwenRolloutEngine
+from .rng import randn_tensor
 from .samples import QwenImageSample
 from .scheduler import FlowMatchEulerDiscreteSDEScheduler, SDESchedulerOutput, set_scheduler_timesteps
 from .trajectory import TrajectoryIndicesType, plan_slots
@@ -120,7 +121,7 @@ class B200QwenImageAdapter:
         h2, w2 = int(height) // self.vae_scale_factor // 2, int(width) // self.vae_scale_factor // 2
         plan = self._plan(B, h2, w2, pos, neg, guidance_scale)
         if latents is None:   # prepare_latents: randn (B, 1, 16, 2*h2, 2*w2) packed 2x2 -> (B, h2*w2, 64)
-            z = torch.randn((B, 16, 2 * h2, 2 * w2), generator=generator, device=dev, dtype=torch.bfloat16)
+            z = randn_tensor((B, 16, 2 * h2, 2 * w2), generator=generator, device=dev, dtype=torch.bfloat16)
             latents = z.view(B, 16, h2, 2, w2, 2).permute(0, 2, 4, 1, 3, 5).reshape(B, h2 * w2, 64)
         x0 = self.cast_latents(latents.to(dev))
         sch = self.scheduler

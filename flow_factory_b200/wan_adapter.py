@@ -11,6 +11,7 @@ from typing import Any, Callable, Dict, List, Optional, Union
 
 import torch
 
+from .rng import randn_tensor
 from .samples import WanT2VSample
 from .scheduler import SDESchedulerOutput, UniPCMultistepSDEScheduler
 from .trajectory import TrajectoryIndicesType, plan_slots
@@ -100,7 +101,7 @@ class B200Wan21Adapter:
         plan = self.engine.plan(B, shape[2], shape[3], shape[4], prompt_embeds.shape[1], cfg=do_cfg)
         self.engine.set_prompts(plan, prompt_embeds, negative_prompt_embeds if do_cfg else None)
         if latents is None:
-            latents = torch.randn(shape, generator=generator, device=dev, dtype=torch.float32)      # prepare_latents(dtype=float32)
+            latents = randn_tensor(shape, generator=generator, device=dev, dtype=torch.float32)      # prepare_latents(dtype=float32)
         x0 = self.cast_latents(latents.to(dev))
         sch = self.scheduler
         timesteps = sch.set_timesteps(T)

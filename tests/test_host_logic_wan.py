@@ -246,6 +246,13 @@ def test_adapter_bookkeeping_with_stub_engine(monkeypatch):
     st = [c for c in eng.calls if c[0] == "step"][0]
     assert st[1] == pytest.approx(float(sch.timesteps[3]) / 1000) and st[2] == pytest.approx(float(sch.timesteps[4]) / 1000) and st[3] == 5.0
     assert o.std_dev_t.shape == (2, 1, 1, 1, 1) and o.next_latents.dtype == torch.float32
+    # GRPOTrainer.evaluate (grpo.py:110-119): per-prompt CPU generators, no trajectory, no log-probs
+    eng.calls.clear()
+    gens = [torch.Generator().manual_seed(s) for s in (1, 2)]
+    ev = ad.inference(height=64, width=96, num_frames=9, num_inference_steps=4, guidance_scale=5.0, prompt_embeds=pe, negative_prompt_embeds=neg,
+                      compute_log_prob=False, trajectory_indices=None, generator=gens)
+    assert eng.calls[1][3] == 0 and eng.calls[1][5] == 0                       # no latent slots, no log-prob slots
+    assert ev[0].all_latents is None and ev[0].log_probs is None and ev[0].latent_index_map is None
     for bad in (dict(guidance_scale_2=3.0), dict(attention_kwargs={"a": 1}), dict(extra_call_back_kwargs=["noise_pred"])):
         with pytest.raises(NotImplementedError):
             ad.inference(height=64, width=96, num_frames=9, num_inference_steps=4, prompt_embeds=pe, **bad)

@@ -325,6 +325,19 @@ def probe(cls):
         res["missing_key"] = "KeyError"
     return res
 out["scheduler_output"] = [probe(RefOut), probe(MyOut)]
+from diffusers.utils.torch_utils import randn_tensor as ref_randn
+from flow_factory_b200.rng import randn_tensor as my_randn
+from flow_factory.utils.base import create_generator_by_prompt
+gens = lambda: create_generator_by_prompt(["a cat", "a dog", "a cat"], 42)          # what GRPOTrainer.evaluate passes (grpo.py:110)
+rr = [bool(torch.equal(ref_randn((3, 4, 2, 2), generator=gens(), device=torch.device("cpu"), dtype=torch.bfloat16),
+                       my_randn((3, 4, 2, 2), generator=gens(), device="cpu", dtype=torch.bfloat16))),
+      bool(torch.equal(ref_randn((2, 5), generator=torch.Generator().manual_seed(3), device=torch.device("cpu"), dtype=torch.float32),
+                       my_randn((2, 5), generator=torch.Generator().manual_seed(3), device="cpu", dtype=torch.float32))),
+      bool(torch.equal(ref_randn((1, 5), generator=[torch.Generator().manual_seed(4)], device=torch.device("cpu"), dtype=torch.float32),
+                       my_randn((1, 5), generator=[torch.Generator().manual_seed(4)], device="cpu", dtype=torch.float32)))]
+g3 = gens()
+rr.append(bool(torch.equal(my_randn((3, 2), generator=g3, dtype=torch.float32)[0], my_randn((3, 2), generator=gens(), dtype=torch.float32)[2])))  # same prompt, same noise
+out["randn_tensor"] = rr
 from flow_factory_b200.adapter import filter_kwargs as my_filter
 def f1(a, b=1): pass
 def f2(a, **kw): pass
@@ -444,3 +457,8 @@ def test_from_reference_adapter_reads_real_reference_objects(hooks):
     assert r["cfg"] == [2, 2] and r["n_keys"] is True
     assert r["sched"] == [0.6, "Dance-SDE", 7, 2, [1, 2, 5]]
     assert r["timesteps_equal"] and r["sde_equal"] and r["decode"] == 0.5
+
+
+def test_randn_tensor_mirror(hooks):
+    """Initial latents from per-prompt CPU generator lists (GRPOTrainer.evaluate) are the same numbers diffusers' randn_tensor draws."""
+    assert hooks["randn_tensor"] == [True, True, True, True]
