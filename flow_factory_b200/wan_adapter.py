@@ -94,6 +94,10 @@ class B200Wan21Adapter:
             raise NotImplementedError("per-step callbacks need the step-by-step path: call forward() in a loop")
         if guidance_scale_2 is not None:
             raise NotImplementedError("guidance_scale_2 / the second transformer of Wan2.2 are not on the accelerated path")
+        if self.scheduler.is_eval:
+            # in eval mode the reference's UniPCMultistepSDEScheduler.step hands over to diffusers' multistep predictor-corrector
+            # (unipc_multistep.py:283-285), not the Euler / SDE arithmetic of the rollout: outside this engine
+            raise NotImplementedError("evaluation-mode sampling (UniPC multistep solver) is not on the accelerated path; use the reference adapter")
         dev = self.device
         T, B = int(num_inference_steps), len(prompt_embeds)
         do_cfg = guidance_scale > 1.0 and negative_prompt_embeds is not None      # wan2_t2v.py:487-495
@@ -170,6 +174,8 @@ class B200Wan21Adapter:
             raise NotImplementedError("attention_kwargs are not on the accelerated path")
         if boundary_timestep is not None or guidance_scale_2 is not None:
             raise NotImplementedError("boundary_timestep / guidance_scale_2 (Wan2.2) are not on the accelerated path")
+        if self.scheduler.is_eval:
+            raise NotImplementedError("evaluation-mode stepping (UniPC multistep solver) is not on the accelerated path; use the reference adapter")
         B, _, Fr, H, W = latents.shape
         do_cfg = negative_prompt_embeds is not None and guidance_scale > 1.0
         plan = self.engine.plan(B, Fr, H, W, prompt_embeds.shape[1], cfg=do_cfg)

@@ -253,6 +253,10 @@ def test_adapter_bookkeeping_with_stub_engine(monkeypatch):
                       compute_log_prob=False, trajectory_indices=None, generator=gens)
     assert eng.calls[1][3] == 0 and eng.calls[1][5] == 0                       # no latent slots, no log-prob slots
     assert ev[0].all_latents is None and ev[0].log_probs is None and ev[0].latent_index_map is None
+    ad.eval()                                                                  # eval mode = diffusers' UniPC multistep solver in the reference
+    with pytest.raises(NotImplementedError, match="UniPC"):
+        ad.inference(height=64, width=96, num_frames=9, num_inference_steps=4, prompt_embeds=pe)
+    ad.rollout()
     for bad in (dict(guidance_scale_2=3.0), dict(attention_kwargs={"a": 1}), dict(extra_call_back_kwargs=["noise_pred"])):
         with pytest.raises(NotImplementedError):
             ad.inference(height=64, width=96, num_frames=9, num_inference_steps=4, prompt_embeds=pe, **bad)
