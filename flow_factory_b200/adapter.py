@@ -21,10 +21,10 @@ import torch
 from . import _lib
 from .engine import RolloutEngine
 from .rng import randn_tensor
+from .stepwise import SUPPORTED_CALLBACKS, per_sample, run_stepwise
 from .samples import SD3_5Sample
 from .scheduler import FlowMatchEulerDiscreteSDEScheduler, SDESchedulerOutput, set_scheduler_timesteps
-from .trajectory import (TrajectoryIndicesType, compute_trajectory_indices, create_callback_collector, create_trajectory_collector,
-                         plan_slots)
+from .trajectory import TrajectoryIndicesType, compute_trajectory_indices, plan_slots
 from .weights import EngineConfig
 
 
@@ -141,7 +141,7 @@ class B200SD3_5Adapter:
                              "(Flow-Factory's dataloader caches them; text encoders are outside the rollout path)")
         if joint_attention_kwargs:
             raise NotImplementedError("joint_attention_kwargs (IP-adapter / LoRA scale) are not on the accelerated path")
-        unsupported = set(extra_call_back_kwargs) - {"noise_pred", "next_latents_mean", "noise_level"}
+        unsupported = set(extra_call_back_kwargs) - SUPPORTED_CALLBACKS
         if unsupported:
             raise NotImplementedError(f"extra_call_back_kwargs {sorted(unsupported)} are not produced by the fused step")
         if extra_call_back_kwargs:
@@ -217,50 +217,22 @@ class B200SD3_5Adapter:
     def _inference_stepwise(self, prompt, negative_prompt, height, width, num_inference_steps, guidance_scale, generator, prompt_ids,
                             prompt_embeds, pooled_prompt_embeds, negative_prompt_ids, negative_prompt_embeds, negative_pooled_prompt_embeds,
                             compute_log_prob, extra_call_back_kwargs, trajectory_indices, latents, noise) -> List[SD3_5Sample]:
-        """SD3_5Adapter.inference's loop (sd3_5.py:266-349) with the reference's collectors around `forward()`."""
+        """SD3_5Adapter.inference's loop (sd3_5.py:266-349) with the reference's collectors around `forward()` (stepwise.py)."""
         dev = self.device
         T, B, C = int(num_inference_steps), len(prompt_embeds), self.model_config.in_channels
         lh, lw = int(height) // self.vae_scale_factor, int(width) // self.vae_scale_factor
         if latents is None:
             latents = randn_tensor((B, C, lh, lw), generator=generator, device=dev, dtype=torch.bfloat16)
-        sch = self.scheduler
         seq_len = (lh // self.model_config.patch_size) * (lw // self.model_config.patch_size)
-        timesteps = set_scheduler_timesteps(sch, T, seq_len=seq_len)
-        latent_collector = create_trajectory_collector(trajectory_indices, T)
-        lat = self.cast_latents(latents.to(dev))
-        latent_collector.collect(lat, step_idx=0)
-        log_prob_collector = create_trajectory_collector(trajectory_indices, T) if compute_log_prob else None
-        callback_collector = create_callback_collector(trajectory_indices, T)
-        for i in range(T):
-            t = timesteps[i]
-            current_noise_level = sch.get_noise_level_for_timestep(t)
-            if sch.is_eval:
-                current_noise_level = 0.0
-            t_next = timesteps[i + 1] if i + 1 < T else torch.tensor(0.0)
-            current_compute_log_prob = bool(compute_log_prob and current_noise_level > 0)
-            return_kwargs = list(set(["next_latents", "log_prob", "noise_pred"] + extra_call_back_kwargs))
-            output = self.forward(t=t, t_next=t_next, latents=lat, prompt_embeds=prompt_embeds, pooled_prompt_embeds=pooled_prompt_embeds,
-                                  negative_prompt_embeds=negative_prompt_embeds, negative_pooled_prompt_embeds=negative_pooled_prompt_embeds,
-                                  guidance_scale=guidance_scale, compute_log_prob=current_compute_log_prob, return_kwargs=return_kwargs,
-                                  noise_level=current_noise_level, noise=None if noise is None else noise[i])
-            lat = self.cast_latents(output.next_latents)
-            latent_collector.collect(lat, i + 1)
-            if current_compute_log_prob:
-                log_prob_collector.collect(output.log_prob, i)
-            callback_collector.collect_step(step_idx=i, output=output, keys=extra_call_back_kwargs, capturable={"noise_level": current_noise_level})
-        images = self.decode_latents(lat, output_type="pt")
-        extra_res = callback_collector.get_result()
-        callback_index_map = callback_collector.get_index_map()
-        all_latents = latent_collector.get_result()
-        all_log_probs = log_prob_collector.get_result() if compute_log_prob else None
+        timesteps = set_scheduler_timesteps(self.scheduler, T, seq_len=seq_len)
+        res = run_stepwise(self, timesteps, latents.to(dev), trajectory_indices, compute_log_prob, extra_call_back_kwargs,
+                           dict(prompt_embeds=prompt_embeds, pooled_prompt_embeds=pooled_prompt_embeds, negative_prompt_embeds=negative_prompt_embeds,
+                                negative_pooled_prompt_embeds=negative_pooled_prompt_embeds, guidance_scale=guidance_scale), noise=noise)
+        images = self.decode_latents(res["final"], output_type="pt")
         samples = []
         for b in range(B):
             samples.append(SD3_5Sample(
                 timesteps=timesteps,
-                all_latents=torch.stack([x[b] for x in all_latents], dim=0) if all_latents is not None else None,
-                log_probs=torch.stack([lp[b] for lp in all_log_probs], dim=0) if all_log_probs is not None else None,
-                latent_index_map=latent_collector.get_index_map(),
-                log_prob_index_map=log_prob_collector.get_index_map() if compute_log_prob else None,
                 prompt=prompt[b] if isinstance(prompt, list) else prompt,
                 prompt_ids=prompt_ids[b] if prompt_ids is not None else None,
                 prompt_embeds=prompt_embeds[b],
@@ -271,8 +243,7 @@ class B200SD3_5Adapter:
                 negative_pooled_prompt_embeds=negative_pooled_prompt_embeds[b] if negative_pooled_prompt_embeds is not None else None,
                 height=height, width=width,
                 image=images[b] if images is not None else None,
-                extra_kwargs={**{k: v[b] for k, v in extra_res.items()},          # as sd3_5.py:340 (tensors are (B, T', ...))
-                              "callback_index_map": callback_index_map, "final_latents": lat[b]},
+                **per_sample(res, b),
             ))
         return samples
 

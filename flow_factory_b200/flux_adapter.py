@@ -13,6 +13,7 @@ import torch
 
 from .flux import FluxRolloutEngine, model_scalar, pack_latents
 from .rng import randn_tensor
+from .stepwise import SUPPORTED_CALLBACKS, per_sample, run_stepwise
 from .samples import Flux1Sample
 from .scheduler import FlowMatchEulerDiscreteSDEScheduler, SDESchedulerOutput, set_scheduler_timesteps
 from .trajectory import TrajectoryIndicesType, plan_slots
@@ -84,8 +85,9 @@ class B200Flux1Adapter:
             raise ValueError("B200Flux1Adapter.inference needs pre-encoded prompt_embeds / pooled_prompt_embeds")
         if joint_attention_kwargs:
             raise NotImplementedError("joint_attention_kwargs (IP-adapter / LoRA scale) are not on the accelerated path")
-        if extra_call_back_kwargs:
-            raise NotImplementedError("per-step callbacks need the step-by-step path: call forward() in a loop")
+        unsupported = set(extra_call_back_kwargs) - SUPPORTED_CALLBACKS
+        if unsupported:
+            raise NotImplementedError(f"extra_call_back_kwargs {sorted(unsupported)} are not produced by the step kernel")
         dev = self.device
         T = int(num_inference_steps)
         B = len(prompt_embeds)
@@ -101,6 +103,17 @@ class B200Flux1Adapter:
         x0 = self.cast_latents(latents.to(dev))
         sch = self.scheduler
         timesteps = set_scheduler_timesteps(sch, T, seq_len=plan.n_img)
+        if extra_call_back_kwargs:
+            # per-step callback values (GRPO-Guard's next_latents_mean, grpo.py:404): the reference's own loop over forward() (stepwise.py)
+            res = run_stepwise(self, timesteps, x0, trajectory_indices, compute_log_prob, list(extra_call_back_kwargs),
+                               dict(prompt_embeds=prompt_embeds, pooled_prompt_embeds=pooled_prompt_embeds, img_ids=plan.img_ids.to(dev),
+                                    guidance_scale=guidance_scale), noise=noise)
+            images = self.decode_latents(res["final"], height, width, output_type="pt")
+            return [Flux1Sample(timesteps=timesteps, prompt=prompt[b] if isinstance(prompt, list) else prompt,
+                                prompt_ids=prompt_ids[b] if prompt_ids is not None else None, prompt_embeds=prompt_embeds[b],
+                                pooled_prompt_embeds=pooled_prompt_embeds[b], height=height, width=width,
+                                image=images[b] if images is not None else None, img_ids=plan.img_ids.to(dev), **per_sample(res, b))
+                    for b in range(B)]
         sde_now = set(sch.current_sde_steps.tolist())
         nls = [(sch.noise_level if (i in sde_now and not sch.is_eval) else 0.0) for i in range(T)]
         has_lp = [bool(compute_log_prob and nls[i] > 0) for i in range(T)]

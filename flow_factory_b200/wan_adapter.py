@@ -12,6 +12,7 @@ from typing import Any, Callable, Dict, List, Optional, Union
 import torch
 
 from .rng import randn_tensor
+from .stepwise import SUPPORTED_CALLBACKS, per_sample, run_stepwise
 from .samples import WanT2VSample
 from .scheduler import SDESchedulerOutput, UniPCMultistepSDEScheduler
 from .trajectory import TrajectoryIndicesType, plan_slots
@@ -90,8 +91,9 @@ class B200Wan21Adapter:
             raise ValueError("B200Wan21Adapter.inference needs pre-encoded prompt_embeds")
         if attention_kwargs:
             raise NotImplementedError("attention_kwargs are not on the accelerated path")
-        if extra_call_back_kwargs:
-            raise NotImplementedError("per-step callbacks need the step-by-step path: call forward() in a loop")
+        unsupported = set(extra_call_back_kwargs) - SUPPORTED_CALLBACKS
+        if unsupported:
+            raise NotImplementedError(f"extra_call_back_kwargs {sorted(unsupported)} are not produced by the step kernel")
         if guidance_scale_2 is not None:
             raise NotImplementedError("guidance_scale_2 / the second transformer of Wan2.2 are not on the accelerated path")
         if self.scheduler.is_eval:
@@ -109,6 +111,18 @@ class B200Wan21Adapter:
         x0 = self.cast_latents(latents.to(dev))
         sch = self.scheduler
         timesteps = sch.set_timesteps(T)
+        if extra_call_back_kwargs:
+            res = run_stepwise(self, timesteps, x0, trajectory_indices, compute_log_prob, list(extra_call_back_kwargs),
+                               dict(prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds, guidance_scale=guidance_scale),
+                               noise=noise, last_t_next=torch.tensor(0))
+            videos = self.decode_latents(res["final"], output_type="pt")
+            return [WanT2VSample(timesteps=timesteps, video=videos[b] if videos is not None else None, height=height, width=width,
+                                 prompt=prompt[b] if isinstance(prompt, list) else prompt,
+                                 prompt_ids=prompt_ids[b] if prompt_ids is not None else None, prompt_embeds=prompt_embeds[b],
+                                 negative_prompt=negative_prompt[b] if isinstance(negative_prompt, list) else negative_prompt,
+                                 negative_prompt_ids=negative_prompt_ids[b] if negative_prompt_ids is not None else None,
+                                 negative_prompt_embeds=negative_prompt_embeds[b] if negative_prompt_embeds is not None else None,
+                                 **per_sample(res, b)) for b in range(B)]
         sde_now = set(sch.current_sde_steps.tolist())
         nls = [(sch.noise_level if (i in sde_now and not sch.is_eval) else 0.0) for i in range(T)]
         has_lp = [bool(compute_log_prob and nls[i] > 0) for i in range(T)]

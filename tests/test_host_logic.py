@@ -309,4 +309,4 @@ def test_callback_collector_and_stepwise_inference_with_stub_engine(monkeypatch)
     c.collect_step(0, object(), ["x"], {"x": 1})
     assert c.is_disabled and c.get_result() == {} and c.get_index_map() is None
     with pytest.raises(NotImplementedError):
-        ad.inference(height=64, width=64, num_inference_steps=2, prompt_embeds=pe, pooled_prompt_embeds=pp, extra_call_back_kwargs=["std_dev_t"])
+        ad.inference(height=64, width=64, num_inference_steps=2, prompt_embeds=pe, pooled_prompt_embeds=pp, extra_call_back_kwargs=["prompt_embeds"])

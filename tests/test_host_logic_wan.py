@@ -257,6 +257,15 @@ def test_adapter_bookkeeping_with_stub_engine(monkeypatch):
     with pytest.raises(NotImplementedError, match="UniPC"):
         ad.inference(height=64, width=96, num_frames=9, num_inference_steps=4, prompt_embeds=pe)
     ad.rollout()
-    for bad in (dict(guidance_scale_2=3.0), dict(attention_kwargs={"a": 1}), dict(extra_call_back_kwargs=["noise_pred"])):
+    # per-step callbacks (GRPO-Guard): the step loop over forward(), integer timesteps, final t_next = 0
+    eng.calls.clear()
+    sch.set_timesteps(T)
+    cb = ad.inference(height=64, width=96, num_frames=9, num_inference_steps=T, guidance_scale=5.0, prompt_embeds=pe, negative_prompt_embeds=neg,
+                      compute_log_prob=True, trajectory_indices=idx, extra_call_back_kwargs=["next_latents_mean"])
+    steps = [c for c in eng.calls if c[0] == "step"]
+    assert len(steps) == T and steps[-1][2] == 0.0 and steps[0][1] == pytest.approx(float(sch.timesteps[0]) / 1000)
+    assert cb[0].callback_index_map.shape == (T,) and cb[0].next_latents_mean.shape[1:] == (16, 3, 8, 12)
+    assert cb[0].all_latents.shape[0] == len(idx) and cb[0].log_probs.shape[0] == len([i for i in sde if i in set(idx)])
+    for bad in (dict(guidance_scale_2=3.0), dict(attention_kwargs={"a": 1}), dict(extra_call_back_kwargs=["prompt_embeds"])):
         with pytest.raises(NotImplementedError):
             ad.inference(height=64, width=96, num_frames=9, num_inference_steps=4, prompt_embeds=pe, **bad)
