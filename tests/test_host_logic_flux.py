@@ -119,3 +119,50 @@ def test_qwen_prompt_densify_and_mask_rules():
     with pytest.raises(ValueError):
         _dense(x, torch.tensor([[1, 1, 1, 1, 1, 1], [0, 0, 0, 0, 0, 0]]), "p")
     assert tuple(_pad_to(x, 8).shape) == (2, 8, 8) and _pad_to(x, 6) is x
+
+
+def test_flux_adapter_stepwise_callbacks_with_stub_engine(monkeypatch):
+    """`extra_call_back_kwargs` on the FLUX.1 adapter: the step loop over forward() (stepwise.py) with a stub engine."""
+    import pytest
+    import torch
+    from flow_factory_b200 import flux_adapter as FA
+    from flow_factory_b200.flux import FluxEngineConfig, latent_image_ids
+    from flow_factory_b200.scheduler import FlowMatchEulerDiscreteSDEScheduler
+    from flow_factory_b200.trajectory import compute_trajectory_indices
+
+    class Plan:
+        def __init__(self, batch, h2, w2, n_text):
+            self.batch, self.h2, self.w2, self.n_text, self.n_img, self.img_ids = batch, h2, w2, n_text, h2 * w2, latent_image_ids(h2, w2)
+
+    class Eng:
+        def __init__(self, model_config, state_dict, device):
+            self.device, self.cfg, self.steps = torch.device("cpu"), FluxEngineConfig(num_layers=1, num_single_layers=1, num_heads=1), []
+
+        def plan(self, batch, h2, w2, n_text, cfg=False):
+            return Plan(batch, h2, w2, n_text)
+
+        def set_prompts(self, *a, **k):
+            pass
+
+        def step(self, plan, latents, coef, noise=None, next_latents=None, seed=0):
+            self.steps.append((coef.sigma, coef.sigma_prev, coef.noise_level))
+            z = latents.float() * 0.5
+            return dict(next_latents=z.half(), next_latents_mean=z, log_prob=torch.zeros(latents.shape[0]) if coef.compute_log_prob else None,
+                        noise_pred=torch.zeros_like(latents, dtype=torch.bfloat16), overflow=torch.zeros(1))
+
+    monkeypatch.setattr(FA, "FluxRolloutEngine", Eng)
+    sch = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, use_dynamic_shifting=True, num_sde_steps=1, seed=2)
+    ad = FA.B200Flux1Adapter(None, {}, device="cpu", scheduler=sch, rng="philox")
+    ad.rollout()
+    T = 5
+    sch.set_timesteps(T, seq_len=16)
+    idx = compute_trajectory_indices(sch.train_timesteps.tolist(), T)
+    pe, pp = torch.zeros(2, 3, 8), torch.zeros(2, 8)
+    out = ad.inference(height=64, width=64, num_inference_steps=T, prompt_embeds=pe, pooled_prompt_embeds=pp, compute_log_prob=True,
+                       trajectory_indices=idx, extra_call_back_kwargs=["next_latents_mean"], latents=torch.ones(2, 16, 64))
+    assert len(ad.engine.steps) == T and ad.engine.steps[-1][1] == 0.0
+    s0 = out[0]
+    assert s0.all_latents.shape == (len(idx), 16, 64) and s0.img_ids.shape == (16, 3) and s0.callback_index_map.shape == (T,)
+    assert s0.next_latents_mean.shape[1:] == (16, 64) and torch.equal(s0.final_latents, (torch.ones(16, 64) * 0.5 ** T).half())
+    with pytest.raises(NotImplementedError):
+        ad.inference(height=64, width=64, num_inference_steps=2, prompt_embeds=pe, pooled_prompt_embeds=pp, extra_call_back_kwargs=["img_ids"])
