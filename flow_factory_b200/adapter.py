@@ -25,6 +25,7 @@ from .stepwise import SUPPORTED_CALLBACKS, per_sample, run_stepwise
 from .samples import SD3_5Sample
 from .scheduler import FlowMatchEulerDiscreteSDEScheduler, SDESchedulerOutput, set_scheduler_timesteps
 from .trajectory import TrajectoryIndicesType, compute_trajectory_indices, plan_slots
+from .trajectory import create_callback_collector
 from .weights import EngineConfig
 
 
@@ -191,6 +192,8 @@ class B200SD3_5Adapter:
                                 noise=noise, seed=seed, use_graph=self.use_graph)
         final = r["final_latents"]
         images = self.decode_latents(final, output_type="pt")
+        # as the reference: the callback gate's map even when no callback key was requested (all -1, or the identity for 'all')
+        callback_index_map = create_callback_collector(trajectory_indices, T).get_index_map()
         samples = []
         for b in range(B):
             samples.append(SD3_5Sample(
@@ -209,7 +212,7 @@ class B200SD3_5Adapter:
                 negative_pooled_prompt_embeds=negative_pooled_prompt_embeds[b] if negative_pooled_prompt_embeds is not None else None,
                 height=height, width=width,
                 image=images[b] if images is not None else None,
-                extra_kwargs={"callback_index_map": None, "final_latents": final[b]},
+                extra_kwargs={"callback_index_map": callback_index_map, "final_latents": final[b]},
             ))
         self._last_overflow = r["overflow"]
         return samples

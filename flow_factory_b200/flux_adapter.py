@@ -17,6 +17,7 @@ from .stepwise import SUPPORTED_CALLBACKS, per_sample, run_stepwise
 from .samples import Flux1Sample
 from .scheduler import FlowMatchEulerDiscreteSDEScheduler, SDESchedulerOutput, set_scheduler_timesteps
 from .trajectory import TrajectoryIndicesType, plan_slots
+from .trajectory import create_callback_collector
 
 
 class B200Flux1Adapter:
@@ -134,6 +135,8 @@ class B200Flux1Adapter:
         final = r["final_latents"]
         images = self.decode_latents(final, height, width, output_type="pt")
         img_ids = plan.img_ids.to(dev)
+        # as the reference: the callback gate's map even when no callback key was requested (all -1, or the identity for 'all')
+        callback_index_map = create_callback_collector(trajectory_indices, T).get_index_map()
         samples = []
         for b in range(B):
             samples.append(Flux1Sample(
@@ -149,7 +152,7 @@ class B200Flux1Adapter:
                 height=height, width=width,
                 image=images[b] if images is not None else None,
                 img_ids=img_ids,
-                extra_kwargs={"callback_index_map": None, "final_latents": final[b]},
+                extra_kwargs={"callback_index_map": callback_index_map, "final_latents": final[b]},
             ))
         self._last_overflow = r["overflow"]
         return samples

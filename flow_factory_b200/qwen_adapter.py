@@ -15,6 +15,7 @@ from .rng import randn_tensor
 from .samples import QwenImageSample
 from .scheduler import FlowMatchEulerDiscreteSDEScheduler, SDESchedulerOutput, set_scheduler_timesteps
 from .trajectory import TrajectoryIndicesType, plan_slots
+from .trajectory import create_callback_collector
 
 
 def _dense(embeds, mask, what: str):
@@ -144,6 +145,8 @@ class B200QwenImageAdapter:
         final = r["final_latents"]
         images = self.decode_fn(final, height, width) if self.decode_fn is not None else None
         mk = lambda e, n: (torch.arange(e.shape[0], device=e.device) < n).long()
+        # as the reference: the callback gate's map even when no callback key was requested (all -1, or the identity for 'all')
+        callback_index_map = create_callback_collector(trajectory_indices, T).get_index_map()
         samples = []
         for b in range(B):
             samples.append(QwenImageSample(
@@ -159,7 +162,7 @@ class B200QwenImageAdapter:
                 negative_prompt_ids=negative_prompt_ids[b] if negative_prompt_ids is not None else None,
                 negative_prompt_embeds=npe[b] if npe is not None else None,
                 negative_prompt_embeds_mask=mk(npe[b], neg[1][b]) if npe is not None else None,
-                extra_kwargs={"callback_index_map": None, "final_latents": final[b]},
+                extra_kwargs={"callback_index_map": callback_index_map, "final_latents": final[b]},
             ))
         self._last_overflow = r["overflow"]
         return samples

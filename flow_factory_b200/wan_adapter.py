@@ -16,6 +16,7 @@ from .stepwise import SUPPORTED_CALLBACKS, per_sample, run_stepwise
 from .samples import WanT2VSample
 from .scheduler import SDESchedulerOutput, UniPCMultistepSDEScheduler
 from .trajectory import TrajectoryIndicesType, plan_slots
+from .trajectory import create_callback_collector
 from .wan import WanRolloutEngine
 
 
@@ -143,6 +144,8 @@ class B200Wan21Adapter:
                                 use_graph=self.use_graph)
         final = r["final_latents"]
         videos = self.decode_latents(final, output_type="pt")
+        # as the reference: the callback gate's map even when no callback key was requested (all -1, or the identity for 'all')
+        callback_index_map = create_callback_collector(trajectory_indices, T).get_index_map()
         samples = []
         for b in range(B):
             samples.append(WanT2VSample(
@@ -159,7 +162,7 @@ class B200Wan21Adapter:
                 negative_prompt=negative_prompt[b] if isinstance(negative_prompt, list) else negative_prompt,
                 negative_prompt_ids=negative_prompt_ids[b] if negative_prompt_ids is not None else None,
                 negative_prompt_embeds=negative_prompt_embeds[b] if negative_prompt_embeds is not None else None,
-                extra_kwargs={"callback_index_map": None, "final_latents": final[b]},
+                extra_kwargs={"callback_index_map": callback_index_map, "final_latents": final[b]},
             ))
         self._last_overflow = r["overflow"]
         return samples
