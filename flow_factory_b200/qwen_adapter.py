@@ -12,6 +12,7 @@ import torch
 
 from .qwen import QwenRolloutEngine
 from .rng import randn_tensor
+from .stepwise import SUPPORTED_CALLBACKS, per_sample, run_stepwise
 from .samples import QwenImageSample
 from .scheduler import FlowMatchEulerDiscreteSDEScheduler, SDESchedulerOutput, set_scheduler_timesteps
 from .trajectory import TrajectoryIndicesType, plan_slots
@@ -112,8 +113,9 @@ class B200QwenImageAdapter:
             raise ValueError("B200QwenImageAdapter.inference needs pre-encoded prompt_embeds (+ masks)")
         if attention_kwargs:
             raise NotImplementedError("attention_kwargs are not on the accelerated path")
-        if extra_call_back_kwargs:
-            raise NotImplementedError("per-step callbacks need the step-by-step path: call forward() in a loop")
+        unsupported = set(extra_call_back_kwargs) - SUPPORTED_CALLBACKS
+        if unsupported:
+            raise NotImplementedError(f"extra_call_back_kwargs {sorted(unsupported)} are not produced by the step kernel")
         dev, T = self.device, int(num_inference_steps)
         pos = _dense(prompt_embeds, prompt_embeds_mask, "prompt_embeds")
         neg = _dense(negative_prompt_embeds, negative_prompt_embeds_mask, "negative_prompt_embeds") if negative_prompt_embeds is not None else None
@@ -127,6 +129,23 @@ class B200QwenImageAdapter:
         x0 = self.cast_latents(latents.to(dev))
         sch = self.scheduler
         timesteps = set_scheduler_timesteps(sch, T, seq_len=plan.n_img)
+        mk = lambda e, n: (torch.arange(e.shape[0], device=e.device) < n).long()
+        if extra_call_back_kwargs:
+            # per-step callback values: the reference's own loop over forward() (stepwise.py)
+            res = run_stepwise(self, timesteps, x0, trajectory_indices, compute_log_prob, list(extra_call_back_kwargs),
+                               dict(prompt_embeds=prompt_embeds, prompt_embeds_mask=prompt_embeds_mask, img_shapes=[[(1, h2, w2)]] * B,
+                                    negative_prompt_embeds=negative_prompt_embeds, negative_prompt_embeds_mask=negative_prompt_embeds_mask,
+                                    guidance_scale=guidance_scale), noise=noise)
+            images = self.decode_fn(res["final"], height, width) if self.decode_fn is not None else None
+            return [QwenImageSample(timesteps=timesteps, height=height, width=width, image=images[b] if images is not None else None,
+                                    img_shapes=[(1, h2, w2)], prompt=prompt[b] if isinstance(prompt, list) else prompt,
+                                    prompt_ids=prompt_ids[b] if prompt_ids is not None else None,
+                                    prompt_embeds=pe[b], prompt_embeds_mask=mk(pe[b], pos[1][b]),
+                                    negative_prompt=negative_prompt[b] if isinstance(negative_prompt, list) else negative_prompt,
+                                    negative_prompt_ids=negative_prompt_ids[b] if negative_prompt_ids is not None else None,
+                                    negative_prompt_embeds=npe[b] if npe is not None else None,
+                                    negative_prompt_embeds_mask=mk(npe[b], neg[1][b]) if npe is not None else None,
+                                    **per_sample(res, b)) for b in range(B)]
         sde_now = set(sch.current_sde_steps.tolist())
         nls = [(sch.noise_level if (i in sde_now and not sch.is_eval and sch.dynamics_type != "ODE") else 0.0) for i in range(T)]
         has_lp = [bool(compute_log_prob and nls[i] > 0) for i in range(T)]
@@ -144,7 +163,6 @@ class B200QwenImageAdapter:
         r = self.engine.rollout(plan, x0, coefs, n_lat, lat_slot[0], n_lp, noise=noise, seed=seed, use_graph=self.use_graph)
         final = r["final_latents"]
         images = self.decode_fn(final, height, width) if self.decode_fn is not None else None
-        mk = lambda e, n: (torch.arange(e.shape[0], device=e.device) < n).long()
         # as the reference: the callback gate's map even when no callback key was requested (all -1, or the identity for 'all')
         callback_index_map = create_callback_collector(trajectory_indices, T).get_index_map()
         samples = []
