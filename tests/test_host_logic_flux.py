@@ -166,3 +166,54 @@ def test_flux_adapter_stepwise_callbacks_with_stub_engine(monkeypatch):
     assert s0.next_latents_mean.shape[1:] == (16, 64) and torch.equal(s0.final_latents, (torch.ones(16, 64) * 0.5 ** T).half())
     with pytest.raises(NotImplementedError):
         ad.inference(height=64, width=64, num_inference_steps=2, prompt_embeds=pe, pooled_prompt_embeds=pp, extra_call_back_kwargs=["img_ids"])
+
+def test_qwen_adapter_stepwise_callbacks_with_stub_engine(monkeypatch):
+    """`extra_call_back_kwargs` on the Qwen-Image adapter: the step loop over forward() with a stub engine (fast path untouched)."""
+    from flow_factory_b200 import qwen_adapter as QA
+    from flow_factory_b200.flux import FluxEngineConfig
+    from flow_factory_b200.scheduler import FlowMatchEulerDiscreteSDEScheduler
+    from flow_factory_b200.trajectory import compute_trajectory_indices
+
+    class Plan:
+        def __init__(self, batch, h2, w2, n_text, cfg):
+            self.batch, self.h2, self.w2, self.n_text, self.n_img, self.cfg = batch, h2, w2, n_text, h2 * w2, cfg
+
+    class Eng:
+        def __init__(self, model_config, state_dict, device):
+            self.device, self.cfg, self.steps, self.prompts = torch.device("cpu"), FluxEngineConfig(num_layers=1, num_single_layers=0, num_heads=1, variant=1), [], []
+
+        def plan(self, batch, h2, w2, n_text, cfg=False):
+            return Plan(batch, h2, w2, n_text, cfg)
+
+        def set_prompts(self, plan, pe, npe, g, prompt_lengths=None, negative_lengths=None):
+            self.prompts.append((tuple(pe.shape), None if npe is None else tuple(npe.shape), g, prompt_lengths, negative_lengths))
+
+        def t_model(self, t, dtype=torch.float16):
+            return float(t) / 1000
+
+        def step(self, plan, latents, coef, noise=None, next_latents=None, seed=0):
+            self.steps.append((coef.sigma, coef.sigma_prev, coef.noise_level))
+            z = latents.float() * 0.5
+            return dict(next_latents=z.half(), next_latents_mean=z, log_prob=torch.zeros(latents.shape[0]) if coef.compute_log_prob else None,
+                        noise_pred=torch.zeros_like(latents, dtype=torch.bfloat16), overflow=torch.zeros(1))
+
+    monkeypatch.setattr(QA, "QwenRolloutEngine", Eng)
+    sch = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, use_dynamic_shifting=True, num_sde_steps=1, seed=2, dynamics_type="Flow-SDE")
+    ad = QA.B200QwenImageAdapter(None, {}, device="cpu", scheduler=sch, rng="philox")
+    ad.rollout()
+    T = 4
+    sch.set_timesteps(T, seq_len=16)
+    idx = compute_trajectory_indices(sch.train_timesteps.tolist(), T)
+    pe = [torch.zeros(5, 8), torch.zeros(3, 8)]                      # ragged prompts, as the reference's list form
+    npe = [torch.zeros(2, 8), torch.zeros(2, 8)]
+    out = ad.inference(prompt=["a", "b"], height=64, width=64, num_inference_steps=T, guidance_scale=4.0, prompt_embeds=pe, negative_prompt_embeds=npe,
+                       compute_log_prob=True, trajectory_indices=idx, extra_call_back_kwargs=["next_latents_mean"], latents=torch.ones(2, 16, 64))
+    eng = ad.engine
+    assert len(eng.steps) == T and eng.steps[-1][1] == 0.0
+    assert eng.prompts[-1][3] == [5, 3] and eng.prompts[-1][4] == [2, 2] and eng.prompts[-1][2] == 4.0
+    s0, s1 = out
+    assert s0.all_latents.shape == (len(idx), 16, 64) and s0.img_shapes == [(1, 4, 4)] and s0.callback_index_map.shape == (T,)
+    assert s0.prompt_embeds_mask.tolist() == [1, 1, 1, 1, 1] and s1.prompt_embeds_mask.tolist() == [1, 1, 1, 0, 0]
+    assert s0.next_latents_mean.shape[1:] == (16, 64) and s1.prompt == "b"
+    with pytest.raises(NotImplementedError):
+        ad.inference(height=64, width=64, num_inference_steps=2, prompt_embeds=pe, extra_call_back_kwargs=["img_shapes"])
