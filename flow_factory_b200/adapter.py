@@ -80,8 +80,8 @@ class B200SD3_5Adapter:
     def rollout(self):
         self._mode = "rollout"; self.scheduler.rollout()
 
-    def train(self):
-        self._mode = "train"; self.scheduler.train()
+    def train(self, mode: bool = True):
+        self._mode = "train" if mode else "eval"; self.scheduler.train(mode=mode)
 
     def eval(self):
         self._mode = "eval"; self.scheduler.eval()

@@ -43,8 +43,8 @@ class B200Wan21Adapter:
     def rollout(self):
         self.scheduler.rollout()
 
-    def train(self):
-        self.scheduler.train()
+    def train(self, mode: bool = True):       # FF/models/abc.py:372-378
+        self.scheduler.train(mode=mode)
 
     def eval(self):
         self.scheduler.eval()
