@@ -243,10 +243,16 @@ class FlowMatchEulerDiscreteSDEScheduler:
     def step_coef(self, timestep, timestep_next, noise_level: Optional[float], dynamics_type: Optional[str] = None,
                   sigma_max: Optional[float] = None, compute_log_prob: bool = True, t_model: float = 0.0,
                   store_slot: int = -1, logp_slot: int = -1):
-        """Host scalars of one step; `timestep`/`timestep_next` in [0, 1000] as the adapters pass them."""
+        """Host scalars of one step; `timestep`/`timestep_next` in [0, 1000] as the adapters pass them.  With `timestep_next=None` the
+        reference looks the step up in its tables and uses `sigmas[i]`, `sigmas[i + 1]` themselves (flow_match...py:262-299), which can
+        differ from `timesteps / 1000` in the last bit - mirrored."""
         dyn = dynamics_type or self.dynamics_type
-        sigma = (torch.as_tensor(timestep, dtype=torch.float32) / 1000).item()
-        sigma_prev = (torch.as_tensor(timestep_next, dtype=torch.float32) / 1000).item()
+        if timestep_next is None:
+            i = self.index_for_timestep(timestep)
+            sigma, sigma_prev = float(self.sigmas[i]), float(self.sigmas[i + 1])
+        else:
+            sigma = (torch.as_tensor(timestep, dtype=torch.float32) / 1000).item()
+            sigma_prev = (torch.as_tensor(timestep_next, dtype=torch.float32) / 1000).item()
         if self.is_eval or dyn == "ODE":
             noise_level = 0.0
         elif noise_level is None:
@@ -261,10 +267,6 @@ class FlowMatchEulerDiscreteSDEScheduler:
              return_kwargs: List[str] = ["next_latents", "next_latents_mean", "std_dev_t", "dt", "log_prob", "noise_pred"],
              dynamics_type: Optional[str] = None, sigma_max: Optional[float] = None, noise: Optional[torch.Tensor] = None,
              seed: int = 0, step_index: int = 0):
-        if timestep_next is None:
-            i = self.index_for_timestep(timestep)
-            timestep = self.timesteps[i]
-            timestep_next = self.timesteps[i + 1] if i + 1 < len(self.timesteps) else torch.tensor(0.0)
         if not latents.is_cuda:
             raise RuntimeError("flow_factory_b200 scheduler.step needs CUDA tensors (no CPU fallback)")
         c = self.step_coef(timestep, timestep_next, noise_level, dynamics_type, sigma_max, compute_log_prob)
@@ -343,3 +345,10 @@ class UniPCMultistepSDEScheduler(FlowMatchEulerDiscreteSDEScheduler):
         nl = torch.zeros(len(self.timesteps), dtype=torch.float32)
         nl[self.current_sde_steps] = self.noise_level
         return nl
+
+    def step_coef(self, timestep, timestep_next, noise_level, *args, **kwargs):
+        if timestep_next is None:
+            # the reference's step() takes an INTEGER timestep without timestep_next for a step index (unipc_multistep.py:246-256) - with the
+            # integer UniPC schedule that path cannot address a timestep; Wan2_T2V_Adapter always passes t_next (wan2_t2v.py:349-355)
+            raise ValueError("UniPC schedule: pass timestep_next (integer timesteps without it are read as step indices by the reference)")
+        return super().step_coef(timestep, timestep_next, noise_level, *args, **kwargs)

@@ -199,10 +199,8 @@ class B200Wan21Adapter:
         self.engine.set_prompts(plan, prompt_embeds, negative_prompt_embeds if do_cfg else None)
         sch = self.scheduler
         t0 = (t if isinstance(t, torch.Tensor) else torch.tensor(t)).flatten()[0].detach().cpu()
-        if t_next is None:
-            i = sch.index_for_timestep(t0)
-            t_next = sch.timesteps[i + 1] if i + 1 < len(sch.timesteps) else torch.tensor(0)
-        tn = (t_next if isinstance(t_next, torch.Tensor) else torch.tensor(t_next)).flatten()[0].detach().cpu()
+        # t_next omitted: the reference's scheduler.step then reads sigmas[i], sigmas[i + 1] from its tables (step_coef mirrors that)
+        tn = None if t_next is None else (t_next if isinstance(t_next, torch.Tensor) else torch.tensor(t_next)).flatten()[0].detach().cpu()
         coef = sch.step_coef(t0, tn, noise_level, compute_log_prob=compute_log_prob, t_model=float(t0))
         if noise is None and next_latents is None and self.rng == "torch" and sch.dynamics_type != "ODE":
             noise = torch.randn(latents.shape, device=self.device, dtype=torch.float32)

@@ -180,6 +180,11 @@ for case in range(60):
     o = r.step(noise_pred=v, timestep=t, latents=x, timestep_next=tn, noise_level=cur, compute_log_prob=False, return_dict=True)
     c = m.step_coef(t, tn, cur, compute_log_prob=False)
     ok = ok and float(o.dt.flatten()[0]) == c.dt and float(torch.as_tensor(o.std_dev_t).flatten()[0]) == c.std_dev_t
+    # timestep_next omitted: the reference reads sigmas[i], sigmas[i + 1] from its tables (FlowMatch only: UniPC reads an integer timestep as an index)
+    if isinstance(r, RefFM):
+        o2 = r.step(noise_pred=v, timestep=t, latents=x, noise_level=cur, compute_log_prob=False, return_dict=True)
+        c2 = m.step_coef(t, None, cur, compute_log_prob=False)
+        ok = ok and float(o2.dt.flatten()[0]) == c2.dt and float(torch.as_tensor(o2.std_dev_t).flatten()[0]) == c2.std_dev_t
     if not ok: smis.append((case, T, dyn, nsde, sde, seed, type(r).__name__))
 out["scheduler_mismatches"] = [repr(m) for m in smis[:5]]
 # ---- positional tables and latent packing vs the real diffusers modules
