@@ -241,8 +241,12 @@ def test_adapter_bookkeeping_with_stub_engine(monkeypatch):
     # forward(): one step on the integer timesteps
     eng.calls.clear()
     sch.set_timesteps(T)
-    o = ad.forward(t=sch.timesteps[3], latents=torch.zeros(2, 16, 3, 8, 12), prompt_embeds=pe, negative_prompt_embeds=neg, guidance_scale=5.0,
-                   noise_level=0.7, compute_log_prob=True)
+    with pytest.raises(ValueError, match="timestep_next"):        # the reference reads an integer timestep without t_next as a step INDEX
+        ad.forward(t=sch.timesteps[3], latents=torch.zeros(2, 16, 3, 8, 12), prompt_embeds=pe, negative_prompt_embeds=neg, guidance_scale=5.0,
+                   noise_level=0.7)
+    eng.calls.clear()
+    o = ad.forward(t=sch.timesteps[3], t_next=sch.timesteps[4], latents=torch.zeros(2, 16, 3, 8, 12), prompt_embeds=pe, negative_prompt_embeds=neg,
+                   guidance_scale=5.0, noise_level=0.7, compute_log_prob=True)
     st = [c for c in eng.calls if c[0] == "step"][0]
     assert st[1] == pytest.approx(float(sch.timesteps[3]) / 1000) and st[2] == pytest.approx(float(sch.timesteps[4]) / 1000) and st[3] == 5.0
     assert o.std_dev_t.shape == (2, 1, 1, 1, 1) and o.next_latents.dtype == torch.float32
