@@ -289,6 +289,28 @@ out["from_reference"] = {"cfg": [b.model_config.num_layers, b.model_config.num_h
                          "timesteps_equal": bool(torch.equal(ra.scheduler.timesteps, b.scheduler.timesteps)),
                          "sde_equal": bool(torch.equal(ra.scheduler.current_sde_steps, b.scheduler.current_sde_steps)),
                          "decode": float(b.decode_latents(torch.zeros(1, 2)).mean())}
+# ---- the reference-side glue file (integration/ff_b200_glue.py, quoted by INTEGRATION.md) driven with the heavy base-class parts stubbed
+sys.path.insert(0, sys.argv[1] + "/integration")
+import ff_b200_glue as GL
+import flow_factory.models.abc as ABC
+_Eng.refresh_weights = lambda self, sd: setattr(self, "refreshed", getattr(self, "refreshed", 0) + 1)
+glue = GL.B200GlueSD3_5Adapter.__new__(GL.B200GlueSD3_5Adapter)
+GL.B200GlueSD3_5Adapter.transformer = property(lambda self: ra.transformer)
+GL.B200GlueSD3_5Adapter.device = property(lambda self: "cpu")
+import types
+glue.pipeline = types.SimpleNamespace(scheduler=ra.scheduler)        # BaseAdapter.scheduler is a property over pipeline.scheduler
+glue.decode_latents = ra.decode_latents
+glue._mode = "train"
+GL.B200GlueSD3_5Adapter.trainable_component_names = property(lambda self: [])   # BaseAdapter.eval / rollout / train loop over these
+glue._b200 = MA.B200SD3_5Adapter.from_reference_adapter(glue, rng="torch")
+ra.scheduler.set_seed(123)
+glue.rollout()
+g1 = [glue.mode, glue._b200.scheduler.seed, glue._b200.scheduler.is_eval, ra.scheduler.is_eval, glue._b200.engine.refreshed]
+glue.eval()
+g2 = [glue.mode, glue._b200.scheduler.is_eval, ra.scheduler.is_eval]
+glue.train(True)
+g3 = [glue.mode, glue._b200.scheduler.is_eval]
+out["glue"] = [g1, g2, g3, [c.__name__ for c in GL.B200GlueSD3_5Adapter.__mro__[:3]]]
 # ---- GRPO / GDPO advantage arithmetic (FF/advantage/advantage_processor.py:314-481) on randomised groups, incl. constant-reward groups
 import numpy as np
 from flow_factory.advantage.advantage_processor import AdvantageProcessor
@@ -467,3 +489,12 @@ def test_from_reference_adapter_reads_real_reference_objects(hooks):
 def test_randn_tensor_mirror(hooks):
     """Initial latents from per-prompt CPU generator lists (GRPOTrainer.evaluate) are the same numbers diffusers' randn_tensor draws."""
     assert hooks["randn_tensor"] == [True, True, True, True]
+
+
+def test_reference_side_glue_file(hooks):
+    """integration/ff_b200_glue.py (subclass of the REAL SD3_5Adapter): rollout() re-packs the weights and syncs the seed, eval() / train()
+    reach both schedulers."""
+    g1, g2, g3, mro = hooks["glue"]
+    assert g1 == ["rollout", 123, False, False, 1]
+    assert g2 == ["eval", True, True] and g3 == ["train", False]
+    assert mro[:2] == ["B200GlueSD3_5Adapter", "SD3_5Adapter"]
