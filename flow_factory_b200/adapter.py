@@ -20,13 +20,14 @@ import torch
 
 from . import _lib
 from .engine import RolloutEngine
+from .per_sample import forward_grouped, split_by_timestep
 from .rng import randn_tensor
 from .stepwise import SUPPORTED_CALLBACKS, per_sample, run_stepwise
 from .samples import SD3_5Sample
 from .scheduler import FlowMatchEulerDiscreteSDEScheduler, SDESchedulerOutput, set_scheduler_timesteps
 from .trajectory import TrajectoryIndicesType, compute_trajectory_indices, plan_slots
 from .trajectory import create_callback_collector
-from .weights import EngineConfig
+from .weights import EngineConfig, has_lora_keys, merge_lora_state_dict
 
 
 def filter_kwargs(fn: Callable, **kwargs) -> Dict[str, Any]:
@@ -61,16 +62,25 @@ class B200SD3_5Adapter:
 
     # -------------------------------------------------------------- construction from the reference objects
     @classmethod
-    def from_reference_adapter(cls, ref_adapter, **kw) -> "B200SD3_5Adapter":
-        """`ref_adapter`: a flow_factory SD3_5Adapter; borrows its transformer weights, scheduler settings and VAE decode."""
+    def from_reference_adapter(cls, ref_adapter, state_dict: Optional[Dict[str, torch.Tensor]] = None, **kw) -> "B200SD3_5Adapter":
+        """`ref_adapter`: a flow_factory SD3_5Adapter; borrows its transformer weights, scheduler settings and VAE decode.
+        BaseAdapter.__init__ applies LoRA BEFORE post_init (FF/models/abc.py:142-148), so the transformer may already be PEFT-wrapped
+        (`base_model.model.*`, `*.base_layer.weight`, `*.lora_A.default.weight`): such a state dict is folded to plain diffusers keys
+        first (weights.merge_lora_state_dict with the adapter's `model_args.lora_alpha`).  `state_dict`: an already-plain one to use."""
         tr = ref_adapter.transformer
         tr = getattr(tr, "module", tr)
+        tr = getattr(tr, "_orig_mod", tr)
+        if state_dict is None:
+            state_dict = tr.state_dict()
+            if has_lora_keys(state_dict):
+                state_dict = merge_lora_state_dict(state_dict, lora_alpha=ref_adapter.model_args.lora_alpha)
+        cfg = tr.config if not hasattr(tr, "get_base_model") else tr.get_base_model().config
         sched = ref_adapter.scheduler
         mine = FlowMatchEulerDiscreteSDEScheduler(noise_level=sched.noise_level,
                                                   sde_steps=None if sched._sde_steps is None else sched._sde_steps.tolist(),
                                                   num_sde_steps=sched._num_sde_steps, seed=sched.seed,
                                                   dynamics_type=sched.dynamics_type, **dict(sched.config))
-        return cls(tr.config, tr.state_dict(), device=ref_adapter.device, scheduler=mine,
+        return cls(cfg, state_dict, device=ref_adapter.device, scheduler=mine,
                    decode_fn=lambda lat: ref_adapter.decode_latents(lat, output_type="pt"), **kw)
 
     def refresh_weights(self, state_dict: Dict[str, torch.Tensor]) -> None:
@@ -275,6 +285,18 @@ class B200SD3_5Adapter:
             raise NotImplementedError("joint_attention_kwargs are not on the accelerated path")
         do_cfg = negative_prompt_embeds is not None and negative_pooled_prompt_embeds is not None and guidance_scale > 1.0
         B, C, lh, lw = latents.shape
+        groups = split_by_timestep(t, t_next, B)
+        if groups is not None:
+            # per-sample timesteps (NFT / AWM / CRD no-grad forward, nft.py:366-374): one engine call per distinct (t, t_next)
+            return forward_grouped(
+                self.forward, groups, B,
+                dict(latents=latents, prompt_embeds=prompt_embeds, pooled_prompt_embeds=pooled_prompt_embeds,
+                     negative_prompt_embeds=negative_prompt_embeds, negative_pooled_prompt_embeds=negative_pooled_prompt_embeds,
+                     guidance_scale=guidance_scale, next_latents=next_latents, noise_level=noise_level, compute_log_prob=compute_log_prob,
+                     return_kwargs=return_kwargs, noise=noise),
+                batched=("latents", "prompt_embeds", "pooled_prompt_embeds", "negative_prompt_embeds", "negative_pooled_prompt_embeds",
+                         "next_latents", "noise"),
+                make_output=SDESchedulerOutput.from_dict)
         plan = self.engine.plan(B, do_cfg, lh, lw, prompt_embeds.shape[1])
         self.engine.set_prompts(plan, prompt_embeds, pooled_prompt_embeds, negative_prompt_embeds if do_cfg else None,
                                 negative_pooled_prompt_embeds if do_cfg else None)

@@ -271,11 +271,10 @@ attention_kernel(const __grid_constant__ AttnParams p) {
 }
 
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+  static DeviceOnce once;                              // dynamic shared memory opt-in, once per device
+  {
+    cudaError_t e = once.run([] { return cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM); });
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const int qb = ATT_QB;
   dim3 grid((p.seq_len + qb - 1) / qb, p.num_heads, p.batch);

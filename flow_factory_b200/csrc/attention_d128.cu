@@ -255,11 +255,10 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
 }
 
 cudaError_t launch_attention_d128(const AttnParams& p, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_d128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A128_SMEM);
+  static DeviceOnce once;                              // dynamic shared memory opt-in, once per device
+  {
+    cudaError_t e = once.run([] { return cudaFuncSetAttribute(attention_d128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A128_SMEM); });
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   dim3 grid((p.seq_len + A128_QB - 1) / A128_QB, p.num_heads, p.batch);
   attention_d128_kernel<false><<<grid, A128_THREADS, A128_SMEM, stream>>>(p);
@@ -268,11 +267,10 @@ cudaError_t launch_attention_d128(const AttnParams& p, cudaStream_t stream) {
 
 cudaError_t launch_attention_d128_cross(const AttnParams& p, cudaStream_t stream) {
   if (p.kv_len <= 0 || p.kv_mask_lo != nullptr) return cudaErrorInvalidValue;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_d128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A128_SMEM);
+  static DeviceOnce once;                              // dynamic shared memory opt-in, once per device
+  {
+    cudaError_t e = once.run([] { return cudaFuncSetAttribute(attention_d128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A128_SMEM); });
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   dim3 grid((p.seq_len + A128_QB - 1) / A128_QB, p.num_heads, p.batch);
   attention_d128_kernel<true><<<grid, A128_THREADS, A128_SMEM, stream>>>(p);

@@ -6,8 +6,27 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <atomic>
 
 namespace ffb {
+
+// cudaFuncSetAttribute is per (function, DEVICE): a process that drives several devices (one engine per device) must opt every device in.
+// One instance per launcher (function-local static); run() executes `fn` once per device ordinal, thread-safe.
+struct DeviceOnce {
+  std::atomic<unsigned long long> done[2] = {};          // 128 device ordinals
+  template <class Fn> cudaError_t run(Fn&& fn) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::atomic<unsigned long long>& word = done[(dev >> 6) & 1];
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (word.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = fn();
+    if (e == cudaSuccess) word.fetch_or(bit, std::memory_order_release);
+    return e;
+  }
+};
+
 
 typedef __nv_bfloat16 bf16;
 

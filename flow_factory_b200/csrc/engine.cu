@@ -19,7 +19,7 @@
 namespace ffb {
 
 static thread_local std::string g_last_error;
-static long long g_launch_count = 0;
+static thread_local long long g_launch_count = 0;   // launches of the LAST entry-point call made by this thread (one driver thread per rank)
 
 static int fail(int code, const char* what) {
   char buf[512];
@@ -27,6 +27,37 @@ static int fail(int code, const char* what) {
            code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "");
   g_last_error = buf;
   return code;
+}
+
+#define FFB_CUDA_EARLY(expr)                                                                       \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) return fail(static_cast<int>(_e), #expr);                               \
+  } while (0)
+
+// Captures `body` on `st` and makes *exec replay it.  The first time (or when the topology changed) the graph is instantiated; afterwards
+// - caller-owned output / noise pointers differ from rollout to rollout, the launch list does not - the instantiated graph is updated IN
+// PLACE (cudaGraphExecUpdate: new kernel arguments, no re-instantiation).
+static int graph_capture_or_update(cudaGraphExec_t* exec, cudaStream_t st, const std::function<int(cudaStream_t)>& body) {
+  cudaGraph_t graph = nullptr;
+  FFB_CUDA_EARLY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int rr = body(st);
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rr) { if (graph) cudaGraphDestroy(graph); return rr; }
+  if (ce != cudaSuccess) return fail(static_cast<int>(ce), "cudaStreamEndCapture");
+  if (*exec) {
+    cudaGraphExecUpdateResultInfo info;
+    if (cudaGraphExecUpdate(*exec, graph, &info) != cudaSuccess) {
+      (void)cudaGetLastError();                       // topology changed: fall back to a fresh instantiation
+      cudaGraphExecDestroy(*exec); *exec = nullptr;
+    }
+  }
+  if (!*exec) {
+    const cudaError_t ie = cudaGraphInstantiate(exec, graph, 0);
+    if (ie != cudaSuccess) { cudaGraphDestroy(graph); *exec = nullptr; return fail(static_cast<int>(ie), "cudaGraphInstantiate"); }
+  }
+  cudaGraphDestroy(graph);
+  return 0;
 }
 #define FFB_CUDA(expr)                                             \
   do {                                                             \
@@ -598,17 +629,10 @@ static int rollout_impl(ffb200_plan* p, const ffb200_rollout_args* a, cudaStream
   if (a->use_graph) {
     const bool same = p->graph_valid && memcmp(&p->graph_sde, &sp, sizeof(sp)) == 0;
     if (!same) {
-      if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
-      cudaGraph_t graph = nullptr;
-      FFB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       const long long before = g_launch_count;
-      int rr = one_step(st);
-      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      const int rr = graph_capture_or_update(&p->graph_exec, st, one_step);
       g_launch_count = before;
-      if (rr) { if (graph) cudaGraphDestroy(graph); return rr; }
-      FFB_CUDA(ce);
-      FFB_CUDA(cudaGraphInstantiate(&p->graph_exec, graph, 0));
-      cudaGraphDestroy(graph);
+      if (rr) { p->graph_valid = false; return rr; }
       p->graph_sde = sp; p->graph_valid = true;
     }
     const long long per_step = static_cast<long long>(p->fwd_ops.size()) - 1 /*memcpy*/ + 1;
@@ -769,8 +793,15 @@ int ffb200_sde_step(const void* noise_pred_bf16, const void* latents_fp16, int B
   // scratch: coefficient entry + block partials (stream-ordered allocation keeps the call re-entrant)
   StepCoef* d_c = nullptr; float* d_part = nullptr;
   FFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_c), sizeof(StepCoef) * (step_index + 1), st));
-  FFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_part), static_cast<size_t>(B) * 64 * sizeof(float), st));
-  FFB_CUDA(cudaMemcpyAsync(d_c + step_index, coef, sizeof(StepCoef), cudaMemcpyHostToDevice, st));
+  {
+    cudaError_t ae = cudaMallocAsync(reinterpret_cast<void**>(&d_part), static_cast<size_t>(B) * 64 * sizeof(float), st);
+    if (ae == cudaSuccess) ae = cudaMemcpyAsync(d_c + step_index, coef, sizeof(StepCoef), cudaMemcpyHostToDevice, st);
+    if (ae != cudaSuccess) {                       // no leak on the error path
+      cudaFreeAsync(d_c, st);
+      if (d_part) cudaFreeAsync(d_part, st);
+      FFB_CUDA(ae);
+    }
+  }
   SdeStepParams sp; memset(&sp, 0, sizeof(sp));
   sp.v_direct = static_cast<const bf16*>(noise_pred_bf16); sp.B = B; sp.C = C; sp.H = H; sp.W = W; sp.patch = 1;
   sp.x = static_cast<const __half*>(latents_fp16); sp.noise = noise; sp.noise_step_stride = 0; sp.seed = seed;

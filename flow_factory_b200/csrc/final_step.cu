@@ -215,11 +215,10 @@ final_step_kernel(const __grid_constant__ FinalStepParams p) {
 }
 
 cudaError_t launch_final_step(const FinalStepParams& p, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(final_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM);
+  static DeviceOnce once;                              // dynamic shared memory opt-in, once per device
+  {
+    cudaError_t e = once.run([] { return cudaFuncSetAttribute(final_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM); });
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const int ntok = (p.sde.H / p.sde.patch) * (p.sde.W / p.sde.patch);
   dim3 grid((ntok + 127) / 128, p.sde.B);

@@ -427,11 +427,10 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
 template <int BN>
 static cudaError_t launch_bn(const GemmParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  static DeviceOnce once;                              // dynamic shared memory opt-in, once per device
+  {
+    cudaError_t e = once.run([] { return cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes); });
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const int units = ((p.num_batch * p.tiles_m_per_batch + 1) / 2) * (p.N / BN);
   const int max_clusters = num_sms / 2;

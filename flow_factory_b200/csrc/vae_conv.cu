@@ -280,11 +280,10 @@ conv_bf16_kernel(const __grid_constant__ ConvParams p) {
 template <int BN>
 static cudaError_t launch_conv_bn(const ConvParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  static DeviceOnce once;                              // dynamic shared memory opt-in, once per device
+  {
+    cudaError_t e = once.run([] { return cudaFuncSetAttribute(conv_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes); });
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const int units = ((p.B * p.tiles_h * p.tiles_w + 1) / 2) * (p.N / BN);
   const int max_clusters = num_sms / 2;

@@ -215,11 +215,10 @@ __global__ void __launch_bounds__(SMR_THREADS) softmax_rows_inplace_kernel(float
 }
 cudaError_t launch_softmax_rows_inplace(float* scores, long rows, int n, long pitch, cudaStream_t stream) {
   if (n <= 0 || n > 16384 || rows <= 0 || rows > 0x7FFFFFFFL) return cudaErrorInvalidValue;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(softmax_rows_inplace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4);
+  static DeviceOnce once;                              // dynamic shared memory opt-in, once per device
+  {
+    cudaError_t e = once.run([] { return cudaFuncSetAttribute(softmax_rows_inplace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4); });
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   softmax_rows_inplace_kernel<<<static_cast<unsigned>(rows), SMR_THREADS, static_cast<size_t>(n) * sizeof(float), stream>>>(scores, n, pitch);
   return cudaGetLastError();

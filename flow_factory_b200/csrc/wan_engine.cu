@@ -429,18 +429,11 @@ int ffb200_wan_rollout(ffb200_wan_plan* p, const ffb200_rollout_args* a, void* s
   if (a->use_graph) {
     const bool same = p->graph_valid && memcmp(&p->graph_sde, &sp, sizeof(sp)) == 0;
     if (!same) {
-      if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
-      cudaGraph_t graph = nullptr;
-      FFB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       const long long before = g_launch_count;
-      int rr = one_step(st);
+      const int rr = graph_capture_or_update(&p->graph_exec, st, one_step);
       const long long per_step = g_launch_count - before;
-      cudaError_t ce = cudaStreamEndCapture(st, &graph);
       g_launch_count = before;
-      if (rr) { if (graph) cudaGraphDestroy(graph); return rr; }
-      FFB_CUDA(ce);
-      FFB_CUDA(cudaGraphInstantiate(&p->graph_exec, graph, 0));
-      cudaGraphDestroy(graph);
+      if (rr) { p->graph_valid = false; return rr; }
       p->graph_sde = sp; p->graph_valid = true; p->graph_launches = per_step;
     }
     for (int i = 0; i < T; ++i) FFB_CUDA(cudaGraphLaunch(p->graph_exec, st));

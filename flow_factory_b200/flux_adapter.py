@@ -12,6 +12,7 @@ from typing import Any, Callable, Dict, List, Optional, Union
 import torch
 
 from .flux import FluxRolloutEngine, model_scalar, pack_latents
+from .per_sample import forward_grouped, split_by_timestep
 from .rng import randn_tensor
 from .stepwise import SUPPORTED_CALLBACKS, per_sample, run_stepwise
 from .samples import Flux1Sample
@@ -185,6 +186,15 @@ class B200Flux1Adapter:
                 raise NotImplementedError("per-sample guidance scales are not on the accelerated path")
             guidance_scale = float(guidance_scale[0])
         B, Ni, _ = latents.shape
+        groups = split_by_timestep(t, t_next, B)
+        if groups is not None:       # per-sample timesteps (NFT / AWM / CRD): one engine call per distinct (t, t_next) - per_sample.py
+            return forward_grouped(
+                self.forward, groups, B,
+                dict(latents=latents, prompt_embeds=prompt_embeds, pooled_prompt_embeds=pooled_prompt_embeds, img_ids=img_ids,
+                     next_latents=next_latents, guidance_scale=guidance_scale, noise_level=noise_level, compute_log_prob=compute_log_prob,
+                     return_kwargs=return_kwargs, noise=noise, height=height, width=width),
+                batched=("latents", "prompt_embeds", "pooled_prompt_embeds", "next_latents", "noise"),
+                make_output=SDESchedulerOutput.from_dict)
         if img_ids is not None:      # recover the token grid from the ids (rows, cols) = max + 1
             h2, w2 = int(img_ids[:, 1].max().item()) + 1, int(img_ids[:, 2].max().item()) + 1
         elif height is not None and width is not None:

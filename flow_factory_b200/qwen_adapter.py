@@ -11,6 +11,7 @@ from typing import Any, Callable, Dict, List, Optional, Union
 import torch
 
 from .qwen import QwenRolloutEngine
+from .per_sample import forward_grouped, split_by_timestep
 from .rng import randn_tensor
 from .stepwise import SUPPORTED_CALLBACKS, per_sample, run_stepwise
 from .samples import QwenImageSample
@@ -207,9 +208,20 @@ class B200QwenImageAdapter:
             raise RuntimeError("B200QwenImageAdapter.forward serves the no-grad path; keep the autograd replay on the reference adapter")
         if attention_kwargs:
             raise NotImplementedError("attention_kwargs are not on the accelerated path")
+        B, Ni, _ = latents.shape
+        groups = split_by_timestep(t, t_next, B)
+        if groups is not None:       # per-sample timesteps (NFT / AWM / CRD): one engine call per distinct (t, t_next) - per_sample.py
+            return forward_grouped(
+                self.forward, groups, B,
+                dict(latents=latents, prompt_embeds=prompt_embeds, prompt_embeds_mask=prompt_embeds_mask, img_shapes=img_shapes,
+                     negative_prompt_embeds=negative_prompt_embeds, negative_prompt_embeds_mask=negative_prompt_embeds_mask,
+                     guidance_scale=guidance_scale, next_latents=next_latents, noise_level=noise_level, compute_log_prob=compute_log_prob,
+                     return_kwargs=return_kwargs, noise=noise),
+                batched=("latents", "prompt_embeds", "prompt_embeds_mask", "img_shapes", "negative_prompt_embeds", "negative_prompt_embeds_mask",
+                         "next_latents", "noise"),
+                make_output=SDESchedulerOutput.from_dict)
         pos = _dense(prompt_embeds, prompt_embeds_mask, "prompt_embeds")
         neg = _dense(negative_prompt_embeds, negative_prompt_embeds_mask, "negative_prompt_embeds") if negative_prompt_embeds is not None else None
-        B, Ni, _ = latents.shape
         shp = img_shapes[0]
         shp = shp[0] if isinstance(shp, (list, tuple)) and isinstance(shp[0], (list, tuple)) else shp
         _, h2, w2 = shp

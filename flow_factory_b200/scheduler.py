@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .rng import randn_tensor
 
 DYNAMICS = {"Flow-SDE": 0, "Dance-SDE": 1, "CPS": 2, "ODE": 3}
 
@@ -266,7 +267,9 @@ class FlowMatchEulerDiscreteSDEScheduler:
              timestep_next=None, generator=None, noise_level=None, compute_log_prob: bool = True, return_dict: bool = True,
              return_kwargs: List[str] = ["next_latents", "next_latents_mean", "std_dev_t", "dt", "log_prob", "noise_pred"],
              dynamics_type: Optional[str] = None, sigma_max: Optional[float] = None, noise: Optional[torch.Tensor] = None,
-             seed: int = 0, step_index: int = 0):
+             seed: Optional[int] = None, step_index: int = 0):
+        """`noise` / `seed` / `step_index` are extensions: caller-provided noise, or (seed given, noise not) the in-kernel Philox stream
+        keyed by (seed, step_index).  With neither, the noise is drawn exactly as the reference draws it."""
         if not latents.is_cuda:
             raise RuntimeError("flow_factory_b200 scheduler.step needs CUDA tensors (no CPU fallback)")
         c = self.step_coef(timestep, timestep_next, noise_level, dynamics_type, sigma_max, compute_log_prob)
@@ -276,8 +279,17 @@ class FlowMatchEulerDiscreteSDEScheduler:
         in_dtype = latents.dtype
         x16 = latents.to(torch.float16).contiguous()
         v16 = noise_pred.to(torch.bfloat16).contiguous()
-        if noise is None and next_latents is None and dyn != "ODE" and generator is not None:
-            noise = torch.randn(noise_pred.shape, generator=generator, device=latents.device, dtype=torch.float32)
+        if latents.dtype != torch.float16:
+            # the reference rounds fresh next_latents through the INPUT latents dtype (flow_match...py:309, 359-362); the native step's
+            # storage round trip is fp16 (Flow-Factory's default latent_storage_dtype) - anything else would silently break the
+            # rollout / replay log-prob consistency, so it is refused rather than approximated
+            raise NotImplementedError(f"scheduler.step: latents are {latents.dtype}; the native step stores fp16 (latent_storage_dtype='fp16')")
+        if latents.dim() != 4:
+            raise NotImplementedError("scheduler.step mirror: (B, C, H, W) latents (the packed / video adapters call the engine step directly)")
+        if noise is None and seed is None and next_latents is None and dyn != "ODE":
+            # as the reference (flow_match...py:350-357): a fresh fp32 draw from `generator` (one, a per-sample list, or None = the device
+            # RNG stream) on EVERY call - never a fixed in-kernel seed, which would correlate the exploration noise across steps
+            noise = randn_tensor(tuple(noise_pred.shape), generator=generator, device=latents.device, dtype=torch.float32)
         nz = noise.to(torch.float32).contiguous() if noise is not None else None
         ng = next_latents.to(torch.float16).contiguous() if next_latents is not None else None
         out_next = torch.empty_like(x16)
@@ -286,7 +298,7 @@ class FlowMatchEulerDiscreteSDEScheduler:
         flag = torch.zeros(1, dtype=torch.int32, device=latents.device)
         st = torch.cuda.current_stream(latents.device).cuda_stream
         _lib.check(L.ffb200_sde_step(v16.data_ptr(), x16.data_ptr(), B, Cc, H, W, c,
-                                     nz.data_ptr() if nz is not None else None, seed, step_index,
+                                     nz.data_ptr() if nz is not None else None, int(seed or 0), step_index,
                                      ng.data_ptr() if ng is not None else None, out_next.data_ptr(), out_mean.data_ptr(),
                                      out_lp.data_ptr() if out_lp is not None else None, flag.data_ptr(), st), "ffb200_sde_step")
         if next_latents is not None:

@@ -11,6 +11,7 @@ from typing import Any, Callable, Dict, List, Optional, Union
 
 import torch
 
+from .per_sample import forward_grouped, split_by_timestep
 from .rng import randn_tensor
 from .stepwise import SUPPORTED_CALLBACKS, per_sample, run_stepwise
 from .samples import WanT2VSample
@@ -195,6 +196,15 @@ class B200Wan21Adapter:
             raise NotImplementedError("evaluation-mode stepping (UniPC multistep solver) is not on the accelerated path; use the reference adapter")
         B, _, Fr, H, W = latents.shape
         do_cfg = negative_prompt_embeds is not None and guidance_scale > 1.0
+        groups = split_by_timestep(t, t_next, B)
+        if groups is not None:       # per-sample timesteps (NFT / AWM / CRD): one engine call per distinct (t, t_next) - per_sample.py
+            return forward_grouped(
+                self.forward, groups, B,
+                dict(latents=latents, prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds, guidance_scale=guidance_scale,
+                     next_latents=next_latents, noise_level=noise_level, compute_log_prob=compute_log_prob, return_kwargs=return_kwargs,
+                     noise=noise),
+                batched=("latents", "prompt_embeds", "negative_prompt_embeds", "next_latents", "noise"),
+                make_output=SDESchedulerOutput.from_dict)
         plan = self.engine.plan(B, Fr, H, W, prompt_embeds.shape[1], cfg=do_cfg)
         self.engine.set_prompts(plan, prompt_embeds, negative_prompt_embeds if do_cfg else None)
         sch = self.scheduler

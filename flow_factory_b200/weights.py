@@ -126,8 +126,13 @@ class PackedWeights:
         return sum(t.numel() * t.element_size() for t in self.tensors.values())
 
 
+def has_lora_keys(state_dict) -> bool:
+    """True for the state dict of a PEFT-wrapped module (`...base_layer.weight`, `...lora_A.<adapter>.weight`, `base_model.model.` prefix)."""
+    return any((".lora_A." in k) or (".base_layer." in k) or k.startswith("base_model.model.") for k in state_dict)
+
+
 def merge_lora_state_dict(state_dict: Dict[str, torch.Tensor], lora_alpha: float, lora_rank: int = 0,
-                          adapter: str = "default") -> Dict[str, torch.Tensor]:
+                          adapter: str = "default", scale: float = 1.0) -> Dict[str, torch.Tensor]:
     """Fold PEFT LoRA pairs into the base weights: W' = W + (alpha / r) * B @ A (FF/models/abc.py:859-949 wraps the
     transformer with `get_peft_model` / `add_adapter('default', LoraConfig(r, lora_alpha))`).
 
@@ -135,6 +140,8 @@ def merge_lora_state_dict(state_dict: Dict[str, torch.Tensor], lora_alpha: float
     `base_model.model.transformer_blocks.0.attn.to_q.base_layer.weight`, `...to_q.lora_A.default.weight`,
     `...to_q.lora_B.default.weight`) or of a diffusers model with an added adapter (no `base_model.model.` prefix) and
     returns a plain state dict with diffusers key names, ready for PackedWeights.pack / RolloutEngine.refresh_weights.
+    `scale` multiplies the folded update: 0.0 returns the BASE weights under plain key names - what the module computes inside PEFT's
+    `disable_adapter()` (the LoRA form of `use_ref_parameters`, FF/models/abc.py:556-577).
     Cost: 2*r*out*in FLOP per adapted linear - negligible next to a rollout (SURVEY 7.2 #4)."""
     strip = lambda k: k[len("base_model.model."):] if k.startswith("base_model.model.") else k
     sd = {strip(k): v for k, v in state_dict.items()}
@@ -153,12 +160,16 @@ def merge_lora_state_dict(state_dict: Dict[str, torch.Tensor], lora_alpha: float
     if set(lora_a) != set(lora_b):
         raise ValueError("unpaired lora_A / lora_B tensors")
     for mod, A in lora_a.items():
+        if scale == 0.0:
+            if mod + ".weight" not in out:
+                raise KeyError(f"LoRA targets {mod} but the base weight {mod}.weight is missing")
+            continue
         B = lora_b[mod]
         r = lora_rank or A.shape[0]
         key = mod + ".weight"
         if key not in out:
             raise KeyError(f"LoRA targets {mod} but the base weight {key} is missing")
         W = out[key]
-        delta = (B.to(torch.float32) @ A.to(torch.float32)) * (float(lora_alpha) / r)
+        delta = (B.to(torch.float32) @ A.to(torch.float32)) * (float(lora_alpha) / r * float(scale))
         out[key] = (W.to(torch.float32) + delta.to(W.device)).to(W.dtype)
     return out

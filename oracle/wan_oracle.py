@@ -166,7 +166,8 @@ def wan_forward(w: Dict[str, torch.Tensor], cfg: WanConfig, hidden_states: torch
     ppf, pph, ppw = Fr // pt, Hh // ph, Ww // pw
     # freqs_cos / freqs_sin are registered (non-persistent) BUFFERS of WanRotaryPosEmbed (389-390): `model.to(bf16)` /
     # `from_pretrained(torch_dtype=bf16)` casts them with the weights, so a bf16 model rotates with bf16-rounded tables
-    rope = tuple(t.to(w["patch_embedding.weight"].dtype) for t in wan_rope(cfg, ppf, pph, ppw))
+    pw_ = w["patch_embedding.weight"]
+    rope = tuple(t.to(device=pw_.device, dtype=pw_.dtype) for t in wan_rope(cfg, ppf, pph, ppw))    # buffers move with the module
     hs = F.conv3d(hidden_states, w["patch_embedding.weight"], w["patch_embedding.bias"], stride=cfg.patch_size)
     hs = hs.flatten(2).transpose(1, 2)
     # WanTimeTextImageEmbedding (330-351)

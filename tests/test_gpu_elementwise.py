@@ -97,3 +97,28 @@ def test_small_linear_matches_torch():
         if add:
             ref = ref + addend
         torch.testing.assert_close(out.float(), ref.float(), rtol=2e-2, atol=2e-2)
+
+
+def test_sde_step_default_noise_is_a_fresh_device_draw():
+    """Called as the reference adapters call it (no generator / noise / seed, sd3_5.py:435-445): every call draws new fp32 noise from the
+    device RNG (flow_match...py:350-357) - two calls differ, and the draw is torch.randn's stream; a generator list works per sample."""
+    from flow_factory_b200 import FlowMatchEulerDiscreteSDEScheduler
+    s = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0)
+    ts = s.set_timesteps(30, seq_len=4096)
+    x = torch.randn(2, 16, 32, 32, device="cuda").half()
+    v = torch.randn(2, 16, 32, 32, device="cuda").bfloat16()
+    torch.manual_seed(11)
+    r1 = s.step(noise_pred=v, timestep=ts[3], latents=x, timestep_next=ts[4], noise_level=0.7)
+    r2 = s.step(noise_pred=v, timestep=ts[3], latents=x, timestep_next=ts[4], noise_level=0.7)
+    assert not torch.equal(r1.next_latents, r2.next_latents)
+    torch.manual_seed(11)
+    z = torch.randn(v.shape, device="cuda", dtype=torch.float32)
+    r3 = s.step(noise_pred=v, timestep=ts[3], latents=x, timestep_next=ts[4], noise_level=0.7, noise=z)
+    assert torch.equal(r1.next_latents, r3.next_latents) and torch.equal(r1.log_prob, r3.log_prob)
+    gens = [torch.Generator(device="cuda").manual_seed(5), torch.Generator(device="cuda").manual_seed(6)]
+    r4 = s.step(noise_pred=v, timestep=ts[3], latents=x, timestep_next=ts[4], noise_level=0.7, generator=gens)
+    z4 = torch.cat([torch.randn((1,) + v.shape[1:], device="cuda", generator=torch.Generator(device="cuda").manual_seed(sd)) for sd in (5, 6)])
+    r5 = s.step(noise_pred=v, timestep=ts[3], latents=x, timestep_next=ts[4], noise_level=0.7, noise=z4)
+    assert torch.equal(r4.next_latents, r5.next_latents)
+    with pytest.raises(NotImplementedError):
+        s.step(noise_pred=v, timestep=ts[3], latents=x.bfloat16(), timestep_next=ts[4], noise_level=0.7)

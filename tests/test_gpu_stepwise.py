@@ -1,14 +1,12 @@
 """`extra_call_back_kwargs` path of B200SD3_5Adapter.inference (the reference's step loop over forward(), used by GRPO-Guard for
 `next_latents_mean`): with the same per-step noise it must reproduce the fused T-step rollout bit for bit, and the collected means must be
-the ones forward() returns.  The kernels are the validated ones, but this host path was added after round 1's GPU budget was spent, so the
-module is gated like the other pending ones (FFB200_PENDING=1) until its first green run."""
+the ones forward() returns.  First green run on a B200: round 2."""
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FFB200_PENDING") != "1", reason="step-by-step inference path: first GPU run pending (set FFB200_PENDING=1)")]
+pytestmark = pytest.mark.gpu
 
 from flow_factory_b200.adapter import B200SD3_5Adapter                        # noqa: E402
 from flow_factory_b200.scheduler import FlowMatchEulerDiscreteSDEScheduler    # noqa: E402

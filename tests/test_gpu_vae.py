@@ -1,16 +1,13 @@
 """Parity of the native VAE decode (csrc/vae_*.cu) against torch ops and the pinned oracle, through the C ABI.
 
-PENDING: these kernels were written after round 1's GPU budget was spent and have not run on a GPU yet.  Until their first green run
-the module is skipped unless FFB200_PENDING=1 (tools/gpu_vae.sh sets it), so an unvalidated kernel can never mask the validated
-suite; remove the gate once they pass."""
+First green run on a B200: round 2 (gpurun call 1, 23 passed)."""
 import os
 
 import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FFB200_PENDING") != "1", reason="VAE decode kernels: first GPU run pending (set FFB200_PENDING=1)")]
+pytestmark = pytest.mark.gpu
 
 from flow_factory_b200 import vae as V          # noqa: E402
 from oracle import vae_oracle as VO              # noqa: E402  (the checker)

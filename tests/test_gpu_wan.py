@@ -1,15 +1,14 @@
 """Parity of the Wan2.1 T2V engine (csrc/wan_*.cu, the cross-attention instantiation of the head-dim-128 attention kernel; SURVEY 8f
 row 4) against the pinned oracle, through the C ABI.
 
-PENDING: written after round 1's GPU budget was spent; not yet run on a GPU.  The module is skipped unless FFB200_PENDING=1
-(tools/gpu_wan.sh sets it) so that an unvalidated kernel can never mask the validated suite; remove the gate after the first green run."""
+First B200 run: round 2 (every kernel-level case and the rollout consistency green at the first attempt; the two forward-vs-oracle cases
+failed on the ORACLE's rope tables living on the CPU - fixed in oracle/wan_oracle.py)."""
 import os
 
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FFB200_PENDING") != "1", reason="Wan2.1 engine: first GPU run pending (set FFB200_PENDING=1)")]
+pytestmark = pytest.mark.gpu
 
 from flow_factory_b200 import wan as W                              # noqa: E402
 from flow_factory_b200.scheduler import UniPCMultistepSDEScheduler  # noqa: E402

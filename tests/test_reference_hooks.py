@@ -293,7 +293,6 @@ out["from_reference"] = {"cfg": [b.model_config.num_layers, b.model_config.num_h
 sys.path.insert(0, sys.argv[1] + "/integration")
 import ff_b200_glue as GL
 import flow_factory.models.abc as ABC
-_Eng.refresh_weights = lambda self, sd: setattr(self, "refreshed", getattr(self, "refreshed", 0) + 1)
 glue = GL.B200GlueSD3_5Adapter.__new__(GL.B200GlueSD3_5Adapter)
 GL.B200GlueSD3_5Adapter.transformer = property(lambda self: ra.transformer)
 GL.B200GlueSD3_5Adapter.device = property(lambda self: "cpu")
@@ -304,8 +303,91 @@ glue._mode = "train"
 GL.B200GlueSD3_5Adapter.trainable_component_names = property(lambda self: [])   # BaseAdapter.eval / rollout / train loop over these
 glue._b200 = MA.B200SD3_5Adapter.from_reference_adapter(glue, rng="torch")
 ra.scheduler.set_seed(123)
+def _refresh(self, sd):
+    self.refreshed = getattr(self, "refreshed", 0) + 1
+    self.last_sd = {k: v.detach().clone() for k, v in sd.items()}
+_Eng.refresh_weights = _refresh
 glue.rollout()
+stale_after_rollout = glue._engine_stale
+glue._sync_engine_if_stale()                          # what inference() / the no-grad forward() do first
 g1 = [glue.mode, glue._b200.scheduler.seed, glue._b200.scheduler.is_eval, ra.scheduler.is_eval, glue._b200.engine.refreshed]
+# ---- weight-swapping contexts (ADVICE r1: the KL-reference / EMA forward must run on the swapped weights, grpo.py:282, nft.py:360)
+from flow_factory.ema import EMAModuleWrapper
+params = list(ra.transformer.parameters())
+GL.B200GlueSD3_5Adapter.get_trainable_parameters = lambda self: params
+GL.B200GlueSD3_5Adapter.target_module_map = property(lambda self: {})
+glue.model_args = types.SimpleNamespace(lora_alpha=8.0, finetune_type="full")
+glue.ema_wrapper = EMAModuleWrapper(parameters=params, decay=0.5, update_step_interval=1, device="cpu")
+glue._ref_ema = EMAModuleWrapper(parameters=params, decay=0.0, update_step_interval=0, device="cpu")
+key = "proj_out.bias"
+with torch.no_grad():
+    for e in glue.ema_wrapper.ema_parameters: e.fill_(0.25)          # the EMA policy
+    for e in glue._ref_ema.ema_parameters: e.fill_(-0.5)             # theta_ref
+    for q in params: q.fill_(1.0)                                     # the current policy (an optimizer step happened)
+glue._b200.forward = lambda *a, **k: float(glue._b200.engine.last_sd[key].mean())   # stand-in: reports which weights the engine holds
+glue.rollout()
+ctx = {}
+with torch.no_grad():
+    ctx["policy"] = glue.forward()
+    with glue.use_ref_parameters():
+        ctx["ref"] = glue.forward()
+        ctx["ref_again_refreshes"] = glue._b200.engine.refreshed
+        glue.forward()
+        ctx["ref_again_refreshes"] = glue._b200.engine.refreshed - ctx["ref_again_refreshes"]
+    ctx["after_ref"] = glue.forward()
+    with glue.use_ema_parameters():
+        ctx["ema"] = glue.forward()
+        with glue.use_ref_parameters():
+            ctx["ema_then_ref"] = glue.forward()
+        ctx["back_in_ema"] = glue.forward()
+    ctx["after_ema"] = glue.forward()
+    ctx["module_restored"] = float(dict(ra.transformer.named_parameters())[key].mean())
+# train mode: the optimizer steps between no-grad calls without any context edge
+glue.train(True)
+with torch.no_grad():
+    for q in params: q.fill_(2.0)
+    ctx["train_mode_tracks_optimizer"] = glue.forward()
+    for q in params: q.fill_(1.0)
+# ---- LoRA (finetune_type='lora'): PEFT key names at post_init time, adapter folded for the policy, NOT folded inside use_ref_parameters
+import torch.nn as nn
+class _LoraLinear(nn.Module):                           # PEFT's lora.Linear layout: base_layer + lora_A / lora_B ModuleDicts keyed by adapter name
+    def __init__(self, base, r):
+        super().__init__()
+        self.base_layer = base
+        self.lora_A = nn.ModuleDict({"default": nn.Linear(base.in_features, r, bias=False)})
+        self.lora_B = nn.ModuleDict({"default": nn.Linear(r, base.out_features, bias=False)})
+class _PeftLike(nn.Module):                             # PeftModel(base_model=LoraModel(model=transformer)) -> keys 'base_model.model.<...>'
+    def __init__(self, model):
+        super().__init__()
+        self.base_model = nn.Module(); self.base_model.model = model
+        self.config = model.config
+tr2 = SD3Transformer2DModel(sample_size=16, patch_size=2, in_channels=16, num_layers=2, attention_head_dim=64, num_attention_heads=2,
+                            joint_attention_dim=64, caption_projection_dim=128, pooled_projection_dim=32, out_channels=16,
+                            pos_embed_max_size=16, dual_attention_layers=(0,), qk_norm="rms_norm")
+base_q = tr2.transformer_blocks[0].attn.to_q.weight.detach().clone()
+tr2.transformer_blocks[0].attn.to_q = _LoraLinear(tr2.transformer_blocks[0].attn.to_q, r=4)
+with torch.no_grad():
+    tr2.transformer_blocks[0].attn.to_q.lora_A["default"].weight.fill_(0.5)
+    tr2.transformer_blocks[0].attn.to_q.lora_B["default"].weight.fill_(0.25)
+peft_like = _PeftLike(tr2)
+GL.B200GlueSD3_5Adapter.transformer = property(lambda self: peft_like)
+glue.model_args = types.SimpleNamespace(lora_alpha=8.0, finetune_type="lora")
+lora = {"peft_keys": sorted(k for k in peft_like.state_dict() if "to_q" in k and "transformer_blocks.0.attn." in k)}
+built = MA.B200SD3_5Adapter.from_reference_adapter(glue, rng="torch")          # what post_init does; raised KeyError before the fix
+lora["post_init_plain_keys"] = built.engine.n_keys == len(ra.transformer.state_dict())
+qk = "transformer_blocks.0.attn.to_q.weight"
+glue._b200.forward = lambda *a, **k: float((glue._b200.engine.last_sd[qk] - base_q).abs().max())
+glue.rollout()
+with torch.no_grad():
+    lora["policy_delta"] = glue.forward()              # (alpha / r) * B A = 2 * (0.25 * 0.5 * 4) = 1.0 on every entry
+    with glue.use_ref_parameters():
+        lora["ref_delta"] = glue.forward()             # adapter disabled: base weights
+    lora["after_delta"] = glue.forward()
+lora["plain_keys_only"] = not any(("lora_" in k) or ("base_layer" in k) or k.startswith("base_model.") for k in glue._b200.engine.last_sd)
+GL.B200GlueSD3_5Adapter.transformer = property(lambda self: ra.transformer)
+glue.model_args = types.SimpleNamespace(lora_alpha=8.0, finetune_type="full")
+glue.rollout(); glue._sync_engine_if_stale()
+out["glue_contexts"] = {"stale_after_rollout": stale_after_rollout, "ctx": ctx, "lora": lora}
 glue.eval()
 g2 = [glue.mode, glue._b200.scheduler.is_eval, ra.scheduler.is_eval]
 glue.train(True)
@@ -498,3 +580,27 @@ def test_reference_side_glue_file(hooks):
     assert g1 == ["rollout", 123, False, False, 1]
     assert g2 == ["eval", True, True] and g3 == ["train", False]
     assert mro[:2] == ["B200GlueSD3_5Adapter", "SD3_5Adapter"]
+
+
+def test_glue_engine_follows_weight_swapping_contexts(hooks):
+    """The engine's packed copy follows use_ref_parameters / use_ema_parameters (nested too) and the optimizer in train mode: the no-grad
+    KL-reference forward (grpo.py:282-292) and NFT's sampling_context forward (nft.py:360) see theta_ref / the EMA policy, not the weights
+    of the last rollout.  The stand-in forward reports the mean of the packed proj_out.bias: policy 1.0, EMA 0.25, theta_ref -0.5."""
+    g = hooks["glue_contexts"]
+    assert g["stale_after_rollout"] is True
+    c = g["ctx"]
+    assert c["policy"] == 1.0 and c["ref"] == -0.5 and c["after_ref"] == 1.0
+    assert c["ref_again_refreshes"] == 0                      # same context, nothing changed: no second re-pack
+    assert c["ema"] == 0.25 and c["ema_then_ref"] == -0.5 and c["back_in_ema"] == 0.25 and c["after_ema"] == 1.0
+    assert c["module_restored"] == 1.0
+    assert c["train_mode_tracks_optimizer"] == 2.0
+
+
+def test_glue_handles_a_peft_wrapped_transformer(hooks):
+    """finetune_type='lora' (examples/grpo/lora/sd3_5/default.yaml): post_init sees PEFT key names; the policy engine holds W + (alpha/r) B A,
+    inside use_ref_parameters() (PEFT disable_adapter: no tensor changes) it holds the base W."""
+    l = hooks["glue_contexts"]["lora"]
+    assert any(k.endswith("to_q.base_layer.weight") for k in l["peft_keys"]) and any("lora_A.default" in k for k in l["peft_keys"])
+    assert all(k.startswith("base_model.model.") for k in l["peft_keys"])
+    assert l["post_init_plain_keys"] and l["plain_keys_only"]
+    assert abs(l["policy_delta"] - 1.0) < 1e-6 and l["ref_delta"] == 0.0 and abs(l["after_delta"] - 1.0) < 1e-6
