@@ -2,7 +2,7 @@
 """bench.py - rollout latents/sec, SD3.5-medium 1024^2 30-step GRPO sampling (BASELINE.json metric, config C2).
 
   python bench.py --gpus N --steps K --warmup W              # our arm (one rank per GPU; torchrun for N > 1)
-  python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port) on host cores
+  python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own CPU classes (oracle/_ref) on host cores
 
 A "step" is ONE ROLLOUT: `batch` prompts per rank x 30 denoise steps x (2 transformer forwards with CFG) + the fused
 Euler/SDE + log-prob step, synthetic inputs of the BASELINE shape, random-init weights of the SD3.5-medium architecture
@@ -48,7 +48,6 @@ def parse():
     ap.add_argument("--num-sde-steps", type=int, default=1)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-res", type=int, default=1024)
     return ap.parse_args()
 
 
@@ -113,76 +112,104 @@ def flops_per_latent(cfg, ni, nt, T, cfg_on):
     return (lin + att) * T * (2 if cfg_on else 1)
 
 
-# ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
-CPU_SAMPLE_LAYERS = 2
+# ------------------------------------------------------------------------------------------------ CPU baseline: the reference's own code
+CPU_STEP_BUDGET_S = 12.0      # a timed C2 sample longer than this is cut to the first L blocks (and scaled by FLOPs; stated in `sample`)
+CPU_MAX_SAMPLES = 5
 
 
-def cpu_reference_sample(cfg, weights_bf16_cpu, res, n_text, T, guidance, threads, reps=1):
-    """Times the reference's CPU path restated in oracle/ (diffusers SD3 forward + scheduler.step, bf16 CPU autocast) on a
-    BOUNDED sample: embeddings + the first CPU_SAMPLE_LAYERS (dual-attention) blocks + norm_out/proj_out of ONE forward at
-    B=1 (no CFG doubling) + one scheduler step, scaled to a full forward by the FLOP model (a block is >99.9 % GEMM +
-    attention work) and to a latent by T x (2 if CFG)."""
+def cpu_reference(args, steps: int, warmup: int, full: bool = True):
+    """The reference's CPU path through its OWN classes (oracle/ref_runner.py over oracle/_ref: SD3Transformer2DModel.forward +
+    FlowMatchEulerDiscreteSDEScheduler.step as SD3_5Adapter.forward calls them, bf16 CPU autocast) on the physical cores of one NUMA node.
+      * BASELINE config C1 (256^2, 4 steps, B=1, no CFG) is timed IN FULL (BASELINE.md section 3);
+      * config C2 (the metric's): `steps` timed samples of ONE full denoising step at B=1 with CFG (2 transformer forwards at 1024^2 +
+        scheduler.step) after `warmup` untimed ones - or, when a full step would take longer than CPU_STEP_BUDGET_S, of its first L blocks,
+        scaled to 24 blocks by FLOPs; latents/s = 1 / (best step x T).
+    Falls back to the oracle PORT (kind "port") only where oracle/_ref is absent."""
+    from oracle import ref_runner as R
     from oracle import sd3_oracle as O
-    torch.set_num_threads(threads)
+    cfg = O.sd35_medium()
+    cores = R.pick_cores()
+    R.pin(cores)
+    T, g, n_text = args.num_inference_steps, args.guidance, args.n_text
+    ni = (args.height // 16) * (args.width // 16)
+    kind = "reference" if R.available() else "port"
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    w = {k: v.cpu() for k, v in O.make_weights(cfg, seed=0, dtype=torch.bfloat16, device=dev).items()}
+    info = {"cores": cores["n"], "cpu_model": cores["model"], "logical_cpus_allowed": cores["logical_allowed"], "kind": kind}
+    if kind == "port":
+        return _cpu_port(args, cfg, w, cores, info, steps, warmup)
+    model = R.build_model(cfg, w)
+    del w
+    lin, att = O.flops_per_forward(cfg, ni, n_text)
+    # calibration on 2 blocks (also warms oneDNN's primitive cache for these shapes)
+    m2 = R.truncated(model, 2)
+    R.time_c2_step(cfg, m2, g, n_text, args.height, T)
+    t2 = min(R.time_c2_step(cfg, m2, g, n_text, args.height, T) for _ in range(2))
+    est_full = t2 * (lin + att) / R.block_flops(cfg, ni, n_text, 2)
+    L = cfg.num_layers if est_full <= CPU_STEP_BUDGET_S else max(2, min(cfg.num_layers, int(cfg.num_layers * CPU_STEP_BUDGET_S / est_full)))
+    mL = model if L == cfg.num_layers else R.truncated(model, L)
+    scale = 1.0 if L == cfg.num_layers else (lin + att) / R.block_flops(cfg, ni, n_text, L)
+    for _ in range(max(0, warmup)):
+        R.time_c2_step(cfg, mL, g, n_text, args.height, T)
+    n = max(1, min(steps, CPU_MAX_SAMPLES))
+    times = [R.time_c2_step(cfg, mL, g, n_text, args.height, T) for _ in range(n)]
+    best = min(times) * scale
+    value = 1.0 / (best * T)
+    info.update({"value": value, "unit": "latents/s", "c2_step_s": best, "c2_step_samples_s": [round(t * scale, 3) for t in times],
+                 "sample": (f"{n} timed samples (min taken) of ONE full C2 denoising step at B=1 (CFG: 2 forwards of the real SD3Transformer2DModel at "
+                            f"{args.height}^2 + scheduler.step, bf16 CPU autocast)" + ("" if L == cfg.num_layers else f", first {L} of {cfg.num_layers} blocks scaled by FLOPs") +
+                            f", x{T} steps; {cores['n']} threads pinned to the physical cores of one NUMA node")})
+    if full:
+        R.time_c1_full(cfg, model)                                   # warm the 256^2 shapes
+        c1_s, c1_v = R.time_c1_full(cfg, model)
+        info["c1_full"] = {"seconds": c1_s, "latents_per_s": c1_v, "config": "SD3.5-medium 256^2 4-step, B=1, guidance 1.0, CPU bf16 autocast, timed in full"}
+    return info, sum(times) / len(times)
+
+
+def _cpu_port(args, cfg, w, cores, info, steps, warmup):
+    """oracle/_ref absent: the oracle port's 2-block sample (round-1 method), min of the timed samples."""
+    from oracle import sd3_oracle as O
+    T, g, n_text, res = args.num_inference_steps, args.guidance, args.n_text, args.height
     lat = res // 8
     ni = (lat // 2) ** 2
     inp = O.make_inputs(cfg, 1, lat, lat, n_text, seed=1)
     ts, sig = O.make_schedule(T, 3.0)
     x = inp["x0"].half()
-    best = None
-    for _ in range(reps):
+
+    def sample():
         t0 = time.perf_counter()
         with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
-            v = O.transformer_forward(weights_bf16_cpu, cfg, x, inp["prompt_embeds"].bfloat16(), inp["pooled"].bfloat16(),
-                                      ts[3].expand(1).half(), max_layers=CPU_SAMPLE_LAYERS)
-        O.sde_step(v, x, (ts[3] / 1000).item(), (ts[4] / 1000).item(), 0.7, float(sig[1]),
-                   noise=torch.randn(x.shape), compute_log_prob=True)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    D, S, n = cfg.inner_dim, ni + n_text, CPU_SAMPLE_LAYERS
-    fl_sample = n * (24 * ni * D * D + 24 * n_text * D * D + 8 * ni * D * D + 4 * S * S * D + 4 * ni * ni * D)
+            v = O.transformer_forward(w, cfg, x, inp["prompt_embeds"].bfloat16(), inp["pooled"].bfloat16(), ts[3].expand(1).half(), max_layers=2)
+        O.sde_step(v, x, (ts[3] / 1000).item(), (ts[4] / 1000).item(), 0.7, float(sig[1]), noise=torch.randn(x.shape), compute_log_prob=True)
+        return time.perf_counter() - t0
+    for _ in range(max(1, warmup)):
+        sample()
+    times = [sample() for _ in range(max(1, min(steps, CPU_MAX_SAMPLES)))]
+    from oracle import ref_runner as R
     lin, att = O.flops_per_forward(cfg, ni, n_text)
-    t_forward = best * (lin + att) / fl_sample
-    fwd_per_latent = T * (2 if guidance > 1.0 else 1)
-    return 1.0 / (t_forward * fwd_per_latent), best
-
-
-def make_cpu_weights(cfg):
-    from oracle import sd3_oracle as O
-    dev = "cuda" if torch.cuda.is_available() else "cpu"
-    w = O.make_weights(cfg, seed=0, dtype=torch.bfloat16, device=dev)
-    return {k: v.cpu() for k, v in w.items()}
+    t_fwd = min(times) * (lin + att) / R.block_flops(cfg, ni, n_text, 2)
+    value = 1.0 / (t_fwd * T * (2 if g > 1.0 else 1))
+    info.update({"value": value, "unit": "latents/s",
+                 "sample": f"oracle PORT (oracle/_ref absent): 2 of 24 blocks of one forward at {res}^2 B=1 + scheduler.step, scaled by FLOPs, x{T} x{2 if g > 1 else 1}"})
+    return info, sum(times) / len(times)
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's own CPU implementation of the path (oracle port; /root/reference is absent on the
-    GPU box and pure Python/diffusers cannot be vendored) on all host threads; each step = a bounded sample of the workload."""
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores (see cpu_reference)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import sd3_oracle as O
-    cfg = O.sd35_medium()
-    threads = os.cpu_count() or 1
-    w = make_cpu_weights(cfg)
-    T = args.num_inference_steps
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_sample(cfg, w, args.cpu_sample_res, args.n_text, T, args.guidance, threads)
     t0 = time.perf_counter()
-    vals = []
-    for _ in range(args.steps):
-        v, dt = cpu_reference_sample(cfg, w, args.cpu_sample_res, args.n_text, T, args.guidance, threads)
-        vals.append(v)
+    info, mean_sample_s = cpu_reference(args, steps=args.steps, warmup=max(2, args.warmup), full=True)
     wall = time.perf_counter() - t0
-    value = sum(vals) / len(vals)
-    sample = (f"{CPU_SAMPLE_LAYERS} of 24 blocks of 1 transformer forward + scheduler.step at {args.cpu_sample_res}^2, B=1, bf16 CPU autocast, "
-              f"scaled to 24 blocks by FLOPs, x{T} steps x{2 if args.guidance > 1 else 1} (CFG); {args.steps} timed samples")
-    line = {"metric": METRIC, "value": value, "unit": "latents/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1000.0 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    T = args.num_inference_steps
+    line = {"metric": METRIC, "value": info["value"], "unit": "latents/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * mean_sample_s, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "impl": "reference",
             "config": {"workload": f"SD3.5-medium {args.height}x{args.width} {T}-step GRPO rollout, guidance {args.guidance}, random-init weights",
-                       "timing": "host wall clock of a bounded sample, extrapolated"},
-            "cpu_baseline": {"value": value, "unit": "latents/s", "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "latents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                       "timing": "host wall clock; a step = one bounded sample (see cpu_baseline.sample)", "wall_s": wall},
+            "cpu_baseline": info,
+            "e2e": {"value": info["value"], "unit": "latents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -350,15 +377,10 @@ def run_b200(args):
                         whole_step_achieved_per_gpu=step_tf / world, whole_step_frac_of_sustained=step_tf / world / peaks["bf16_tflops_sustained"],
                         flops_per_latent=fl_latent)
 
-    # ---------------- CPU baseline: the oracle port on this box's host cores, bounded sample ----------------
+    # ---------------- CPU baseline: the reference's own classes on this box's host cores, bounded sample (rank 0, N=1 only) ----------------
     cpu = None
-    if not args.skip_cpu_baseline:
-        threads = os.cpu_count() or 1
-        wcpu = make_cpu_weights(cfg)
-        v, dt = cpu_reference_sample(cfg, wcpu, args.cpu_sample_res, args.n_text, T, args.guidance, threads)
-        cpu = {"value": v, "unit": "latents/s", "cores": threads, "kind": "port",
-               "sample": f"{CPU_SAMPLE_LAYERS} of 24 blocks of 1 forward + scheduler.step at {args.cpu_sample_res}^2 B=1 bf16 CPU autocast ({dt:.1f} s), "
-                         f"scaled to 24 blocks by FLOPs, x{T} steps x{2 if cfg_on else 1} (CFG)"}
+    if not args.skip_cpu_baseline and world == 1:
+        cpu, _ = cpu_reference(args, steps=3, warmup=2, full=True)
 
     line = {"metric": METRIC, "value": value, "unit": "latents/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",

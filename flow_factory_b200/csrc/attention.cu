@@ -141,11 +141,6 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         __syncwarp();
       };
       mbar_wait(q_full, 0, 0x52);
-#ifdef FFB_ATT_STAGGER
-      // EXPERIMENT (tools/gpu_maxfree.sh): start sub-tile x a fraction of a tile late, to test whether the three identical softmax
-      // groups of an SM sub-partition run in lockstep (synchronised stalls) - costs x * FFB_ATT_STAGGER cycles once per CTA.
-      if (x > 0) { const long long t0 = clock64(); while (clock64() - t0 < static_cast<long long>(x) * FFB_ATT_STAGGER) {} }
-#endif
       issue_qk(0);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % ATT_STAGES;
@@ -183,7 +178,8 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       const uint32_t tPx = tmem_base + lane_off + ATT_TMEM_P + x * (ATT_BN / 2);
       const uint32_t tOx = tmem_base + lane_off + ATT_TMEM_O + x * ATT_D;
       const float sc = p.scale_log2;
-      float m_run = -INFINITY, l_run = 0.f;
+      const bool pre = p.k_prescaled != 0;              // the scores already are base-2 exponents (softmax.cuh)
+      SoftmaxState sm;
       const long long pc0 = prof_begin();
       long long lap = prof_begin();
       for (int j = 0; j < n_tiles; ++j) {
@@ -202,7 +198,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
 
         uint32_t pk[32];                               // P(j) as packed bf16 pairs
         float alpha;
-        const bool rescale = softmax_block64(s0, s1, S - j * ATT_BN, sc, m_run, l_run, pk, alpha);
+        const bool rescale = softmax_block64(s0, s1, S - j * ATT_BN, sc, pre, j == 0, sm, pk, alpha);
         prof_lap(&lap, 0x64);                          // max + exp2 + sum + pack
 
         if (j > 0) {                                   // P V of tile j-1 retired (issued a whole softmax ago): P_x free, O_x quiescent
@@ -243,11 +239,11 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         for (int i = 0; i < 32; ++i) { o_acc[i] = __uint_as_float(o0[i]); o_acc[32 + i] = __uint_as_float(o1[i]); }
       }
       prof_end(pc0, 0x70 + warp);
-      // O_x and l_run are both relative to the final running max m_run.
+      // O_x and sm.l_run are both relative to the final reference.
       const int q = q0 + x * ATT_BM + r;
       if (q < S) {
-        softmax_final_check(l_run);
-        const float inv = 1.0f / l_run;
+        softmax_final_check(sm.l_run);
+        const float inv = 1.0f / sm.l_run;
         bf16* dst = p.out + static_cast<long>(b) * p.out_batch_stride + static_cast<long>(q) * p.inner_dim + head * ATT_D;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {

@@ -173,7 +173,8 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
       const uint32_t tPx = tmem_base + lane_off + A128_TMEM_P + x * (A128_BN / 2);
       const uint32_t tOx = tmem_base + lane_off + A128_TMEM_O + x * A128_D;
       const float sc = p.scale_log2;
-      float m_run = -INFINITY, l_run = 0.f;
+      const bool pre = p.k_prescaled != 0;              // the scores already are base-2 exponents (softmax.cuh)
+      SoftmaxState sm;
       const int mask_hi = p.kv_mask_lo ? p.kv_mask_hi : 0;
       const int mask_lo = p.kv_mask_lo ? max(__ldg(p.kv_mask_lo + b), 1) : 0;   // key 0 always stays (keeps the running max finite)
       for (int j = 0; j < n_tiles; ++j) {
@@ -198,7 +199,7 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
         }
         uint32_t pk[32];
         float alpha;
-        const bool rescale = softmax_block64(s0, s1, Skv - j * A128_BN, sc, m_run, l_run, pk, alpha);
+        const bool rescale = softmax_block64(s0, s1, Skv - j * A128_BN, sc, pre, j == 0, sm, pk, alpha);
         if (j > 0) {
           mbar_wait(&p_free[x], (j - 1) & 1, 0x61);
           tc_fence_after();
@@ -223,8 +224,8 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
       mbar_wait(&o_full[x], 0, 0x69);
       tc_fence_after();
       const int q = q0 + x * A128_BM + r;
-      if (q < S) softmax_final_check(l_run);
-      const float inv = 1.0f / l_run;
+      if (q < S) softmax_final_check(sm.l_run);
+      const float inv = 1.0f / sm.l_run;
       bf16* dst = p.out + static_cast<long>(b) * p.out_batch_stride + static_cast<long>(q) * p.out_row_stride + head * A128_D;
 #pragma unroll 1
       for (int c = 0; c < A128_D; c += 32) {

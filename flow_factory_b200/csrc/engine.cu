@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <functional>
 #include <string>
 #include <vector>
@@ -123,6 +124,7 @@ struct GemmSpec {
   const float* row_table;
   const float* rope_cos; const float* rope_sin; int rope_row_offset;   // EPI_QKV_RMSNORM_ROPE128
   int rms_round_first;
+  float k_scale;           // see GemmParams::k_scale (0 = none)
 };
 static int build_gemm(const GemmSpec& s, GemmParams* p) {
   memset(p, 0, sizeof(*p));
@@ -162,7 +164,15 @@ static int build_gemm(const GemmSpec& s, GemmParams* p) {
   p->norm_q = static_cast<const bf16*>(s.norm_q); p->norm_k = static_cast<const bf16*>(s.norm_k);
   p->qk_dim = s.qk_dim; p->eps = s.eps; p->row_table = s.row_table;
   p->rope_cos = s.rope_cos; p->rope_sin = s.rope_sin; p->rope_row_offset = s.rope_row_offset; p->rms_round_first = s.rms_round_first;
+  p->k_scale = s.k_scale;
   return 0;
+}
+// The engines fold softmax_scale * log2(e) into the key heads in the QKV GEMM epilogue (GemmParams::k_scale) and tell the attention kernel
+// (AttnParams::k_prescaled): the per-score FFMA of the softmax disappears (softmax.cuh).  FFB200_NO_PRESCALE=1 keeps the general path
+// (A/B measurements only; read once).
+static bool engine_prescale() {
+  static const bool on = getenv("FFB200_NO_PRESCALE") == nullptr;
+  return on;
 }
 static int build_attn(const void* qkv, int batch, int seq, int heads, void* out, AttnParams* p, int head_dim = 64,
                       int out_row_stride = 0) {
@@ -317,6 +327,7 @@ static int add_attn(ffb200_plan* p, const void* qkv, int seq, void* out) {
   AttnParams ap;
   int r = build_attn(qkv, p->Bp, seq, p->e->cfg.num_heads, out, &ap);
   if (r) return r;
+  ap.k_prescaled = engine_prescale() ? 1 : 0;       // every QKV GEMM of this engine folds the scale into k (below)
   p->fwd_ops.push_back([ap](cudaStream_t st) { ++g_launch_count; return launch_attention(ap, st); });
   return 0;
 }
@@ -424,9 +435,11 @@ int ffb200_plan_create(ffb200_engine* e, int batch, int cfg, int lat_h, int lat_
     // fused q|k|v projections + per-head RMSNorm, written token-major into the joint [Bp, S, 3D] buffer (image rows first)
     GemmSpec sq = {p->a1, Bp, Ni, 0, D, D, L.qkv_w, 3 * D, L.qkv_b, p->qkv, static_cast<long>(S) * 3 * D, 0, 3 * D,
                    EPI_QKV_RMSNORM, nullptr, 0, L.norm_q, L.norm_k, D, 1e-6f, nullptr};
+    sq.k_scale = engine_prescale() ? 0.125f * 1.4426950408889634f : 0.f;
     if ((r = add_gemm(p, sq))) break;
     GemmSpec sc = {p->ac, Bp, Nt, 0, D, D, L.add_qkv_w, 3 * D, L.add_qkv_b, p->qkv, static_cast<long>(S) * 3 * D, Ni, 3 * D,
                    EPI_QKV_RMSNORM, nullptr, 0, L.norm_added_q, L.norm_added_k, D, 1e-6f, nullptr};
+    sc.k_scale = engine_prescale() ? 0.125f * 1.4426950408889634f : 0.f;
     if ((r = add_gemm(p, sc))) break;
     if ((r = add_attn(p, p->qkv, S, p->att))) break;
     // to_out + gate_msa residual (image rows of the joint attention output)
@@ -441,6 +454,7 @@ int ffb200_plan_create(ffb200_engine* e, int batch, int cfg, int lat_h, int lat_
     if (dual) {  // attn2: image-only self attention (attention.py:714-717)
       GemmSpec s2 = {p->a2, Bp, Ni, 0, D, D, L.qkv2_w, 3 * D, L.qkv2_b, p->qkv2, static_cast<long>(Ni) * 3 * D, 0, 3 * D,
                      EPI_QKV_RMSNORM, nullptr, 0, L.norm_q2, L.norm_k2, D, 1e-6f, nullptr};
+      s2.k_scale = engine_prescale() ? 0.125f * 1.4426950408889634f : 0.f;
       if ((r = add_gemm(p, s2))) break;
       if ((r = add_attn(p, p->qkv2, Ni, p->att2))) break;
       GemmSpec so2 = {p->att2, Bp, Ni, 0, D, D, L.out2_w, D, L.out2_b, p->h_img, static_cast<long>(Ni) * D, 0, D,
@@ -753,6 +767,22 @@ int ffb200_attention_ex(const void* qkv, int batch, int seq_len, int num_heads, 
   int r = build_attn(qkv, batch, seq_len, num_heads, out, &ap, head_dim, out_row_stride);
   if (r) return r;
   if (head_dim == 64 && ap.out_row_stride != ap.inner_dim) return fail(-2, "ffb200_attention_ex: head_dim 64 writes dense rows only");
+  g_launch_count = 1;
+  FFB_CUDA(head_dim == 64 ? launch_attention(ap, static_cast<cudaStream_t>(stream)) : launch_attention_d128(ap, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int ffb200_attention_scaled(const void* qkv, int batch, int seq_len, int num_heads, int head_dim, void* out, int out_row_stride,
+                            float softmax_scale, int k_prescaled, void* stream) {
+  FFB_CHECK(qkv && out && batch > 0 && seq_len > 0 && num_heads > 0, "bad argument");
+  if (head_dim != 64 && head_dim != 128) return fail(-2, "ffb200_attention_scaled: head_dim must be 64 or 128");
+  if (out_row_stride != 0 && out_row_stride < num_heads * head_dim) return fail(-2, "ffb200_attention_scaled: out_row_stride < inner dim");
+  AttnParams ap;
+  int r = build_attn(qkv, batch, seq_len, num_heads, out, &ap, head_dim, out_row_stride);
+  if (r) return r;
+  if (head_dim == 64 && ap.out_row_stride != ap.inner_dim) return fail(-2, "ffb200_attention_scaled: head_dim 64 writes dense rows only");
+  if (softmax_scale > 0.f) ap.scale_log2 = softmax_scale * 1.4426950408889634f;
+  ap.k_prescaled = k_prescaled ? 1 : 0;
   g_launch_count = 1;
   FFB_CUDA(head_dim == 64 ? launch_attention(ap, static_cast<cudaStream_t>(stream)) : launch_attention_d128(ap, static_cast<cudaStream_t>(stream)));
   return 0;

@@ -216,13 +216,16 @@ int ffb200_flux_plan_create_ex(ffb200_flux_engine* e, int batch, int cfg, int n_
     fadd_lnmod(p, h_ctx, hS, Nt, mc1 + 0 * D, mc1 + 1 * D, a_ctx, hS);
     GemmSpec sc = {a_ctx, B, Nt, hS, D, D, L.add_qkv_w, 3 * D, L.add_qkv_b, p->qkv, 3 * hS, 0, 3 * D, EPI_QKV_RMSNORM_ROPE128,
                    nullptr, 0, L.norm_added_q, L.norm_added_k, D, 1e-6f, nullptr, p->rope_cos, p->rope_sin, 0, mc.variant == 1};
+    sc.k_scale = engine_prescale() ? 0.08838834764831845f * 1.4426950408889634f : 0.f;
     if ((r = fadd_gemm(p, sc))) break;
     GemmSpec sq = {a_img, B, Ni, hS, D, D, L.qkv_w, 3 * D, L.qkv_b, p->qkv, 3 * hS, Nt, 3 * D, EPI_QKV_RMSNORM_ROPE128,
                    nullptr, 0, L.norm_q, L.norm_k, D, 1e-6f, nullptr, p->rope_cos, p->rope_sin, Nt, mc.variant == 1};
+    sq.k_scale = engine_prescale() ? 0.08838834764831845f * 1.4426950408889634f : 0.f;
     if ((r = fadd_gemm(p, sq))) break;
     {
       AttnParams ap;
       if ((r = build_attn(p->qkv, B, S, mc.num_heads, p->att, &ap, 128, 0))) break;
+      ap.k_prescaled = engine_prescale() ? 1 : 0;
       if (mc.variant == 1) { ap.kv_mask_lo = p->d_txt_len; ap.kv_mask_hi = Nt; }   // padded text keys (set_text_lengths; default: none)
       ops.push_back([ap](cudaStream_t st) { ++g_launch_count; return launch_attention_d128(ap, st); });
     }
@@ -250,6 +253,7 @@ int ffb200_flux_plan_create_ex(ffb200_flux_engine* e, int batch, int cfg, int n_
     fadd_lnmod(p, p->h, 0, S, ms + 0 * D, ms + 1 * D, p->a1, 0);
     GemmSpec sq = {p->a1, B, S, 0, D, D, L.qkv_w, 3 * D, L.qkv_b, p->qkv, 3 * hS, 0, 3 * D, EPI_QKV_RMSNORM_ROPE128,
                    nullptr, 0, L.norm_q, L.norm_k, D, 1e-6f, nullptr, p->rope_cos, p->rope_sin, 0};
+    sq.k_scale = engine_prescale() ? 0.08838834764831845f * 1.4426950408889634f : 0.f;
     if ((r = fadd_gemm(p, sq))) break;
     // proj_mlp + GELU -> columns [D, 5D) of the cat buffer ; attention -> columns [0, D)
     GemmSpec sm = {p->a1, B, S, 0, D, D, L.mlp_w, 4 * D, L.mlp_b, p->cat + D, 5 * hS, 0, 5 * D, EPI_BIAS_GELU};
@@ -257,6 +261,7 @@ int ffb200_flux_plan_create_ex(ffb200_flux_engine* e, int batch, int cfg, int n_
     {
       AttnParams ap;
       if ((r = build_attn(p->qkv, B, S, mc.num_heads, p->cat, &ap, 128, 5 * D))) break;
+      ap.k_prescaled = engine_prescale() ? 1 : 0;
       ops.push_back([ap](cudaStream_t st) { ++g_launch_count; return launch_attention_d128(ap, st); });
     }
     GemmSpec so = {p->cat, B, S, 0, 5 * D, 5 * D, L.out_w, D, L.out_b, p->h, hS, 0, D, EPI_GATE_RESIDUAL, ms + 2 * D, R};

@@ -321,6 +321,10 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
                   v[q * 8 + e + 1] = __fadd_rn(__fmul_rn(b2, cc[e + 1]), __fmul_rn(a, sv[e + 1]));
                 }
               }
+              if (which == 1 && p.k_scale != 0.f) {       // keys carry softmax_scale * log2(e) (softmax.cuh): folded before the ONE bf16 store
+#pragma unroll
+                for (int j = 0; j < 64; ++j) v[j] *= p.k_scale;
+              }
             }
             flush_chunk(c, v);
           }
@@ -376,6 +380,10 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
                 v[q * 8 + e] = a * wf[e];
                 v[q * 8 + e + 1] = b * wf[e + 1];
               }
+            }
+            if (which == 1 && p.k_scale != 0.f) {         // keys carry softmax_scale * log2(e) (softmax.cuh): folded before the ONE bf16 store
+#pragma unroll
+              for (int j = 0; j < 64; ++j) v[j] *= p.k_scale;
             }
           }
         } else if (p.epi == EPI_BIAS_GELU) {

@@ -43,6 +43,7 @@ struct GemmParams {
   const float* rope_cos;   // EPI_QKV_RMSNORM_ROPE128: fp32 [tokens, 128] (values repeated pairwise, FluxPosEmbed), row = rope_row_offset + row
   const float* rope_sin;
   int rope_row_offset;
+  float k_scale;           // EPI_QKV_RMSNORM[_ROPE128]: factor folded into the k heads before their bf16 store (0 = 1): softmax_scale * log2(e)
   int rms_round_first;     // 0: torch.nn.RMSNorm bf16((x*rs)*w) (FLUX.1) ; 1: diffusers RMSNorm bf16(bf16(x*rs)*w) (Qwen-Image)
 };
 
@@ -61,6 +62,7 @@ struct AttnParams {
   long out_batch_stride;
   int out_row_stride; // elements between consecutive token rows of `out` (D, or wider when the output is a column block)
   float scale_log2;   // (1/sqrt(head_dim)) * log2(e)
+  int k_prescaled;    // 1: the producer of K folded scale_log2 into the keys (GemmParams::k_scale): scores are base-2 exponents as they are
   // optional key-padding mask (head_dim 128 kernel only): keys [kv_mask_lo[b], kv_mask_hi) of batch b are excluded - the padded tail
   // of the text rows of a joint [text ; image] sequence (Qwen-Image attention_mask, transformer_qwenimage.py:952-958); null = none
   const int* kv_mask_lo;

@@ -1,22 +1,47 @@
 // Online-softmax building blocks shared by the attention kernels (attention.cu: head_dim 64, attention_d128.cu: head_dim 128):
 // thread = query row = TMEM lane; scores arrive as fp32 register blocks of 64 columns.
+//
+// What the SIMT side has to do per score is the whole cost of these kernels (at head_dim 64 the tensor core needs 8 cycles per SM for 256
+// scores, the MUFU unit alone 16), so the routine below is built around doing as little as possible per element:
+//   * no per-tile row maximum.  Online softmax needs A reference that keeps 2^(x - ref) inside the fp32 / bf16 exponent range (8 bits
+//     both), not THE maximum.  Only the first tile of a row block looks at its maximum (to choose the reference); afterwards the reference
+//     moves by an exact power of two when the running sum - an upper bound of every P so far - passes 2^64.  (round 2 measurement of this
+//     alone: +5 % at head_dim 64, +4.5 % at 128.)
+//   * reference ZERO whenever the first tile's scores are within 2^+-32 (always, for RMS-normed q / k): x - 0 needs no instruction.
+//   * scores that already ARE base-2 exponents (`pre`): the engines fold softmax_scale * log2(e) into the key's RMSNorm weight multiply in
+//     the QKV GEMM epilogue (one rounding to bf16, as the reference has), so the usual per-element FFMA (s * scale - max * scale) disappears:
+//     MUFU-slot elements go from the TMEM load straight into ex2.
+//   * part of the elements take a polynomial exp2 on the FMA pipe (the MUFU unit, 16 ex2/clk/SM, is the scarcest pipe), spread evenly
+//     between the MUFU slots; the row sum uses packed f32x2 adds.
+// Anything that could leave the representable range fails loudly (device error tag 0x6F), never silently.
 #pragma once
 #include "common.cuh"
 
 namespace ffb {
 
-// exp2 on the FMA/ALU pipes for part of the elements (the MUFU unit, 16 ex2/clk/SM, is the binding resource at d = 64):
-// 2^x = 2^round(x) * p(x - round(x)), p = degree-3 minimax of 2^f on [-0.5, 0.5] (max rel. error 7.5e-5, far below the
-// bf16 rounding of P); round() through the 1.5*2^23 magic-number add, exponent inserted with one shift-add.
-// Operates on a packed pair.  x must be <= ~+100; clamped below at -126.
-__device__ __forceinline__ void exp2_poly_pair(uint64_t x2, float& e0, float& e1) {
-  float x0, x1;
-  unpack_f32x2(x2, x0, x1);
-  x0 = fmaxf(x0, -126.0f);
-  x1 = fmaxf(x1, -126.0f);
+#ifndef FFB_ATT_POLY_NUM
+#define FFB_ATT_POLY_NUM 2           // product value (of every 8 element pairs); -DFFB_ATT_POLY_NUM=n only for A/B builds
+#endif
+constexpr int ATT_POLY_PERIOD = 8;
+constexpr int ATT_POLY_NUM = FFB_ATT_POLY_NUM;
+// pair c goes through the polynomial: ATT_POLY_NUM slots of every 8, evenly spread (3 -> {0,3,6}, 2 -> {0,4}, 4 -> {0,2,4,6})
+#ifdef FFB_ATT_POLY_CLUSTER            // A/B only: the first ATT_POLY_NUM pairs of every 8
+__host__ __device__ constexpr bool att_poly_slot(int c) { return (c % ATT_POLY_PERIOD) < ATT_POLY_NUM; }
+#else
+__host__ __device__ constexpr bool att_poly_slot(int c) { return ((c % ATT_POLY_PERIOD) * ATT_POLY_NUM) % ATT_POLY_PERIOD < ATT_POLY_NUM; }
+#endif
+
+constexpr float ATT_REF_ZERO_BAND = 32.0f;        // first-tile |max exponent| up to which the reference stays 0
+constexpr float ATT_SHIFT_AT = 18446744073709551616.0f;        // 2^64: running sum at which the reference moves
+constexpr float ATT_FAIL_AT = 7.922816251426434e28f;           // 2^96: more than 2^90 of growth inside ONE tile - refuse (tag 0x6F)
+
+// 2^x for a PAIR on the FMA / ALU pipes: 2^x = 2^round(x) * p(x - round(x)), p = degree-3 minimax of 2^f on [-0.5, 0.5] (max rel. error
+// 7.5e-5, far below the bf16 rounding of P); round() through the 1.5*2^23 magic-number add, exponent inserted with one shift-add.
+// Valid for |x| <= 126 ONLY (the exponent insert wraps beyond): the caller checks the polynomial slots of a tile with one 3-input max
+// per pair (softmax_poly_range_ok) and sends an out-of-range tile through MUFU instead - cheaper than clamping every element.
+__device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& e0, float& e1) {
   const uint64_t xc = pack_f32x2(x0, x1);
-  const uint64_t magic = pack_f32x2(12582912.0f, 12582912.0f);
-  const uint64_t xr = fadd2(xc, magic);                                   // round(x) sits in the low mantissa bits
+  const uint64_t xr = fadd2(xc, pack_f32x2(12582912.0f, 12582912.0f));    // round(x) sits in the low mantissa bits
   const uint64_t r = fadd2(xr, pack_f32x2(-12582912.0f, -12582912.0f));   // round(x) as float
   const uint64_t f = ffma2(r, pack_f32x2(-1.0f, -1.0f), xc);              // x - round(x) in [-0.5, 0.5]
   uint64_t p = ffma2(f, pack_f32x2(0.05517132207751274f, 0.05517132207751274f), pack_f32x2(0.24261054396629333f, 0.24261054396629333f));
@@ -28,116 +53,124 @@ __device__ __forceinline__ void exp2_poly_pair(uint64_t x2, float& e0, float& e1
   e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(r0) << 23));
   e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
 }
-constexpr int ATT_POLY_PERIOD = 8;   // of every ATT_POLY_PERIOD element pairs ...
-#ifndef FFB_ATT_POLY_NUM
-#define FFB_ATT_POLY_NUM 3           // product value; -DFFB_ATT_POLY_NUM=n only for the A/B builds of tools/gpu_maxfree.sh
-#endif
-constexpr int ATT_POLY_NUM = FFB_ATT_POLY_NUM;   // ... this many go through exp2_poly_pair, the rest through MUFU.EX2
+
+// exp2 of the 32 scores of `a` into pk[quarter*16 ..], partial row sums into sums2.  kPre: the scores are the exponents (pre-scaled keys,
+// reference 0); else exponent = s * sc - ref.  kPoly: the polynomial slots are in use (false: every element through MUFU).
+template <bool kPre, bool kPoly, bool kSum>
+__device__ __forceinline__ void softmax_exp32(const uint32_t (&a)[32], int quarter, uint64_t sc2, uint64_t mneg2, uint64_t (&sums2)[2],
+                                              uint32_t (&pk)[32]) {
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    float t0 = __uint_as_float(a[2 * c]), t1 = __uint_as_float(a[2 * c + 1]);
+    if (!kPre) unpack_f32x2(ffma2(pack_f32x2(t0, t1), sc2, mneg2), t0, t1);
+    float e0, e1;
+    if (kPoly && att_poly_slot(c)) {
+      exp2_poly_pair(t0, t1, e0, e1);
+    } else {
+      e0 = ex2_approx(t0); e1 = ex2_approx(t1);
+    }
+    if (kSum) sums2[c & 1] = fadd2(sums2[c & 1], pack_f32x2(e0, e1));
+    pk[quarter * 16 + c] = pack_bf16x2(e0, e1);
+  }
+}
+
+// max |exponent| over the polynomial slots of a tile (one 3-input max per pair; |.| is an operand modifier): the polynomial is used only
+// if it is <= 126.  -inf (masked keys), inf and NaN fail the test and take the MUFU path, which handles them.
+template <bool kPre>
+__device__ __forceinline__ float softmax_poly_absmax(const uint32_t (&s0)[32], const uint32_t (&s1)[32], float sce, float m_run) {
+  float mx[2] = {0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    if (att_poly_slot(c)) {
+      mx[0] = fmax3(mx[0], fabsf(__uint_as_float(s0[2 * c])), fabsf(__uint_as_float(s0[2 * c + 1])));
+      mx[1] = fmax3(mx[1], fabsf(__uint_as_float(s1[2 * c])), fabsf(__uint_as_float(s1[2 * c + 1])));
+    }
+  }
+  const float a = fmaxf(mx[0], mx[1]);
+  return kPre ? a : fmaf(a, sce, fabsf(m_run));          // |s * sc - ref| <= |s| sc + |ref|
+}
+
+struct SoftmaxState {
+  float m_run = -INFINITY;   // the reference, in EXPONENT units (score * sc); set by the first tile
+  float l_run = 0.f;         // running row sum relative to it
+  bool zero_ref = false;     // warp-uniform: every row of the warp still has reference 0
+};
 
 // Online-softmax step of one thread (= one query row) over a 128 x 64 block of scores held in registers (s0: columns 0-31,
-// s1: 32-63).  Updates the running max / sum, returns P as 32 packed bf16 pairs, the factor `alpha` by which the accumulator has
+// s1: 32-63).  Updates the running reference / sum, returns P as 32 packed bf16 pairs and the factor `alpha` by which the accumulator has
 // to be scaled if the (warp-uniform) return value is true.  Shared by the d = 64 and d = 128 kernels.
-// kSum = false (experimental/attention_summma.cu only): the row sum is NOT accumulated here - the tensor core produces it as an extra
-// accumulator column (V extended by a panel of ones) - and l_run is left untouched.
+//   sc    : softmax_scale * log2(e); ignored when `pre`.
+//   pre   : warp-uniform; the scores already are base-2 exponents (keys pre-scaled by the producer).
+//   first : warp-uniform; first KV tile of the row block.
 template <bool kSum = true>
-__device__ __forceinline__ bool softmax_block64(uint32_t (&s0)[32], uint32_t (&s1)[32], int kv_valid, float sc, float& m_run,
-                                                float& l_run, uint32_t (&pk)[32], float& alpha) {
-  // row max of this tile: 8 independent chains (a single serial fmax chain is 128 x 4 cycles of pure latency)
-  float mxs[8];
+__device__ __forceinline__ bool softmax_block64(uint32_t (&s0)[32], uint32_t (&s1)[32], int kv_valid, float sc, bool pre, bool first,
+                                                SoftmaxState& st, uint32_t (&pk)[32], float& alpha) {
+  if (kv_valid < 64) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) mxs[i] = -INFINITY;
-  auto max32 = [&](uint32_t(&a)[32], int base) {
-    if (kv_valid < 64) {
-#pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (base + c >= kv_valid) a[c] = 0xFF800000u;  // -inf: key beyond the sequence
+    for (int c = 0; c < 32; ++c) {
+      if (c >= kv_valid) s0[c] = 0xFF800000u;      // -inf: key beyond the sequence
+      if (32 + c >= kv_valid) s1[c] = 0xFF800000u;
     }
-#pragma unroll
-    for (int c = 0; c < 32; c += 2) mxs[(c >> 1) & 7] = fmax3(mxs[(c >> 1) & 7], __uint_as_float(a[c]), __uint_as_float(a[c + 1]));
-  };
-#ifdef FFB_ATT_MAXFREE
-  // EXPERIMENT (not the product build; tools/gpu_maxfree.sh): the row-max pass costs ~14 % of the kernel (profiles/
-  // r01_attention_whatif.md) and online softmax does not need the MAX as its reference, only A reference that keeps 2^((s - m) sc)
-  // inside the fp32 / bf16 exponent range (both have 8 exponent bits).  So only the first tile of a row takes its exact maximum;
-  // later tiles reuse the reference and move it by a power of two whenever the running sum - an upper bound of every P so far -
-  // has grown past 2^24.  P may exceed 1 (by at most the growth of one tile); a score more than 127 / sc above the reference within
-  // a single tile would overflow: that is detected (l_run = inf) and trapped by softmax_final_check / the next tile, never silent.
+  }
+  const float sce = pre ? 1.0f : sc;
   bool rescale;
   alpha = 1.0f;
-  if (__any_sync(0xffffffffu, m_run == -INFINITY)) {     // first tile of the row block: exact maximum
-    max32(s0, 0); max32(s1, 32);
-    const float mt = fmax3(fmax3(mxs[0], mxs[1], mxs[2]), fmax3(mxs[3], mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7]));
-    const float mnew = fmaxf(m_run, mt);                 // per lane: a row that already has state keeps it consistent
-    alpha = ex2_approx((m_run - mnew) * sc);             // 0 on the first tile
-    m_run = mnew;
+  if (first) {
+    // first tile of the row block: its exact maximum (8 independent 3-input chains) chooses the reference
+    float mxs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mxs[i] = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      mxs[(c >> 1) & 7] = fmax3(mxs[(c >> 1) & 7], __uint_as_float(s0[c]), __uint_as_float(s0[c + 1]));
+      mxs[(c >> 1) & 7] = fmax3(mxs[(c >> 1) & 7], __uint_as_float(s1[c]), __uint_as_float(s1[c + 1]));
+    }
+    const float mt = fmax3(fmax3(mxs[0], mxs[1], mxs[2]), fmax3(mxs[3], mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])) * sce;
+    st.zero_ref = __all_sync(0xffffffffu, fabsf(mt) <= ATT_REF_ZERO_BAND);     // also false for a NaN / inf maximum
+    st.m_run = st.zero_ref ? 0.0f : mt;
+    st.l_run = 0.f;
+    alpha = 0.0f;                                   // nothing accumulated yet
     rescale = true;
   } else {
-    if (kv_valid < 64) {
-#pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        if (c >= kv_valid) s0[c] = 0xFF800000u;
-        if (32 + c >= kv_valid) s1[c] = 0xFF800000u;
-      }
-    }
-    const bool grow = !(l_run <= 16777216.0f);            // also true for inf / NaN
+    const bool grow = !(st.l_run <= ATT_SHIFT_AT);  // also true for inf / NaN
     rescale = __any_sync(0xffffffffu, grow);
     if (rescale) {
-      if (!(l_run < 3.0e38f)) mbar_timeout(0x6F);         // overflow inside one tile: fail loudly (tag 0x6F)
+      if (!(st.l_run < ATT_FAIL_AT)) mbar_timeout(0x6F);   // a score jumped by more than 2^90 within one tile (or is not finite): fail loudly
       if (grow) {
-        const int e = static_cast<int>((__float_as_uint(l_run) >> 23) & 0xFF) - 127;   // floor(log2(l_run)) >= 24
-        alpha = __uint_as_float(static_cast<uint32_t>(127 - e) << 23);                 // 2^-e, exact
-        m_run += __fdividef(static_cast<float>(e), sc);                                 // reference up by e in exponent units
+        const int e = static_cast<int>((__float_as_uint(st.l_run) >> 23) & 0xFF) - 127;   // floor(log2(l_run)) >= 64
+        alpha = __uint_as_float(static_cast<uint32_t>(127 - e) << 23);                    // 2^-e, exact
+        st.m_run += static_cast<float>(e);                                                 // reference up by e exponent units, exact
       }
+      st.zero_ref = false;
     }
   }
-#else
-  max32(s0, 0); max32(s1, 32);
-  const float mt = fmax3(fmax3(mxs[0], mxs[1], mxs[2]), fmax3(mxs[3], mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7]));
-  // lazy rescale: adopt the new max only if some row of the warp grew by more than 2^8 (warp-uniform decision)
-  const bool grow = (mt - m_run) * sc > 8.0f;           // true on the first tile (m_run = -inf)
-  const bool rescale = __any_sync(0xffffffffu, grow);
-  alpha = 1.0f;
-  if (rescale) {
-    const float mnew = fmaxf(m_run, mt);
-    alpha = ex2_approx((m_run - mnew) * sc);             // 0 on the first tile
-    m_run = mnew;
-  }
-#endif
-  const uint64_t sc2 = pack_f32x2(sc, sc), mneg2 = pack_f32x2(-m_run * sc, -m_run * sc);
   uint64_t sums2[2] = {0ull, 0ull};              // 4 partial row sums as two packed pairs
-  auto exp32 = [&](uint32_t(&a)[32], int quarter) {
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const uint64_t x2 = ffma2(pack_f32x2(__uint_as_float(a[2 * c]), __uint_as_float(a[2 * c + 1])), sc2, mneg2);
-      float e0, e1;
-      if ((c % ATT_POLY_PERIOD) < ATT_POLY_NUM) {
-        exp2_poly_pair(x2, e0, e1);
-      } else {
-        float t0, t1;
-        unpack_f32x2(x2, t0, t1);
-        e0 = ex2_approx(t0); e1 = ex2_approx(t1);
-      }
-      if (kSum) sums2[c & 1] = fadd2(sums2[c & 1], pack_f32x2(e0, e1));
-      pk[quarter * 16 + c] = pack_bf16x2(e0, e1);
-    }
-  };
-  exp32(s0, 0); exp32(s1, 1);
+  const uint64_t sc2 = pack_f32x2(sce, sce), mneg2 = pack_f32x2(-st.m_run, -st.m_run);
+  const bool fast = pre && st.zero_ref;          // warp-uniform
+  bool poly = ATT_POLY_NUM > 0;
+  if (poly) {
+    const float amax = fast ? softmax_poly_absmax<true>(s0, s1, sce, 0.f) : softmax_poly_absmax<false>(s0, s1, sce, st.m_run);
+    poly = __all_sync(0xffffffffu, amax <= 126.0f);
+  }
+  if (fast) {
+    if (poly) { softmax_exp32<true, true, kSum>(s0, 0, sc2, mneg2, sums2, pk); softmax_exp32<true, true, kSum>(s1, 1, sc2, mneg2, sums2, pk); }
+    else { softmax_exp32<true, false, kSum>(s0, 0, sc2, mneg2, sums2, pk); softmax_exp32<true, false, kSum>(s1, 1, sc2, mneg2, sums2, pk); }
+  } else {
+    if (poly) { softmax_exp32<false, true, kSum>(s0, 0, sc2, mneg2, sums2, pk); softmax_exp32<false, true, kSum>(s1, 1, sc2, mneg2, sums2, pk); }
+    else { softmax_exp32<false, false, kSum>(s0, 0, sc2, mneg2, sums2, pk); softmax_exp32<false, false, kSum>(s1, 1, sc2, mneg2, sums2, pk); }
+  }
   if (kSum) {
     float sa, sb, sc_, sd;
     unpack_f32x2(sums2[0], sa, sb);
     unpack_f32x2(sums2[1], sc_, sd);
-    l_run = l_run * alpha + ((sa + sb) + (sc_ + sd));
+    st.l_run = st.l_run * alpha + ((sa + sb) + (sc_ + sd));
   }
   return rescale;
 }
 
-// End-of-row check of the max-free experiment (no code in the product build).
+// End-of-row check: a sum that left the supported range during the LAST tile (no later tile to notice it) fails loudly too.
 __device__ __forceinline__ void softmax_final_check(float l_run) {
-#ifdef FFB_ATT_MAXFREE
-  if (!(l_run < 3.0e38f)) mbar_timeout(0x6F);
-#else
-  (void)l_run;
-#endif
+  if (!(l_run < ATT_FAIL_AT)) mbar_timeout(0x6F);
 }
 
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }

@@ -43,13 +43,18 @@ def linear_qkv_rope(A, W, bias, out, norm_q, norm_k, rope_cos, rope_sin, *, num_
 
 
 def attention(qkv: torch.Tensor, num_heads: int, out: Optional[torch.Tensor] = None, head_dim: int = 64,
-              out_row_stride: int = 0) -> torch.Tensor:
+              out_row_stride: int = 0, scale: Optional[float] = None, k_prescaled: bool = False) -> torch.Tensor:
     """Joint attention over a fused token-major qkv buffer bf16 [B, S, 3*head_dim*H] -> bf16 [B, S, head_dim*H].
-    head_dim 128 (FLUX.1) may write into a wider row (`out` [B, S, out_row_stride], columns [0, head_dim*H))."""
+    head_dim 128 (FLUX.1) may write into a wider row (`out` [B, S, out_row_stride], columns [0, head_dim*H)).
+    `scale`: softmax scale (default 1/sqrt(head_dim)); `k_prescaled`: the keys already carry scale * log2(e) (the engines' layout)."""
     B, S, _ = qkv.shape
     if out is None:
         out = torch.empty((B, S, out_row_stride or head_dim * num_heads), dtype=torch.bfloat16, device=qkv.device)
-    if head_dim == 64 and out_row_stride == 0:
+    if scale is not None or k_prescaled:
+        _lib.check(_lib.lib().ffb200_attention_scaled(_ptr(qkv), B, S, num_heads, head_dim, _ptr(out), out_row_stride,
+                                                      float(scale) if scale is not None else 0.0, int(k_prescaled), _stream(qkv)),
+                   "ffb200_attention_scaled")
+    elif head_dim == 64 and out_row_stride == 0:
         _lib.check(_lib.lib().ffb200_attention(_ptr(qkv), B, S, num_heads, _ptr(out), _stream(qkv)), "ffb200_attention")
     else:
         _lib.check(_lib.lib().ffb200_attention_ex(_ptr(qkv), B, S, num_heads, head_dim, _ptr(out), out_row_stride, _stream(qkv)),

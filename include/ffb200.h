@@ -169,6 +169,11 @@ int ffb200_attention(const void* qkv, int batch, int seq_len, int num_heads, voi
  * (transformer_flux.py:400) be the attention kernel's own store.  head_dim 64 accepts dense rows only. */
 int ffb200_attention_ex(const void* qkv, int batch, int seq_len, int num_heads, int head_dim, void* out, int out_row_stride,
                         void* stream);
+/* Same with an explicit softmax scale (`scale=` of F.scaled_dot_product_attention / dispatch_attention_fn, DF/models/attention_dispatch.py:
+ * 2930-2945; <= 0 selects 1/sqrt(head_dim)), and `k_prescaled`: 1 = the caller already multiplied the keys by softmax_scale * log2(e)
+ * (what the engines' QKV projection epilogue does), so the kernel takes the q.k scores as base-2 exponents and skips the per-score multiply. */
+int ffb200_attention_scaled(const void* qkv, int batch, int seq_len, int num_heads, int head_dim, void* out, int out_row_stride,
+                            float softmax_scale, int k_prescaled, void* stream);
 /* LayerNorm(no affine) * (1 + scale) + shift  (DF/models/normalization.py:120-126). vectors: [num_batch, *] with stride. */
 int ffb200_ln_modulate(const void* x, int num_batch, int rows_per_batch, int D, float eps, const void* shift1,
                        const void* scale1, void* out1, const void* shift2, const void* scale2, void* out2,

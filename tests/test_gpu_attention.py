@@ -89,3 +89,73 @@ def test_attention_d128_strided_output_and_peaked_softmax():
     ref = _ref_d(qkv, H, 128)
     assert float((wide[..., : 128 * H].float() - ref).abs().max()) <= 3e-2
     assert bool((wide[..., 128 * H:] == 7.0).all())        # columns beyond the head block untouched
+
+
+LOG2E = 1.4426950408889634
+
+
+@pytest.mark.parametrize("d,B,S,H", [(64, 2, 589, 2), (64, 1, 4429, 3), (128, 2, 640, 2), (128, 1, 2100, 3)])
+def test_attention_prescaled_keys(d, B, S, H):
+    """The engines' layout: k already carries softmax_scale * log2(e) (folded into the key RMSNorm multiply, ONE bf16 rounding), the
+    kernel takes q.k as base-2 exponents without any per-score multiply.  Reference: fp32 softmax of q.k' in base 2."""
+    from flow_factory_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(7 * S + H + d)
+    q = torch.randn(B, S, H * d, device="cuda", generator=g)
+    k = torch.randn(B, S, H * d, device="cuda", generator=g)
+    v = torch.randn(B, S, H * d, device="cuda", generator=g)
+    kp = (k * (d ** -0.5 * LOG2E)).bfloat16()                       # what the QKV epilogue stores
+    qkv = torch.cat([q.bfloat16(), kp, v.bfloat16()], dim=-1).contiguous()
+    out = ops.attention(qkv, H, head_dim=d, k_prescaled=True)
+    torch.cuda.synchronize()
+    sp = lambda t: t.float().reshape(B, S, H, d).transpose(1, 2)
+    ref = torch.nn.functional.scaled_dot_product_attention(sp(q.bfloat16()), sp(kp), sp(v.bfloat16()), scale=1.0 / LOG2E)   # e^(x ln 2) = 2^x
+    ref = ref.transpose(1, 2).reshape(B, S, H * d)
+    assert torch.isfinite(out.float()).all()
+    assert float((out.float() - ref).abs().max()) <= 2e-2
+    # and the same numbers as the general path on the unscaled keys, up to the one differently-placed bf16 rounding of k
+    gen = ops.attention(torch.cat([q.bfloat16(), k.bfloat16(), v.bfloat16()], dim=-1).contiguous(), H, head_dim=d)
+    assert float((out.float() - gen.float()).norm() / gen.float().norm()) <= 6e-3
+
+
+@pytest.mark.parametrize("d", [64, 128])
+@pytest.mark.parametrize("pre", [False, True])
+def test_attention_reference_shift_on_rising_scores(d, pre):
+    """No per-tile row maximum (softmax.cuh): the reference starts at 0 and moves by an exact power of two when the running sum passes
+    2^64.  Scores rising along the keys by ~90 nats force that path (and the accumulator rescale in TMEM) on every row."""
+    from flow_factory_b200 import ops
+    B, S, H = 1, 1536, 2
+    g = torch.Generator(device="cuda").manual_seed(1)
+    q = torch.randn(B, S, H, d, generator=g, device="cuda")
+    k = torch.randn(B, S, H, d, generator=g, device="cuda")
+    q[..., 0] = 8.0
+    k[..., 0] = torch.linspace(0, 11.0 * d ** 0.5, S, device="cuda")[None, :, None]      # + 88 nats = 127 exponent units along the sequence
+    v = torch.randn(B, S, H, d, generator=g, device="cuda")
+    scale = d ** -0.5
+    kk = (k * (scale * LOG2E)) if pre else k
+    qkv = torch.cat([q.reshape(B, S, H * d), kk.reshape(B, S, H * d), v.reshape(B, S, H * d)], -1).bfloat16().contiguous()
+    out = ops.attention(qkv, H, head_dim=d, k_prescaled=pre)
+    torch.cuda.synchronize()
+    qb, kb, vb = (t.reshape(B, S, H, d).transpose(1, 2).float() for t in qkv.split(H * d, dim=-1))
+    ref = torch.nn.functional.scaled_dot_product_attention(qb, kb, vb, scale=(1.0 / LOG2E) if pre else scale).transpose(1, 2).reshape(B, S, H * d)
+    assert torch.isfinite(out.float()).all()
+    assert float((out.float() - ref).norm() / ref.norm()) <= 4e-3
+
+
+def test_attention_large_first_tile_takes_a_nonzero_reference():
+    """First-tile scores beyond 2^+-32: the reference is that tile's row maximum (general subtract path), not 0."""
+    from flow_factory_b200 import ops
+    B, S, H, d = 1, 400, 2, 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q = torch.randn(B, S, H, d, generator=g, device="cuda")
+    k = torch.randn(B, S, H, d, generator=g, device="cuda")
+    q[..., 1] = 20.0
+    k[..., 1] = 20.0                                                                        # + 50 nats on every score
+    k[:, :, 1, 1] = -20.0                                                                   # head 1: - 50 nats (far below 2^-32)
+    v = torch.randn(B, S, H, d, generator=g, device="cuda")
+    qkv = torch.cat([q.reshape(B, S, H * d), k.reshape(B, S, H * d), v.reshape(B, S, H * d)], -1).bfloat16().contiguous()
+    out = ops.attention(qkv, H, head_dim=d)
+    torch.cuda.synchronize()
+    qb, kb, vb = (t.reshape(B, S, H, d).transpose(1, 2).float() for t in qkv.split(H * d, dim=-1))
+    ref = torch.nn.functional.scaled_dot_product_attention(qb, kb, vb).transpose(1, 2).reshape(B, S, H * d)
+    assert torch.isfinite(out.float()).all()
+    assert float((out.float() - ref).norm() / ref.norm()) <= 4e-3

@@ -457,6 +457,75 @@ register_scheduler("UniPCMultistepScheduler", "flow_factory_b200.scheduler.UniPC
 class FlowMatchEulerDiscreteScheduler: pass
 class UniPCMultistepScheduler: pass
 out["sched"] = [get_sde_scheduler_class(FlowMatchEulerDiscreteScheduler()).__module__, get_sde_scheduler_class(UniPCMultistepScheduler).__module__]
+# ---- diffusers' own attention plug points (SURVEY 8b ii / iii) with the real vendored classes; the kernels need a GPU, so the native forward
+# is replaced by an SDPA stand-in HERE and everything around it (registry slot, dispatch, (B,S,H,D) layout, scale, the SD3 processor's joint
+# [image ; text] order, output split, to_out / to_add_out, autograd) is the shipped code
+import flow_factory_b200.diffusers_hooks as DH
+from diffusers.models.attention_dispatch import AttentionBackendName, _AttentionBackendRegistry as REG, dispatch_attention_fn
+import torch.nn.functional as F
+hk = {}
+try:
+    dispatch_attention_fn(torch.zeros(1, 4, 2, 64), torch.zeros(1, 4, 2, 64), torch.zeros(1, 4, 2, 64), backend=DH.install_attention_backend("_native_flash"))
+    hk["cpu_call_raises"] = False
+except RuntimeError as e:
+    hk["cpu_call_raises"] = "CUDA tensors only" in str(e)                  # dispatch reached OUR function, which has no CPU path
+hk["slot"] = [REG._backends[AttentionBackendName._NATIVE_FLASH] is DH.b200_attention_backend,
+              sorted(REG._supported_arg_names[AttentionBackendName._NATIVE_FLASH]) == sorted(REG._supported_arg_names[AttentionBackendName.NATIVE]),
+              REG._constraints[AttentionBackendName._NATIVE_FLASH] == []]
+calls = []
+def _stand_in(q, k, v, scale):
+    calls.append((tuple(q.shape), tuple(k.shape), scale))
+    return F.scaled_dot_product_attention(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3), scale=scale).permute(0, 2, 1, 3)
+DH._forward_native = _stand_in
+DH._check_device_dtype = lambda q, k, v: None
+torch.manual_seed(0)
+fl = FluxTransformer2DModel(patch_size=1, in_channels=16, num_layers=1, num_single_layers=1, attention_head_dim=64, num_attention_heads=2,
+                            joint_attention_dim=32, pooled_projection_dim=16, guidance_embeds=True, axes_dims_rope=(8, 28, 28)).eval()
+fin = dict(hidden_states=torch.randn(2, 12, 16), encoder_hidden_states=torch.randn(2, 5, 32), pooled_projections=torch.randn(2, 16),
+           timestep=torch.tensor([0.5, 0.5]), img_ids=torch.zeros(12, 3), txt_ids=torch.zeros(5, 3), guidance=torch.tensor([3.5, 3.5]))
+with torch.no_grad():
+    base = fl(**fin).sample
+    fl.set_attention_backend("_native_flash")            # what model.attn_backend: "_native_flash" does (FF/models/abc.py:782-798)
+    n0 = len(calls)
+    hooked = fl(**fin).sample
+hk["flux_calls"] = len(calls) - n0
+hk["flux_shapes"] = [list(calls[-1][0]), calls[-1][2]]
+hk["flux_max_diff"] = float((base - hooked).abs().max())
+# autograd through the backend function: native forward, gradients from the SDPA recomputation
+q = torch.randn(1, 6, 2, 64, requires_grad=True); k = torch.randn(1, 6, 2, 64, requires_grad=True); v = torch.randn(1, 6, 2, 64, requires_grad=True)
+o = DH.b200_attention_backend(q, k, v, scale=0.2); o.square().sum().backward()
+q2, k2, v2 = (t.detach().clone().requires_grad_(True) for t in (q, k, v))
+o2 = F.scaled_dot_product_attention(q2.permute(0, 2, 1, 3), k2.permute(0, 2, 1, 3), v2.permute(0, 2, 1, 3), scale=0.2).permute(0, 2, 1, 3); o2.square().sum().backward()
+hk["grad_max_diff"] = max(float((a.grad - b.grad).abs().max()) for a, b in ((q, q2), (k, k2), (v, v2)))
+rej = []
+for kw in (dict(attn_mask=torch.ones(1, 6, dtype=torch.bool)), dict(is_causal=True), dict(dropout_p=0.1), dict(return_lse=True), dict(enable_gqa=True)):
+    try:
+        DH.b200_attention_backend(q.detach(), k.detach(), v.detach(), **kw); rej.append(False)
+    except (NotImplementedError, ValueError):
+        rej.append(True)
+hk["unsupported_arguments_raise"] = rej
+DH.uninstall_attention_backend("_native_flash")
+hk["uninstalled"] = REG._backends[AttentionBackendName._NATIVE_FLASH] is not DH.b200_attention_backend
+fl.reset_attention_backend()
+# the SD3 processor on a real SD3Transformer2DModel (dual-attention block 0 + a context_pre_only last block)
+sd = SD3Transformer2DModel(sample_size=16, patch_size=2, in_channels=16, num_layers=2, attention_head_dim=64, num_attention_heads=2,
+                           joint_attention_dim=64, caption_projection_dim=128, pooled_projection_dim=32, out_channels=16,
+                           pos_embed_max_size=16, dual_attention_layers=(0,), qk_norm="rms_norm").eval()
+sin = dict(hidden_states=torch.randn(2, 16, 8, 8), encoder_hidden_states=torch.randn(2, 7, 64), pooled_projections=torch.randn(2, 32),
+           timestep=torch.tensor([500.0, 500.0]))
+with torch.no_grad():
+    base = sd(**sin).sample
+    proc = DH.install_sd3_attn_processor(sd)
+    n0 = len(calls)
+    hooked = sd(**sin).sample
+hk["sd3_processors"] = sorted({type(p_).__name__ for p_ in sd.attn_processors.values()})
+hk["sd3_calls"] = len(calls) - n0                       # block 0: joint + attn2, block 1: joint
+hk["sd3_joint_len"] = sorted({c[0][1] for c in calls[n0:]})
+hk["sd3_max_diff"] = float((base - hooked).abs().max())
+import inspect as _insp
+from diffusers.models.attention_processor import JointAttnProcessor2_0
+hk["sd3_signature"] = list(_insp.signature(DH.B200JointAttnProcessor.__call__).parameters)[:5] == list(_insp.signature(JointAttnProcessor2_0.__call__).parameters)[:5]
+out["diffusers_hooks"] = hk
 print("RESULT " + json.dumps(out))
 '''
 
@@ -604,3 +673,25 @@ def test_glue_handles_a_peft_wrapped_transformer(hooks):
     assert all(k.startswith("base_model.model.") for k in l["peft_keys"])
     assert l["post_init_plain_keys"] and l["plain_keys_only"]
     assert abs(l["policy_delta"] - 1.0) < 1e-6 and l["ref_delta"] == 0.0 and abs(l["after_delta"] - 1.0) < 1e-6
+
+
+def test_attention_backend_slot_routes_to_the_b200_function(hooks):
+    """`install_attention_backend` + the reference's own `set_attention_backend` / `dispatch_attention_fn`: the registry slot holds our
+    function with the registry's argument names; a FLUX forward through it (kernel replaced by an SDPA stand-in on this GPU-less box) is
+    the default backend's output - layout (B,S,H,D), scale and call count (1 dual + 1 single block) are right; gradients come from the
+    SDPA recomputation; unsupported arguments raise instead of being ignored; uninstall restores the slot."""
+    h = hooks["diffusers_hooks"]
+    assert h["cpu_call_raises"] is True and h["slot"] == [True, True, True]
+    assert h["flux_calls"] == 2 and h["flux_shapes"][0] == [2, 17, 2, 64] and h["flux_max_diff"] <= 1e-5
+    assert h["grad_max_diff"] <= 1e-5
+    assert all(h["unsupported_arguments_raise"]) and h["uninstalled"] is True
+
+
+def test_sd3_attn_processor_is_a_drop_in_for_joint_attn_processor(hooks):
+    """`B200JointAttnProcessor` installed through `set_attn_processor` on a real SD3Transformer2DModel: same call signature as
+    JointAttnProcessor2_0, three attention calls (joint + attn2 in the dual block, joint in the context_pre_only block) over
+    [image ; text] (16 + 7 tokens) and image-only (16) sequences, and the model output of the stock processor."""
+    h = hooks["diffusers_hooks"]
+    assert h["sd3_processors"] == ["B200JointAttnProcessor"] and h["sd3_signature"] is True
+    assert h["sd3_calls"] == 3 and h["sd3_joint_len"] == [16, 23]
+    assert h["sd3_max_diff"] <= 2e-3          # q / k / v pass through bf16 (the kernel's input type); a wrong token order would be O(1)
