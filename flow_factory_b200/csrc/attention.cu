@@ -168,7 +168,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
     }
   } else {
     // ===================== softmax: warps 4x .. 4x+3 -> sub-tile x =====================
-    setmaxnreg_inc<152>();   // pool: 512 x 128 regs at launch = 12 x 32 x 152 + 4 x 32 x 24 (+ 4096 spare)
+    setmaxnreg_inc<160>();   // pool: 512 x 128 regs at launch = 12 x 32 x 160 + 4 x 32 x 24 (+ 1024 spare)
     const int x = warp >> 2;                          // sub-tile
     if (x < n_sub) {
       const int wq = warp & 3;                        // TMEM lane quadrant
@@ -182,50 +182,61 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       SoftmaxState sm;
       const long long pc0 = prof_begin();
       long long lap = prof_begin();
+      // Software pipeline over the KV tiles: the TMEM load of S(j+1) is issued between / after the two halves of tile j (the registers of a
+      // half are dead once its exponentials are taken), and both TMEM waits (S(j+1) arrived, P(j) stored) are taken together at the top of
+      // the next tile - the mbarrier round trip softmax -> issuer -> tensor core -> softmax and the TMEM latencies run under the exp2 work.
+      uint32_t s0[32], s1[32];
+      mbar_wait(&s_full[x], 0, 0x60);
+      tc_fence_after();
+      tmem_ld32(tSx + 0, s0);
+      tmem_ld32(tSx + 32, s1);
       for (int j = 0; j < n_tiles; ++j) {
-        prof_lap(&lap, 0x67);                          // loop overhead / previous arrive
-        mbar_wait(&s_full[x], j & 1, 0x60);
-        tc_fence_after();
-        prof_lap(&lap, 0x68);                          // wait s_full
-        uint32_t s0[32], s1[32];
-        tmem_ld32(tSx + 0, s0);
-        tmem_ld32(tSx + 32, s1);
-        tmem_ld_wait();
+        prof_lap(&lap, 0x67);                          // loop overhead
+        tmem_ld_wait();                                // S(j) is in registers ...
+        if (j > 0) tmem_st_wait();                     // ... and P(j-1) is in TMEM
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[x]);        // Q K^T of the next tile may overwrite S_x now
-        prof_lap(&lap, 0x62);                          // TMEM load of S
+        if (lane == 0) {
+          mbar_arrive(&s_free[x]);                     // Q K^T of the next tile may overwrite S_x now
+          if (j > 0) mbar_arrive(&p_full[x]);          // P V of the previous tile may start
+        }
+        prof_lap(&lap, 0x62);                          // TMEM waits, arrives
 
-        uint32_t pk[32];                               // P(j) as packed bf16 pairs
-        float alpha;
-        const bool rescale = softmax_block64(s0, s1, S - j * ATT_BN, sc, pre, j == 0, sm, pk, alpha);
-        prof_lap(&lap, 0x64);                          // max + exp2 + sum + pack
-
-        if (j > 0) {                                   // P V of tile j-1 retired (issued a whole softmax ago): P_x free, O_x quiescent
+        SoftmaxTile t;
+        softmax_begin(s0, s1, S - j * ATT_BN, sc, pre, j == 0, sm, t);
+        uint32_t pk[16];                               // P(j), one half at a time, as packed bf16 pairs
+        softmax_half(s0, t, pk);
+        const bool more = j + 1 < n_tiles;
+        if (more) {
+          mbar_wait(&s_full[x], (j + 1) & 1, 0x60);    // Q K^T (j+1) was released at the top of this tile: normally long complete
+          tc_fence_after();
+          tmem_ld32(tSx + 0, s0);                      // S(j+1), first half, into the registers just consumed
+        }
+        if (j > 0) {                                   // P V of tile j-1 (released at the top of this tile) retired: P_x free, O_x quiescent
           mbar_wait(&p_free[x], (j - 1) & 1, 0x61);
           tc_fence_after();
         }
-        if (j > 0 && rescale) {                          // rare: O_x *= alpha in TMEM
-          uint32_t o0[32], o1[32];
-          tmem_ld32(tOx, o0);
-          tmem_ld32(tOx + 32, o1);
-          tmem_ld_wait();
+        if (j > 0 && t.rescale) {                      // rare: O_x *= alpha in TMEM (its tcgen05.wait::ld also covers the S(j+1) load)
+          uint32_t o0[32];
+#pragma unroll 1
+          for (int c = 0; c < ATT_D; c += 32) {
+            tmem_ld32(tOx + c, o0);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
-            o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
+            for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * t.alpha);
+            tmem_st32(tOx + c, o0);
           }
-          tmem_st32(tOx, o0);
-          tmem_st32(tOx + 32, o1);
         }
-        prof_lap(&lap, 0x65);                          // wait p_free, rare O rescale
-        tmem_st32(tPx, pk);                            // P_x(j): 64 bf16 per row = 32 columns
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[x]);
-        prof_lap(&lap, 0x66);                          // P -> TMEM, arrive
+        tmem_st16(tPx, pk);                            // P_x(j) columns [0, 16): keys 0-31
+        softmax_half(s1, t, pk);
+        if (more) tmem_ld32(tSx + 32, s1);
+        tmem_st16(tPx + 16, pk);                       // columns [16, 32): keys 32-63; completion is awaited at the next loop top
+        softmax_end(sm, t);
       }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[x]);          // the last P V
       // final output: O_x / l
       mbar_wait(&o_full[x], 0, 0x69);
       tc_fence_after();

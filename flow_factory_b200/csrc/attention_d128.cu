@@ -177,16 +177,22 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
       SoftmaxState sm;
       const int mask_hi = p.kv_mask_lo ? p.kv_mask_hi : 0;
       const int mask_lo = p.kv_mask_lo ? max(__ldg(p.kv_mask_lo + b), 1) : 0;   // key 0 always stays (keeps the running max finite)
+      // Software pipeline over the KV tiles (as attention.cu): the TMEM load of S(j+1) is issued between / after the two halves of tile j,
+      // both TMEM waits are taken together at the top of the next tile.
+      uint32_t s0[32], s1[32];
+      mbar_wait(&s_full[x], 0, 0x60);
+      tc_fence_after();
+      tmem_ld32(tSx + 0, s0);
+      tmem_ld32(tSx + 32, s1);
       for (int j = 0; j < n_tiles; ++j) {
-        mbar_wait(&s_full[x], j & 1, 0x60);
-        tc_fence_after();
-        uint32_t s0[32], s1[32];
-        tmem_ld32(tSx + 0, s0);
-        tmem_ld32(tSx + 32, s1);
-        tmem_ld_wait();
+        tmem_ld_wait();                                // S(j) is in registers ...
+        if (j > 0) tmem_st_wait();                     // ... and P(j-1) is in TMEM
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[x]);
+        if (lane == 0) {
+          mbar_arrive(&s_free[x]);
+          if (j > 0) mbar_arrive(&p_full[x]);
+        }
         if (mask_lo < mask_hi) {                        // key-padding mask: only the first few KV tiles overlap the text rows
           const int k0 = j * A128_BN;
           if (k0 < mask_hi && k0 + A128_BN > mask_lo) {
@@ -197,30 +203,41 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
             }
           }
         }
-        uint32_t pk[32];
-        float alpha;
-        const bool rescale = softmax_block64(s0, s1, Skv - j * A128_BN, sc, pre, j == 0, sm, pk, alpha);
-        if (j > 0) {
+        SoftmaxTile t;
+        softmax_begin(s0, s1, Skv - j * A128_BN, sc, pre, j == 0, sm, t);
+        uint32_t pk[16];                               // P(j), one half at a time, as packed bf16 pairs
+        softmax_half(s0, t, pk);
+        const bool more = j + 1 < n_tiles;
+        if (more) {
+          mbar_wait(&s_full[x], (j + 1) & 1, 0x60);    // Q K^T (j+1) was released at the top of this tile: normally long complete
+          tc_fence_after();
+          tmem_ld32(tSx + 0, s0);                      // S(j+1), first half, into the registers just consumed
+        }
+        if (j > 0) {                                   // P V of tile j-1 (released at the top of this tile) retired: P_x free, O_x quiescent
           mbar_wait(&p_free[x], (j - 1) & 1, 0x61);
           tc_fence_after();
         }
-        if (j > 0 && rescale) {                          // rare: O_x *= alpha in TMEM (128 columns, 32 at a time)
+        if (j > 0 && t.rescale) {                      // rare: O_x *= alpha in TMEM (128 columns, 32 at a time)
+          uint32_t o0[32];
 #pragma unroll 1
           for (int c = 0; c < A128_D; c += 32) {
-            uint32_t o0[32];
             tmem_ld32(tOx + c, o0);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
+            for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * t.alpha);
             tmem_st32(tOx + c, o0);
           }
         }
-        tmem_st32(tPx, pk);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[x]);
+        tmem_st16(tPx, pk);                            // P_x(j) columns [0, 16): keys 0-31
+        softmax_half(s1, t, pk);
+        if (more) tmem_ld32(tSx + 32, s1);
+        tmem_st16(tPx + 16, pk);                       // columns [16, 32): keys 32-63; completion is awaited at the next loop top
+        softmax_end(sm, t);
       }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[x]);
       mbar_wait(&o_full[x], 0, 0x69);
       tc_fence_after();
       const int q = q0 + x * A128_BM + r;

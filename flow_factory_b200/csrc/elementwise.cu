@@ -287,9 +287,35 @@ cudaError_t launch_timestep_proj(const StepCoef* table, const int* step_ptr, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// latent storage dtype (cast_latents, FF/models/abc.py:172-182): fp16 (default; +-65504 clamp + sticky flag), bf16 or fp32
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lat_load(const void* base, long i, int st) {
+  if (st == LAT_F16) return __half2float(static_cast<const __half*>(base)[i]);
+  if (st == LAT_BF16) return __bfloat162float(static_cast<const bf16*>(base)[i]);
+  return static_cast<const float*>(base)[i];
+}
+// the storage round trip of a freshly sampled value (flow_match...py:359-362: `.to(input dtype).float()`), before any clamp
+__device__ __forceinline__ float lat_round(float v, int st) {
+  if (st == LAT_F16) return __half2float(__float2half_rn(v));
+  if (st == LAT_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+  return v;
+}
+// store one value (already through lat_round, or teacher-forced / ODE mean): fp16 clamps to the finite range and raises the flag
+__device__ __forceinline__ void lat_store(void* base, long i, int st, float v, int* overflow_flag) {
+  if (st == LAT_F16) {
+    if (fabsf(v) > 65504.0f) { v = copysignf(65504.0f, v); if (overflow_flag) *overflow_flag = 1; }
+    static_cast<__half*>(base)[i] = __float2half_rn(v);
+  } else if (st == LAT_BF16) {
+    static_cast<bf16*>(base)[i] = __float2bfloat16_rn(v);
+  } else {
+    static_cast<float*>(base)[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // patchify (im2col): out[(r*B + b)*Ni + i*wp + j][c*p*p + py*p + px] = bf16(x[b, c, i*p+py, j*p+px])
 // ------------------------------------------------------------------------------------------------
-__global__ void patchify_kernel(const __half* x, int B, int reps, int C, int H, int W, int patch, bf16* out) {
+__global__ void patchify_kernel(const void* x, int storage, int B, int reps, int C, int H, int W, int patch, bf16* out) {
   const int hp = H / patch, wp = W / patch;
   const int KK = C * patch * patch;
   const long total = static_cast<long>(B) * hp * wp * KK;
@@ -301,16 +327,16 @@ __global__ void patchify_kernel(const __half* x, int B, int reps, int C, int H, 
     const int i = static_cast<int>((tok / wp) % hp);
     const int b = static_cast<int>(tok / (static_cast<long>(wp) * hp));
     const int px = k % patch, py = (k / patch) % patch, c = k / (patch * patch);
-    const float v = __half2float(x[((static_cast<long>(b) * C + c) * H + i * patch + py) * W + j * patch + px]);
+    const float v = lat_load(x, ((static_cast<long>(b) * C + c) * H + i * patch + py) * W + j * patch + px, storage);
     const bf16 o = __float2bfloat16_rn(v);
     for (int r = 0; r < reps; ++r)
       out[((static_cast<long>(r) * B + b) * hp * wp + static_cast<long>(i) * wp + j) * KK + k] = o;
   }
 }
-cudaError_t launch_patchify(const __half* x, int B, int reps, int C, int H, int W, int patch, bf16* out, cudaStream_t stream) {
+cudaError_t launch_patchify(const void* x, int storage, int B, int reps, int C, int H, int W, int patch, bf16* out, cudaStream_t stream) {
   const long total = static_cast<long>(B) * (H / patch) * (W / patch) * C * patch * patch;
   const int grid = static_cast<int>(std::min<long>((total + 255) / 256, 148 * 8));
-  patchify_kernel<<<grid, 256, 0, stream>>>(x, B, reps, C, H, W, patch, out);
+  patchify_kernel<<<grid, 256, 0, stream>>>(x, storage, B, reps, C, H, W, patch, out);
   return cudaGetLastError();
 }
 
@@ -457,19 +483,14 @@ __device__ __forceinline__ float sde_mean(const StepCoef& k, float x, float v) {
   const float x1p = __fadd_rn(x, __fmul_rn(v, k.c_v /* 1-sigma */));
   return __fadd_rn(__fmul_rn(x0p, k.cps_a), __fmul_rn(x1p, k.cps_b));
 }
-// mean + scale*z, rounded through the fp16 storage dtype (flow_match...py:359-362)
-__device__ __forceinline__ float sde_sample(const StepCoef& k, float mean, float z) {
-  return __half2float(__float2half_rn(__fadd_rn(mean, __fmul_rn(k.noise_scale, z))));
+// mean + scale*z, rounded through the storage dtype (flow_match...py:359-362)
+__device__ __forceinline__ float sde_sample(const StepCoef& k, float mean, float z, int storage) {
+  return lat_round(__fadd_rn(mean, __fmul_rn(k.noise_scale, z)), storage);
 }
 __device__ __forceinline__ float sde_logp_term(const StepCoef& k, float nxt, float mean) {
   const float d = __fsub_rn(nxt, mean);
   const float d2 = __fmul_rn(d, d);
   return k.dynamics == DYN_CPS ? -d2 : __fdiv_rn(-d2, k.two_var);
-}
-// cast_latents (abc.py:172-182): clamp to the fp16 range, raise the sticky flag
-__device__ __forceinline__ __half sde_store_half(float s, int* overflow_flag) {
-  if (fabsf(s) > 65504.0f) { s = copysignf(65504.0f, s); if (overflow_flag) *overflow_flag = 1; }
-  return __float2half_rn(s);
 }
 
 constexpr int SDE_THREADS = 256;
@@ -479,8 +500,10 @@ __global__ void __launch_bounds__(SDE_THREADS) sde_step_kernel(const SdeStepPara
   const StepCoef k = p.coef_table[sidx];
   const int b = blockIdx.y;
   const float* noise = p.noise ? p.noise + static_cast<long>(sidx) * p.noise_step_stride : nullptr;
-  __half* traj = (p.traj != nullptr && k.store_slot >= 0) ? p.traj + static_cast<long>(b) * p.traj_batch_stride + static_cast<long>(k.store_slot) * (p.C * p.H * p.W) : nullptr;
   const int CHW = p.C * p.H * p.W;
+  const int st = p.storage;
+  const long traj_off = static_cast<long>(b) * p.traj_batch_stride + static_cast<long>(k.store_slot) * CHW;   // elements
+  const bool has_traj = p.traj != nullptr && k.store_slot >= 0;
   const int quads = CHW >> 2;
   float part = 0.f;
   const int hp = p.H / p.patch, wp = p.W / p.patch;
@@ -514,9 +537,15 @@ __global__ void __launch_bounds__(SDE_THREADS) sde_step_kernel(const SdeStepPara
       v[i] = vc;
     }
     // ---- current latents ----
-    const uint2 xr = *reinterpret_cast<const uint2*>(p.x + base);
-    const __half2 xa = *reinterpret_cast<const __half2*>(&xr.x), xb = *reinterpret_cast<const __half2*>(&xr.y);
-    const float xs[4] = {__low2float(xa), __high2float(xa), __low2float(xb), __high2float(xb)};
+    float xs[4];
+    if (st == LAT_F16) {
+      const uint2 xr = *reinterpret_cast<const uint2*>(static_cast<const __half*>(p.x) + base);
+      const __half2 xa = *reinterpret_cast<const __half2*>(&xr.x), xb = *reinterpret_cast<const __half2*>(&xr.y);
+      xs[0] = __low2float(xa); xs[1] = __high2float(xa); xs[2] = __low2float(xb); xs[3] = __high2float(xb);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xs[i] = lat_load(p.x, base + i, st);
+    }
     // ---- mean ----
     float mean[4];
 #pragma unroll
@@ -524,9 +553,8 @@ __global__ void __launch_bounds__(SDE_THREADS) sde_step_kernel(const SdeStepPara
     // ---- next sample ----
     float nxt[4];
     if (p.next_given != nullptr) {
-      const uint2 nr = *reinterpret_cast<const uint2*>(p.next_given + base);
-      const __half2 na = *reinterpret_cast<const __half2*>(&nr.x), nb = *reinterpret_cast<const __half2*>(&nr.y);
-      nxt[0] = __low2float(na); nxt[1] = __high2float(na); nxt[2] = __low2float(nb); nxt[3] = __high2float(nb);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) nxt[i] = lat_load(p.next_given, base + i, st);
     } else if (k.dynamics == DYN_ODE) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) nxt[i] = mean[i];
@@ -543,18 +571,15 @@ __global__ void __launch_bounds__(SDE_THREADS) sde_step_kernel(const SdeStepPara
         box_muller(r[2], r[3], &z[2], &z[3]);
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) nxt[i] = sde_sample(k, mean[i], z[i]);
+      for (int i = 0; i < 4; ++i) nxt[i] = sde_sample(k, mean[i], z[i], st);
     }
-    // ---- store (cast_latents: clamp to +-65504 on overflow) ----
-    if (p.x_next != nullptr || traj != nullptr) {
-      __half h[4];
+    // ---- store (cast_latents: fp16 clamps to +-65504 on overflow) ----
+    if (p.x_next != nullptr || has_traj) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) h[i] = sde_store_half(nxt[i], p.overflow_flag);
-      uint2 o;
-      o.x = *reinterpret_cast<uint32_t*>(&h[0]);
-      o.y = *reinterpret_cast<uint32_t*>(&h[2]);
-      if (p.x_next) *reinterpret_cast<uint2*>(p.x_next + base) = o;
-      if (traj) *reinterpret_cast<uint2*>(traj + e0) = o;
+      for (int i = 0; i < 4; ++i) {
+        if (p.x_next) lat_store(p.x_next, base + i, st, nxt[i], p.overflow_flag);
+        if (has_traj) lat_store(p.traj, traj_off + e0 + i, st, nxt[i], p.overflow_flag);
+      }
     }
     if (p.mean_out) *reinterpret_cast<float4*>(p.mean_out + base) = make_float4(mean[0], mean[1], mean[2], mean[3]);
     if (p.v_out) {

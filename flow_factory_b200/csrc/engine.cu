@@ -219,7 +219,8 @@ struct ffb200_plan {
   // buffers
   bf16 *c0, *temb_p, *tp_a, *tproj, *ta, *temb, *mod, *peA, *h_img, *h_ctx, *a1, *a2, *ac, *qkv, *qkv2, *att, *att2, *ff, *ffc, *vout;
   float* pos_crop;
-  __half* x_cur;
+  __half* x_cur;                // current latents, `storage` dtype (allocated for 4-byte elements)
+  int storage;                  // LAT_F16 (default) | LAT_BF16 | LAT_F32
   float* logp_partial;
   int* d_step;
   StepCoef* d_coefs; int coef_cap;
@@ -359,6 +360,7 @@ int ffb200_plan_create(ffb200_engine* e, int batch, int cfg, int lat_h, int lat_
   p->e = e; p->B = batch; p->cfg = cfg ? 1 : 0; p->Bp = batch * (cfg ? 2 : 1);
   p->C = mc.in_channels; p->H = lat_h; p->W = lat_w; p->hp = lat_h / mc.patch_size; p->wp = lat_w / mc.patch_size;
   p->Ni = p->hp * p->wp; p->Nt = n_text; p->S = p->Ni + p->Nt; p->D = e->D;
+  p->storage = LAT_F16;
   p->ws_bytes = 0; p->graph_exec = nullptr; p->graph_valid = false; p->prompts_set = false; p->coef_cap = 0; p->d_coefs = nullptr;
   p->d_prompt = p->d_pooled = p->d_x0 = p->d_traj = p->d_final = nullptr; p->d_logp = nullptr; p->d_noise = nullptr; p->d_flag = nullptr;
   p->staged_traj_bytes = p->staged_logp_bytes = p->staged_noise_bytes = 0;
@@ -387,7 +389,7 @@ int ffb200_plan_create(ffb200_engine* e, int batch, int cfg, int lat_h, int lat_
   ALLOC(ff, static_cast<size_t>(Bp) * Ni * 4 * D, bf16);
   ALLOC(ffc, static_cast<size_t>(Bp) * Nt * 4 * D, bf16);
   ALLOC(vout, static_cast<size_t>(Bp) * Ni * 64, bf16);
-  ALLOC(x_cur, static_cast<size_t>(p->B) * p->C * p->H * p->W, __half);
+  ALLOC(x_cur, static_cast<size_t>(p->B) * p->C * p->H * p->W * 2, __half);   // room for fp32 storage
   ALLOC(logp_partial, static_cast<size_t>(p->B) * std::max(64, (Ni + 127) / 128), float);
   ALLOC(d_step, 1, int);
   ALLOC(d_done, 1, unsigned int);
@@ -416,7 +418,7 @@ int ffb200_plan_create(ffb200_engine* e, int batch, int cfg, int lat_h, int lat_
   {  // patch embed (embeddings.py:554-583)
     ffb200_plan* pp = p;
     const int reps = p->cfg ? 2 : 1, patch = mc.patch_size;
-    ops.push_back([pp, reps, patch](cudaStream_t st) { ++g_launch_count; return launch_patchify(pp->x_cur, pp->B, reps, pp->C, pp->H, pp->W, patch, pp->peA, st); });
+    ops.push_back([pp, reps, patch](cudaStream_t st) { ++g_launch_count; return launch_patchify(pp->x_cur, pp->storage, pp->B, reps, pp->C, pp->H, pp->W, patch, pp->peA, st); });
     GemmSpec s = {p->peA, Bp, Ni, 0, 64, 64, w.pe_w, D, w.pe_b, p->h_img, static_cast<long>(Ni) * D, 0, D,
                   EPI_BIAS_ADD_ROWTABLE, nullptr, 0, nullptr, nullptr, 0, 0.f, p->pos_crop};
     if ((r = add_gemm(p, s))) { ffb200_plan_destroy(p); return r; }
@@ -560,6 +562,14 @@ static void fill_sde(const ffb200_plan* p, SdeStepParams* sp) {
   memset(sp, 0, sizeof(*sp));
   sp->B = p->B; sp->C = p->C; sp->H = p->H; sp->W = p->W; sp->patch = p->e->cfg.patch_size;
   sp->cfg = p->cfg; sp->x = p->x_cur; sp->logp_partial = p->logp_partial; sp->coef_table = p->d_coefs;
+  sp->storage = p->storage;
+}
+
+int ffb200_plan_set_latent_dtype(ffb200_plan* p, int dtype) {
+  FFB_CHECK(p, "null plan");
+  FFB_CHECK(dtype == LAT_F16 || dtype == LAT_BF16 || dtype == LAT_F32, "latent dtype: 0 = fp16, 1 = bf16, 2 = fp32");
+  if (p->storage != dtype) { p->storage = dtype; p->graph_valid = false; }
+  return 0;
 }
 
 int ffb200_transformer_forward(ffb200_plan* p, const void* latents_fp16, float t_model, void* noise_pred_nchw, void* stream) {
@@ -572,7 +582,7 @@ int ffb200_transformer_forward(ffb200_plan* p, const void* latents_fp16, float t
   StepCoef c; memset(&c, 0, sizeof(c)); c.t_model = t_model;
   FFB_CUDA(cudaMemcpyAsync(p->d_coefs, &c, sizeof(c), cudaMemcpyHostToDevice, st));
   FFB_CUDA(cudaMemsetAsync(p->d_step, 0, sizeof(int), st));
-  FFB_CUDA(cudaMemcpyAsync(p->x_cur, latents_fp16, static_cast<size_t>(p->B) * p->C * p->H * p->W * 2, cudaMemcpyDeviceToDevice, st));
+  FFB_CUDA(cudaMemcpyAsync(p->x_cur, latents_fp16, static_cast<size_t>(p->B) * p->C * p->H * p->W * lat_elem_bytes(p->storage), cudaMemcpyDeviceToDevice, st));
   if ((r = run_forward(p, st))) return r;
   FFB_CUDA(p->proj_op(st));
   if (noise_pred_nchw) {
@@ -593,12 +603,12 @@ int ffb200_step(ffb200_plan* p, const ffb200_step_args* a, void* stream) {
   static_assert(sizeof(StepCoef) == sizeof(ffb200_step_coef), "StepCoef layout");
   FFB_CUDA(cudaMemcpyAsync(p->d_coefs, &a->coef, sizeof(StepCoef), cudaMemcpyHostToDevice, st));
   FFB_CUDA(cudaMemsetAsync(p->d_step, 0, sizeof(int), st));
-  FFB_CUDA(cudaMemcpyAsync(p->x_cur, a->latents, static_cast<size_t>(p->B) * p->C * p->H * p->W * 2, cudaMemcpyDeviceToDevice, st));
+  FFB_CUDA(cudaMemcpyAsync(p->x_cur, a->latents, static_cast<size_t>(p->B) * p->C * p->H * p->W * lat_elem_bytes(p->storage), cudaMemcpyDeviceToDevice, st));
   if ((r = run_forward(p, st))) return r;
   SdeStepParams sp; fill_sde(p, &sp);
   sp.guidance = a->guidance_scale; sp.noise = a->noise; sp.seed = a->seed; sp.coef_index = 0;
-  sp.next_given = static_cast<const __half*>(a->next_latents);
-  sp.x_next = static_cast<__half*>(a->out_next_latents);
+  sp.next_given = a->next_latents;
+  sp.x_next = a->out_next_latents;
   sp.mean_out = a->out_mean; sp.log_prob = a->out_log_prob; sp.v_out = static_cast<bf16*>(a->out_noise_pred);
   sp.overflow_flag = a->overflow_flag;
   FinalStepParams fs = p->fs;
@@ -616,16 +626,17 @@ static int rollout_impl(ffb200_plan* p, const ffb200_rollout_args* a, cudaStream
   if (r) return r;
   FFB_CUDA(cudaMemcpyAsync(p->d_coefs, a->coefs, static_cast<size_t>(T) * sizeof(StepCoef), cudaMemcpyHostToDevice, st));
   FFB_CUDA(cudaMemsetAsync(p->d_step, 0, sizeof(int), st));
-  FFB_CUDA(cudaMemcpyAsync(p->x_cur, a->x0, lat_elems * 2, cudaMemcpyDeviceToDevice, st));
+  const size_t eb = static_cast<size_t>(lat_elem_bytes(p->storage));
+  FFB_CUDA(cudaMemcpyAsync(p->x_cur, a->x0, lat_elems * eb, cudaMemcpyDeviceToDevice, st));
   if (a->all_latents && a->store_initial_slot >= 0) {
-    FFB_CUDA(cudaMemcpy2DAsync(static_cast<__half*>(a->all_latents) + static_cast<size_t>(a->store_initial_slot) * chw,
-                               static_cast<size_t>(a->n_latent_slots) * chw * 2, a->x0, static_cast<size_t>(chw) * 2,
-                               static_cast<size_t>(chw) * 2, p->B, cudaMemcpyDeviceToDevice, st));
+    FFB_CUDA(cudaMemcpy2DAsync(static_cast<char*>(a->all_latents) + static_cast<size_t>(a->store_initial_slot) * chw * eb,
+                               static_cast<size_t>(a->n_latent_slots) * chw * eb, a->x0, static_cast<size_t>(chw) * eb,
+                               static_cast<size_t>(chw) * eb, p->B, cudaMemcpyDeviceToDevice, st));
   }
   SdeStepParams sp; fill_sde(p, &sp);
   sp.guidance = a->guidance_scale; sp.noise = a->noise; sp.noise_step_stride = static_cast<long>(lat_elems); sp.seed = a->seed;
   sp.x_next = p->x_cur;  // in place: every thread reads its own 4 pixels before writing them
-  sp.traj = static_cast<__half*>(a->all_latents); sp.traj_batch_stride = static_cast<long>(a->n_latent_slots) * chw;
+  sp.traj = a->all_latents; sp.traj_batch_stride = static_cast<long>(a->n_latent_slots) * chw;
   sp.logp_traj = a->log_probs; sp.logp_batch_stride = a->n_logp_slots;
   sp.overflow_flag = a->overflow_flag; sp.step_ptr = p->d_step;
 
@@ -658,7 +669,7 @@ static int rollout_impl(ffb200_plan* p, const ffb200_rollout_args* a, cudaStream
       if (rr) return rr;
     }
   }
-  if (a->final_latents) FFB_CUDA(cudaMemcpyAsync(a->final_latents, p->x_cur, lat_elems * 2, cudaMemcpyDeviceToDevice, st));
+  if (a->final_latents) FFB_CUDA(cudaMemcpyAsync(a->final_latents, p->x_cur, lat_elems * eb, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
 
@@ -682,11 +693,12 @@ int ffb200_rollout_host(ffb200_plan* p, const ffb200_rollout_args* a, const void
   if (!p->d_prompt) {
     if ((r = plan_alloc(p, &p->d_prompt, prompt_bytes))) return r;
     if ((r = plan_alloc(p, &p->d_pooled, pooled_bytes))) return r;
-    if ((r = plan_alloc(p, &p->d_x0, lat_elems * 2))) return r;
-    if ((r = plan_alloc(p, &p->d_final, lat_elems * 2))) return r;
+    if ((r = plan_alloc(p, &p->d_x0, lat_elems * 4))) return r;       // sized for fp32 storage
+    if ((r = plan_alloc(p, &p->d_final, lat_elems * 4))) return r;
     if ((r = plan_alloc(p, reinterpret_cast<void**>(&p->d_flag), sizeof(int)))) return r;
   }
-  const long long traj_bytes = a->all_latents ? static_cast<long long>(lat_elems) * a->n_latent_slots * 2 : 0;
+  const long long eb = lat_elem_bytes(p->storage);
+  const long long traj_bytes = a->all_latents ? static_cast<long long>(lat_elems) * a->n_latent_slots * eb : 0;
   const long long logp_bytes = a->log_probs ? static_cast<long long>(p->B) * a->n_logp_slots * 4 : 0;
   const long long noise_bytes = a->noise ? static_cast<long long>(lat_elems) * a->num_steps * 4 : 0;
   if (traj_bytes > p->staged_traj_bytes) { if ((r = plan_alloc(p, &p->d_traj, traj_bytes))) return r; p->staged_traj_bytes = traj_bytes; }
@@ -694,7 +706,7 @@ int ffb200_rollout_host(ffb200_plan* p, const ffb200_rollout_args* a, const void
   if (noise_bytes > p->staged_noise_bytes) { if ((r = plan_alloc(p, reinterpret_cast<void**>(&p->d_noise), noise_bytes))) return r; p->staged_noise_bytes = noise_bytes; }
   FFB_CUDA(cudaMemcpyAsync(p->d_prompt, prompt_embeds_bf16, prompt_bytes, cudaMemcpyHostToDevice, st));
   FFB_CUDA(cudaMemcpyAsync(p->d_pooled, pooled_bf16, pooled_bytes, cudaMemcpyHostToDevice, st));
-  FFB_CUDA(cudaMemcpyAsync(p->d_x0, a->x0, lat_elems * 2, cudaMemcpyHostToDevice, st));
+  FFB_CUDA(cudaMemcpyAsync(p->d_x0, a->x0, lat_elems * eb, cudaMemcpyHostToDevice, st));
   if (a->noise) FFB_CUDA(cudaMemcpyAsync(p->d_noise, a->noise, noise_bytes, cudaMemcpyHostToDevice, st));
   FFB_CUDA(cudaMemsetAsync(p->d_flag, 0, sizeof(int), st));
   g_launch_count = 0;
@@ -707,7 +719,7 @@ int ffb200_rollout_host(ffb200_plan* p, const ffb200_rollout_args* a, const void
   if ((r = rollout_impl(p, &d, st))) return r;
   if (a->all_latents) FFB_CUDA(cudaMemcpyAsync(a->all_latents, p->d_traj, traj_bytes, cudaMemcpyDeviceToHost, st));
   if (a->log_probs) FFB_CUDA(cudaMemcpyAsync(a->log_probs, p->d_logp, logp_bytes, cudaMemcpyDeviceToHost, st));
-  if (a->final_latents) FFB_CUDA(cudaMemcpyAsync(a->final_latents, p->d_final, lat_elems * 2, cudaMemcpyDeviceToHost, st));
+  if (a->final_latents) FFB_CUDA(cudaMemcpyAsync(a->final_latents, p->d_final, lat_elems * eb, cudaMemcpyDeviceToHost, st));
   if (a->overflow_flag) FFB_CUDA(cudaMemcpyAsync(a->overflow_flag, p->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   FFB_CUDA(cudaStreamSynchronize(st));
   return 0;
@@ -814,9 +826,10 @@ int ffb200_small_linear(const void* in, int batch, int K, long long in_stride, c
   return 0;
 }
 
-int ffb200_sde_step(const void* noise_pred_bf16, const void* latents_fp16, int B, int C, int H, int W, const ffb200_step_coef* coef,
+int ffb200_sde_step_ex(const void* noise_pred_bf16, const void* latents_fp16, int B, int C, int H, int W, const ffb200_step_coef* coef,
                     const float* noise, unsigned long long seed, int step_index, const void* next_latents_fp16, void* out_next_fp16,
-                    float* out_mean, float* out_log_prob, int* overflow_flag, void* stream) {
+                    float* out_mean, float* out_log_prob, int* overflow_flag, int storage_dtype, void* stream) {
+  FFB_CHECK(storage_dtype == LAT_F16 || storage_dtype == LAT_BF16 || storage_dtype == LAT_F32, "latent dtype: 0 = fp16, 1 = bf16, 2 = fp32");
   FFB_CHECK(noise_pred_bf16 && latents_fp16 && coef, "null argument");
   FFB_CHECK(W % 4 == 0, "W must be a multiple of 4");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -834,8 +847,9 @@ int ffb200_sde_step(const void* noise_pred_bf16, const void* latents_fp16, int B
   }
   SdeStepParams sp; memset(&sp, 0, sizeof(sp));
   sp.v_direct = static_cast<const bf16*>(noise_pred_bf16); sp.B = B; sp.C = C; sp.H = H; sp.W = W; sp.patch = 1;
-  sp.x = static_cast<const __half*>(latents_fp16); sp.noise = noise; sp.noise_step_stride = 0; sp.seed = seed;
-  sp.next_given = static_cast<const __half*>(next_latents_fp16); sp.x_next = static_cast<__half*>(out_next_fp16);
+  sp.storage = storage_dtype;
+  sp.x = latents_fp16; sp.noise = noise; sp.noise_step_stride = 0; sp.seed = seed;
+  sp.next_given = next_latents_fp16; sp.x_next = out_next_fp16;
   sp.mean_out = out_mean; sp.log_prob = out_log_prob; sp.logp_partial = d_part; sp.overflow_flag = overflow_flag;
   sp.coef_table = d_c; sp.coef_index = step_index;
   if (noise) sp.noise = noise - 0;  // single step: no per-step offset (stride 0)
@@ -845,6 +859,13 @@ int ffb200_sde_step(const void* noise_pred_bf16, const void* latents_fp16, int B
   cudaFreeAsync(d_part, st);
   FFB_CUDA(le);
   return 0;
+}
+
+int ffb200_sde_step(const void* noise_pred_bf16, const void* latents_fp16, int B, int C, int H, int W, const ffb200_step_coef* coef,
+                    const float* noise, unsigned long long seed, int step_index, const void* next_latents_fp16, void* out_next_fp16,
+                    float* out_mean, float* out_log_prob, int* overflow_flag, void* stream) {
+  return ffb200_sde_step_ex(noise_pred_bf16, latents_fp16, B, C, H, W, coef, noise, seed, step_index, next_latents_fp16, out_next_fp16, out_mean,
+                            out_log_prob, overflow_flag, LAT_F16, stream);
 }
 
 }  // extern "C"

@@ -96,10 +96,10 @@ final_step_kernel(const __grid_constant__ FinalStepParams p) {
     const int ti = tok / wp, tj = tok % wp;
     const int CHW = s.C * s.H * s.W;
     const float* noise = s.noise ? s.noise + static_cast<long>(sidx) * s.noise_step_stride + static_cast<long>(b) * CHW : nullptr;
-    const __half* xin = s.x + static_cast<long>(b) * CHW;
-    __half* xout = s.x_next ? s.x_next + static_cast<long>(b) * CHW : nullptr;
-    __half* traj = (s.traj != nullptr && k.store_slot >= 0) ? s.traj + static_cast<long>(b) * s.traj_batch_stride + static_cast<long>(k.store_slot) * CHW : nullptr;
-    const __half* given = s.next_given ? s.next_given + static_cast<long>(b) * CHW : nullptr;
+    const int st = s.storage;
+    const long xoff = static_cast<long>(b) * CHW;                                     // element offsets into the storage-dtype buffers
+    const bool has_traj = s.traj != nullptr && k.store_slot >= 0;
+    const long toff = static_cast<long>(b) * s.traj_batch_stride + static_cast<long>(k.store_slot) * CHW;
     float* mean_out = s.mean_out ? s.mean_out + static_cast<long>(b) * CHW : nullptr;
     bf16* v_out = s.v_out ? s.v_out + static_cast<long>(b) * CHW : nullptr;
 
@@ -133,14 +133,18 @@ final_step_kernel(const __grid_constant__ FinalStepParams p) {
         for (int c = 0; c < 16; ++c) {
           const int e0 = (c * s.H + y) * s.W + tj * 2;          // element index of the px = 0 pixel
           const float vv[2] = {v[c], v[16 + c]};                // px = 0, 1
-          const __half2 xh = *reinterpret_cast<const __half2*>(xin + e0);
-          const float xs[2] = {__low2float(xh), __high2float(xh)};
+          float xs[2];
+          if (st == LAT_F16) {
+            const __half2 xh = *reinterpret_cast<const __half2*>(static_cast<const __half*>(s.x) + xoff + e0);
+            xs[0] = __low2float(xh); xs[1] = __high2float(xh);
+          } else {
+            xs[0] = lat_load(s.x, xoff + e0, st); xs[1] = lat_load(s.x, xoff + e0 + 1, st);
+          }
           float mean[2], nxt[2];
           mean[0] = sde_mean(k, xs[0], vv[0]);
           mean[1] = sde_mean(k, xs[1], vv[1]);
-          if (given != nullptr) {
-            const __half2 nh = *reinterpret_cast<const __half2*>(given + e0);
-            nxt[0] = __low2float(nh); nxt[1] = __high2float(nh);
+          if (s.next_given != nullptr) {
+            nxt[0] = lat_load(s.next_given, xoff + e0, st); nxt[1] = lat_load(s.next_given, xoff + e0 + 1, st);
           } else if (k.dynamics == DYN_ODE) {
             nxt[0] = mean[0]; nxt[1] = mean[1];
           } else {
@@ -155,14 +159,11 @@ final_step_kernel(const __grid_constant__ FinalStepParams p) {
               if (e0 & 2) box_muller(r[2], r[3], &z[0], &z[1]);
               else box_muller(r[0], r[1], &z[0], &z[1]);
             }
-            nxt[0] = sde_sample(k, mean[0], z[0]);
-            nxt[1] = sde_sample(k, mean[1], z[1]);
+            nxt[0] = sde_sample(k, mean[0], z[0], st);
+            nxt[1] = sde_sample(k, mean[1], z[1], st);
           }
-          if (xout != nullptr || traj != nullptr) {
-            const __half2 o = __halves2half2(sde_store_half(nxt[0], s.overflow_flag), sde_store_half(nxt[1], s.overflow_flag));
-            if (xout) *reinterpret_cast<__half2*>(xout + e0) = o;
-            if (traj) *reinterpret_cast<__half2*>(traj + e0) = o;
-          }
+          if (s.x_next != nullptr) { lat_store(s.x_next, xoff + e0, st, nxt[0], s.overflow_flag); lat_store(s.x_next, xoff + e0 + 1, st, nxt[1], s.overflow_flag); }
+          if (has_traj) { lat_store(s.traj, toff + e0, st, nxt[0], s.overflow_flag); lat_store(s.traj, toff + e0 + 1, st, nxt[1], s.overflow_flag); }
           if (mean_out) *reinterpret_cast<float2*>(mean_out + e0) = make_float2(mean[0], mean[1]);
           if (v_out) *reinterpret_cast<uint32_t*>(v_out + e0) = pack_bf16x2(vv[0], vv[1]);
           if (k.compute_log_prob && k.dynamics != DYN_ODE) part += sde_logp_term(k, nxt[0], mean[0]) + sde_logp_term(k, nxt[1], mean[1]);

@@ -124,7 +124,7 @@ cudaError_t launch_timestep_proj(const StepCoef* table, const int* step_ptr, int
                                  float post_scale = 1.0f);   // post_scale: Timesteps(scale=...) of Qwen-Image (1000)
 
 // im2col for the 2x2/stride-2 patch-embed conv: fp16 latents [B,C,H,W] -> bf16 [Bp*Ni, C*p*p] (Bp = B*reps)
-cudaError_t launch_patchify(const __half* x, int B, int reps, int C, int H, int W, int patch, bf16* out, cudaStream_t stream);
+cudaError_t launch_patchify(const void* x, int storage, int B, int reps, int C, int H, int W, int patch, bf16* out, cudaStream_t stream);
 
 // cast helpers
 cudaError_t launch_cast_f32_to_bf16(const float* in, bf16* out, long n, cudaStream_t stream);
@@ -199,6 +199,10 @@ cudaError_t launch_wan_gate_residual(bf16* h, const bf16* y, const float* gate, 
 cudaError_t launch_wan_rms_rope(bf16* x, long rows, int rows_per_batch, int ld, int D, const bf16* weight, float eps, const float* cos_t,
                                 const float* sin_t, cudaStream_t stream);
 
+// latent storage dtypes (element type of the x / next / trajectory buffers)
+enum { LAT_F16 = 0, LAT_BF16 = 1, LAT_F32 = 2 };
+inline int lat_elem_bytes(int storage) { return storage == LAT_F32 ? 4 : 2; }
+
 // ------------------------------------------------------------------ fused Euler/SDE step + log-prob (K14)
 
 struct SdeStepParams {
@@ -207,13 +211,13 @@ struct SdeStepParams {
   int B, C, H, W, patch;
   int cfg;                // 1: v = vu + g*(vc - vu) in bf16 steps (sd3_5.py:431-433)
   float guidance;
-  const __half* x;        // [B,C,H,W] fp16 current latents
+  const void* x;          // [B,C,H,W] current latents in the storage dtype (`storage`)
   const float* noise;     // fp32 N(0,1) [(steps,) B,C,H,W] or null -> in-kernel Philox4x32-10 + Box-Muller
   long noise_step_stride; // elements between steps (0 for a single step)
   unsigned long long seed;
-  const __half* next_given; // teacher-forced next latents (fp16) or null
-  __half* x_next;         // [B,C,H,W] fp16 (next_latents rounded to storage dtype, +-65504 clamp); may alias x
-  __half* traj;           // all_latents base [B, n_slots, C,H,W] or null; slot = coef.store_slot
+  const void* next_given; // teacher-forced next latents (storage dtype) or null
+  void* x_next;           // [B,C,H,W] next_latents rounded to the storage dtype (fp16: +-65504 clamp); may alias x
+  void* traj;             // all_latents base [B, n_slots, C,H,W] (storage dtype) or null; slot = coef.store_slot
   long traj_batch_stride; // elements
   float* mean_out;        // optional fp32 next_latents_mean or null
   bf16* v_out;            // optional bf16 [B,C,H,W] noise_pred after CFG or null
@@ -225,6 +229,7 @@ struct SdeStepParams {
   const StepCoef* coef_table;
   int* step_ptr;          // device step counter (entry = *step_ptr, incremented by the finalize kernel) or null
   int coef_index;         // used when step_ptr == null
+  int storage;            // latent_storage_dtype (FF/hparams/training_args.py:245-252): LAT_F16 (default) | LAT_BF16 | LAT_F32
 };
 cudaError_t launch_sde_step(const SdeStepParams& p, cudaStream_t stream);
 

@@ -54,11 +54,11 @@ __device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& e0, fl
   e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
 }
 
-// exp2 of the 32 scores of `a` into pk[quarter*16 ..], partial row sums into sums2.  kPre: the scores are the exponents (pre-scaled keys,
+// exp2 of the 32 scores of `a` into 16 packed bf16 pairs, partial row sums into sums2.  kPre: the scores are the exponents (pre-scaled keys,
 // reference 0); else exponent = s * sc - ref.  kPoly: the polynomial slots are in use (false: every element through MUFU).
 template <bool kPre, bool kPoly, bool kSum>
-__device__ __forceinline__ void softmax_exp32(const uint32_t (&a)[32], int quarter, uint64_t sc2, uint64_t mneg2, uint64_t (&sums2)[2],
-                                              uint32_t (&pk)[32]) {
+__device__ __forceinline__ void softmax_exp32(const uint32_t (&a)[32], uint64_t sc2, uint64_t mneg2, uint64_t (&sums2)[2],
+                                              uint32_t (&pk)[16]) {
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
     float t0 = __uint_as_float(a[2 * c]), t1 = __uint_as_float(a[2 * c + 1]);
@@ -70,7 +70,7 @@ __device__ __forceinline__ void softmax_exp32(const uint32_t (&a)[32], int quart
       e0 = ex2_approx(t0); e1 = ex2_approx(t1);
     }
     if (kSum) sums2[c & 1] = fadd2(sums2[c & 1], pack_f32x2(e0, e1));
-    pk[quarter * 16 + c] = pack_bf16x2(e0, e1);
+    pk[c] = pack_bf16x2(e0, e1);
   }
 }
 
@@ -96,15 +96,27 @@ struct SoftmaxState {
   bool zero_ref = false;     // warp-uniform: every row of the warp still has reference 0
 };
 
-// Online-softmax step of one thread (= one query row) over a 128 x 64 block of scores held in registers (s0: columns 0-31,
-// s1: 32-63).  Updates the running reference / sum, returns P as 32 packed bf16 pairs and the factor `alpha` by which the accumulator has
-// to be scaled if the (warp-uniform) return value is true.  Shared by the d = 64 and d = 128 kernels.
+// Per-tile decisions of one thread (= one query row), taken once the 64 scores of the tile are in registers.
+struct SoftmaxTile {
+  bool rescale;        // warp-uniform: the accumulator has to be scaled by `alpha` (first tile: alpha = 0, nothing accumulated yet)
+  float alpha;
+  bool fast;           // warp-uniform: the scores are the exponents (pre-scaled keys, reference 0)
+  bool poly;           // warp-uniform: the polynomial slots may be used on this tile (all their exponents within +-126)
+  uint64_t sc2, mneg2; // general path: exponent = s * sc - ref, as packed pairs
+  uint64_t sums2[2];   // 4 partial row sums of this tile as two packed pairs
+};
+
+// Online-softmax step of one thread over a 128 x 64 block of scores held in registers (s0: columns 0-31, s1: 32-63), in three parts so
+// that the attention kernels can put the TMEM load of the NEXT tile's scores between the two halves (the registers of a half are dead as
+// soon as its exponentials are taken):
+//   softmax_begin : masking of keys beyond the sequence, reference policy (first tile / growth), polynomial range check
+//   softmax_half  : exp2 + partial sums + bf16 packing of 32 columns (16 packed registers: stored to TMEM per half)
+//   softmax_end   : running-sum update
 //   sc    : softmax_scale * log2(e); ignored when `pre`.
 //   pre   : warp-uniform; the scores already are base-2 exponents (keys pre-scaled by the producer).
 //   first : warp-uniform; first KV tile of the row block.
-template <bool kSum = true>
-__device__ __forceinline__ bool softmax_block64(uint32_t (&s0)[32], uint32_t (&s1)[32], int kv_valid, float sc, bool pre, bool first,
-                                                SoftmaxState& st, uint32_t (&pk)[32], float& alpha) {
+__device__ __forceinline__ void softmax_begin(uint32_t (&s0)[32], uint32_t (&s1)[32], int kv_valid, float sc, bool pre, bool first,
+                                              SoftmaxState& st, SoftmaxTile& t) {
   if (kv_valid < 64) {
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
@@ -113,8 +125,7 @@ __device__ __forceinline__ bool softmax_block64(uint32_t (&s0)[32], uint32_t (&s
     }
   }
   const float sce = pre ? 1.0f : sc;
-  bool rescale;
-  alpha = 1.0f;
+  t.alpha = 1.0f;
   if (first) {
     // first tile of the row block: its exact maximum (8 independent 3-input chains) chooses the reference
     float mxs[8];
@@ -129,43 +140,48 @@ __device__ __forceinline__ bool softmax_block64(uint32_t (&s0)[32], uint32_t (&s
     st.zero_ref = __all_sync(0xffffffffu, fabsf(mt) <= ATT_REF_ZERO_BAND);     // also false for a NaN / inf maximum
     st.m_run = st.zero_ref ? 0.0f : mt;
     st.l_run = 0.f;
-    alpha = 0.0f;                                   // nothing accumulated yet
-    rescale = true;
+    t.alpha = 0.0f;                                 // nothing accumulated yet
+    t.rescale = true;
   } else {
     const bool grow = !(st.l_run <= ATT_SHIFT_AT);  // also true for inf / NaN
-    rescale = __any_sync(0xffffffffu, grow);
-    if (rescale) {
+    t.rescale = __any_sync(0xffffffffu, grow);
+    if (t.rescale) {
       if (!(st.l_run < ATT_FAIL_AT)) mbar_timeout(0x6F);   // a score jumped by more than 2^90 within one tile (or is not finite): fail loudly
       if (grow) {
         const int e = static_cast<int>((__float_as_uint(st.l_run) >> 23) & 0xFF) - 127;   // floor(log2(l_run)) >= 64
-        alpha = __uint_as_float(static_cast<uint32_t>(127 - e) << 23);                    // 2^-e, exact
+        t.alpha = __uint_as_float(static_cast<uint32_t>(127 - e) << 23);                  // 2^-e, exact
         st.m_run += static_cast<float>(e);                                                 // reference up by e exponent units, exact
       }
       st.zero_ref = false;
     }
   }
-  uint64_t sums2[2] = {0ull, 0ull};              // 4 partial row sums as two packed pairs
-  const uint64_t sc2 = pack_f32x2(sce, sce), mneg2 = pack_f32x2(-st.m_run, -st.m_run);
-  const bool fast = pre && st.zero_ref;          // warp-uniform
-  bool poly = ATT_POLY_NUM > 0;
-  if (poly) {
-    const float amax = fast ? softmax_poly_absmax<true>(s0, s1, sce, 0.f) : softmax_poly_absmax<false>(s0, s1, sce, st.m_run);
-    poly = __all_sync(0xffffffffu, amax <= 126.0f);
+  t.sums2[0] = t.sums2[1] = 0ull;
+  t.sc2 = pack_f32x2(sce, sce);
+  t.mneg2 = pack_f32x2(-st.m_run, -st.m_run);
+  t.fast = pre && st.zero_ref;
+  t.poly = ATT_POLY_NUM > 0;
+  if (t.poly) {
+    const float amax = t.fast ? softmax_poly_absmax<true>(s0, s1, sce, 0.f) : softmax_poly_absmax<false>(s0, s1, sce, st.m_run);
+    t.poly = __all_sync(0xffffffffu, amax <= 126.0f);
   }
-  if (fast) {
-    if (poly) { softmax_exp32<true, true, kSum>(s0, 0, sc2, mneg2, sums2, pk); softmax_exp32<true, true, kSum>(s1, 1, sc2, mneg2, sums2, pk); }
-    else { softmax_exp32<true, false, kSum>(s0, 0, sc2, mneg2, sums2, pk); softmax_exp32<true, false, kSum>(s1, 1, sc2, mneg2, sums2, pk); }
+}
+
+template <bool kSum = true>
+__device__ __forceinline__ void softmax_half(const uint32_t (&a)[32], SoftmaxTile& t, uint32_t (&pk)[16]) {
+  if (t.fast) {
+    if (t.poly) softmax_exp32<true, true, kSum>(a, t.sc2, t.mneg2, t.sums2, pk);
+    else softmax_exp32<true, false, kSum>(a, t.sc2, t.mneg2, t.sums2, pk);
   } else {
-    if (poly) { softmax_exp32<false, true, kSum>(s0, 0, sc2, mneg2, sums2, pk); softmax_exp32<false, true, kSum>(s1, 1, sc2, mneg2, sums2, pk); }
-    else { softmax_exp32<false, false, kSum>(s0, 0, sc2, mneg2, sums2, pk); softmax_exp32<false, false, kSum>(s1, 1, sc2, mneg2, sums2, pk); }
+    if (t.poly) softmax_exp32<false, true, kSum>(a, t.sc2, t.mneg2, t.sums2, pk);
+    else softmax_exp32<false, false, kSum>(a, t.sc2, t.mneg2, t.sums2, pk);
   }
-  if (kSum) {
-    float sa, sb, sc_, sd;
-    unpack_f32x2(sums2[0], sa, sb);
-    unpack_f32x2(sums2[1], sc_, sd);
-    st.l_run = st.l_run * alpha + ((sa + sb) + (sc_ + sd));
-  }
-  return rescale;
+}
+
+__device__ __forceinline__ void softmax_end(SoftmaxState& st, const SoftmaxTile& t) {
+  float sa, sb, sc_, sd;
+  unpack_f32x2(t.sums2[0], sa, sb);
+  unpack_f32x2(t.sums2[1], sc_, sd);
+  st.l_run = st.l_run * t.alpha + ((sa + sb) + (sc_ + sd));
 }
 
 // End-of-row check: a sum that left the supported range during the LAST tile (no later tile to notice it) fails loudly too.

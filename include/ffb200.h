@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define FFB200_ABI_VERSION 1
+#define FFB200_ABI_VERSION 2   /* 2: + ffb200_attention_scaled, ffb200_plan_set_latent_dtype, ffb200_sde_step_ex (additions only) */
 
 /* ---------------------------------------------------------------- errors */
 const char* ffb200_last_error(void);
@@ -83,6 +83,14 @@ int ffb200_plan_create(ffb200_engine* e, int batch, int cfg, int lat_h, int lat_
 void ffb200_plan_destroy(ffb200_plan* p);
 long long ffb200_plan_workspace_bytes(const ffb200_plan* p);
 
+/* latent_storage_dtype of this plan's latents buffers (FF/hparams/training_args.py:245-252, BaseAdapter.cast_latents, FF/models/abc.py:172-182):
+ * 0 = fp16 (default; values beyond +-65504 are clamped and the overflow flag raised), 1 = bf16, 2 = fp32.  It is the element type of every
+ * `latents` / `next_latents` / `all_latents` / `final_latents` pointer of ffb200_step / ffb200_rollout[_host] and the dtype freshly sampled
+ * next_latents are rounded through before the log-prob (FF/scheduler/flow_match_euler_discrete.py:359-362). */
+#define FFB200_LAT_F16 0
+#define FFB200_LAT_BF16 1
+#define FFB200_LAT_F32 2
+int ffb200_plan_set_latent_dtype(ffb200_plan* p, int dtype);
 /* Prompt conditioning for the next forward()/rollout() calls: bf16 [Bp, n_text, joint_dim] and [Bp, pooled_dim]
  * with Bp = batch * (cfg ? 2 : 1), negative (unconditional) half FIRST (sd3_5.py:409-413).  Runs context_embedder
  * and the pooled-text MLP once (they do not depend on the timestep). */
@@ -187,6 +195,10 @@ int ffb200_sde_step(const void* noise_pred_bf16, const void* latents_fp16, int B
                     const ffb200_step_coef* coef, const float* noise, unsigned long long seed, int step_index,
                     const void* next_latents_fp16, void* out_next_fp16, float* out_mean, float* out_log_prob,
                     int* overflow_flag, void* stream);
+/* Same with the latents' storage dtype (FFB200_LAT_*): element type of latents / next_latents / out_next, and the round trip of a sample. */
+int ffb200_sde_step_ex(const void* noise_pred_bf16, const void* latents, int B, int C, int H, int W, const ffb200_step_coef* coef,
+                       const float* noise, unsigned long long seed, int step_index, const void* next_latents, void* out_next,
+                       float* out_mean, float* out_log_prob, int* overflow_flag, int storage_dtype, void* stream);
 
 /* ================================================================ FLUX.1 (BASELINE config 3)
  * Same boundary for the FLUX.1 rollout path: FluxTransformer2DModel.forward (DF/models/transformers/transformer_flux.py:676-778)
