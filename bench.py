@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--num-sde-steps", type=int, default=1)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="sd35", choices=["sd35", "flux1", "wan21", "qwen_image"],
+                    help="BASELINE.json config: sd35 = C2 (the metric's, default); flux1 / wan21 / qwen_image = configs 3-5, each through its own "
+                         "bench tool under tools/ with the same line contract (examples/grpo/*/{flux1/default,wan21/t2v,qwen_image/default}.yaml)")
     return ap.parse_args()
 
 
@@ -399,6 +402,19 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_other_config(args):
+    """BASELINE configs 3-5 behind the same entry point: hands over (same process, so torchrun's environment carries) to the model's
+    bench tool, which prints one JSON line with the same contract (metric, value, e2e, clocks, gpu_launches, roofline ...)."""
+    import runpy
+    tool, extra = {
+        "flux1": ("tools/flux_bench.py", ["--num-inference-steps", "28"]),                       # FLUX.1-dev 1024^2 28-step
+        "wan21": ("tools/wan_bench.py", ["--frames", "49", "--num-inference-steps", "40"]),      # Wan2.1-T2V-1.3B 480p 49-frame 40-step
+        "qwen_image": ("tools/qwen_bench.py", ["--num-inference-steps", "50"]),                  # Qwen-Image 20B 1024^2 50-step DGPO (ODE)
+    }[args.config]
+    sys.argv = [os.path.join(ROOT, tool), "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)] + extra
+    runpy.run_path(sys.argv[0], run_name="__main__")
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -406,7 +422,10 @@ def main():
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a B200 (no CPU fallback for the engine arm); use --impl reference for the CPU baseline")
-        run_b200(args)
+        if args.config != "sd35":
+            run_other_config(args)
+        else:
+            run_b200(args)
 
 
 if __name__ == "__main__":

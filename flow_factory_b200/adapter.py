@@ -30,6 +30,10 @@ from .trajectory import create_callback_collector
 from .weights import EngineConfig, has_lora_keys, merge_lora_state_dict
 
 
+STORAGE_DTYPES = {"fp16": torch.float16, "float16": torch.float16, "bf16": torch.bfloat16, "bfloat16": torch.bfloat16,
+                  "fp32": torch.float32, "float32": torch.float32, None: torch.bfloat16}
+
+
 def filter_kwargs(fn: Callable, **kwargs) -> Dict[str, Any]:
     """FF/utils/base.py:38-63: keep only the keyword arguments `fn` names - everything if `fn` itself takes **kwargs."""
     params = inspect.signature(fn).parameters
@@ -45,8 +49,11 @@ class B200SD3_5Adapter:
                  scheduler: Optional[FlowMatchEulerDiscreteSDEScheduler] = None, latent_storage_dtype: str = "fp16",
                  decode_fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, vae_scale_factor: int = 8,
                  rng: str = "torch", use_graph: bool = True):
-        if latent_storage_dtype != "fp16":
-            raise ValueError("the fused step kernel stores latents as fp16 (Flow-Factory's default latent_storage_dtype)")
+        # latent_storage_dtype (FF/hparams/training_args.py:245-252): "fp16" (default), "bf16", "fp32"; None = the transformer's dtype
+        # (cast_latents' `default_dtype`, FF/models/abc.py:172-182), which is bf16 on this path
+        if latent_storage_dtype not in STORAGE_DTYPES:
+            raise ValueError(f"latent_storage_dtype must be one of {list(STORAGE_DTYPES)}, got {latent_storage_dtype!r}")
+        self.latent_dtype = STORAGE_DTYPES[latent_storage_dtype]
         if rng not in ("torch", "philox"):
             raise ValueError("rng must be 'torch' (reference-identical noise stream) or 'philox' (in-kernel)")
         self.engine = RolloutEngine(model_config, state_dict, torch.device(device))
@@ -97,10 +104,13 @@ class B200SD3_5Adapter:
         self._mode = "eval"; self.scheduler.eval()
 
     def cast_latents(self, latents: torch.Tensor, default_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-        """FF/models/abc.py:172-182, without the per-call host sync: clamp is a no-op unless something overflowed."""
-        if latents.dtype == torch.float16:
+        """FF/models/abc.py:172-182, without the per-call host sync: the fp16 clamp is a no-op unless something overflowed."""
+        target = self.latent_dtype
+        if latents.dtype == target:
             return latents
-        return latents.clamp(-65504.0, 65504.0).to(torch.float16)
+        if target == torch.float16:
+            return latents.clamp(-65504.0, 65504.0).to(torch.float16)
+        return latents.to(target)
 
     def decode_latents(self, latents: torch.Tensor, output_type: str = "pt"):
         if self.decode_fn is None:
@@ -169,7 +179,7 @@ class B200SD3_5Adapter:
         C = self.model_config.in_channels
         lh, lw = int(height) // self.vae_scale_factor, int(width) // self.vae_scale_factor
         n_text = prompt_embeds.shape[1]
-        plan = self.engine.plan(B, do_cfg, lh, lw, n_text)
+        plan = self.engine.plan(B, do_cfg, lh, lw, n_text, self.latent_dtype)
         self.engine.set_prompts(plan, prompt_embeds, pooled_prompt_embeds,
                                 negative_prompt_embeds if do_cfg else None, negative_pooled_prompt_embeds if do_cfg else None)
         # 3. initial latents: randn in the transformer dtype (pipeline_stable_diffusion_3.py:633-662), then cast_latents
@@ -189,7 +199,7 @@ class B200SD3_5Adapter:
         coefs = []
         for i in range(T):
             t, tn = timesteps[i], (timesteps[i + 1] if i + 1 < T else torch.tensor(0.0))
-            t_model = float(t.to(torch.float16))                      # sd3_5.py:394: timestep cast to the latents dtype
+            t_model = float(t.to(self.latent_dtype))                  # sd3_5.py:394: timestep cast to the latents dtype
             coefs.append(sch.step_coef(t, tn, nls[i], compute_log_prob=has_lp[i], t_model=t_model,
                                        store_slot=lat_slot[i + 1], logp_slot=lp_slot[i]))
         n_lat = sum(1 for s in lat_slot if s >= 0)
@@ -297,7 +307,7 @@ class B200SD3_5Adapter:
                 batched=("latents", "prompt_embeds", "pooled_prompt_embeds", "negative_prompt_embeds", "negative_pooled_prompt_embeds",
                          "next_latents", "noise"),
                 make_output=SDESchedulerOutput.from_dict)
-        plan = self.engine.plan(B, do_cfg, lh, lw, prompt_embeds.shape[1])
+        plan = self.engine.plan(B, do_cfg, lh, lw, prompt_embeds.shape[1], self.latent_dtype)
         self.engine.set_prompts(plan, prompt_embeds, pooled_prompt_embeds, negative_prompt_embeds if do_cfg else None,
                                 negative_pooled_prompt_embeds if do_cfg else None)
         sch = self.scheduler
@@ -305,7 +315,7 @@ class B200SD3_5Adapter:
         t0 = t0.flatten()[0].detach().cpu().float()
         # t_next omitted: the reference's scheduler.step then reads sigmas[i], sigmas[i + 1] from its tables (step_coef mirrors that)
         tn = None if t_next is None else (t_next if isinstance(t_next, torch.Tensor) else torch.tensor(float(t_next))).flatten()[0].detach().cpu().float()
-        coef = sch.step_coef(t0, tn, noise_level, compute_log_prob=compute_log_prob, t_model=float(t0.to(latents.dtype)))
+        coef = sch.step_coef(t0, tn, noise_level, compute_log_prob=compute_log_prob, t_model=float(t0.to(self.latent_dtype)))
         if noise is None and next_latents is None and self.rng == "torch" and sch.dynamics_type != "ODE":
             noise = torch.randn(latents.shape, device=self.device, dtype=torch.float32)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if noise is None else 0

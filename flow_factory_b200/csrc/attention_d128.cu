@@ -177,22 +177,17 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
       SoftmaxState sm;
       const int mask_hi = p.kv_mask_lo ? p.kv_mask_hi : 0;
       const int mask_lo = p.kv_mask_lo ? max(__ldg(p.kv_mask_lo + b), 1) : 0;   // key 0 always stays (keeps the running max finite)
-      // Software pipeline over the KV tiles (as attention.cu): the TMEM load of S(j+1) is issued between / after the two halves of tile j,
-      // both TMEM waits are taken together at the top of the next tile.
+      // P(j) is stored per 32-key half and released at once (see attention.cu for the measured alternatives).
       uint32_t s0[32], s1[32];
-      mbar_wait(&s_full[x], 0, 0x60);
-      tc_fence_after();
-      tmem_ld32(tSx + 0, s0);
-      tmem_ld32(tSx + 32, s1);
       for (int j = 0; j < n_tiles; ++j) {
-        tmem_ld_wait();                                // S(j) is in registers ...
-        if (j > 0) tmem_st_wait();                     // ... and P(j-1) is in TMEM
+        mbar_wait(&s_full[x], j & 1, 0x60);
+        tc_fence_after();
+        tmem_ld32(tSx + 0, s0);
+        tmem_ld32(tSx + 32, s1);
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&s_free[x]);
-          if (j > 0) mbar_arrive(&p_full[x]);
-        }
+        if (lane == 0) mbar_arrive(&s_free[x]);        // Q K^T of the next tile may overwrite S_x now
         if (mask_lo < mask_hi) {                        // key-padding mask: only the first few KV tiles overlap the text rows
           const int k0 = j * A128_BN;
           if (k0 < mask_hi && k0 + A128_BN > mask_lo) {
@@ -207,13 +202,7 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
         softmax_begin(s0, s1, Skv - j * A128_BN, sc, pre, j == 0, sm, t);
         uint32_t pk[16];                               // P(j), one half at a time, as packed bf16 pairs
         softmax_half(s0, t, pk);
-        const bool more = j + 1 < n_tiles;
-        if (more) {
-          mbar_wait(&s_full[x], (j + 1) & 1, 0x60);    // Q K^T (j+1) was released at the top of this tile: normally long complete
-          tc_fence_after();
-          tmem_ld32(tSx + 0, s0);                      // S(j+1), first half, into the registers just consumed
-        }
-        if (j > 0) {                                   // P V of tile j-1 (released at the top of this tile) retired: P_x free, O_x quiescent
+        if (j > 0) {                                   // P V of tile j-1 (released at the end of that tile) retired: P_x free, O_x quiescent
           mbar_wait(&p_free[x], (j - 1) & 1, 0x61);
           tc_fence_after();
         }
@@ -230,14 +219,13 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
         }
         tmem_st16(tPx, pk);                            // P_x(j) columns [0, 16): keys 0-31
         softmax_half(s1, t, pk);
-        if (more) tmem_ld32(tSx + 32, s1);
-        tmem_st16(tPx + 16, pk);                       // columns [16, 32): keys 32-63; completion is awaited at the next loop top
+        tmem_st16(tPx + 16, pk);                       // columns [16, 32): keys 32-63
         softmax_end(sm, t);
+        tmem_st_wait();                                // P(j) is in TMEM
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[x]);        // P V (j) may start: a whole tile of slack before its P_x / O_x are needed again
       }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[x]);
       mbar_wait(&o_full[x], 0, 0x69);
       tc_fence_after();
       const int q = q0 + x * A128_BM + r;

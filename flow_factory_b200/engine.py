@@ -13,12 +13,20 @@ from .scheduler import FlowMatchEulerDiscreteSDEScheduler, make_step_coef
 from .weights import EngineConfig, PackedWeights
 
 
+LATENT_DTYPES = {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}      # FFB200_LAT_* of include/ffb200.h
+
+
 class Plan:
-    def __init__(self, engine: "RolloutEngine", batch: int, cfg: bool, lat_h: int, lat_w: int, n_text: int):
+    def __init__(self, engine: "RolloutEngine", batch: int, cfg: bool, lat_h: int, lat_w: int, n_text: int,
+                 latent_dtype: torch.dtype = torch.float16):
+        if latent_dtype not in LATENT_DTYPES:
+            raise ValueError(f"latent storage dtype must be one of {list(LATENT_DTYPES)}, got {latent_dtype}")
         self.engine, self.batch, self.cfg, self.lat_h, self.lat_w, self.n_text = engine, batch, cfg, lat_h, lat_w, n_text
+        self.latent_dtype = latent_dtype
         self.handle = C.c_void_p()
         _lib.check(_lib.lib().ffb200_plan_create(engine.handle, batch, int(cfg), lat_h, lat_w, n_text, C.byref(self.handle)),
                    "ffb200_plan_create")
+        _lib.check(_lib.lib().ffb200_plan_set_latent_dtype(self.handle, LATENT_DTYPES[latent_dtype]), "ffb200_plan_set_latent_dtype")
         self._keep: List[torch.Tensor] = []
 
     @property
@@ -62,10 +70,12 @@ class RolloutEngine:
         self.weights.pack(state_dict)
         _lib.check(_lib.lib().ffb200_engine_set_weights(self.handle, C.byref(self.weights.struct)), "ffb200_engine_set_weights")
 
-    def plan(self, batch: int, cfg: bool, lat_h: int, lat_w: int, n_text: int) -> Plan:
-        key = (batch, bool(cfg), lat_h, lat_w, n_text)
+    def plan(self, batch: int, cfg: bool, lat_h: int, lat_w: int, n_text: int, latent_dtype: torch.dtype = torch.float16) -> Plan:
+        """`latent_dtype`: Flow-Factory's latent_storage_dtype (fp16 default, bf16, fp32) - the element type of every latents tensor that
+        goes into / comes out of this plan, and the dtype a freshly sampled next_latents is rounded through before its log-prob."""
+        key = (batch, bool(cfg), lat_h, lat_w, n_text, latent_dtype)
         if key not in self._plans:
-            self._plans[key] = Plan(self, batch, bool(cfg), lat_h, lat_w, n_text)
+            self._plans[key] = Plan(self, batch, bool(cfg), lat_h, lat_w, n_text, latent_dtype)
         return self._plans[key]
 
     def stream(self) -> torch.cuda.Stream:
@@ -92,7 +102,7 @@ class RolloutEngine:
     # ------------------------------------------------------------------ single forward / step
     def transformer_forward(self, plan: Plan, latents: torch.Tensor, t_model: float) -> torch.Tensor:
         """-> noise_pred bf16 [Bp, C, H, W] (both CFG halves, uncond first)."""
-        x = latents.to(device=self.device, dtype=torch.float16).contiguous()
+        x = latents.to(device=self.device, dtype=plan.latent_dtype).contiguous()
         bp = plan.batch * (2 if plan.cfg else 1)
         out = torch.empty((bp, self.cfg.in_channels, plan.lat_h, plan.lat_w), dtype=torch.bfloat16, device=self.device)
         st = torch.cuda.current_stream(self.device).cuda_stream
@@ -103,11 +113,11 @@ class RolloutEngine:
     def step(self, plan: Plan, latents: torch.Tensor, coef: "_lib.StepCoef", guidance_scale: float,
              noise: Optional[torch.Tensor] = None, next_latents: Optional[torch.Tensor] = None, seed: int = 0,
              step_index: int = 0, want_mean: bool = True, want_noise_pred: bool = True) -> Dict[str, torch.Tensor]:
-        x = latents.to(device=self.device, dtype=torch.float16).contiguous()
+        x = latents.to(device=self.device, dtype=plan.latent_dtype).contiguous()
         shp = tuple(x.shape)
         nz = noise.to(device=self.device, dtype=torch.float32).contiguous() if noise is not None else None
-        ng = next_latents.to(device=self.device, dtype=torch.float16).contiguous() if next_latents is not None else None
-        o_next = torch.empty(shp, dtype=torch.float16, device=self.device)
+        ng = next_latents.to(device=self.device, dtype=plan.latent_dtype).contiguous() if next_latents is not None else None
+        o_next = torch.empty(shp, dtype=plan.latent_dtype, device=self.device)
         o_mean = torch.empty(shp, dtype=torch.float32, device=self.device) if want_mean else None
         o_lp = torch.zeros(shp[0], dtype=torch.float32, device=self.device) if coef.compute_log_prob else None
         o_v = torch.empty(shp, dtype=torch.bfloat16, device=self.device) if want_noise_pred else None
@@ -130,16 +140,16 @@ class RolloutEngine:
     def rollout(self, plan: Plan, x0: torch.Tensor, coefs: Sequence["_lib.StepCoef"], guidance_scale: float,
                 n_latent_slots: int, store_initial_slot: int, n_logp_slots: int, noise: Optional[torch.Tensor] = None,
                 seed: int = 0, use_graph: bool = True) -> Dict[str, torch.Tensor]:
-        """Runs all steps on the device without host synchronisation.  Returns all_latents fp16 [B, slots, C,H,W],
-        log_probs fp32 [B, logp_slots], final latents fp16 [B,C,H,W], overflow flag."""
+        """Runs all steps on the device without host synchronisation.  Returns all_latents [B, slots, C,H,W] and final latents [B,C,H,W] in
+        the plan's latent storage dtype, log_probs fp32 [B, logp_slots], overflow flag."""
         T = len(coefs)
         B, Cc, H, W = plan.batch, self.cfg.in_channels, plan.lat_h, plan.lat_w
-        x = x0.to(device=self.device, dtype=torch.float16).contiguous()
+        x = x0.to(device=self.device, dtype=plan.latent_dtype).contiguous()
         assert tuple(x.shape) == (B, Cc, H, W)
         arr = (_lib.StepCoef * T)(*coefs)
-        traj = torch.empty((B, max(n_latent_slots, 1), Cc, H, W), dtype=torch.float16, device=self.device) if n_latent_slots else None
+        traj = torch.empty((B, max(n_latent_slots, 1), Cc, H, W), dtype=plan.latent_dtype, device=self.device) if n_latent_slots else None
         lps = torch.zeros((B, max(n_logp_slots, 1)), dtype=torch.float32, device=self.device) if n_logp_slots else None
-        final = torch.empty((B, Cc, H, W), dtype=torch.float16, device=self.device)
+        final = torch.empty((B, Cc, H, W), dtype=plan.latent_dtype, device=self.device)
         flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         nz = None
         if noise is not None:
@@ -174,11 +184,11 @@ class RolloutEngine:
         B, Cc, H, W = plan.batch, self.cfg.in_channels, plan.lat_h, plan.lat_w
         for t in (x0, prompt_embeds, pooled):
             assert not t.is_cuda and t.is_contiguous()
-        assert x0.dtype == torch.float16 and prompt_embeds.dtype == torch.bfloat16 and pooled.dtype == torch.bfloat16
+        assert x0.dtype == plan.latent_dtype and prompt_embeds.dtype == torch.bfloat16 and pooled.dtype == torch.bfloat16
         pin = lambda *shape, dtype: torch.empty(shape, dtype=dtype, pin_memory=True)
-        traj = pin(B, max(n_latent_slots, 1), Cc, H, W, dtype=torch.float16) if n_latent_slots else None
+        traj = pin(B, max(n_latent_slots, 1), Cc, H, W, dtype=plan.latent_dtype) if n_latent_slots else None
         lps = pin(B, max(n_logp_slots, 1), dtype=torch.float32) if n_logp_slots else None
-        final = pin(B, Cc, H, W, dtype=torch.float16)
+        final = pin(B, Cc, H, W, dtype=plan.latent_dtype)
         flag = torch.zeros(1, dtype=torch.int32).pin_memory()
         arr = (_lib.StepCoef * T)(*coefs)
         a = _lib.RolloutArgs()

@@ -277,13 +277,12 @@ class FlowMatchEulerDiscreteSDEScheduler:
         L = _lib.lib()
         B, Cc, H, W = latents.shape
         in_dtype = latents.dtype
-        x16 = latents.to(torch.float16).contiguous()
+        x16 = latents.contiguous()                 # storage dtype as given
         v16 = noise_pred.to(torch.bfloat16).contiguous()
-        if latents.dtype != torch.float16:
-            # the reference rounds fresh next_latents through the INPUT latents dtype (flow_match...py:309, 359-362); the native step's
-            # storage round trip is fp16 (Flow-Factory's default latent_storage_dtype) - anything else would silently break the
-            # rollout / replay log-prob consistency, so it is refused rather than approximated
-            raise NotImplementedError(f"scheduler.step: latents are {latents.dtype}; the native step stores fp16 (latent_storage_dtype='fp16')")
+        # the reference rounds fresh next_latents through the INPUT latents dtype (flow_match...py:309, 359-362) - the latents' storage dtype
+        codes = {torch.float16: 0, torch.bfloat16: 1, torch.float32: 2}
+        if latents.dtype not in codes:
+            raise NotImplementedError(f"scheduler.step: latents are {latents.dtype}; supported storage dtypes: fp16, bf16, fp32")
         if latents.dim() != 4:
             raise NotImplementedError("scheduler.step mirror: (B, C, H, W) latents (the packed / video adapters call the engine step directly)")
         if noise is None and seed is None and next_latents is None and dyn != "ODE":
@@ -291,16 +290,16 @@ class FlowMatchEulerDiscreteSDEScheduler:
             # RNG stream) on EVERY call - never a fixed in-kernel seed, which would correlate the exploration noise across steps
             noise = randn_tensor(tuple(noise_pred.shape), generator=generator, device=latents.device, dtype=torch.float32)
         nz = noise.to(torch.float32).contiguous() if noise is not None else None
-        ng = next_latents.to(torch.float16).contiguous() if next_latents is not None else None
+        ng = next_latents.to(latents.dtype).contiguous() if next_latents is not None else None
         out_next = torch.empty_like(x16)
         out_mean = torch.empty(latents.shape, dtype=torch.float32, device=latents.device)
         out_lp = torch.zeros(B, dtype=torch.float32, device=latents.device) if compute_log_prob else None
         flag = torch.zeros(1, dtype=torch.int32, device=latents.device)
         st = torch.cuda.current_stream(latents.device).cuda_stream
-        _lib.check(L.ffb200_sde_step(v16.data_ptr(), x16.data_ptr(), B, Cc, H, W, c,
+        _lib.check(L.ffb200_sde_step_ex(v16.data_ptr(), x16.data_ptr(), B, Cc, H, W, c,
                                      nz.data_ptr() if nz is not None else None, int(seed or 0), step_index,
                                      ng.data_ptr() if ng is not None else None, out_next.data_ptr(), out_mean.data_ptr(),
-                                     out_lp.data_ptr() if out_lp is not None else None, flag.data_ptr(), st), "ffb200_sde_step")
+                                     out_lp.data_ptr() if out_lp is not None else None, flag.data_ptr(), codes[latents.dtype], st), "ffb200_sde_step_ex")
         if next_latents is not None:
             nxt = next_latents.float()
         elif dyn == "ODE":

@@ -10,6 +10,15 @@ what `self.transformer` computes has to reach that copy before the next no-grad 
   * `use_ref_parameters()` (abc.py:556-585): full fine-tuning swaps parameter values (same as above); LoRA enters PEFT's
     `disable_adapter()`, which changes NO tensor - inside it the engine must hold the BASE weights, i.e. the LoRA pair is not folded.
 The copy is refreshed lazily, at the next `inference()` / no-grad `forward()`, so nested contexts cost one re-pack, not one per edge.
+
+Rollout / replay consistency.  GRPO's importance ratio exp(new_log_prob - old_log_prob) is clipped at ~1e-4, and the two
+log-probs come from two different bf16 implementations here: the engine's kernels (rollout) and diffusers + autograd (replay).  Measured on
+a B200 at the benchmarked size (tests/test_gpu_parity_c2.py -> profiles/r02_parity_c2_rollout.json): the engine's own log-probs agree with
+the reference numerics to 6e-7 .. 2e-5 relative, but |ratio - 1| of a cross-path replay reaches 1e-4 .. 2e-4 at late steps (bf16 noise of two
+independent forwards, amplified by CFG) - the size of the clip range.  So, as SURVEY 7.2 #1 option (b) prescribes, `inference()` re-evaluates
+`old_log_prob` of the stored SDE transitions (<= num_sde_steps per rollout, 1 by default) with the REFERENCE forward, teacher-forced on
+the engine's own latents: the ratio of the first optimisation step is then exactly 1, as in the reference, at the cost of num_sde_steps of
+T transformer forwards on the diffusers path.  `B200GlueSD3_5Adapter.recompute_old_log_probs = False` keeps the engine's values.
 """
 from contextlib import contextmanager
 
@@ -23,6 +32,7 @@ class B200GlueSD3_5Adapter(SD3_5Adapter):
     """Rollout + no-grad steps on the B200 engine; everything else (load_pipeline, LoRA, EMA, checkpointing,
     decode_latents, the autograd replay in optimize()) is inherited from the reference."""
 
+    recompute_old_log_probs = True   # see "Rollout / replay consistency" above
     _engine_stale = True          # the packed copy may differ from what self.transformer computes right now
     _lora_off = 0                 # depth of active use_ref_parameters() contexts under LoRA (adapter disabled)
 
@@ -93,7 +103,31 @@ class B200GlueSD3_5Adapter(SD3_5Adapter):
                                      device=self.device)
             kwargs.update({k: v for k, v in enc.items() if v is not None})
         self._sync_engine_if_stale()
-        return self._b200.inference(*args, **kwargs)
+        samples = self._b200.inference(*args, **kwargs)
+        if self.recompute_old_log_probs and kwargs.get("compute_log_prob", True) and self.mode != "eval":
+            self._recompute_old_log_probs(samples, kwargs)
+        return samples
+
+    def _recompute_old_log_probs(self, samples, kw):
+        """old_log_prob of every stored SDE transition through the reference's own forward (teacher-forced on the engine's latents)."""
+        if not samples or samples[0].log_probs is None or samples[0].log_probs.numel() == 0:
+            return
+        s0 = samples[0]
+        lmap, pmap, ts = s0.latent_index_map.tolist(), s0.log_prob_index_map.tolist(), s0.timesteps
+        for i, slot in enumerate(pmap):
+            if slot < 0 or lmap[i] < 0 or lmap[i + 1] < 0:
+                continue                                        # no log-prob kept here, or the transition's end points are not both stored
+            x_t = torch.stack([s.all_latents[lmap[i]] for s in samples]).to(self.device)
+            x_n = torch.stack([s.all_latents[lmap[i + 1]] for s in samples]).to(self.device)
+            t = ts[i].to(self.device)
+            t_next = (ts[i + 1] if i + 1 < len(ts) else torch.zeros((), dtype=ts.dtype)).to(self.device)
+            out = SD3_5Adapter.forward(                          # the reference path, NOT self.forward (which serves no-grad calls natively)
+                self, t=t, t_next=t_next, latents=x_t, next_latents=x_n, prompt_embeds=kw["prompt_embeds"],
+                pooled_prompt_embeds=kw["pooled_prompt_embeds"], negative_prompt_embeds=kw.get("negative_prompt_embeds"),
+                negative_pooled_prompt_embeds=kw.get("negative_pooled_prompt_embeds"), guidance_scale=kw.get("guidance_scale", 7.5),
+                noise_level=self.scheduler.get_noise_level_for_timestep(t), compute_log_prob=True, return_kwargs=["log_prob"])
+            for b, s in enumerate(samples):
+                s.log_probs[slot] = out.log_prob[b].to(s.log_probs.dtype)
 
     def forward(self, *args, **kwargs):                     # grpo.py:242-263 (with grad) / 282-292 (no grad, inside use_ref_parameters)
         if torch.is_grad_enabled():

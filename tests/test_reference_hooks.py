@@ -387,7 +387,31 @@ lora["plain_keys_only"] = not any(("lora_" in k) or ("base_layer" in k) or k.sta
 GL.B200GlueSD3_5Adapter.transformer = property(lambda self: ra.transformer)
 glue.model_args = types.SimpleNamespace(lora_alpha=8.0, finetune_type="full")
 glue.rollout(); glue._sync_engine_if_stale()
-out["glue_contexts"] = {"stale_after_rollout": stale_after_rollout, "ctx": ctx, "lora": lora}
+# ---- option (b) of SURVEY 7.2 #1: old_log_prob of the stored SDE transitions re-evaluated through the REFERENCE forward
+from flow_factory_b200.samples import SD3_5Sample as MySample
+from flow_factory_b200.scheduler import SDESchedulerOutput as MyOut
+def _mk(b):
+    # T = 4: latents kept at positions 0, 1, 2, 4 (slots 0..3); log-probs kept for steps 0, 1 (slots 0, 1) and step 3 (slot 2), whose start
+    # latent (position 3) is NOT stored
+    return MySample(timesteps=torch.tensor([1000.0, 900.0, 750.0, 500.0]), all_latents=torch.arange(4.0).view(4, 1, 1, 1) + 10 * b,
+                    log_probs=torch.full((3,), -1.0), latent_index_map=torch.tensor([0, 1, 2, -1, 3]), log_prob_index_map=torch.tensor([0, 1, -1, 2]))
+fake = [_mk(0), _mk(1)]
+glue._b200.inference = lambda *a, **k: fake
+calls_b = []
+def _ref_forward(self, **kw):
+    calls_b.append({"t": float(kw["t"]), "t_next": float(kw["t_next"]), "x_t": kw["latents"].flatten().tolist(), "x_n": kw["next_latents"].flatten().tolist(),
+                    "g": kw["guidance_scale"], "rk": kw["return_kwargs"], "nl": kw["noise_level"], "pe": kw["prompt_embeds"].shape[0]})
+    return MyOut(log_prob=torch.tensor([100.0 + kw["latents"].flatten()[0].item(), 200.0 + kw["latents"].flatten()[1].item()]))
+GL.SD3_5Adapter.forward = _ref_forward
+ra.scheduler.get_noise_level_for_timestep = lambda t: 0.7
+glue._mode = "rollout"
+res = glue.inference(prompt_embeds=torch.zeros(2, 3, 4), pooled_prompt_embeds=torch.zeros(2, 4), guidance_scale=4.5, compute_log_prob=True)
+rec = {"calls": calls_b, "log_probs": [s_.log_probs.tolist() for s_ in res]}
+glue.recompute_old_log_probs = False
+fake[0].log_probs.fill_(-1.0); n_before = len(calls_b)
+glue.inference(prompt_embeds=torch.zeros(2, 3, 4), pooled_prompt_embeds=torch.zeros(2, 4), guidance_scale=4.5, compute_log_prob=True)
+rec["disabled_keeps_engine_values"] = [len(calls_b) == n_before, fake[0].log_probs.tolist()]
+out["glue_contexts"] = {"stale_after_rollout": stale_after_rollout, "ctx": ctx, "lora": lora, "recompute": rec}
 glue.eval()
 g2 = [glue.mode, glue._b200.scheduler.is_eval, ra.scheduler.is_eval]
 glue.train(True)
@@ -695,3 +719,15 @@ def test_sd3_attn_processor_is_a_drop_in_for_joint_attn_processor(hooks):
     assert h["sd3_processors"] == ["B200JointAttnProcessor"] and h["sd3_signature"] is True
     assert h["sd3_calls"] == 3 and h["sd3_joint_len"] == [16, 23]
     assert h["sd3_max_diff"] <= 2e-3          # q / k / v pass through bf16 (the kernel's input type); a wrong token order would be O(1)
+
+
+def test_glue_recomputes_old_log_probs_through_the_reference_forward(hooks):
+    """SURVEY 7.2 #1 option (b): the stored SDE transitions (both end points kept) are replayed teacher-forced through SD3_5Adapter.forward
+    (the reference path, not the engine) and their log-probs replace the engine's; a log-prob whose start latent is not stored keeps the
+    engine's value; the switch turns it off."""
+    r = hooks["glue_contexts"]["recompute"]
+    assert [(c["t"], c["t_next"]) for c in r["calls"]] == [(1000.0, 900.0), (900.0, 750.0)]
+    assert r["calls"][0]["x_t"] == [0.0, 10.0] and r["calls"][0]["x_n"] == [1.0, 11.0] and r["calls"][1]["x_t"] == [1.0, 11.0]
+    assert all(c["g"] == 4.5 and c["rk"] == ["log_prob"] and c["nl"] == 0.7 and c["pe"] == 2 for c in r["calls"])
+    assert r["log_probs"] == [[100.0, 101.0, -1.0], [210.0, 211.0, -1.0]]
+    assert r["disabled_keeps_engine_values"] == [True, [-1.0, -1.0, -1.0]]
