@@ -24,6 +24,7 @@
 // The MUFU unit (16 ex2/clk/SM) is the scarcest pipe at d = 64: 3 of every 8 element pairs go through a polynomial exp2 on the
 // FMA pipe; scale / sum use packed fp32x2 arithmetic; the row max uses 3-input max in independent chains.
 #include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "kernels.h"
 #include "softmax.cuh"
@@ -277,7 +278,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
 // warps for free: 16 softmax warps (4 per sub-partition) over two 128-row sub-tiles per CTA, and - the sub-tiles now need only 320 of the
 // 512 TMEM columns - the score tile S is DOUBLE-buffered, so Q K^T runs two tiles ahead of the softmax and never waits for it.
 //   warps 0-15 : softmax.  warp w: lane quadrant w % 4 (TMEM lanes), sub-tile (w / 4) % 2, key half w / 8.
-//   warp  16   : TMA producer;  warps 17 / 18 : MMA issuers of sub-tile 0 / 1;  warp 19 idle.
+//   then       : TMA producer, the MMA issuers of sub-tile 0 / 1, one idle warp.
 // Agreement between the two halves of a row (the reference of online softmax must be the same in both, they feed one accumulator):
 //   * first tile: the half maxima are exchanged through shared memory (one named barrier per CTA lifetime) - both halves take the same
 //     decision (reference 0 or the row maximum);
@@ -297,7 +298,85 @@ constexpr int AT2_TMEM_P = 256;      // P_x at 256 + x * 32
 constexpr int AT2_TMEM_O = 320;      // O_x at 320 + x * 64
 constexpr float AT2_SHIFT = 64.0f;   // the reference moves by exactly 2^64
 
-__global__ void __launch_bounds__(AT2_THREADS, 1)
+// One warp per 32 query rows, all 64 keys of a tile (kHalves == 1 of attention_split_kernel): the row-per-thread softmax of attention_kernel
+// on the double-buffered S of the split layout.
+__device__ __forceinline__ void attention_rowpair_softmax(const AttnParams& p, uint32_t tmem_base, int wq, int x, int lane, int q0, int head,
+                                                          int b, int S, int n_tiles, uint64_t* s_full, uint64_t* s_free, uint64_t* p_full,
+                                                          uint64_t* p_free, uint64_t* o_full) {
+  const int r = wq * 32 + lane;
+  const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+  const uint32_t tSx = tmem_base + lane_off + 0 /*AT2_TMEM_S*/ + x * 2 * ATT_BN;
+  const uint32_t tPx = tmem_base + lane_off + 256 /*AT2_TMEM_P*/ + x * (ATT_BN / 2);
+  const uint32_t tOx = tmem_base + lane_off + 320 /*AT2_TMEM_O*/ + x * ATT_D;
+  const float sc = p.scale_log2;
+  const bool pre = p.k_prescaled != 0;
+  SoftmaxState sm;
+  uint32_t s0[32], s1[32];
+  for (int j = 0; j < n_tiles; ++j) {
+    const int buf = j & 1;
+    mbar_wait(&s_full[x * 2 + buf], (j >> 1) & 1, 0x60);
+    tc_fence_after();
+    tmem_ld32(tSx + buf * ATT_BN, s0);
+    tmem_ld32(tSx + buf * ATT_BN + 32, s1);
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_free[x * 2 + buf]);
+    SoftmaxTile t;
+    softmax_begin(s0, s1, S - j * ATT_BN, sc, pre, j == 0, sm, t);
+    uint32_t pk[16];
+    softmax_half(s0, t, pk);
+    if (j > 0) {
+      mbar_wait(&p_free[x], (j - 1) & 1, 0x61);
+      tc_fence_after();
+    }
+    if (j > 0 && t.rescale) {
+      uint32_t o0[32];
+#pragma unroll 1
+      for (int c = 0; c < ATT_D; c += 32) {
+        tmem_ld32(tOx + c, o0);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * t.alpha);
+        tmem_st32(tOx + c, o0);
+      }
+    }
+    tmem_st16(tPx, pk);
+    softmax_half(s1, t, pk);
+    tmem_st16(tPx + 16, pk);
+    softmax_end(sm, t);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&p_full[x]);
+  }
+  mbar_wait(&o_full[x], 0, 0x69);
+  tc_fence_after();
+  const int q = q0 + x * ATT_BM + r;
+  if (q < S) softmax_final_check(sm.l_run);
+  const float inv = 1.0f / sm.l_run;
+  bf16* dst = p.out + static_cast<long>(b) * p.out_batch_stride + static_cast<long>(q) * p.inner_dim + head * ATT_D;
+#pragma unroll 1
+  for (int c = 0; c < ATT_D; c += 32) {
+    uint32_t o0[32];
+    tmem_ld32(tOx + c, o0);
+    tmem_ld_wait();
+    if (q < S) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(o0[g * 8 + 0]) * inv, __uint_as_float(o0[g * 8 + 1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(o0[g * 8 + 2]) * inv, __uint_as_float(o0[g * 8 + 3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(o0[g * 8 + 4]) * inv, __uint_as_float(o0[g * 8 + 5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(o0[g * 8 + 6]) * inv, __uint_as_float(o0[g * 8 + 7]) * inv);
+        reinterpret_cast<uint4*>(dst + c)[g] = o;
+      }
+    }
+  }
+}
+
+template <int kHalves>      // 2: two warps per row (16 softmax warps); 1: one warp per row (8 softmax warps), same double-buffered S
+__global__ void __launch_bounds__((8 * kHalves + 4) * 32, 1)
 attention_split_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                                            // [2 sub-tiles][128][64]
@@ -325,7 +404,8 @@ attention_split_kernel(const __grid_constant__ AttnParams p) {
   const int n_tiles = (S + ATT_BN - 1) / ATT_BN;
   const int n_sub = min(AT2_NSUB, (S - q0 + ATT_BM - 1) / ATT_BM);
 
-  if (warp == 16 && lane == 0) {
+  constexpr int kTma = 8 * kHalves;                 // warp roles after the softmax warps: TMA producer, two MMA issuers, one idle
+  if (warp == kTma && lane == 0) {
     tma_prefetch_desc(&p.tmQKV);
     tma_prefetch_desc(&p.tmKV);
     mbar_init(q_full, 1);
@@ -333,17 +413,17 @@ attention_split_kernel(const __grid_constant__ AttnParams p) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], n_sub);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], n_sub);
     }
-    for (int i = 0; i < 2 * AT2_NSUB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 8); }
-    for (int i = 0; i < AT2_NSUB; ++i) { mbar_init(&p_full[i], 8); mbar_init(&p_free[i], 1); mbar_init(&o_full[i], 1); }
+    for (int i = 0; i < 2 * AT2_NSUB; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4 * kHalves); }
+    for (int i = 0; i < AT2_NSUB; ++i) { mbar_init(&p_full[i], 4 * kHalves); mbar_init(&p_free[i], 1); mbar_init(&o_full[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 17) tmem_alloc(tmem_ptr_smem, 512);
+  if (warp == kTma + 1) tmem_alloc(tmem_ptr_smem, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 16) {
+  if (warp == kTma) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       const int cq = head * ATT_D, ck = p.inner_dim + head * ATT_D, cv = 2 * p.inner_dim + head * ATT_D;
@@ -360,9 +440,9 @@ attention_split_kernel(const __grid_constant__ AttnParams p) {
         tma_load_3d(sV + st * ATT_KV_BYTES, &p.tmKV, &v_full[st], cv, j * ATT_BN, b);
       }
     }
-  } else if (warp == 17 || warp == 18) {
-    // ===================== MMA issuers: warp 17 + x -> sub-tile x =====================
-    const int x = warp - 17;
+  } else if (warp == kTma + 1 || warp == kTma + 2) {
+    // ===================== MMA issuers: warp kTma + 1 + x -> sub-tile x =====================
+    const int x = warp - (kTma + 1);
     if (x < n_sub) {
       constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);  // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);   // P (TMEM) x V (MN-major)
@@ -409,10 +489,12 @@ attention_split_kernel(const __grid_constant__ AttnParams p) {
         }
       }
     }
-  } else if (warp < 16) {
+  } else if (warp < 8 * kHalves) {
     // ===================== softmax: 32 keys of 32 query rows per warp and tile =====================
     const int wq = warp & 3, x = (warp >> 2) & 1, h = warp >> 3;
-    if (x < n_sub) {
+    if (kHalves == 1) {
+      if (x < n_sub) attention_rowpair_softmax(p, tmem_base, wq, x, lane, q0, head, b, S, n_tiles, s_full, s_free, p_full, p_free, o_full);
+    } else if (x < n_sub) {
       const int r = wq * 32 + lane;                                       // query row in the sub-tile == TMEM lane
       const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
       const uint32_t tSx = tmem_base + lane_off + AT2_TMEM_S + x * 2 * ATT_BN + 32 * h;
@@ -540,16 +622,24 @@ attention_split_kernel(const __grid_constant__ AttnParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 17) {
+  if (warp == kTma + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
 
-// FFB200_ATT_ROW=1 selects the row-per-thread kernel (A/B measurements; read once)
-static bool attention_use_split() {
-  static const bool split = getenv("FFB200_ATT_ROW") == nullptr;
-  return split;
+// FFB200_ATT_VARIANT selects the head_dim-64 kernel (A/B measurements; read once): "row3" = three sub-tiles, one warp per 32 rows,
+// single-buffered S (attention_kernel); "row2" = two sub-tiles, one warp per 32 rows, double-buffered S; "split2" = two sub-tiles, two warps
+// per row, double-buffered S.
+static int attention_variant() {
+  static const int v = [] {
+    const char* e = getenv("FFB200_ATT_VARIANT");
+    if (e == nullptr) return 0;
+    if (strcmp(e, "row2") == 0) return 1;
+    if (strcmp(e, "split2") == 0) return 2;
+    return 0;
+  }();
+  return v;
 }
 
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
@@ -557,16 +647,20 @@ cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
   {
     cudaError_t e = once.run([] {
       cudaError_t e1 = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-      return e1 != cudaSuccess ? e1 : cudaFuncSetAttribute(attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attention_split_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attention_split_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM);
+      return e1;
     });
     if (e != cudaSuccess) return e;
   }
-  if (attention_use_split()) {
-    dim3 grid((p.seq_len + AT2_QB - 1) / AT2_QB, p.num_heads, p.batch);
-    attention_split_kernel<<<grid, AT2_THREADS, AT2_SMEM, stream>>>(p);
-  } else {
+  const int v = attention_variant();
+  if (v == 0) {
     dim3 grid((p.seq_len + ATT_QB - 1) / ATT_QB, p.num_heads, p.batch);
     attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(p);
+  } else {
+    dim3 grid((p.seq_len + AT2_QB - 1) / AT2_QB, p.num_heads, p.batch);
+    if (v == 1) attention_split_kernel<1><<<grid, 12 * 32, AT2_SMEM, stream>>>(p);
+    else attention_split_kernel<2><<<grid, 20 * 32, AT2_SMEM, stream>>>(p);
   }
   return cudaGetLastError();
 }

@@ -54,23 +54,64 @@ __device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& e0, fl
   e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
 }
 
+// Pacing of the MUFU stream (round 2 hypothesis test): MUFU.EX2 and the kernels' mbarrier / TMEM instructions share the per-sub-partition
+// MIO queue; three warps that each run dozens of MUFUs ahead keep it full, and every latency-critical skeleton instruction (try_wait, arrive,
+// tcgen05.ld / st - of the softmax warps AND of the MMA issuer warp of that sub-partition) then waits behind them.  With
+// FFB_ATT_MUFU_WINDOW = W > 0 the MUFU pairs of a warp are issued in program order (volatile) and pair c is consumed (sum, pack) before
+// pair c + W is issued, so a warp never has more than W pairs in the queue.  0 = the compiler schedules freely.
+#ifndef FFB_ATT_MUFU_WINDOW
+#define FFB_ATT_MUFU_WINDOW 0
+#endif
+__device__ __forceinline__ float ex2_approx_ordered(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_ordered(float lo, float hi) {
+  uint32_t r;
+  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // exp2 of the 32 scores of `a` into 16 packed bf16 pairs, partial row sums into sums2.  kPre: the scores are the exponents (pre-scaled keys,
 // reference 0); else exponent = s * sc - ref.  kPoly: the polynomial slots are in use (false: every element through MUFU).
 template <bool kPre, bool kPoly, bool kSum>
 __device__ __forceinline__ void softmax_exp32(const uint32_t (&a)[32], uint64_t sc2, uint64_t mneg2, uint64_t (&sums2)[2],
                                               uint32_t (&pk)[16]) {
+  constexpr int W = FFB_ATT_MUFU_WINDOW;
+  if (W == 0) {
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    float t0 = __uint_as_float(a[2 * c]), t1 = __uint_as_float(a[2 * c + 1]);
-    if (!kPre) unpack_f32x2(ffma2(pack_f32x2(t0, t1), sc2, mneg2), t0, t1);
-    float e0, e1;
-    if (kPoly && att_poly_slot(c)) {
-      exp2_poly_pair(t0, t1, e0, e1);
-    } else {
-      e0 = ex2_approx(t0); e1 = ex2_approx(t1);
+    for (int c = 0; c < 16; ++c) {
+      float t0 = __uint_as_float(a[2 * c]), t1 = __uint_as_float(a[2 * c + 1]);
+      if (!kPre) unpack_f32x2(ffma2(pack_f32x2(t0, t1), sc2, mneg2), t0, t1);
+      float e0, e1;
+      if (kPoly && att_poly_slot(c)) {
+        exp2_poly_pair(t0, t1, e0, e1);
+      } else {
+        e0 = ex2_approx(t0); e1 = ex2_approx(t1);
+      }
+      if (kSum) sums2[c & 1] = fadd2(sums2[c & 1], pack_f32x2(e0, e1));
+      pk[c] = pack_bf16x2(e0, e1);
     }
-    if (kSum) sums2[c & 1] = fadd2(sums2[c & 1], pack_f32x2(e0, e1));
-    pk[c] = pack_bf16x2(e0, e1);
+  } else {
+    float e0[16], e1[16];
+#pragma unroll
+    for (int c = 0; c < 16 + W; ++c) {
+      if (c < 16) {
+        float t0 = __uint_as_float(a[2 * c]), t1 = __uint_as_float(a[2 * c + 1]);
+        if (!kPre) unpack_f32x2(ffma2(pack_f32x2(t0, t1), sc2, mneg2), t0, t1);
+        if (kPoly && att_poly_slot(c)) {
+          exp2_poly_pair(t0, t1, e0[c], e1[c]);
+        } else {
+          e0[c] = ex2_approx_ordered(t0); e1[c] = ex2_approx_ordered(t1);
+        }
+      }
+      if (c >= W) {                                  // consume pair c - W before the next MUFU pair goes out
+        const int d = c - W;
+        if (kSum) sums2[d & 1] = fadd2(sums2[d & 1], pack_f32x2(e0[d], e1[d]));
+        pk[d] = pack_bf16x2_ordered(e0[d], e1[d]);
+      }
+    }
   }
 }
 

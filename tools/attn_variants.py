@@ -49,5 +49,5 @@ def trend_error(d):
 
 
 r64, r128 = timed(8, 4429, 24, 64), timed(2, 4608, 24, 128)
-print(json.dumps({"lib": os.path.basename(os.environ.get("FFB200_LIB", "libffb200.so")), "prescaled_keys": PRE, "d64_kernel": "row" if os.environ.get("FFB200_ATT_ROW") else "split", "ms": r64[0], "tflops": r64[1],
+print(json.dumps({"lib": os.path.basename(os.environ.get("FFB200_LIB", "libffb200.so")), "prescaled_keys": PRE, "d64_kernel": os.environ.get("FFB200_ATT_VARIANT", "row3"), "ms": r64[0], "tflops": r64[1],
                   "d128_ms": r128[0], "d128_tflops": r128[1], "trend_rel_err_d64": trend_error(64), "trend_rel_err_d128": trend_error(128)}))
