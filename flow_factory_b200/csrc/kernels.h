@@ -197,7 +197,7 @@ cudaError_t launch_wan_ln(const WanLnParams& p, cudaStream_t stream);
 cudaError_t launch_wan_gate_residual(bf16* h, const bf16* y, const float* gate, long gate_batch_stride, int num_batch, long rows_per_batch,
                                      int D, cudaStream_t stream);
 cudaError_t launch_wan_rms_rope(bf16* x, long rows, int rows_per_batch, int ld, int D, const bf16* weight, float eps, const float* cos_t,
-                                const float* sin_t, cudaStream_t stream);
+                                const float* sin_t, cudaStream_t stream, float out_scale = 1.0f);
 
 // latent storage dtypes (element type of the x / next / trajectory buffers)
 enum { LAT_F16 = 0, LAT_BF16 = 1, LAT_F32 = 2 };

@@ -19,16 +19,27 @@
 
 namespace ffb {
 
-#ifndef FFB_ATT_POLY_NUM
-#define FFB_ATT_POLY_NUM 2           // product value (of every 8 element pairs); -DFFB_ATT_POLY_NUM=n only for A/B builds
-#endif
+// Which pairs of a 32-score block take the polynomial: kNum of every 8, evenly spread (3 -> {0,3,6}, 2 -> {0,4}, 4 -> {0,2,4,6}) or clustered
+// (the first kNum of every 8).  A per-kernel choice - what ptxas makes of the mix differs between the two attention kernels (round 2
+// measurements, profiles/r02_attention_experiments.md): head_dim 64 runs best with 2 of 8 spread, head_dim 128 with 3 of 8 clustered.
 constexpr int ATT_POLY_PERIOD = 8;
-constexpr int ATT_POLY_NUM = FFB_ATT_POLY_NUM;
-// pair c goes through the polynomial: ATT_POLY_NUM slots of every 8, evenly spread (3 -> {0,3,6}, 2 -> {0,4}, 4 -> {0,2,4,6})
-#ifdef FFB_ATT_POLY_CLUSTER            // A/B only: the first ATT_POLY_NUM pairs of every 8
-__host__ __device__ constexpr bool att_poly_slot(int c) { return (c % ATT_POLY_PERIOD) < ATT_POLY_NUM; }
+template <int kNum, bool kCluster>
+struct PolyPolicy {
+  static constexpr int num = kNum;
+  __host__ __device__ static constexpr bool slot(int c) {
+    return kCluster ? (c % ATT_POLY_PERIOD) < kNum : ((c % ATT_POLY_PERIOD) * kNum) % ATT_POLY_PERIOD < kNum;
+  }
+};
+#ifdef FFB_ATT_POLY_NUM                 // A/B builds only: one policy for both kernels
+#ifdef FFB_ATT_POLY_CLUSTER
+using PolyD64 = PolyPolicy<FFB_ATT_POLY_NUM, true>;
 #else
-__host__ __device__ constexpr bool att_poly_slot(int c) { return ((c % ATT_POLY_PERIOD) * ATT_POLY_NUM) % ATT_POLY_PERIOD < ATT_POLY_NUM; }
+using PolyD64 = PolyPolicy<FFB_ATT_POLY_NUM, false>;
+#endif
+using PolyD128 = PolyD64;
+#else
+using PolyD64 = PolyPolicy<2, false>;
+using PolyD128 = PolyPolicy<3, true>;
 #endif
 
 constexpr float ATT_REF_ZERO_BAND = 32.0f;        // first-tile |max exponent| up to which the reference stays 0
@@ -54,75 +65,34 @@ __device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& e0, fl
   e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(r1) << 23));
 }
 
-// Pacing of the MUFU stream (round 2 hypothesis test): MUFU.EX2 and the kernels' mbarrier / TMEM instructions share the per-sub-partition
-// MIO queue; three warps that each run dozens of MUFUs ahead keep it full, and every latency-critical skeleton instruction (try_wait, arrive,
-// tcgen05.ld / st - of the softmax warps AND of the MMA issuer warp of that sub-partition) then waits behind them.  With
-// FFB_ATT_MUFU_WINDOW = W > 0 the MUFU pairs of a warp are issued in program order (volatile) and pair c is consumed (sum, pack) before
-// pair c + W is issued, so a warp never has more than W pairs in the queue.  0 = the compiler schedules freely.
-#ifndef FFB_ATT_MUFU_WINDOW
-#define FFB_ATT_MUFU_WINDOW 0
-#endif
-__device__ __forceinline__ float ex2_approx_ordered(float x) {
-  float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ uint32_t pack_bf16x2_ordered(float lo, float hi) {
-  uint32_t r;
-  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-
 // exp2 of the 32 scores of `a` into 16 packed bf16 pairs, partial row sums into sums2.  kPre: the scores are the exponents (pre-scaled keys,
 // reference 0); else exponent = s * sc - ref.  kPoly: the polynomial slots are in use (false: every element through MUFU).
-template <bool kPre, bool kPoly, bool kSum>
+template <bool kPre, bool kPoly, bool kSum, class Poly>
 __device__ __forceinline__ void softmax_exp32(const uint32_t (&a)[32], uint64_t sc2, uint64_t mneg2, uint64_t (&sums2)[2],
                                               uint32_t (&pk)[16]) {
-  constexpr int W = FFB_ATT_MUFU_WINDOW;
-  if (W == 0) {
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      float t0 = __uint_as_float(a[2 * c]), t1 = __uint_as_float(a[2 * c + 1]);
-      if (!kPre) unpack_f32x2(ffma2(pack_f32x2(t0, t1), sc2, mneg2), t0, t1);
-      float e0, e1;
-      if (kPoly && att_poly_slot(c)) {
-        exp2_poly_pair(t0, t1, e0, e1);
-      } else {
-        e0 = ex2_approx(t0); e1 = ex2_approx(t1);
-      }
-      if (kSum) sums2[c & 1] = fadd2(sums2[c & 1], pack_f32x2(e0, e1));
-      pk[c] = pack_bf16x2(e0, e1);
+  for (int c = 0; c < 16; ++c) {
+    float t0 = __uint_as_float(a[2 * c]), t1 = __uint_as_float(a[2 * c + 1]);
+    if (!kPre) unpack_f32x2(ffma2(pack_f32x2(t0, t1), sc2, mneg2), t0, t1);
+    float e0, e1;
+    if (kPoly && Poly::slot(c)) {
+      exp2_poly_pair(t0, t1, e0, e1);
+    } else {
+      e0 = ex2_approx(t0); e1 = ex2_approx(t1);
     }
-  } else {
-    float e0[16], e1[16];
-#pragma unroll
-    for (int c = 0; c < 16 + W; ++c) {
-      if (c < 16) {
-        float t0 = __uint_as_float(a[2 * c]), t1 = __uint_as_float(a[2 * c + 1]);
-        if (!kPre) unpack_f32x2(ffma2(pack_f32x2(t0, t1), sc2, mneg2), t0, t1);
-        if (kPoly && att_poly_slot(c)) {
-          exp2_poly_pair(t0, t1, e0[c], e1[c]);
-        } else {
-          e0[c] = ex2_approx_ordered(t0); e1[c] = ex2_approx_ordered(t1);
-        }
-      }
-      if (c >= W) {                                  // consume pair c - W before the next MUFU pair goes out
-        const int d = c - W;
-        if (kSum) sums2[d & 1] = fadd2(sums2[d & 1], pack_f32x2(e0[d], e1[d]));
-        pk[d] = pack_bf16x2_ordered(e0[d], e1[d]);
-      }
-    }
+    if (kSum) sums2[c & 1] = fadd2(sums2[c & 1], pack_f32x2(e0, e1));
+    pk[c] = pack_bf16x2(e0, e1);
   }
 }
 
 // max |exponent| over the polynomial slots of a tile (one 3-input max per pair; |.| is an operand modifier): the polynomial is used only
 // if it is <= 126.  -inf (masked keys), inf and NaN fail the test and take the MUFU path, which handles them.
-template <bool kPre>
+template <bool kPre, class Poly>
 __device__ __forceinline__ float softmax_poly_absmax(const uint32_t (&s0)[32], const uint32_t (&s1)[32], float sce, float m_run) {
   float mx[2] = {0.f, 0.f};
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
-    if (att_poly_slot(c)) {
+    if (Poly::slot(c)) {
       mx[0] = fmax3(mx[0], fabsf(__uint_as_float(s0[2 * c])), fabsf(__uint_as_float(s0[2 * c + 1])));
       mx[1] = fmax3(mx[1], fabsf(__uint_as_float(s1[2 * c])), fabsf(__uint_as_float(s1[2 * c + 1])));
     }
@@ -156,6 +126,7 @@ struct SoftmaxTile {
 //   sc    : softmax_scale * log2(e); ignored when `pre`.
 //   pre   : warp-uniform; the scores already are base-2 exponents (keys pre-scaled by the producer).
 //   first : warp-uniform; first KV tile of the row block.
+template <class Poly>
 __device__ __forceinline__ void softmax_begin(uint32_t (&s0)[32], uint32_t (&s1)[32], int kv_valid, float sc, bool pre, bool first,
                                               SoftmaxState& st, SoftmaxTile& t) {
   if (kv_valid < 64) {
@@ -200,21 +171,21 @@ __device__ __forceinline__ void softmax_begin(uint32_t (&s0)[32], uint32_t (&s1)
   t.sc2 = pack_f32x2(sce, sce);
   t.mneg2 = pack_f32x2(-st.m_run, -st.m_run);
   t.fast = pre && st.zero_ref;
-  t.poly = ATT_POLY_NUM > 0;
+  t.poly = Poly::num > 0;
   if (t.poly) {
-    const float amax = t.fast ? softmax_poly_absmax<true>(s0, s1, sce, 0.f) : softmax_poly_absmax<false>(s0, s1, sce, st.m_run);
+    const float amax = t.fast ? softmax_poly_absmax<true, Poly>(s0, s1, sce, 0.f) : softmax_poly_absmax<false, Poly>(s0, s1, sce, st.m_run);
     t.poly = __all_sync(0xffffffffu, amax <= 126.0f);
   }
 }
 
-template <bool kSum = true>
+template <class Poly, bool kSum = true>
 __device__ __forceinline__ void softmax_half(const uint32_t (&a)[32], SoftmaxTile& t, uint32_t (&pk)[16]) {
   if (t.fast) {
-    if (t.poly) softmax_exp32<true, true, kSum>(a, t.sc2, t.mneg2, t.sums2, pk);
-    else softmax_exp32<true, false, kSum>(a, t.sc2, t.mneg2, t.sums2, pk);
+    if (t.poly) softmax_exp32<true, true, kSum, Poly>(a, t.sc2, t.mneg2, t.sums2, pk);
+    else softmax_exp32<true, false, kSum, Poly>(a, t.sc2, t.mneg2, t.sums2, pk);
   } else {
-    if (t.poly) softmax_exp32<false, true, kSum>(a, t.sc2, t.mneg2, t.sums2, pk);
-    else softmax_exp32<false, false, kSum>(a, t.sc2, t.mneg2, t.sums2, pk);
+    if (t.poly) softmax_exp32<false, true, kSum, Poly>(a, t.sc2, t.mneg2, t.sums2, pk);
+    else softmax_exp32<false, false, kSum, Poly>(a, t.sc2, t.mneg2, t.sums2, pk);
   }
 }
 

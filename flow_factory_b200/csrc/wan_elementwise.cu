@@ -188,9 +188,10 @@ cudaError_t launch_wan_gate_residual(bf16* h, const bf16* y, const float* gate, 
 // inside, one rounding), then - if tables are given - per head of 128 the interleaved-pair rotation evaluated in bf16 like the
 // reference's tensor arithmetic (x1 * cos - x2 * sin, x1 * sin + x2 * cos: every product and the sum are bf16 tensors).
 // cos / sin: fp32 [tokens_per_batch][128] holding the (bf16-rounded, pairwise repeated) table values.
+// out_scale != 1: the result is multiplied by it before the final bf16 store (the engine's key pre-scaling, GemmParams::k_scale's twin).
 constexpr int WRR_MAXC = 12;
 __global__ void __launch_bounds__(256, 3) wan_rms_rope_kernel(bf16* x, long rows, int rows_per_batch, int ld, int D, const bf16* weight,
-                                                              float eps, const float* cos_t, const float* sin_t) {
+                                                              float eps, const float* cos_t, const float* sin_t, float out_scale) {
   const long warp = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -238,14 +239,18 @@ __global__ void __launch_bounds__(256, 3) wan_rms_rope_kernel(bf16* x, long rows
           v[e] = a; v[e + 1] = b2;
         }
       }
+      if (out_scale != 1.0f) {                                      // keys: softmax_scale * log2(e) folded in (softmax.cuh, pre-scaled keys)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= out_scale;
+      }
       *reinterpret_cast<uint4*>(xr + c * 8) = wan_pack8(v);
     }
   }
 }
 cudaError_t launch_wan_rms_rope(bf16* x, long rows, int rows_per_batch, int ld, int D, const bf16* weight, float eps, const float* cos_t,
-                                const float* sin_t, cudaStream_t stream) {
+                                const float* sin_t, cudaStream_t stream, float out_scale) {
   if (D % 8 != 0 || D > WRR_MAXC * 32 * 8 || ld % 8 != 0 || (cos_t != nullptr && D % 128 != 0)) return cudaErrorInvalidValue;
-  wan_rms_rope_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(x, rows, rows_per_batch, ld, D, weight, eps, cos_t, sin_t);
+  wan_rms_rope_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(x, rows, rows_per_batch, ld, D, weight, eps, cos_t, sin_t, out_scale);
   return cudaGetLastError();
 }
 

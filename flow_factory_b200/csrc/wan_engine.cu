@@ -139,11 +139,13 @@ static int wan_build_forward(ffb200_wan_plan* p) {
       bf16* x = p->qkv + which * D;
       const bf16* nw = static_cast<const bf16*>(which == 0 ? w.norm_q : w.norm_k);
       const float *cs = p->rope_cos, *sn = p->rope_sin; const float eps = c.eps;
-      ops.push_back([x, rows, S, D, nw, eps, cs, sn](cudaStream_t st) { ++g_launch_count; return launch_wan_rms_rope(x, rows, S, 3 * D, D, nw, eps, cs, sn, st); });
+      const float ks = (which == 1 && engine_prescale()) ? 0.08838834764831845f * 1.4426950408889634f : 1.0f;      // keys carry the softmax scale
+      ops.push_back([x, rows, S, D, nw, eps, cs, sn, ks](cudaStream_t st) { ++g_launch_count; return launch_wan_rms_rope(x, rows, S, 3 * D, D, nw, eps, cs, sn, st, ks); });
     }
     {
       AttnParams ap;
       if ((r = build_attn(p->qkv, Bp, S, D / 128, p->att, &ap, 128, 0))) return r;
+      ap.k_prescaled = engine_prescale() ? 1 : 0;
       ops.push_back([ap](cudaStream_t st) { ++g_launch_count; return launch_attention_d128(ap, st); });
     }
     {
@@ -170,6 +172,7 @@ static int wan_build_forward(ffb200_wan_plan* p) {
       AttnParams ap;
       const bf16* kv = p->kv2 + static_cast<long>(l) * Bp * Nt * 2 * D;
       if ((r = wbuild_attn(p, p->q2, D, kv, 2 * D, Nt, p->att, &ap))) return r;
+      ap.k_prescaled = engine_prescale() ? 1 : 0;
       ops.push_back([ap](cudaStream_t st) { ++g_launch_count; return launch_attention_d128_cross(ap, st); });
     }
     {
@@ -343,7 +346,8 @@ int ffb200_wan_set_prompts(ffb200_wan_plan* p, const void* prompt_embeds_bf16, v
     GemmSpec s = {p->ctx, Bp, Nt, 0, D, D, w.kv2_w, 2 * D, w.kv2_b, kv, static_cast<long>(Nt) * 2 * D, 0, 2 * D, EPI_BIAS};
     if ((r = wadd_gemm(ops, s))) return r;
     const bf16* nw = static_cast<const bf16*>(w.norm_k2); const float eps = e->cfg.eps; const long rows = static_cast<long>(Bp) * Nt;
-    ops.push_back([kv, rows, Nt, D, nw, eps](cudaStream_t s2) { ++g_launch_count; return launch_wan_rms_rope(kv, rows, Nt, 2 * D, D, nw, eps, nullptr, nullptr, s2); });
+    const float ks = engine_prescale() ? 0.08838834764831845f * 1.4426950408889634f : 1.0f;                         // cross-attention keys carry the softmax scale
+    ops.push_back([kv, rows, Nt, D, nw, eps, ks](cudaStream_t s2) { ++g_launch_count; return launch_wan_rms_rope(kv, rows, Nt, 2 * D, D, nw, eps, nullptr, nullptr, s2, ks); });
   }
   for (auto& op : ops) FFB_CUDA(op(st));
   p->prompts_set = true;
