@@ -28,9 +28,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "rollout latents/sec SD3.5-medium 1024^2 30-step"
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE attention launch, keyed by (forward batch, joint tokens, heads), from the committed
-# `ncu --set full` captures (profiles/r01_ncu_full_summaries.md)
-ATTENTION_NCU_TRAFFIC = {(4, 4429, 24): 90.3e6, (16, 4429, 24): 854.0e6}
+
+
+def ncu_traffic(kernel: str, shape: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel` at `shape`, read from profiles/ncu_traffic.json - the table
+    tools/ncu_traffic.py extracts from the `ncu --set full` captures of exactly these launches; None when that shape was never captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)[kernel][shape]["dram_bytes"]
+    except Exception:
+        return None
 
 
 def parse():
@@ -169,6 +176,39 @@ def cpu_reference(args, steps: int, warmup: int, full: bool = True):
     return info, sum(times) / len(times)
 
 
+def gpu_eager_reference(args, B, cfg_on):
+    """Informational: the reference NUMERICS run eagerly on this GPU - the oracle's transformer forward (the reference's torch ops in the
+    reference's order: F.linear / cuBLAS, F.scaled_dot_product_attention, F.layer_norm ...) under CUDA bf16 autocast at the bench's
+    forward batch, timed with CUDA events; latents/s = B / (T x forward) ignores the scheduler step and every host sync of the reference
+    loop, so it flatters the reference.  Part of the reference leg (the only place bench.py may execute oracle/)."""
+    try:
+        from oracle import sd3_oracle as O
+        cfg = O.sd35_medium()
+        dev = "cuda"
+        w = O.make_weights(cfg, seed=0, dtype=torch.bfloat16, device=dev)
+        Bp = B * (2 if cfg_on else 1)
+        lat = args.height // 8
+        g = torch.Generator(device=dev).manual_seed(3)
+        x = torch.randn(Bp, cfg.in_channels, lat, lat, generator=g, device=dev).half()
+        pe = torch.randn(Bp, args.n_text, cfg.joint_attention_dim, generator=g, device=dev).bfloat16()
+        pp = torch.randn(Bp, cfg.pooled_projection_dim, generator=g, device=dev).bfloat16()
+        tt = torch.full((Bp,), 612.5, device=dev).half()
+        def fwd():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                return O.transformer_forward(w, cfg, x, pe, pp, tt)
+        fwd(); fwd()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fwd(); fwd(); fwd(); e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        del w
+        torch.cuda.empty_cache()
+        return {"ms_per_forward": ms, "forward_batch": Bp, "value": B / (args.num_inference_steps * ms / 1e3), "unit": "latents/s",
+                "what": "oracle transformer forward (reference numerics, torch eager: cuBLAS + SDPA) under CUDA bf16 autocast; no scheduler step, no host syncs"}
+    except Exception as exc:                        # informational only
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+
+
 def _cpu_port(args, cfg, w, cores, info, steps, warmup):
     """oracle/_ref absent: the oracle port's 2-block sample (round-1 method), min of the timed samples."""
     from oracle import sd3_oracle as O
@@ -286,6 +326,33 @@ def run_b200(args):
     clk = clocks.stop() if rank == 0 else None
     value = world * B * args.steps / (ms_total / 1e3)
 
+    # ---------------- the same rollout with the WHOLE SDE window noisy (num_sde_steps = T - 1 = 29: noise + log-prob on every step but the
+    # last; SURVEY 8d asks for {1, 29}) - one warm-up (the graph is re-used, only the step coefficients change), then timed ----------------
+    sde_all = None
+    if args.num_sde_steps is not None and args.steps > 0:
+        sched._num_sde_steps = None
+        sched.set_timesteps(T, seq_len=ni)
+        kw_all = dict(kw, trajectory_indices=compute_trajectory_indices(sched.train_timesteps, T))      # every step is a train timestep now
+
+        def rollout_all():
+            s = adapter.inference(prompt_embeds=inp["prompt_embeds"], pooled_prompt_embeds=inp["pooled"],
+                                  negative_prompt_embeds=inp["neg_prompt_embeds"], negative_pooled_prompt_embeds=inp["neg_pooled"],
+                                  latents=inp["x0"], **kw_all)
+            if world > 1:
+                all_gather_rollout(torch.stack([x.all_latents for x in s]), torch.stack([x.log_probs for x in s]))
+            return s
+        rollout_all(); barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(); s_all = rollout_all(); f1.record(); barrier()
+        ms_all = torch.tensor([f0.elapsed_time(f1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms_all, op=dist.ReduceOp.MAX)
+        sde_all = {"num_sde_steps": T - 1, "value": world * B / (float(ms_all) / 1e3), "unit": "latents/s", "ms_per_step": float(ms_all),
+                   "log_probs_per_sample": int(s_all[0].log_probs.numel()), "latents_kept_per_sample": int(s_all[0].all_latents.shape[0])}
+        sched._num_sde_steps = args.num_sde_steps
+        sched.set_timesteps(T, seq_len=ni)
+        rollout_device(); barrier()
+
     # ---------------- end to end through the public API with host buffers ----------------
     host = {k: v.cpu().pin_memory() for k, v in inp.items() if k != "x0"}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
@@ -338,41 +405,42 @@ def run_b200(args):
     gemm_tf = 2.0 * M * N * K / gemm_ms / 1e9
     fl_latent = flops_per_latent(cfg, ni, args.n_text, T, cfg_on)
     step_tf = value * fl_latent / 1e12
-    # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture (profiles/r01_ncu_full_summaries.md,
-    # dram__bytes_read.sum + dram__bytes_write.sum at M=65536 N=6144 K=1536): only valid for that shape, else null.
+    # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture of this shape (profiles/ncu_traffic.json), else null.
     # Algorithmic bytes of the launch: A + W + out = 2 * (M*K + N*K + M*N).
-    traffic = 1139.5e6 if (M, N, K) == (65536, 6144, 1536) else None
+    traffic = ncu_traffic("gemm_mlp_up", f"{M}x{N}x{K}")
     roofline_gemm = {"bound": "tensor", "kernel": "gemm_bf16_kernel<256> (MLP up, bias+GELU epilogue)", "achieved": gemm_tf,
                      "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["bf16_tflops"], "traffic": traffic,
                      "traffic_unit": "bytes/launch (ncu dram read+write)", "algorithmic_bytes_per_launch": 2.0 * (M * K + N * K + M * N),
                      "peak_source": f"{peak_kind} cuBLAS bf16 burst", "flops_per_launch": 2.0 * M * N * K, "launch_ms": gemm_ms,
-                     "time_share_of_step": "43.9 % (profiles/r01_launch_list_one_step_b8.md)"}
+                     "time_share_of_step": "45.9 % (profiles/r02_launch_list_one_step_b8.md)"}
     # The kernel with the largest TIME share of the step is the joint attention (51 %, profiles/r01_launch_list_one_step_b8.md): it is
     # the `roofline` entry; the GEMM that carries most of the FLOPs is reported beside it as `roofline_gemm`.
     try:
         from flow_factory_b200.ops import attention as op_attention
         S_joint, Hh = ni + args.n_text, cfg.num_attention_heads
-        qkv = torch.randn(Bp, S_joint, 3 * cfg.inner_dim, device=dev).bfloat16()
+        # the engine's layout: keys pre-scaled by softmax_scale * log2(e) in the QKV GEMM epilogue (csrc/softmax.cuh)
+        qkv = torch.randn(Bp, S_joint, 3 * cfg.inner_dim, device=dev)
+        qkv[..., cfg.inner_dim: 2 * cfg.inner_dim] *= 64 ** -0.5 * 1.4426950408889634
+        qkv = qkv.bfloat16()
         ao = torch.empty(Bp, S_joint, cfg.inner_dim, device=dev, dtype=torch.bfloat16)
         for _ in range(3):
-            op_attention(qkv, Hh, ao)
+            op_attention(qkv, Hh, ao, k_prescaled=True)
         ts = []
         for _ in range(10):
             flush.zero_()
             a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); op_attention(qkv, Hh, ao); b_.record(); torch.cuda.synchronize()
+            a.record(); op_attention(qkv, Hh, ao, k_prescaled=True); b_.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b_))
         att_ms = sorted(ts)[len(ts) // 2]
         att_fl = 4.0 * Bp * Hh * S_joint * S_joint * 64
         att_tf = att_fl / att_ms / 1e9
-        # DRAM bytes of one launch at this shape from the committed ncu capture (profiles/r01_ncu_full_summaries.md); else null
-        att_traffic = ATTENTION_NCU_TRAFFIC.get((Bp, S_joint, Hh))
+        att_traffic = ncu_traffic("attention_d64", f"{Bp}x{S_joint}x{Hh}")
         roofline = {"bound": "tensor", "kernel": "attention_kernel (joint image+text attention, head_dim 64)", "achieved": att_tf,
                     "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": att_tf / peaks["bf16_tflops"], "traffic": att_traffic,
                     "traffic_unit": "bytes/launch (ncu dram read+write)",
                     "algorithmic_bytes_per_launch": 2.0 * Bp * S_joint * 4 * cfg.inner_dim, "peak_source": f"{peak_kind} cuBLAS bf16 burst",
-                    "flops_per_launch": att_fl, "launch_ms": att_ms, "time_share_of_step": "51.2 % (profiles/r01_launch_list_one_step_b8.md)",
-                    "note": "SIMT-softmax-limited at head_dim 64 (cuDNN SDPA on the same box: 0.53 of this peak), see DESIGN.md section 5",
+                    "flops_per_launch": att_fl, "launch_ms": att_ms, "time_share_of_step": "49.8 % (profiles/r02_launch_list_one_step_b8.md)",
+                    "note": "softmax-skeleton-limited at head_dim 64 (cuDNN SDPA on the same shape: 0.53 of this peak), see DESIGN.md section 4 / profiles/r02_attention_experiments.md",
                     "whole_step_achieved_per_gpu": step_tf / world, "whole_step_frac_of_sustained": step_tf / world / peaks["bf16_tflops_sustained"],
                     "flops_per_latent": fl_latent}
     except Exception as exc:   # the attention micro-timing is reporting only: never lose the bench line over it
@@ -384,6 +452,7 @@ def run_b200(args):
     cpu = None
     if not args.skip_cpu_baseline and world == 1:
         cpu, _ = cpu_reference(args, steps=3, warmup=2, full=True)
+        cpu["gpu_eager_reference"] = gpu_eager_reference(args, B, cfg_on)
 
     line = {"metric": METRIC, "value": value, "unit": "latents/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -396,7 +465,8 @@ def run_b200(args):
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "latents/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches_per_rollout * args.steps),
-            "roofline": roofline, "roofline_gemm": roofline_gemm, "cpu_baseline": cpu, "wall_s_timed_region": wall}
+            "roofline": roofline, "roofline_gemm": roofline_gemm, "cpu_baseline": cpu, "sde_window_all": sde_all,
+            "wall_s_timed_region": wall}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -138,6 +138,10 @@ __device__ __forceinline__ void softmax_begin(uint32_t (&s0)[32], uint32_t (&s1)
   }
   const float sce = pre ? 1.0f : sc;
   t.alpha = 1.0f;
+  t.rescale = false;
+  t.poly = Poly::num > 0;
+  t.sums2[0] = t.sums2[1] = 0ull;
+  t.sc2 = pack_f32x2(sce, sce);
   if (first) {
     // first tile of the row block: its exact maximum (8 independent 3-input chains) chooses the reference
     float mxs[8];
@@ -154,10 +158,18 @@ __device__ __forceinline__ void softmax_begin(uint32_t (&s0)[32], uint32_t (&s1)
     st.l_run = 0.f;
     t.alpha = 0.0f;                                 // nothing accumulated yet
     t.rescale = true;
-  } else {
-    const bool grow = !(st.l_run <= ATT_SHIFT_AT);  // also true for inf / NaN
-    t.rescale = __any_sync(0xffffffffu, grow);
-    if (t.rescale) {
+  }
+  t.fast = pre && st.zero_ref;
+  // ONE vote per tile covers both rare events - "my running sum passed 2^64" and "a polynomial slot of this tile is outside +-126" -
+  // and only a warp that saw one of them sorts out which (the common tile pays a single VOTE + branch for its bookkeeping)
+  const bool grow = !first && !(st.l_run <= ATT_SHIFT_AT);       // also true for inf / NaN
+  bool over = false;
+  if (Poly::num > 0) {
+    const float amax = t.fast ? softmax_poly_absmax<true, Poly>(s0, s1, sce, 0.f) : softmax_poly_absmax<false, Poly>(s0, s1, sce, st.m_run);
+    over = !(amax <= 126.0f);
+  }
+  if (__any_sync(0xffffffffu, grow || over)) {
+    if (__any_sync(0xffffffffu, grow)) {
       if (!(st.l_run < ATT_FAIL_AT)) mbar_timeout(0x6F);   // a score jumped by more than 2^90 within one tile (or is not finite): fail loudly
       if (grow) {
         const int e = static_cast<int>((__float_as_uint(st.l_run) >> 23) & 0xFF) - 127;   // floor(log2(l_run)) >= 64
@@ -165,17 +177,14 @@ __device__ __forceinline__ void softmax_begin(uint32_t (&s0)[32], uint32_t (&s1)
         st.m_run += static_cast<float>(e);                                                 // reference up by e exponent units, exact
       }
       st.zero_ref = false;
+      t.fast = false;
+      t.rescale = true;
+      // the range check was made against the old reference: re-evaluate it (general path) against the new one
+      over = Poly::num > 0 && !(softmax_poly_absmax<false, Poly>(s0, s1, sce, st.m_run) <= 126.0f);
     }
+    t.poly = Poly::num > 0 && !__any_sync(0xffffffffu, over);
   }
-  t.sums2[0] = t.sums2[1] = 0ull;
-  t.sc2 = pack_f32x2(sce, sce);
   t.mneg2 = pack_f32x2(-st.m_run, -st.m_run);
-  t.fast = pre && st.zero_ref;
-  t.poly = Poly::num > 0;
-  if (t.poly) {
-    const float amax = t.fast ? softmax_poly_absmax<true, Poly>(s0, s1, sce, 0.f) : softmax_poly_absmax<false, Poly>(s0, s1, sce, st.m_run);
-    t.poly = __all_sync(0xffffffffu, amax <= 126.0f);
-  }
 }
 
 template <class Poly, bool kSum = true>
