@@ -40,6 +40,16 @@ def ncu_traffic(kernel: str, shape: str):
         return None
 
 
+def launch_shares():
+    """Kernel shares of one denoise step from the committed ncu launch list of this command (profiles/launch_shares.json, written by
+    tools/launchlist_summary.py); empty when absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "launch_shares.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -257,6 +267,46 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def time_roofline_kernels(cfg, args, dev, B, cfg_on, ni):
+    """Isolated launches of the two roofline kernels at the bench shapes (CUDA events on the launching stream, 256 MB L2 flush between
+    repetitions, median of 10 after 3 warm-ups): the MLP-up GEMM (bias + GELU epilogue) and the joint attention in the engine's layout
+    (keys pre-scaled by softmax_scale * log2(e) in the QKV GEMM epilogue, csrc/softmax.cuh).  Returns (gemm_ms, (M, N, K), att_ms | None, note)."""
+    from flow_factory_b200.ops import linear as op_linear
+    Bp = B * (2 if cfg_on else 1)
+    M, N, K = Bp * ni, 4 * cfg.inner_dim, cfg.inner_dim
+    A = torch.randn(M, K, device=dev).bfloat16(); Wt = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    bb = torch.zeros(N, device=dev).bfloat16(); oo = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def median_ms(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b_.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b_))
+        return sorted(ts)[len(ts) // 2]
+    gemm_ms = median_ms(lambda: op_linear(A, Wt, bb, oo, epi=1))
+    del A, Wt, oo
+    att_ms, note = None, None
+    try:
+        from flow_factory_b200.ops import attention as op_attention
+        S_joint, Hh = ni + args.n_text, cfg.num_attention_heads
+        qkv = torch.randn(Bp, S_joint, 3 * cfg.inner_dim, device=dev)
+        qkv[..., cfg.inner_dim: 2 * cfg.inner_dim] *= 64 ** -0.5 * 1.4426950408889634
+        qkv = qkv.bfloat16()
+        ao = torch.empty(Bp, S_joint, cfg.inner_dim, device=dev, dtype=torch.bfloat16)
+        att_ms = median_ms(lambda: op_attention(qkv, Hh, ao, k_prescaled=True))
+        del qkv, ao
+    except Exception as exc:   # the attention micro-timing is reporting only: never lose the bench line over it
+        note = f"{type(exc).__name__}: {exc}"
+    del flush
+    torch.cuda.empty_cache()
+    return gemm_ms, (M, N, K), att_ms, note
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def run_b200(args):
     import torch.distributed as dist
@@ -302,6 +352,10 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---------------- the two roofline kernels, each timed ALONE on an idle GPU (burst peak is the matching denominator) ----------------
+    roof_cold = time_roofline_kernels(cfg, args, dev, B, cfg_on, ni) if rank == 0 else None
+    barrier()
 
     # ---------------- device-resident timing ----------------
     for _ in range(args.warmup):
@@ -385,26 +439,19 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    # ---------------- rooflines, timed live: the tcgen05 GEMM (MLP-up shape of this batch) and the joint attention ----------------
+    # ---------------- rooflines: the tcgen05 GEMM (MLP-up shape of this batch) and the joint attention ----------------
+    # `achieved` / `frac`: the kernel timed alone before the rollouts (idle GPU, full clocks) against the measured BURST cuBLAS figure;
+    # `achieved_after_rollouts`: the same launches repeated right after the timed rollouts, when the GPU sits at its power cap (see `clocks`),
+    # against the SUSTAINED figure - the state the kernel runs in inside a step.
     peaks, peak_kind = load_peaks()
-    from flow_factory_b200.ops import linear as op_linear
+    roof_hot = time_roofline_kernels(cfg, args, dev, B, cfg_on, ni)
+    gemm_ms, (M, N, K), att_ms, att_note = roof_cold
+    gemm_ms_hot, _, att_ms_hot, _ = roof_hot
     Bp = B * (2 if cfg_on else 1)
-    M, N, K = Bp * ni, 4 * cfg.inner_dim, cfg.inner_dim
-    A = torch.randn(M, K, device=dev).bfloat16(); Wt = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
-    bb = torch.zeros(N, device=dev).bfloat16(); oo = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for _ in range(3):
-        op_linear(A, Wt, bb, oo, epi=1)
-    ts = []
-    for _ in range(10):
-        flush.zero_()
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); op_linear(A, Wt, bb, oo, epi=1); b_.record(); torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b_))
-    gemm_ms = sorted(ts)[len(ts) // 2]
-    gemm_tf = 2.0 * M * N * K / gemm_ms / 1e9
+    gemm_tf, gemm_tf_hot = 2.0 * M * N * K / gemm_ms / 1e9, 2.0 * M * N * K / gemm_ms_hot / 1e9
     fl_latent = flops_per_latent(cfg, ni, args.n_text, T, cfg_on)
     step_tf = value * fl_latent / 1e12
+    shares = launch_shares()
     # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture of this shape (profiles/ncu_traffic.json), else null.
     # Algorithmic bytes of the launch: A + W + out = 2 * (M*K + N*K + M*N).
     traffic = ncu_traffic("gemm_mlp_up", f"{M}x{N}x{K}")
@@ -412,41 +459,27 @@ def run_b200(args):
                      "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["bf16_tflops"], "traffic": traffic,
                      "traffic_unit": "bytes/launch (ncu dram read+write)", "algorithmic_bytes_per_launch": 2.0 * (M * K + N * K + M * N),
                      "peak_source": f"{peak_kind} cuBLAS bf16 burst", "flops_per_launch": 2.0 * M * N * K, "launch_ms": gemm_ms,
-                     "time_share_of_step": "45.9 % (profiles/r02_launch_list_one_step_b8.md)"}
-    # The kernel with the largest TIME share of the step is the joint attention (51 %, profiles/r01_launch_list_one_step_b8.md): it is
-    # the `roofline` entry; the GEMM that carries most of the FLOPs is reported beside it as `roofline_gemm`.
-    try:
-        from flow_factory_b200.ops import attention as op_attention
+                     "achieved_after_rollouts": gemm_tf_hot, "frac_of_sustained_after_rollouts": gemm_tf_hot / peaks["bf16_tflops_sustained"],
+                     "time_share_of_step": shares.get("gemm")}
+    # The kernel with the largest TIME share of the step is the joint attention: it is the `roofline` entry; the GEMM that carries most
+    # of the FLOPs is reported beside it as `roofline_gemm`.
+    whole = {"whole_step_achieved_per_gpu": step_tf / world, "whole_step_frac_of_sustained": step_tf / world / peaks["bf16_tflops_sustained"],
+             "flops_per_latent": fl_latent}
+    if att_ms is not None and att_ms_hot is not None:
         S_joint, Hh = ni + args.n_text, cfg.num_attention_heads
-        # the engine's layout: keys pre-scaled by softmax_scale * log2(e) in the QKV GEMM epilogue (csrc/softmax.cuh)
-        qkv = torch.randn(Bp, S_joint, 3 * cfg.inner_dim, device=dev)
-        qkv[..., cfg.inner_dim: 2 * cfg.inner_dim] *= 64 ** -0.5 * 1.4426950408889634
-        qkv = qkv.bfloat16()
-        ao = torch.empty(Bp, S_joint, cfg.inner_dim, device=dev, dtype=torch.bfloat16)
-        for _ in range(3):
-            op_attention(qkv, Hh, ao, k_prescaled=True)
-        ts = []
-        for _ in range(10):
-            flush.zero_()
-            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); op_attention(qkv, Hh, ao, k_prescaled=True); b_.record(); torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b_))
-        att_ms = sorted(ts)[len(ts) // 2]
         att_fl = 4.0 * Bp * Hh * S_joint * S_joint * 64
-        att_tf = att_fl / att_ms / 1e9
-        att_traffic = ncu_traffic("attention_d64", f"{Bp}x{S_joint}x{Hh}")
+        att_tf, att_tf_hot = att_fl / att_ms / 1e9, att_fl / att_ms_hot / 1e9
         roofline = {"bound": "tensor", "kernel": "attention_kernel (joint image+text attention, head_dim 64)", "achieved": att_tf,
-                    "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": att_tf / peaks["bf16_tflops"], "traffic": att_traffic,
-                    "traffic_unit": "bytes/launch (ncu dram read+write)",
+                    "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": att_tf / peaks["bf16_tflops"],
+                    "traffic": ncu_traffic("attention_d64", f"{Bp}x{S_joint}x{Hh}"), "traffic_unit": "bytes/launch (ncu dram read+write)",
                     "algorithmic_bytes_per_launch": 2.0 * Bp * S_joint * 4 * cfg.inner_dim, "peak_source": f"{peak_kind} cuBLAS bf16 burst",
-                    "flops_per_launch": att_fl, "launch_ms": att_ms, "time_share_of_step": "49.8 % (profiles/r02_launch_list_one_step_b8.md)",
-                    "note": "softmax-skeleton-limited at head_dim 64 (cuDNN SDPA on the same shape: 0.53 of this peak), see DESIGN.md section 4 / profiles/r02_attention_experiments.md",
-                    "whole_step_achieved_per_gpu": step_tf / world, "whole_step_frac_of_sustained": step_tf / world / peaks["bf16_tflops_sustained"],
-                    "flops_per_latent": fl_latent}
-    except Exception as exc:   # the attention micro-timing is reporting only: never lose the bench line over it
-        roofline = dict(roofline_gemm, note=f"attention roofline unavailable ({type(exc).__name__}: {exc}); GEMM reported instead",
-                        whole_step_achieved_per_gpu=step_tf / world, whole_step_frac_of_sustained=step_tf / world / peaks["bf16_tflops_sustained"],
-                        flops_per_latent=fl_latent)
+                    "flops_per_launch": att_fl, "launch_ms": att_ms,
+                    "achieved_after_rollouts": att_tf_hot, "frac_of_sustained_after_rollouts": att_tf_hot / peaks["bf16_tflops_sustained"],
+                    "time_share_of_step": shares.get("attention"),
+                    "note": "SIMT-softmax-limited at head_dim 64 (its speed follows the SM clock; cuDNN SDPA on the same shape: 0.53 of this peak), "
+                            "see DESIGN.md section 4 / profiles/r02_attention_experiments.md", **whole}
+    else:
+        roofline = dict(roofline_gemm, note=f"attention roofline unavailable ({att_note}); GEMM reported instead", **whole)
 
     # ---------------- CPU baseline: the reference's own classes on this box's host cores, bounded sample (rank 0, N=1 only) ----------------
     cpu = None

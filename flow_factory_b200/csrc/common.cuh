@@ -422,4 +422,8 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// warp-group register re-allocation (all four warps of a warp group execute the same one)
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 }  // namespace ffb

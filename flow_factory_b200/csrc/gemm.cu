@@ -6,16 +6,21 @@
 //   warp 0    : TMA producer   (A tile 128x64, half W tile (BN/2)x64, SWIZZLE_128B, mbarrier ring)
 //   warp 1    : MMA issuer     (one elected thread, tcgen05.mma cta_group::2 kind::f16, M=256 N=BN K=16, fp32 accum in TMEM)
 //   warp 2    : TMEM allocator
-//   warps 4-7 : epilogue       (tcgen05.ld 32x32b -> registers; thread == accumulator row; fused bias /
-//                               GELU-tanh / adaLN gate + residual / per-head RMSNorm(q,k) / row-table add)
+//   warps 4-11: epilogue       (tcgen05.ld 32x32b -> registers; thread == accumulator row; fused bias /
+//                               GELU-tanh / adaLN gate + residual / per-head RMSNorm(q,k) / row-table add).
+//                               Two warps per TMEM lane quadrant (w and w+4), each taking half of the tile's columns: with one warp
+//                               per quadrant the GELU / gate-residual epilogues of a K = 1536 tile took longer than its MMAs
+//                               (ncu r01: tensor pipe 85 % / 81 % on MLP-up / attention-out against 97 % on the QKV projection).
+//   setmaxnreg moves registers from warps 0-3 (40 each) to the epilogue warps (232 each).
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 // CTAs run as pairs (cluster of 2, tcgen05 cta_group::2): one MMA instruction spans both SMs (M = 256 x BN): each CTA
 // stages its own 128 A rows and HALF of the W tile, the tensor cores read the other half from the peer's shared memory.
 // Per CTA that is 32 KB per k-block instead of 48 KB: deeper TMA pipeline (6 stages) for the same shared memory and
 // 128 FLOP/B of L2 -> SM traffic instead of 85.
 // The epilogue goes through a per-warp shared-memory staging tile so that every global load/store instruction moves
-// whole 128-byte lines (a thread-per-row store touches 32 different lines per instruction); bias / gate vectors are staged
-// in shared memory once per tile, the q/k RMSNorm weights once per kernel.
+// whole 128-byte lines (a thread-per-row store touches 32 different lines per instruction); bias / gate slices are read with
+// warp-uniform 16-byte __ldg loads (one L1 line serves the whole warp and stays resident over the consecutive tiles of an n-column),
+// the q/k RMSNorm weights sit in shared memory once per kernel.
 //
 // A is addressed as a 3-D tensor [batch][rows_per_batch][K] so that token sub-ranges of a joint
 // [B, S, D] buffer (image rows / text rows) are separate GEMM problems with zero-filled ragged tails.
@@ -26,7 +31,8 @@ namespace ffb {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_EPI_WARPS = 8;
 
 template <int BN> struct GemmCfg {
   static constexpr int kStages = (BN == 256) ? 6 : 8;
@@ -34,9 +40,10 @@ template <int BN> struct GemmCfg {
   static constexpr int kBBytes = (BN / 2) * GEMM_BK * 2;   // this CTA's half of the W tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int kStagingBytes = 4 * 32 * 128;        // per epilogue warp: 32 rows x 64 bf16
-  static constexpr int kVecBytes = 4 * (2 * BN * 2 + 2 * 128 * 2);  // per warp: bias[BN], gate[BN], norm_q[<=128], norm_k[<=128]
+  static constexpr int kStagingBytes = GEMM_EPI_WARPS * 32 * 128;   // per epilogue warp: 32 rows x 64 bf16
+  static constexpr int kVecBytes = 2 * 128 * 2;              // norm_q[<=128], norm_k[<=128]: one copy per CTA
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kVecBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget of one CTA per SM");
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
@@ -82,6 +89,10 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // column units of a tile the epilogue splits between its two warp groups: 64-column chunks, or whole 128-column heads for the
+  // head_dim-128 q/k epilogue; a tile with a single unit is handled by group 0 alone
+  const int epi_units = p.epi == EPI_QKV_RMSNORM_ROPE128 ? BN / 128 : BN / 64;
+  const int epi_groups = epi_units >= 2 ? 2 : 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -91,7 +102,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
     // full: the LEADER's barrier collects the bytes of both CTAs' loads; empty / tmem_full: the leader's commits arrive in
     // both CTAs; tmem_empty: the leader's barrier collects the 4 + 4 epilogue warps of the pair
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8 * epi_groups); }
     fence_barrier_init();
   }
   cluster_sync_all();   // both CTAs resident + barrier inits visible cluster-wide before the pair-wide TMEM allocation
@@ -110,6 +121,9 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
   const int num_units = pairs_m * tiles_n;      // unit = two vertically adjacent 128 x BN tiles sharing one W tile
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
 
+  // register pool: 384 x 168 at launch = 128 x 40 (warps 0-3) + 256 x 232 (epilogue warps)
+  if (warp < 4) {
+  setmaxnreg_dec<40>();
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
     const long long pc0 = prof_begin();
@@ -168,24 +182,30 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
       }
       prof_end(pc0, 0x71);
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    setmaxnreg_inc<232>();
     // ===================== epilogue =====================
-    const int ew = warp - 4;                 // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
-    const uint32_t stg = smem_stage + ew * (32 * 128);                    // this warp's 32 x 128 B staging tile
-    const uint32_t vec_bias = smem_vec + ew * (2 * BN * 2 + 512);         // bias[BN] | gate[BN] | norm_q[<=128] | norm_k[<=128]
-    const uint32_t vec_gate = vec_bias + BN * 2;
-    const uint32_t vec_nq = vec_gate + BN * 2, vec_nk = vec_nq + 256;
+    const int ew = warp & 3;                 // TMEM lanes [32*ew, 32*ew+32): a warp reaches the quadrant warp % 4
+    const int grp = (warp - 4) >> 2;         // column half of the tile this warp takes
+    const uint32_t stg = smem_stage + (warp - 4) * (32 * 128);            // this warp's 32 x 128 B staging tile
+    const uint32_t vec_nq = smem_vec, vec_nk = smem_vec + 256;            // norm_q[<=128] | norm_k[<=128], one copy per CTA
     const int coop_row = lane >> 3, coop_c = lane & 7;                    // cooperative (coalesced) access: 8 lanes per 128-B row
     const long long pc0 = prof_begin();
-    if (p.epi == EPI_QKV_RMSNORM) {
-      if (lane < 8) st_shared_v4x(vec_nq + lane * 16, __ldg(reinterpret_cast<const uint4*>(p.norm_q) + lane));
-      else if (lane < 16) st_shared_v4x(vec_nk + (lane - 8) * 16, __ldg(reinterpret_cast<const uint4*>(p.norm_k) + (lane - 8)));
-      __syncwarp();
-    } else if (p.epi == EPI_QKV_RMSNORM_ROPE128) {
-      if (lane < 16) st_shared_v4x(vec_nq + lane * 16, __ldg(reinterpret_cast<const uint4*>(p.norm_q) + lane));
-      else st_shared_v4x(vec_nk + (lane - 16) * 16, __ldg(reinterpret_cast<const uint4*>(p.norm_k) + (lane - 16)));
-      __syncwarp();
+    if (p.epi == EPI_QKV_RMSNORM || p.epi == EPI_QKV_RMSNORM_ROPE128) {
+      if (warp == 4) {
+        if (p.epi == EPI_QKV_RMSNORM) {
+          if (lane < 8) st_shared_v4x(vec_nq + lane * 16, __ldg(reinterpret_cast<const uint4*>(p.norm_q) + lane));
+          else if (lane < 16) st_shared_v4x(vec_nk + (lane - 8) * 16, __ldg(reinterpret_cast<const uint4*>(p.norm_k) + (lane - 8)));
+        } else {
+          if (lane < 16) st_shared_v4x(vec_nq + lane * 16, __ldg(reinterpret_cast<const uint4*>(p.norm_q) + lane));
+          else st_shared_v4x(vec_nk + (lane - 16) * 16, __ldg(reinterpret_cast<const uint4*>(p.norm_k) + (lane - 16)));
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(GEMM_EPI_WARPS * 32) : "memory");   // the eight epilogue warps only
     }
+    const int u_begin = grp * epi_units / epi_groups, u_end = (grp + 1) * epi_units / epi_groups;   // this group's column units
+    if (grp < epi_groups) {
     int it = 0;
     for (int unit = cluster_id; unit < num_units; unit += num_clusters, ++it) {
       const int acc = it & 1;
@@ -197,15 +217,11 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
       const int b = tile_ok ? tm / p.tiles_m_per_batch : 0;
       const int row_base = (tm % p.tiles_m_per_batch) * GEMM_BM + ew * 32;   // first row (within the batch) of this warp
       bf16* out_base = p.out + static_cast<long>(b) * p.out_batch_stride + static_cast<long>(p.out_row_offset + row_base) * p.ldo + tn * BN;
-      // stage this tile's bias / gate slices while the MMAs of the tile are still running
-      if (lane * 8 < BN) {
-        uint4 bv = make_uint4(0, 0, 0, 0);
-        if (p.bias) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + tn * BN) + lane);
-        st_shared_v4x(vec_bias + lane * 16, bv);
-        if (p.epi == EPI_GATE_RESIDUAL)
-          st_shared_v4x(vec_gate + lane * 16, __ldg(reinterpret_cast<const uint4*>(p.gate + static_cast<long>(b) * p.gate_batch_stride + tn * BN) + lane));
-      }
-      __syncwarp();
+      // bias / gate slices of this tile: warp-uniform 16-byte loads through L1 (the same lines serve the consecutive tiles of an n-column)
+      const uint4* bias_v = p.bias ? reinterpret_cast<const uint4*>(p.bias + tn * BN) : nullptr;      // [BN / 8] groups of 8 columns
+      const uint4* gate_v = p.epi == EPI_GATE_RESIDUAL
+                                ? reinterpret_cast<const uint4*>(p.gate + static_cast<long>(b) * p.gate_batch_stride + tn * BN) : nullptr;
+      auto bias8 = [&](int col8) { return bias_v ? __ldg(bias_v + col8) : make_uint4(0, 0, 0, 0); };
       // residual mode: the h chunk (whole-line loads, 8 lanes per 128-B row) is fetched one chunk AHEAD into registers - chunk 0
       // before the accumulator wait, chunk c+1 while chunk c is processed - so its HBM latency never sits on the epilogue's
       // critical path (at K = 1536 the epilogue, not the MMA, paces the attention out-projection).
@@ -219,7 +235,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
             hv[i] = *reinterpret_cast<const uint4*>(out_base + static_cast<long>(rr) * p.ldo + c * 64 + coop_c * 8);
         }
       };
-      if (p.epi == EPI_GATE_RESIDUAL) load_residual(0);
+      if (p.epi == EPI_GATE_RESIDUAL) load_residual(u_begin);
       mbar_wait(&tmem_full[acc], acc_phase, 0x30);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
@@ -249,7 +265,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
         // sum of squares (TMEM reads are cheap), pass 2 normalises, rotates and stores.  thread == token row.
         const bool row_ok = tile_ok && row_base + lane < p.rows_per_batch;
         const long token = static_cast<long>(p.rope_row_offset + row_base + lane);
-        for (int hc = 0; hc < BN / 128; ++hc) {
+        for (int hc = u_begin; hc < u_end; ++hc) {
           const int which = (tn * BN + hc * 128) / p.qk_dim;   // 0 = q, 1 = k, 2 = v
           float rs = 1.0f;
           if (which < 2) {
@@ -263,7 +279,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
                 float bf[8];
-                unpack8_bf16(ld_shared_v4(vec_bias + (hc * 128 + half * 64 + q * 8) * 2), bf);
+                unpack8_bf16(bias8(hc * 16 + half * 8 + q), bf);
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) {
                   const int j = q * 8 + e;
@@ -287,7 +303,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               float bf[8];
-              unpack8_bf16(ld_shared_v4(vec_bias + (c * 64 + q * 8) * 2), bf);
+              unpack8_bf16(bias8(c * 8 + q), bf);
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const int j = q * 8 + e;
@@ -330,7 +346,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
           }
         }
       } else
-      for (int c = 0; c < BN / 64; ++c) {
+      for (int c = u_begin; c < u_end; ++c) {
         const int n0 = tn * BN + c * 64;       // global column of this 64-wide chunk
         // (1) residual mode: prefetched h chunk -> staging tile (16-B chunks XOR-swizzled by row); start the next chunk's loads
         if (p.epi == EPI_GATE_RESIDUAL) {
@@ -339,7 +355,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
             const int rr = i * 4 + coop_row;
             st_shared_v4x(stg + rr * 128 + ((coop_c ^ (rr & 7)) << 4), hv[i]);
           }
-          if (c + 1 < BN / 64) load_residual(c + 1);
+          if (c + 1 < u_end) load_residual(c + 1);
           __syncwarp();
         }
         // (2) thread == row: accumulator chunk -> registers -> fused math -> bf16 -> own row of the staging tile
@@ -351,7 +367,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           float bf[8];
-          unpack8_bf16(ld_shared_v4(vec_bias + (c * 64 + q * 8) * 2), bf);
+          unpack8_bf16(bias8(c * 8 + q), bf);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int j = q * 8 + e;
@@ -394,7 +410,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             float gf[8], hf[8];
-            unpack8_bf16(ld_shared_v4(vec_gate + (c * 64 + q * 8) * 2), gf);
+            unpack8_bf16(__ldg(gate_v + c * 8 + q), gf);
             unpack8_bf16(ld_shared_v4(stg + lane * 128 + ((q ^ (lane & 7)) << 4)), hf);
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
@@ -419,7 +435,8 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);   // the leader's MMA warp waits for all 8 epilogue warps
+      if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0);   // the leader's MMA warp waits for all 8 * epi_groups epilogue warps
+    }
     }
     prof_end(pc0, 0x72 + ew);
   }

@@ -210,7 +210,5 @@ __device__ __forceinline__ void softmax_final_check(float l_run) {
   if (!(l_run < ATT_FAIL_AT)) mbar_timeout(0x6F);
 }
 
-template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 }  // namespace ffb

@@ -8,8 +8,8 @@
 // image (the convolution's padding), outside the channel range (Cin < 64) or outside the batch (ghost tile of an odd tile count),
 // so there is no im2col buffer, no halo exchange and no bounds logic on the load side.  Weights are pre-packed [N][tap][Cin_pad].
 //
-// STATUS: written after round 1's GPU budget was spent - compiled for sm_100a, host logic unit-tested, NOT yet run on a GPU
-// (tests/test_gpu_vae.py is gated on FFB200_PENDING=1 until its first green run).
+// Validated on B200 in round 2 (tests/test_gpu_vae.py; the TMA zero-fill assumptions - boxes wider than the channel extent, negative and
+// beyond-extent coordinates - hold on sm_100a).
 #include "common.cuh"
 #include "kernels.h"
 

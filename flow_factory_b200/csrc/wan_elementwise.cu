@@ -5,8 +5,7 @@
 //   gate_residual_f32   : hs = (hs.float() + y * gate).type_as(hs)                                    (transformer_wan.py:489, 503)
 //   rms_rope_rows       : torch.nn.RMSNorm ACROSS heads + interleaved-pair RoPE in the tensor dtype   (transformer_wan.py:96-117)
 //
-// STATUS: written after round 1's GPU budget was spent - compiled for sm_100a, NOT yet run on a GPU (tests/test_gpu_wan.py is gated
-// on FFB200_PENDING=1 until its first green run).
+// Validated on B200 in round 2 (tests/test_gpu_wan.py).
 #include "common.cuh"
 #include "kernels.h"
 #include <algorithm>

@@ -13,8 +13,7 @@
 // RMSNorm -> cross-attention to the text tokens (keys / values of all blocks are computed once per prompt set: they do not depend on
 // the timestep) -> out-projection with the residual in the GEMM epilogue; fp32 LayerNorm + modulate -> GELU-tanh FFN -> gated residual.
 //
-// STATUS: written after round 1's GPU budget was spent - compiled for sm_100a, NOT yet run on a GPU (tests/test_gpu_wan.py is gated on
-// FFB200_PENDING=1 until its first green run).
+// Validated on B200 in round 2 (tests/test_gpu_wan.py).
 #include "common.cuh"
 #include "kernels.h"
 #include "../../include/ffb200.h"

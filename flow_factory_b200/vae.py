@@ -3,8 +3,8 @@
 Mirrors `SD3_5Adapter.decode_latents` (FF/models/stable_diffusion/sd3_5.py:161-172): `latents.to(vae.dtype) / scaling_factor +
 shift_factor -> AutoencoderKL.decode -> image_processor.postprocess(output_type="pt")`.
 
-STATUS: written after round 1's GPU budget was spent.  The packing below is unit-tested on CPU (tests/test_host_logic_vae.py); the
-CUDA side compiles for sm_100a but has not run on a GPU yet (tests/test_gpu_vae.py, gated on FFB200_PENDING=1).
+STATUS: validated on B200 in round 2 (tests/test_gpu_vae.py: layer ops and the whole decoder against the pinned oracle; 1024^2 decode
+12.6 ms per image at batch 8, profiles/r02_vae_decode_1024.json).  The packing below is also unit-tested on CPU (tests/test_host_logic_vae.py).
 
 Weight order handed to `ffb200_vae_decoder_create` (all bf16, contiguous):
 

@@ -1,9 +1,9 @@
 """Host side of the Wan2.1 T2V rollout path (SURVEY.md section 8f row 4 / BASELINE config 4): weight packing, RoPE tables, the ctypes
 binding of `ffb200_wan_*` and a rollout-level engine class in the style of `flux.py`.
 
-STATUS: written after round 1's GPU budget was spent.  Packing, RoPE tables and the UniPC schedule are unit-tested on CPU against the
-pinned oracle / reference-minted fixtures (tests/test_host_logic_wan.py); the CUDA side compiles for sm_100a but has not run on a GPU
-yet (tests/test_gpu_wan.py, gated on FFB200_PENDING=1).
+STATUS: validated on B200 in round 2 (tests/test_gpu_wan.py against the pinned oracle; rollout lines under profiles/r02_*wan21*).
+Packing, RoPE tables and the UniPC schedule are also unit-tested on CPU against the pinned oracle / reference-minted fixtures
+(tests/test_host_logic_wan.py).
 
 Reference: WanTransformer3DModel (DF/models/transformers/transformer_wan.py:507-740) behind Wan2_T2V_Adapter
 (FF/models/wan/wan2_t2v.py:235-543)."""

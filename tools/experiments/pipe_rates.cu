@@ -49,6 +49,14 @@ __global__ void __launch_bounds__(1024, 1) k(float* out, long long* cyc, float s
       }
       if (OP == 13) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b[i]), "f"(a[(i + 1) % CHAINS]));  // 3 distinct varying regs
       if (OP == 14) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(pa[i]) : "l"(pa[(i + 3) % CHAINS]), "l"(pa[(i + 5) % CHAINS]));
+      // round 2: 16-bit packed transcendental forms (does one MUFU slot deliver two results?) and the conversions around them
+      if (OP == 15) { uint32_t r = __float_as_uint(a[i]); asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(r)); a[i] = __uint_as_float(r); }
+      if (OP == 16) { uint32_t r = __float_as_uint(a[i]); asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(r)); a[i] = __uint_as_float(r); }
+      if (OP == 17) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a[i]));
+      if (OP == 18) { uint32_t r; asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a[i]), "f"(b[i])); a[i] = __uint_as_float(r); }   // F2FP.F16
+      if (OP == 19) { uint32_t r = __float_as_uint(a[i]); asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(r) : "r"(__float_as_uint(c1))); a[i] = __uint_as_float(r); }  // HADD2
+      if (OP == 20) { uint32_t r = __float_as_uint(a[i]); asm volatile("{.reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.f32.f16 %0, lo;}" : "=f"(b[i]) : "r"(r)); a[i] += b[i]; }  // f16 -> f32 + FADD
+      if (OP == 21) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[i]));                                      // MUFU.RCP
     }
   }
   long long t1 = clock64();
@@ -96,6 +104,13 @@ int main() {
     run<10>("shl_add", 2, w);
     run<11>("mufu+2ffma_imm (per inst, 3 per group)", 3, w);
     run<12>("ffma2+fmnmx3 (per inst, 2 per group)", 2, w);
+    run<15>("mufu_ex2_f16x2", 1, w);
+    run<16>("mufu_ex2_bf16x2", 1, w);
+    run<17>("mufu_tanh_f32", 1, w);
+    run<18>("f2fp_f16x2", 1, w);
+    run<19>("hadd2_f16x2", 1, w);
+    run<20>("cvt_f32_f16+fadd (per inst, 2 per group)", 2, w);
+    run<21>("mufu_rcp", 1, w);
   }
   return 0;
 }

@@ -28,3 +28,15 @@ by = collections.defaultdict(float)
 for k, v in agg.items():
     by[k[0]] += v[1]
 print("\nBy kernel: " + ", ".join(f"{k.replace('ffb::', '')} {100 * v / tot:.1f} %" for k, v in sorted(by.items(), key=lambda kv: -kv[1])))
+
+# kernel-family shares for bench.py's `time_share_of_step` (profiles/launch_shares.json), when asked: python tools/launchlist_summary.py x.csv --shares out.json
+if "--shares" in sys.argv:
+    import json
+    fam = collections.defaultdict(float)
+    for k, v in by.items():
+        key = "attention" if "attention" in k else "gemm" if "gemm" in k else "ln_modulate" if "ln_modulate" in k else "other"
+        fam[key] += v
+    with open(sys.argv[sys.argv.index("--shares") + 1], "w") as f:
+        json.dump({"source": "ncu launch list of one denoise step at the bench batch (tools/launchlist_summary.py; per-launch times are cold-cache and "
+                             "serialised at full clocks - shares, not absolutes)", "launches_per_step": len(seg), "ms_summed": round(tot, 3),
+                   **{k: f"{100 * v / tot:.1f} %" for k, v in sorted(fam.items(), key=lambda kv: -kv[1])}}, f, indent=1)
