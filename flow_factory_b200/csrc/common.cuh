@@ -207,12 +207,15 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
-// arrive on the mbarrier at the same smem offset in CTA `cta` of the cluster
+// arrive on the mbarrier at the same smem offset in CTA `cta` of the cluster.  Default semantics (.release at CTA scope), as CUTLASS's
+// ClusterBarrier::arrive: what the arrive has to order here are TMEM reads, which the tcgen05 fences on both sides cover.  The
+// `.release.cluster` form compiled to MEMBAR.ALL.GPU in front of every arrive, i.e. each epilogue warp waited for the acknowledgement of
+// all its global stores of the tile before it could hand the accumulator stage back (ncu round 2: 0.6-0.8 membar stalls per issue).
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }

@@ -24,6 +24,7 @@
 //
 // A is addressed as a 3-D tensor [batch][rows_per_batch][K] so that token sub-ranges of a joint
 // [B, S, D] buffer (image rows / text rows) are separate GEMM problems with zero-filled ragged tails.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -92,7 +93,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
   // column units of a tile the epilogue splits between its two warp groups: 64-column chunks, or whole 128-column heads for the
   // head_dim-128 q/k epilogue; a tile with a single unit is handled by group 0 alone
   const int epi_units = p.epi == EPI_QKV_RMSNORM_ROPE128 ? BN / 128 : BN / 64;
-  const int epi_groups = epi_units >= 2 ? 2 : 1;
+  const int epi_groups = (epi_units >= 2 && p.epi_split == 2) ? 2 : 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -466,7 +467,18 @@ static cudaError_t launch_bn(const GemmParams& p, int num_sms, cudaStream_t stre
 
 int gemm_pick_bn(int N) { return (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : 64); }
 
-cudaError_t launch_gemm(const GemmParams& p, int num_sms, cudaStream_t stream) {
+// Column split of the epilogue between its two warp groups: on by default for every epilogue.  Measured on B200 (round 2, call 15,
+// profiles/r02_kernel_bench_gemm.jsonl, TFLOP/s split / single group / the previous four-warp kernel): MLP-up M = 65536 1457 / 1181 / 1403,
+// M = 8192 1424 / 1180 / 1348; attention out-projection M = 65536 1438 / 1118 / 1398; QKV M = 65536 1578 / 1546 / 1578 (M = 8192: 1452 /
+// 1381 / 1489, the one shape that lost 2.5 %).  FFB200_GEMM_EPI_SPLIT = 1 | 2 forces a mode for A/B runs.
+static int gemm_epi_split() {
+  static const int forced = [] { const char* e = getenv("FFB200_GEMM_EPI_SPLIT"); return e ? atoi(e) : 0; }();
+  return forced == 1 ? 1 : 2;
+}
+
+cudaError_t launch_gemm(const GemmParams& p0, int num_sms, cudaStream_t stream) {
+  GemmParams p = p0;
+  p.epi_split = gemm_epi_split();
   switch (p.bn) {
     case 256: return launch_bn<256>(p, num_sms, stream);
     case 128: return launch_bn<128>(p, num_sms, stream);

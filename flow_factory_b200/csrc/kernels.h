@@ -45,6 +45,7 @@ struct GemmParams {
   int rope_row_offset;
   float k_scale;           // EPI_QKV_RMSNORM[_ROPE128]: factor folded into the k heads before their bf16 store (0 = 1): softmax_scale * log2(e)
   int rms_round_first;     // 0: torch.nn.RMSNorm bf16((x*rs)*w) (FLUX.1) ; 1: diffusers RMSNorm bf16(bf16(x*rs)*w) (Qwen-Image)
+  int epi_split;           // set by launch_gemm: 1 = one epilogue warp group takes the whole tile, 2 = the two groups take half the columns each
 };
 
 int gemm_pick_bn(int N);

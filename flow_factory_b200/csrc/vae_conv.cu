@@ -33,10 +33,25 @@ __device__ __forceinline__ void conv_tile_origin(const ConvParams& p, int tm, in
   w0 = (rem - ty * p.tiles_w) << p.tw_log2;
 }
 
+// Shared-memory layout of the convolution kernel: the GEMM kernel's pipeline stages with FOUR epilogue warps (one per TMEM lane quadrant)
+// and per-warp bias vectors - the layout gemm.cu had before its epilogue was split over eight warps (the convolution epilogues are light).
+constexpr int CONV_THREADS = 256;
+template <int BN> struct ConvCfg {
+  static constexpr int kStages = GemmCfg<BN>::kStages;
+  static constexpr int kABytes = GemmCfg<BN>::kABytes;
+  static constexpr int kBBytes = GemmCfg<BN>::kBBytes;
+  static constexpr int kStageBytes = GemmCfg<BN>::kStageBytes;
+  static constexpr int kTmemCols = GemmCfg<BN>::kTmemCols;
+  static constexpr int kStagingBytes = 4 * 32 * 128;        // per epilogue warp: 32 rows x 64 bf16
+  static constexpr int kVecBytes = 4 * (2 * BN * 2 + 2 * 128 * 2);  // per warp: bias[BN] (+ the slots the GEMM epilogues used)
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kVecBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget of one CTA per SM");
+};
+
 template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
 conv_bf16_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = ConvCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t smem_base = smem_u32(smem);
@@ -279,7 +294,7 @@ conv_bf16_kernel(const __grid_constant__ ConvParams p) {
 
 template <int BN>
 static cudaError_t launch_conv_bn(const ConvParams& p, int num_sms, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = ConvCfg<BN>;
   static DeviceOnce once;                              // dynamic shared memory opt-in, once per device
   {
     cudaError_t e = once.run([] { return cudaFuncSetAttribute(conv_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes); });
@@ -288,7 +303,7 @@ static cudaError_t launch_conv_bn(const ConvParams& p, int num_sms, cudaStream_t
   const int units = ((p.B * p.tiles_h * p.tiles_w + 1) / 2) * (p.N / BN);
   const int max_clusters = num_sms / 2;
   const int grid = 2 * (units < max_clusters ? units : max_clusters);
-  conv_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(p);
+  conv_bf16_kernel<BN><<<grid, CONV_THREADS, Cfg::kSmemBytes, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -24,12 +24,20 @@ def dump(name, obj):
         json.dump(obj, f, indent=1, default=lambda o: o.tolist() if hasattr(o, "tolist") else str(o))
 
 
+def record(file: str, obj):
+    """Append one JSON line to gpurun_out/<file>: the MEASURED error of every parity case, so tolerances can be set from numbers."""
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, file), "a") as f:
+        f.write(json.dumps(obj, default=lambda o: o.tolist() if hasattr(o, "tolist") else str(o)) + "\n")
+
+
 def err_report(got: torch.Tensor, ref: torch.Tensor, tag: str):
     g, r = got.float(), ref.float()
     d = (g - r).abs()
     rep = dict(tag=tag, shape=list(g.shape), max_abs=float(d.max()), mean_abs=float(d.mean()), ref_absmax=float(r.abs().max()),
                got_absmax=float(g.abs().max()), n_nan=int(torch.isnan(g).sum()),
                frac_bad=float((d > 0.05 * r.abs().max()).float().mean()))
+    record("parity_measured.jsonl", {k: rep[k] for k in ("tag", "max_abs", "mean_abs", "ref_absmax", "n_nan")})
     if g.dim() == 2:
         bad = d > 0.05 * r.abs().max()
         rep["bad_rows_first"] = bad.any(1).nonzero().flatten()[:16].tolist()

@@ -56,7 +56,7 @@ def test_flux_forward_matches_oracle(name):
                mean_engine=float((got - truth).abs().mean()), mean_ref=float((ref_bf16 - truth).abs().mean()))
     dump(f"flux_fwd_{name}.json", rep)
     assert torch.isfinite(got).all()
-    assert e_eng <= max(3.0 * e_ref, 0.02 * scale), rep
+    assert e_eng <= max(1.3 * e_ref, 0.005 * scale), rep     # measured on B200: 0.60 - 0.98 x the bf16 reference's own error
     assert rep["mean_engine"] <= max(3.0 * rep["mean_ref"], 0.004 * scale), rep
 
 

@@ -47,7 +47,7 @@ def test_qkv_rmsnorm_rope_epilogue(B, S, H, K, off):
     ref = _qkv_rope_ref(x, W, b, nq, nk, cos[off:], sin[off:], H)
     got = out[:, off:]
     rep = err_report(got.reshape(-1, 3 * D), ref.reshape(-1, 3 * D).float(), f"qkv_rope_{B}_{S}_{H}")
-    ok = rep["n_nan"] == 0 and rep["max_abs"] <= 6e-2 and rep.get("mean_abs", 0) <= 2e-3
+    ok = rep["n_nan"] == 0 and rep["max_abs"] <= 2.1e-2 and rep.get("mean_abs", 0) <= 2e-3
     if not ok:
         rep["device_error"] = device_error()
         dump(f"diag_qkv_rope_{B}_{S}_{H}.json", rep)
@@ -111,4 +111,4 @@ def test_flux_joint_attention_chain_matches_oracle():
         M._linear = orig
     ref = torch.cat([captured[pre + "to_add_out"], captured[pre + "to_out.0"]], dim=1)
     rep = err_report(att.reshape(-1, D), ref.reshape(-1, D), "flux_attn_chain")
-    assert rep["n_nan"] == 0 and rep["max_abs"] <= 5e-2, rep
+    assert rep["n_nan"] == 0 and rep["max_abs"] <= 5.2e-3, rep

@@ -15,7 +15,7 @@ def _mk(M, N, K, seed=0):
     return A, W, b
 
 
-def _check(got, ref, tag, tol=2e-2):
+def _check(got, ref, tag, tol=4.5e-3):     # measured on B200: <= 3.4e-3 of the reference maximum (one bf16 rounding of the output)
     rep = err_report(got, ref, tag)
     ok = rep["n_nan"] == 0 and rep["max_abs"] <= tol * max(1.0, rep["ref_absmax"])
     if not ok:

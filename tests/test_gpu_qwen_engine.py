@@ -50,7 +50,7 @@ def test_qwen_forward_and_true_cfg_match_oracle(name):
                mean_engine=float((got - truth).abs().mean()), mean_ref=float((ref_bf16 - truth).abs().mean()))
     dump(f"qwen_fwd_{name}.json", rep)
     assert torch.isfinite(got).all()
-    assert e_eng <= max(3.0 * e_ref, 0.02 * scale), rep
+    assert e_eng <= max(1.3 * e_ref, 0.005 * scale), rep     # measured on B200: 0.60 - 0.98 x the bf16 reference's own error
     assert rep["mean_engine"] <= max(3.0 * rep["mean_ref"], 0.004 * scale), rep
     # --- true CFG with per-token norm rescale (qwen_image.py:580-587)
     gs = 4.0
@@ -66,7 +66,7 @@ def test_qwen_forward_and_true_cfg_match_oracle(name):
     e_eng_c, e_ref_c = float((gotc - truth_c).abs().max()), float((ref_c - truth_c).abs().max())
     repc = dict(tag=f"qwen_cfg_{name}", e_engine=e_eng_c, e_ref_bf16=e_ref_c, truth_absmax=float(truth_c.abs().max()))
     dump(f"qwen_cfg_{name}.json", repc)
-    assert e_eng_c <= max(3.0 * e_ref_c, 0.03 * repc["truth_absmax"]), repc
+    assert e_eng_c <= max(1.3 * e_ref_c, 0.005 * repc["truth_absmax"]), repc
 
 
 def test_qwen_ode_rollout_matches_oracle_loop():
