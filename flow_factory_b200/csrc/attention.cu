@@ -11,7 +11,7 @@
 //   warp  12               : TMA producer (Q once; ring of 64x64 K and V tiles shared by the three sub-tiles)
 //   warps 13 / 14 / 15     : MMA issuers, one per sub-tile (S = Q K^T : M128 N64 K64 ; O += P V : M128 N64 K64, V as MN-major
 //                            operand).  One issuer per sub-tile keeps the softmax groups out of lockstep.
-//   setmaxnreg moves registers from warps 12-15 (24 each) to the softmax warps (160 each).
+//   setmaxnreg: warps 12-15 keep 64 registers each, the softmax warps get 144.
 // TMEM (all 512 columns): per sub-tile S (64 columns, fp32), P (32 columns, bf16 pairs) and the output accumulator O (64, fp32).
 //   * P has its OWN columns, so S is free again as soon as the softmax warps hold S(j) in registers: Q K^T of tile j+1 is issued
 //     right then and runs on the tensor core WHILE the softmax of tile j is computed - the softmax -> tensor core -> softmax
@@ -25,6 +25,7 @@
 // unit alone 16.  What is left per score on the product path (keys pre-scaled by softmax_scale * log2(e) in the QKV GEMM epilogue,
 // reference 0): one MUFU.EX2 or, for 2 of every 8 pairs, a polynomial exp2 on the FMA pipe; half a packed add for the row sum; half a
 // bf16 pack.  Measured history, rejected alternatives and the ncu picture: profiles/r02_attention_experiments.md.
+#include <type_traits>
 #include "common.cuh"
 #include "kernels.h"
 #include "softmax.cuh"
@@ -99,7 +100,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp >= 12) {
-    setmaxnreg_dec<24>();
+    setmaxnreg_dec<64>();
     if (warp == 12) {
       // ===================== TMA producer =====================
       if (lane == 0) {
@@ -170,7 +171,8 @@ attention_kernel(const __grid_constant__ AttnParams p) {
     }
   } else {
     // ===================== softmax: warps 4x .. 4x+3 -> sub-tile x =====================
-    setmaxnreg_inc<160>();   // pool: 512 x 128 regs at launch = 12 x 32 x 160 + 4 x 32 x 24 (+ 1024 spare)
+    setmaxnreg_inc<144>();   // pool: 512 x 128 regs at launch >= 12 x 32 x 144 + 4 x 32 x 64 (the softmax uses ~106; 24 for the helpers
+                             // spilled the MMA issuers' descriptors and the producer's ring state to local memory)
     const int x = warp >> 2;                          // sub-tile
     if (x < n_sub) {
       const int wq = warp & 3;                        // TMEM lane quadrant
@@ -189,7 +191,11 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       // under the exp2 work of tile j (-12 % at head_dim 64, -26 % at 128: the mid-tile wait lands before the tensor core delivers) and
       // deferring the P(j) release to the next tile's top (-10 .. -28 %: P V then sits on the p_free critical path).
       uint32_t s0[32], s1[32];
-      for (int j = 0; j < n_tiles; ++j) {
+      // One KV tile.  kFirst / kLast are compile-time so that the steady-state body (tiles 1 .. n-2) carries neither the first-tile maximum
+      // nor the key mask of the ragged last tile, and its common case - scores are the exponents (pre-scaled keys, reference 0), the
+      // polynomial slots in range, nothing to rescale - is ONE branch body instead of a dispatch per 32-key half.
+      auto tile = [&](const int j, auto first_c, auto last_c) {
+        constexpr bool kFirst = decltype(first_c)::value, kLast = decltype(last_c)::value;
         prof_lap(&lap, 0x67);                          // loop overhead
         mbar_wait(&s_full[x], j & 1, 0x60);
         tc_fence_after();
@@ -202,33 +208,49 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         prof_lap(&lap, 0x62);                          // TMEM waits, arrives
 
         SoftmaxTile t;
-        softmax_begin<PolyD64>(s0, s1, S - j * ATT_BN, sc, pre, j == 0, sm, t);
+        softmax_begin<PolyD64>(s0, s1, kLast ? S - j * ATT_BN : ATT_BN, sc, pre, kFirst, sm, t);
         uint32_t pk[16];                               // P(j), one half at a time, as packed bf16 pairs
-        softmax_half<PolyD64>(s0, t, pk);
-        if (j > 0) {                                   // P V of tile j-1 (released at the end of that tile) retired: P_x free, O_x quiescent
-          mbar_wait(&p_free[x], (j - 1) & 1, 0x61);
-          tc_fence_after();
-        }
-        if (j > 0 && t.rescale) {                      // rare: O_x *= alpha in TMEM 
-          uint32_t o0[32];
-#pragma unroll 1
-          for (int c = 0; c < ATT_D; c += 32) {
-            tmem_ld32(tOx + c, o0);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * t.alpha);
-            tmem_st32(tOx + c, o0);
+        auto wait_p_free = [&]() {                     // P V of tile j-1 (released at the end of that tile) retired: P_x free, O_x quiescent
+          if (!kFirst) {
+            mbar_wait(&p_free[x], (j - 1) & 1, 0x61);
+            tc_fence_after();
           }
+        };
+        if (!kFirst && !kLast && t.fast && t.poly && !t.rescale) {
+          softmax_exp32<true, true, true, PolyD64>(s0, t.sc2, t.mneg2, t.sums2, pk);
+          wait_p_free();
+          tmem_st16(tPx, pk);                          // P_x(j) columns [0, 16): keys 0-31
+          softmax_exp32<true, true, true, PolyD64>(s1, t.sc2, t.mneg2, t.sums2, pk);
+          tmem_st16(tPx + 16, pk);                     // columns [16, 32): keys 32-63
+        } else {
+          softmax_half<PolyD64>(s0, t, pk);
+          wait_p_free();
+          if (!kFirst && t.rescale) {                  // rare: O_x *= alpha in TMEM
+            uint32_t o0[32];
+#pragma unroll 1
+            for (int c = 0; c < ATT_D; c += 32) {
+              tmem_ld32(tOx + c, o0);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * t.alpha);
+              tmem_st32(tOx + c, o0);
+            }
+          }
+          tmem_st16(tPx, pk);
+          softmax_half<PolyD64>(s1, t, pk);
+          tmem_st16(tPx + 16, pk);
         }
-        tmem_st16(tPx, pk);                            // P_x(j) columns [0, 16): keys 0-31
-        softmax_half<PolyD64>(s1, t, pk);
-        tmem_st16(tPx + 16, pk);                       // columns [16, 32): keys 32-63
         softmax_end(sm, t);
         tmem_st_wait();                                // P(j) is in TMEM
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[x]);        // P V (j) may start: a whole tile of slack before its P_x / O_x are needed again
-      }
+      };
+      using T_ = std::true_type; using F_ = std::false_type;
+      tile(0, T_{}, T_{});                             // first tile: exact maximum, key mask when it is also the last (S <= 64)
+#pragma unroll 1
+      for (int j = 1; j < n_tiles - 1; ++j) tile(j, F_{}, F_{});
+      if (n_tiles > 1) tile(n_tiles - 1, F_{}, T_{});  // ragged last tile: keys beyond the sequence masked
       // final output: O_x / l
       mbar_wait(&o_full[x], 0, 0x69);
       tc_fence_after();
