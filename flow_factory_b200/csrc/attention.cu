@@ -66,7 +66,11 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   uint64_t* o_full = p_free + ATT_NSUB;          // [3]  final O_x complete
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + ATT_NSUB);
 
+#ifdef FFB_ATT_UWARP     // A/B: warp index through a shuffle, so that ptxas knows it is warp-uniform (TMEM addresses in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+#else
   const int warp = threadIdx.x >> 5;
+#endif
   const int lane = threadIdx.x & 31;
   if ((smem_u32(smem) & 1023u) != 0) mbar_timeout(0xA11);   // swizzled tiles would be silently misread
   const int q0 = blockIdx.x * ATT_QB;
@@ -204,7 +208,11 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
+#ifdef FFB_ATT_ELECT     // A/B: elected lane instead of the lane index (which ptxas keeps in local memory across setmaxnreg)
+        if (elect_one()) mbar_arrive(&s_free[x]);
+#else
         if (lane == 0) mbar_arrive(&s_free[x]);        // Q K^T of the next tile may overwrite S_x now
+#endif
         prof_lap(&lap, 0x62);                          // TMEM waits, arrives
 
         SoftmaxTile t;
@@ -244,7 +252,11 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         tmem_st_wait();                                // P(j) is in TMEM
         tc_fence_before();
         __syncwarp();
+#ifdef FFB_ATT_ELECT
+        if (elect_one()) mbar_arrive(&p_full[x]);
+#else
         if (lane == 0) mbar_arrive(&p_full[x]);        // P V (j) may start: a whole tile of slack before its P_x / O_x are needed again
+#endif
       };
       using T_ = std::true_type; using F_ = std::false_type;
       tile(0, T_{}, T_{});                             // first tile: exact maximum, key mask when it is also the last (S <= 64)

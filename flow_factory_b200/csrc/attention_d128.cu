@@ -11,6 +11,7 @@
 //   * Q / K / V tiles are two 64-column SWIZZLE_128B panels each (a TMA box cannot be wider than the 128-byte swizzle span):
 //     Q K^T walks 8 K16 steps over the two panels, P V is one M128 N128 K16 MMA per step whose MN-major V operand spans both
 //     panels (leading-dimension byte offset = the panel stride).
+#include <type_traits>
 #include "common.cuh"
 #include "kernels.h"
 #include "softmax.cuh"
@@ -55,7 +56,11 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
   uint64_t* o_full = p_free + A128_NSUB;       // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + A128_NSUB);
 
+#ifdef FFB_ATT_UWARP     // A/B: see attention.cu
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+#else
   const int warp = threadIdx.x >> 5;
+#endif
   const int lane = threadIdx.x & 31;
   if ((smem_u32(smem) & 1023u) != 0) mbar_timeout(0xA12);
   const int q0 = blockIdx.x * A128_QB;
@@ -90,7 +95,7 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp >= 8) {
-    setmaxnreg_dec<24>();
+    setmaxnreg_dec<64>();
     if (warp == 8) {
       // ===================== TMA producer =====================
       if (lane == 0) {
@@ -163,7 +168,7 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
     }
   } else {
     // ===================== softmax: warps 4x .. 4x+3 -> sub-tile x =====================
-    setmaxnreg_inc<200>();   // pool: 384 x 168 regs at launch >= 8 x 32 x 200 + 4 x 32 x 24
+    setmaxnreg_inc<200>();   // pool: 384 x 168 regs at launch >= 8 x 32 x 200 + 4 x 32 x 64
     const int x = warp >> 2;
     if (x < n_sub) {
       const int wq = warp & 3;
@@ -179,31 +184,23 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
       const int mask_lo = p.kv_mask_lo ? max(__ldg(p.kv_mask_lo + b), 1) : 0;   // key 0 always stays (keeps the running max finite)
       // P(j) is stored per 32-key half and released at once (see attention.cu for the measured alternatives).
       uint32_t s0[32], s1[32];
-#ifndef FFB_ATT128_NO_PEEL        // the first tile's S load sits in front of the loop: same work, but ptxas schedules the loop body ~10 %
-                                  // faster this way (round 2 calls 5 / 11: 1228-1252 vs 1115-1156 TFLOP/s); -DFFB_ATT128_NO_PEEL for the A/B
-      mbar_wait(&s_full[x], 0, 0x60);
-      tc_fence_after();
-      tmem_ld32(tSx + 0, s0);
-      tmem_ld32(tSx + 32, s1);
-#endif
-      for (int j = 0; j < n_tiles; ++j) {
-#ifndef FFB_ATT128_NO_PEEL
-        if (j > 0) {
-          mbar_wait(&s_full[x], j & 1, 0x60);
-          tc_fence_after();
-          tmem_ld32(tSx + 0, s0);
-          tmem_ld32(tSx + 32, s1);
-        }
-#else
+      // One KV tile; kFirst / kLast are compile-time as in attention.cu: the steady-state tiles carry neither the first-tile maximum nor the
+      // tail mask, and their common case (scores are the exponents, polynomial slots in range, nothing to rescale) is one branch body.
+      // (Round 2 history: peeling only the first tile's S load already made ptxas schedule the loop ~10 % faster, 1228-1252 vs 1115-1156.)
+      auto tile = [&](const int j, auto first_c, auto last_c) {
+        constexpr bool kFirst = decltype(first_c)::value, kLast = decltype(last_c)::value;
         mbar_wait(&s_full[x], j & 1, 0x60);
         tc_fence_after();
         tmem_ld32(tSx + 0, s0);
         tmem_ld32(tSx + 32, s1);
-#endif
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
+#ifdef FFB_ATT_ELECT
+        if (elect_one()) mbar_arrive(&s_free[x]);
+#else
         if (lane == 0) mbar_arrive(&s_free[x]);        // Q K^T of the next tile may overwrite S_x now
+#endif
         if (mask_lo < mask_hi) {                        // key-padding mask: only the first few KV tiles overlap the text rows
           const int k0 = j * A128_BN;
           if (k0 < mask_hi && k0 + A128_BN > mask_lo) {
@@ -215,33 +212,53 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
           }
         }
         SoftmaxTile t;
-        softmax_begin<PolyD128>(s0, s1, Skv - j * A128_BN, sc, pre, j == 0, sm, t);
+        softmax_begin<PolyD128>(s0, s1, kLast ? Skv - j * A128_BN : A128_BN, sc, pre, kFirst, sm, t);
         uint32_t pk[16];                               // P(j), one half at a time, as packed bf16 pairs
-        softmax_half<PolyD128>(s0, t, pk);
-        if (j > 0) {                                   // P V of tile j-1 (released at the end of that tile) retired: P_x free, O_x quiescent
-          mbar_wait(&p_free[x], (j - 1) & 1, 0x61);
-          tc_fence_after();
-        }
-        if (j > 0 && t.rescale) {                      // rare: O_x *= alpha in TMEM (128 columns, 32 at a time)
-          uint32_t o0[32];
-#pragma unroll 1
-          for (int c = 0; c < A128_D; c += 32) {
-            tmem_ld32(tOx + c, o0);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * t.alpha);
-            tmem_st32(tOx + c, o0);
+        auto wait_p_free = [&]() {                     // P V of tile j-1 (released at the end of that tile) retired: P_x free, O_x quiescent
+          if (!kFirst) {
+            mbar_wait(&p_free[x], (j - 1) & 1, 0x61);
+            tc_fence_after();
           }
+        };
+        if (!kFirst && !kLast && t.fast && t.poly && !t.rescale) {
+          softmax_exp32<true, true, true, PolyD128>(s0, t.sc2, t.mneg2, t.sums2, pk);
+          wait_p_free();
+          tmem_st16(tPx, pk);                          // P_x(j) columns [0, 16): keys 0-31
+          softmax_exp32<true, true, true, PolyD128>(s1, t.sc2, t.mneg2, t.sums2, pk);
+          tmem_st16(tPx + 16, pk);                     // columns [16, 32): keys 32-63
+        } else {
+          softmax_half<PolyD128>(s0, t, pk);
+          wait_p_free();
+          if (!kFirst && t.rescale) {                  // rare: O_x *= alpha in TMEM (128 columns, 32 at a time)
+            uint32_t o0[32];
+#pragma unroll 1
+            for (int c = 0; c < A128_D; c += 32) {
+              tmem_ld32(tOx + c, o0);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * t.alpha);
+              tmem_st32(tOx + c, o0);
+            }
+          }
+          tmem_st16(tPx, pk);
+          softmax_half<PolyD128>(s1, t, pk);
+          tmem_st16(tPx + 16, pk);
         }
-        tmem_st16(tPx, pk);                            // P_x(j) columns [0, 16): keys 0-31
-        softmax_half<PolyD128>(s1, t, pk);
-        tmem_st16(tPx + 16, pk);                       // columns [16, 32): keys 32-63
         softmax_end(sm, t);
         tmem_st_wait();                                // P(j) is in TMEM
         tc_fence_before();
         __syncwarp();
+#ifdef FFB_ATT_ELECT
+        if (elect_one()) mbar_arrive(&p_full[x]);
+#else
         if (lane == 0) mbar_arrive(&p_full[x]);        // P V (j) may start: a whole tile of slack before its P_x / O_x are needed again
-      }
+#endif
+      };
+      using T_ = std::true_type; using F_ = std::false_type;
+      tile(0, T_{}, T_{});                             // first tile: exact maximum, tail mask when it is also the last
+#pragma unroll 1
+      for (int j = 1; j < n_tiles - 1; ++j) tile(j, F_{}, F_{});
+      if (n_tiles > 1) tile(n_tiles - 1, F_{}, T_{});  // ragged last tile: keys beyond the sequence masked
       mbar_wait(&o_full[x], 0, 0x69);
       tc_fence_after();
       const int q = q0 + x * A128_BM + r;

@@ -21,7 +21,8 @@ namespace ffb {
 
 // Which pairs of a 32-score block take the polynomial: kNum of every 8, evenly spread (3 -> {0,3,6}, 2 -> {0,4}, 4 -> {0,2,4,6}) or clustered
 // (the first kNum of every 8).  A per-kernel choice - what ptxas makes of the mix differs between the two attention kernels (round 2
-// measurements, profiles/r02_attention_experiments.md): head_dim 64 runs best with 2 of 8 spread, head_dim 128 with 3 of 8 clustered.
+// measurements, profiles/r02_attention_experiments.md): with the lean steady-state loop of call 17 both kernels run best with 3 of 8 clustered
+// (head_dim 64, call 18: 2 of 8 spread 881, 1 of 8 864, 3 of 8 spread 935, 3 of 8 clustered 947 TFLOP/s; before that loop 2 of 8 spread won).
 constexpr int ATT_POLY_PERIOD = 8;
 template <int kNum, bool kCluster>
 struct PolyPolicy {
@@ -38,7 +39,7 @@ using PolyD64 = PolyPolicy<FFB_ATT_POLY_NUM, false>;
 #endif
 using PolyD128 = PolyD64;
 #else
-using PolyD64 = PolyPolicy<2, false>;
+using PolyD64 = PolyPolicy<3, true>;
 using PolyD128 = PolyPolicy<3, true>;
 #endif
 
