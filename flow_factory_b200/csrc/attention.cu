@@ -32,6 +32,14 @@
 
 namespace ffb {
 
+// Warp barrier between tcgen05.wait::ld / wait::st and the elected lane's arrive in the softmax tiles.  Both waits are .sync.aligned (the
+// whole warp passes them together), so the barrier is arguably redundant; -DFFB_ATT_NO_SYNCWARP drops it (A/B only, not the product).
+#ifdef FFB_ATT_NO_SYNCWARP
+#define ATT_TILE_SYNCWARP() ((void)0)
+#else
+#define ATT_TILE_SYNCWARP() __syncwarp()
+#endif
+
 constexpr int ATT_BM = 128;     // query rows per sub-tile
 constexpr int ATT_NSUB = 3;     // sub-tiles per CTA
 constexpr int ATT_QB = ATT_NSUB * ATT_BM;   // query rows per CTA
@@ -66,7 +74,10 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   uint64_t* o_full = p_free + ATT_NSUB;          // [3]  final O_x complete
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + ATT_NSUB);
 
-#ifdef FFB_ATT_UWARP     // A/B: warp index through a shuffle, so that ptxas knows it is warp-uniform (TMEM addresses in uniform registers)
+  // warp index through a shuffle: ptxas then knows it is warp-uniform and keeps everything derived from it (TMEM addresses, barrier
+  // addresses, role tests) in uniform registers - no R2UR in front of every LDTM / STTM / SYNCS of the softmax loop (round 2, call 19:
+  // 950 -> 981 TFLOP/s at head_dim 64, 1290 -> 1360 at head_dim 128; -DFFB_ATT_NO_UWARP for the A/B)
+#ifndef FFB_ATT_NO_UWARP
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
 #else
   const int warp = threadIdx.x >> 5;
@@ -198,17 +209,19 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       // One KV tile.  kFirst / kLast are compile-time so that the steady-state body (tiles 1 .. n-2) carries neither the first-tile maximum
       // nor the key mask of the ragged last tile, and its common case - scores are the exponents (pre-scaled keys, reference 0), the
       // polynomial slots in range, nothing to rescale - is ONE branch body instead of a dispatch per 32-key half.
-      auto tile = [&](const int j, auto first_c, auto last_c) {
+      auto tile = [&](const int j, auto first_c, auto last_c, auto par_c) {
         constexpr bool kFirst = decltype(first_c)::value, kLast = decltype(last_c)::value;
+        constexpr int kPar = decltype(par_c)::value;           // barrier parity of tile j when known at compile time, else -1
+        const uint32_t par = kPar >= 0 ? static_cast<uint32_t>(kPar) : static_cast<uint32_t>(j & 1);
         prof_lap(&lap, 0x67);                          // loop overhead
-        mbar_wait(&s_full[x], j & 1, 0x60);
+        mbar_wait(&s_full[x], par, 0x60);
         tc_fence_after();
         tmem_ld32(tSx + 0, s0);
         tmem_ld32(tSx + 32, s1);
         tmem_ld_wait();
         tc_fence_before();
-        __syncwarp();
-#ifdef FFB_ATT_ELECT     // A/B: elected lane instead of the lane index (which ptxas keeps in local memory across setmaxnreg)
+        ATT_TILE_SYNCWARP();
+#ifndef FFB_ATT_NO_ELECT  // elected lane instead of the lane index (which ptxas keeps in local memory across setmaxnreg): +1 % (call 19)
         if (elect_one()) mbar_arrive(&s_free[x]);
 #else
         if (lane == 0) mbar_arrive(&s_free[x]);        // Q K^T of the next tile may overwrite S_x now
@@ -220,7 +233,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         uint32_t pk[16];                               // P(j), one half at a time, as packed bf16 pairs
         auto wait_p_free = [&]() {                     // P V of tile j-1 (released at the end of that tile) retired: P_x free, O_x quiescent
           if (!kFirst) {
-            mbar_wait(&p_free[x], (j - 1) & 1, 0x61);
+            mbar_wait(&p_free[x], par ^ 1u, 0x61);
             tc_fence_after();
           }
         };
@@ -251,18 +264,26 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         softmax_end(sm, t);
         tmem_st_wait();                                // P(j) is in TMEM
         tc_fence_before();
-        __syncwarp();
-#ifdef FFB_ATT_ELECT
+        ATT_TILE_SYNCWARP();
+#ifndef FFB_ATT_NO_ELECT
         if (elect_one()) mbar_arrive(&p_full[x]);
 #else
         if (lane == 0) mbar_arrive(&p_full[x]);        // P V (j) may start: a whole tile of slack before its P_x / O_x are needed again
 #endif
       };
       using T_ = std::true_type; using F_ = std::false_type;
-      tile(0, T_{}, T_{});                             // first tile: exact maximum, key mask when it is also the last (S <= 64)
+      using PR_ = std::integral_constant<int, -1>; using P0_ = std::integral_constant<int, 0>; using P1_ = std::integral_constant<int, 1>;
+      tile(0, T_{}, T_{}, P0_{});                      // first tile: exact maximum, key mask when it is also the last (S <= 64)
+#ifdef FFB_ATT_UNROLL2     // A/B: steady-state tiles two at a time, barrier parities compile-time
+      int j = 1;
 #pragma unroll 1
-      for (int j = 1; j < n_tiles - 1; ++j) tile(j, F_{}, F_{});
-      if (n_tiles > 1) tile(n_tiles - 1, F_{}, T_{});  // ragged last tile: keys beyond the sequence masked
+      for (; j + 1 < n_tiles - 1; j += 2) { tile(j, F_{}, F_{}, P1_{}); tile(j + 1, F_{}, F_{}, P0_{}); }
+      if (j < n_tiles - 1) tile(j, F_{}, F_{}, P1_{});
+#else
+#pragma unroll 1
+      for (int j = 1; j < n_tiles - 1; ++j) tile(j, F_{}, F_{}, PR_{});
+#endif
+      if (n_tiles > 1) tile(n_tiles - 1, F_{}, T_{}, PR_{});  // ragged last tile: keys beyond the sequence masked
       // final output: O_x / l
       mbar_wait(&o_full[x], 0, 0x69);
       tc_fence_after();

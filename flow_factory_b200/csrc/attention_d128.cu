@@ -56,7 +56,7 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
   uint64_t* o_full = p_free + A128_NSUB;       // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + A128_NSUB);
 
-#ifdef FFB_ATT_UWARP     // A/B: see attention.cu
+#ifndef FFB_ATT_NO_UWARP  // warp-uniform warp index: see attention.cu
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
 #else
   const int warp = threadIdx.x >> 5;
@@ -195,8 +195,8 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
         tmem_ld32(tSx + 32, s1);
         tmem_ld_wait();
         tc_fence_before();
-        __syncwarp();
-#ifdef FFB_ATT_ELECT
+        ATT_TILE_SYNCWARP();
+#ifndef FFB_ATT_NO_ELECT
         if (elect_one()) mbar_arrive(&s_free[x]);
 #else
         if (lane == 0) mbar_arrive(&s_free[x]);        // Q K^T of the next tile may overwrite S_x now
@@ -247,8 +247,8 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
         softmax_end(sm, t);
         tmem_st_wait();                                // P(j) is in TMEM
         tc_fence_before();
-        __syncwarp();
-#ifdef FFB_ATT_ELECT
+        ATT_TILE_SYNCWARP();
+#ifndef FFB_ATT_NO_ELECT
         if (elect_one()) mbar_arrive(&p_full[x]);
 #else
         if (lane == 0) mbar_arrive(&p_full[x]);        // P V (j) may start: a whole tile of slack before its P_x / O_x are needed again

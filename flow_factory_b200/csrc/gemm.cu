@@ -88,7 +88,12 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams p) {
   uint64_t* tmem_empty = bars + 2 * Cfg::kStages + 2; // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
 
+  // warp index through a shuffle: warp-uniform for ptxas (see attention.cu); +2 % on the MLP-up shape in the bench (round 2, call 20)
+#ifndef FFB_GEMM_NO_UWARP
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+#else
   const int warp = threadIdx.x >> 5;
+#endif
   const int lane = threadIdx.x & 31;
   // column units of a tile the epilogue splits between its two warp groups: 64-column chunks, or whole 128-column heads for the
   // head_dim-128 q/k epilogue; a tile with a single unit is handled by group 0 alone

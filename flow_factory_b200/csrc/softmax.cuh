@@ -22,7 +22,8 @@ namespace ffb {
 // Which pairs of a 32-score block take the polynomial: kNum of every 8, evenly spread (3 -> {0,3,6}, 2 -> {0,4}, 4 -> {0,2,4,6}) or clustered
 // (the first kNum of every 8).  A per-kernel choice - what ptxas makes of the mix differs between the two attention kernels (round 2
 // measurements, profiles/r02_attention_experiments.md): with the lean steady-state loop of call 17 both kernels run best with 3 of 8 clustered
-// (head_dim 64, call 18: 2 of 8 spread 881, 1 of 8 864, 3 of 8 spread 935, 3 of 8 clustered 947 TFLOP/s; before that loop 2 of 8 spread won).
+// (head_dim 64, call 18: 2 of 8 spread 881, 1 of 8 864, 3 of 8 spread 935, 3 of 8 clustered 947 TFLOP/s; before that loop 2 of 8 spread won);
+// re-checked on the final loops in call 20: head_dim 64 2 / 3 / 4 clustered 965 / 990 / 955, head_dim 128 1379 / 1368 / 1343 -> 3 and 2.
 constexpr int ATT_POLY_PERIOD = 8;
 template <int kNum, bool kCluster>
 struct PolyPolicy {
@@ -40,7 +41,7 @@ using PolyD64 = PolyPolicy<FFB_ATT_POLY_NUM, false>;
 using PolyD128 = PolyD64;
 #else
 using PolyD64 = PolyPolicy<3, true>;
-using PolyD128 = PolyPolicy<3, true>;
+using PolyD128 = PolyPolicy<2, true>;
 #endif
 
 constexpr float ATT_REF_ZERO_BAND = 32.0f;        // first-tile |max exponent| up to which the reference stays 0
