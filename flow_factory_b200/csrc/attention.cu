@@ -229,7 +229,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         prof_lap(&lap, 0x62);                          // TMEM waits, arrives
 
         SoftmaxTile t;
-        softmax_begin<PolyD64>(s0, s1, kLast ? S - j * ATT_BN : ATT_BN, sc, pre, kFirst, sm, t);
+        softmax_begin<PolyD64, PolyD64G>(s0, s1, kLast ? S - j * ATT_BN : ATT_BN, sc, pre, kFirst, sm, t);
         uint32_t pk[16];                               // P(j), one half at a time, as packed bf16 pairs
         auto wait_p_free = [&]() {                     // P V of tile j-1 (released at the end of that tile) retired: P_x free, O_x quiescent
           if (!kFirst) {
@@ -244,7 +244,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
           softmax_exp32<true, true, true, PolyD64>(s1, t.sc2, t.mneg2, t.sums2, pk);
           tmem_st16(tPx + 16, pk);                     // columns [16, 32): keys 32-63
         } else {
-          softmax_half<PolyD64>(s0, t, pk);
+          softmax_half<PolyD64, PolyD64G>(s0, t, pk);
           wait_p_free();
           if (!kFirst && t.rescale) {                  // rare: O_x *= alpha in TMEM
             uint32_t o0[32];
@@ -258,7 +258,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
             }
           }
           tmem_st16(tPx, pk);
-          softmax_half<PolyD64>(s1, t, pk);
+          softmax_half<PolyD64, PolyD64G>(s1, t, pk);
           tmem_st16(tPx + 16, pk);
         }
         softmax_end(sm, t);

@@ -212,7 +212,7 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
           }
         }
         SoftmaxTile t;
-        softmax_begin<PolyD128>(s0, s1, kLast ? Skv - j * A128_BN : A128_BN, sc, pre, kFirst, sm, t);
+        softmax_begin<PolyD128, PolyD128G>(s0, s1, kLast ? Skv - j * A128_BN : A128_BN, sc, pre, kFirst, sm, t);
         uint32_t pk[16];                               // P(j), one half at a time, as packed bf16 pairs
         auto wait_p_free = [&]() {                     // P V of tile j-1 (released at the end of that tile) retired: P_x free, O_x quiescent
           if (!kFirst) {
@@ -227,7 +227,7 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
           softmax_exp32<true, true, true, PolyD128>(s1, t.sc2, t.mneg2, t.sums2, pk);
           tmem_st16(tPx + 16, pk);                     // columns [16, 32): keys 32-63
         } else {
-          softmax_half<PolyD128>(s0, t, pk);
+          softmax_half<PolyD128, PolyD128G>(s0, t, pk);
           wait_p_free();
           if (!kFirst && t.rescale) {                  // rare: O_x *= alpha in TMEM (128 columns, 32 at a time)
             uint32_t o0[32];
@@ -241,7 +241,7 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
             }
           }
           tmem_st16(tPx, pk);
-          softmax_half<PolyD128>(s1, t, pk);
+          softmax_half<PolyD128, PolyD128G>(s1, t, pk);
           tmem_st16(tPx + 16, pk);
         }
         softmax_end(sm, t);

@@ -43,6 +43,14 @@ using PolyD128 = PolyD64;
 using PolyD64 = PolyPolicy<3, true>;
 using PolyD128 = PolyPolicy<2, true>;
 #endif
+// general path (unscaled keys: op-level entry, diffusers backend hook): the per-pair FFMA2 of the exponent already loads the FMA pipe
+#ifdef FFB_ATT_POLY_NUM
+using PolyD64G = PolyD64;
+using PolyD128G = PolyD128;
+#else
+using PolyD64G = PolyPolicy<2, false>;
+using PolyD128G = PolyPolicy<2, true>;
+#endif
 
 constexpr float ATT_REF_ZERO_BAND = 32.0f;        // first-tile |max exponent| up to which the reference stays 0
 constexpr float ATT_SHIFT_AT = 18446744073709551616.0f;        // 2^64: running sum at which the reference moves
@@ -128,7 +136,7 @@ struct SoftmaxTile {
 //   sc    : softmax_scale * log2(e); ignored when `pre`.
 //   pre   : warp-uniform; the scores already are base-2 exponents (keys pre-scaled by the producer).
 //   first : warp-uniform; first KV tile of the row block.
-template <class Poly>
+template <class Poly, class PolyG = Poly>
 __device__ __forceinline__ void softmax_begin(uint32_t (&s0)[32], uint32_t (&s1)[32], int kv_valid, float sc, bool pre, bool first,
                                               SoftmaxState& st, SoftmaxTile& t) {
   if (kv_valid < 64) {
@@ -141,7 +149,7 @@ __device__ __forceinline__ void softmax_begin(uint32_t (&s0)[32], uint32_t (&s1)
   const float sce = pre ? 1.0f : sc;
   t.alpha = 1.0f;
   t.rescale = false;
-  t.poly = Poly::num > 0;
+  t.poly = Poly::num > 0 || PolyG::num > 0;
   t.sums2[0] = t.sums2[1] = 0ull;
   t.sc2 = pack_f32x2(sce, sce);
   if (first) {
@@ -166,8 +174,8 @@ __device__ __forceinline__ void softmax_begin(uint32_t (&s0)[32], uint32_t (&s1)
   // and only a warp that saw one of them sorts out which (the common tile pays a single VOTE + branch for its bookkeeping)
   const bool grow = !first && !(st.l_run <= ATT_SHIFT_AT);       // also true for inf / NaN
   bool over = false;
-  if (Poly::num > 0) {
-    const float amax = t.fast ? softmax_poly_absmax<true, Poly>(s0, s1, sce, 0.f) : softmax_poly_absmax<false, Poly>(s0, s1, sce, st.m_run);
+  if (Poly::num > 0 || PolyG::num > 0) {      // the general path (exponent = s * sc - ref: one more FFMA2 per pair) has its own slot policy
+    const float amax = t.fast ? softmax_poly_absmax<true, Poly>(s0, s1, sce, 0.f) : softmax_poly_absmax<false, PolyG>(s0, s1, sce, st.m_run);
     over = !(amax <= 126.0f);
   }
   if (__any_sync(0xffffffffu, grow || over)) {
@@ -182,21 +190,21 @@ __device__ __forceinline__ void softmax_begin(uint32_t (&s0)[32], uint32_t (&s1)
       t.fast = false;
       t.rescale = true;
       // the range check was made against the old reference: re-evaluate it (general path) against the new one
-      over = Poly::num > 0 && !(softmax_poly_absmax<false, Poly>(s0, s1, sce, st.m_run) <= 126.0f);
+      over = PolyG::num > 0 && !(softmax_poly_absmax<false, PolyG>(s0, s1, sce, st.m_run) <= 126.0f);
     }
-    t.poly = Poly::num > 0 && !__any_sync(0xffffffffu, over);
+    t.poly = (Poly::num > 0 || PolyG::num > 0) && !__any_sync(0xffffffffu, over);
   }
   t.mneg2 = pack_f32x2(-st.m_run, -st.m_run);
 }
 
-template <class Poly, bool kSum = true>
+template <class Poly, class PolyG = Poly, bool kSum = true>
 __device__ __forceinline__ void softmax_half(const uint32_t (&a)[32], SoftmaxTile& t, uint32_t (&pk)[16]) {
   if (t.fast) {
-    if (t.poly) softmax_exp32<true, true, kSum, Poly>(a, t.sc2, t.mneg2, t.sums2, pk);
+    if (t.poly && Poly::num > 0) softmax_exp32<true, true, kSum, Poly>(a, t.sc2, t.mneg2, t.sums2, pk);
     else softmax_exp32<true, false, kSum, Poly>(a, t.sc2, t.mneg2, t.sums2, pk);
   } else {
-    if (t.poly) softmax_exp32<false, true, kSum, Poly>(a, t.sc2, t.mneg2, t.sums2, pk);
-    else softmax_exp32<false, false, kSum, Poly>(a, t.sc2, t.mneg2, t.sums2, pk);
+    if (t.poly && PolyG::num > 0) softmax_exp32<false, true, kSum, PolyG>(a, t.sc2, t.mneg2, t.sums2, pk);
+    else softmax_exp32<false, false, kSum, PolyG>(a, t.sc2, t.mneg2, t.sums2, pk);
   }
 }
 
