@@ -95,131 +95,16 @@ __global__ void __launch_bounds__(256, 4) ln_modulate_kernel(const LnModParams p
   }
 }
 
-// Persistent variant: a fixed grid of warps walks the rows with a stride, and the 16-byte loads of a warp's NEXT row are issued before the
-// three register passes over the current one, so a warp always has a row in flight (the one-row-per-warp kernel above reaches ~3.5 TB/s:
-// every warp alternates between "all loads outstanding" and "two shuffle reductions + stores with nothing in flight").  The row streams
-// past L1 (ld.global.nc.L1::no_allocate / st.global.cs) so that the modulation vectors, re-read for every row, stay L1-resident.
-// MAXC = 16-byte chunks per lane: 6 covers D <= 1536 with half the registers and predicated-off work of the general 12.
-__device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ void st_stream_v4(void* p, const uint4& v) {
-  asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-template <int MAXC>
-__global__ void __launch_bounds__(256, 2) ln_modulate_persistent_kernel(const LnModParams p) {
-  const int lane = threadIdx.x & 31;
-  const long rows = static_cast<long>(p.rows_per_batch) * p.num_batch;
-  const long stride = static_cast<long>(gridDim.x) * (blockDim.x >> 5);
-  long row = static_cast<long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int nchunk = p.D >> 3;
-  const long dense = static_cast<long>(p.rows_per_batch) * p.D;
-  const float inv_d = 1.0f / static_cast<float>(p.D);
-  auto load_row = [&](long r, uint4 (&raw)[MAXC]) {
-    const int b = static_cast<int>(r / p.rows_per_batch);
-    const long rib = r - static_cast<long>(b) * p.rows_per_batch;
-    const bf16* xr = p.x + static_cast<long>(b) * (p.x_batch_stride ? p.x_batch_stride : dense) + rib * p.D;
-#pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      const int c = lane + 32 * i;
-      raw[i] = make_uint4(0, 0, 0, 0);
-      if (c < nchunk) raw[i] = ld_stream_v4(xr + c * 8);
-    }
-  };
-  auto process_row = [&](long r, const uint4 (&raw)[MAXC]) {
-    const int b = static_cast<int>(r / p.rows_per_batch);
-    const long rib = r - static_cast<long>(b) * p.rows_per_batch;
-    const long orow = static_cast<long>(b) * (p.out_batch_stride ? p.out_batch_stride : dense) + rib * p.D;
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      if (lane + 32 * i < nchunk) {
-        float v[8];
-        unpack8(raw[i], v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) sum += v[e];
-      }
-    }
-    const float mean = warp_sum(sum) * inv_d;          // same operation order as ln_modulate_kernel: bit-identical results
-    float sq = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      if (lane + 32 * i < nchunk) {
-        float v[8];
-        unpack8(raw[i], v);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { const float d = v[e] - mean; sq += d * d; }
-      }
-    }
-    const float rstd = rsqrtf(warp_sum(sq) * inv_d + p.eps);
-    const long mo = static_cast<long>(b) * p.mod_batch_stride;
-#pragma unroll
-    for (int i = 0; i < MAXC; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunk) {
-        float y[8], sc[8], sh[8], o[8];
-        unpack8(raw[i], y);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) y[e] = (y[e] - mean) * rstd;
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p.scale1 + mo + c * 8)), sc);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p.shift1 + mo + c * 8)), sh);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = __fadd_rn(__fmul_rn(y[e], bf16_round(1.0f + sc[e])), sh[e]);
-        st_stream_v4(p.out1 + orow + c * 8, pack8(o));
-        if (p.out2 != nullptr) {
-          unpack8(__ldg(reinterpret_cast<const uint4*>(p.scale2 + mo + c * 8)), sc);
-          unpack8(__ldg(reinterpret_cast<const uint4*>(p.shift2 + mo + c * 8)), sh);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = __fadd_rn(__fmul_rn(y[e], bf16_round(1.0f + sc[e])), sh[e]);
-          st_stream_v4(p.out2 + orow + c * 8, pack8(o));
-        }
-      }
-    }
-  };
-  uint4 buf_a[MAXC], buf_b[MAXC];
-  load_row(row, buf_a);
-  while (true) {                                       // two rows per iteration: the buffers alternate without register copies
-    long nxt = row + stride;
-    if (nxt < rows) load_row(nxt, buf_b);
-    process_row(row, buf_a);
-    if (nxt >= rows) break;
-    row = nxt;
-    nxt = row + stride;
-    if (nxt < rows) load_row(nxt, buf_a);
-    process_row(row, buf_b);
-    if (nxt >= rows) break;
-    row = nxt;
-  }
-}
-
-// FFB200_LN_PERSISTENT = 0 selects the one-row-per-warp kernel (A/B).
-static bool ln_use_persistent() {
-  static const bool on = [] { const char* e = getenv("FFB200_LN_PERSISTENT"); return e ? atoi(e) != 0 : true; }();
-  return on;
-}
-
+// Measured and NOT adopted (round 2, call 22, tools/ln_bench.py -> profiles/r02_ln_modulate_experiment.md): a persistent grid whose warps
+// prefetch their next row (two rows in registers, streaming loads / stores that bypass L1) - 0.113 / 0.184 ms (single / dual output, 16 x 4096
+// x 1536) against 0.106 / 0.158 ms for this one-row-per-warp kernel: the 16 warps per SM that fit with two rows in registers carry fewer
+// bytes in flight than 32 short-lived warps.
 cudaError_t launch_ln_modulate(const LnModParams& p, cudaStream_t stream) {
   if (p.D % 8 != 0 || p.D > LN_MAXC * 32 * 8) return cudaErrorInvalidValue;
   const long rows = static_cast<long>(p.rows_per_batch) * p.num_batch;
   const int wpb = 8;
-  const long blocks = (rows + wpb - 1) / wpb;
-  if (ln_use_persistent() && p.D <= 6 * 32 * 8) {     // wider rows (FLUX.1: 3072) would spill with two rows in registers: one-row kernel
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    static int cached_sms[64] = {0};
-    if (dev >= 0 && dev < 64) {
-      if (cached_sms[dev] == 0) cudaDeviceGetAttribute(&cached_sms[dev], cudaDevAttrMultiProcessorCount, dev);
-      sms = cached_sms[dev];
-    }
-    const int grid = static_cast<int>(std::min<long>(blocks, static_cast<long>(sms) * 2));
-    ln_modulate_persistent_kernel<6><<<grid, wpb * 32, 0, stream>>>(p);
-    return cudaGetLastError();
-  }
-  ln_modulate_kernel<<<static_cast<int>(blocks), wpb * 32, 0, stream>>>(p);
+  const int grid = static_cast<int>((rows + wpb - 1) / wpb);
+  ln_modulate_kernel<<<grid, wpb * 32, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -1,5 +1,5 @@
 """Times ffb200_ln_modulate at the SD3.5 bench shape (16 forward samples x 4096 image tokens x 1536; single and dual output) and checks it
-bit for bit against a torch model of the same operation order.  FFB200_LN_PERSISTENT=0 selects the one-row-per-warp kernel (A/B)."""
+against a torch model of the same operation order."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
