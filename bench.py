@@ -9,8 +9,9 @@ Euler/SDE + log-prob step, synthetic inputs of the BASELINE shape, random-init w
 (no checkpoints offline).  `value` = whole-job latents/s with inputs resident in HBM, device-timed (CUDA events, max over
 ranks); `e2e` = the same metric through the public adapter API with HOST (pinned) inputs and host outputs, copies inside
 the timed region.  Working set (4.5 GB of weights + GBs of activations per step) is far larger than the 126 MB L2.
-`roofline`: the kernel with the largest time share of a step (joint attention), `roofline_gemm`: the kernel with the largest FLOP
-share (MLP-up GEMM); both timed live here, DRAM traffic from the committed ncu captures.
+`roofline`: the single kernel shape with the largest time share of a step (joint attention, 46 %), `roofline_gemm`: the GEMM kernel (49 %
+over its 216 launches) at the shape with the largest FLOP share (MLP-up); both timed live here, alone before the rollouts and again right
+after them; DRAM traffic from the committed ncu captures.
 """
 from __future__ import annotations
 
@@ -461,8 +462,8 @@ def run_b200(args):
                      "peak_source": f"{peak_kind} cuBLAS bf16 burst", "flops_per_launch": 2.0 * M * N * K, "launch_ms": gemm_ms,
                      "achieved_after_rollouts": gemm_tf_hot, "frac_of_sustained_after_rollouts": gemm_tf_hot / peaks["bf16_tflops_sustained"],
                      "time_share_of_step": shares.get("gemm")}
-    # The kernel with the largest TIME share of the step is the joint attention: it is the `roofline` entry; the GEMM that carries most
-    # of the FLOPs is reported beside it as `roofline_gemm`.
+    # The single kernel shape with the largest TIME share of the step is the joint attention: it is the `roofline` entry; the GEMM kernel
+    # (the larger share over all its launches since round 2) is reported beside it as `roofline_gemm` at its most FLOP-heavy shape.
     whole = {"whole_step_achieved_per_gpu": step_tf / world, "whole_step_frac_of_sustained": step_tf / world / peaks["bf16_tflops_sustained"],
              "flops_per_latent": fl_latent}
     if att_ms is not None and att_ms_hot is not None:
@@ -476,7 +477,7 @@ def run_b200(args):
                     "flops_per_launch": att_fl, "launch_ms": att_ms,
                     "achieved_after_rollouts": att_tf_hot, "frac_of_sustained_after_rollouts": att_tf_hot / peaks["bf16_tflops_sustained"],
                     "time_share_of_step": shares.get("attention"),
-                    "note": "SIMT-softmax-limited at head_dim 64 (its speed follows the SM clock; cuDNN SDPA on the same shape: 0.53 of this peak), "
+                    "note": "SIMT-softmax-limited at head_dim 64 (MUFU and FMA pipes balanced, DESIGN.md section 4; cuDNN SDPA on the same shape: 0.53 of the measured burst peak), "
                             "see DESIGN.md section 4 / profiles/r02_attention_experiments.md", **whole}
     else:
         roofline = dict(roofline_gemm, note=f"attention roofline unavailable ({att_note}); GEMM reported instead", **whole)
