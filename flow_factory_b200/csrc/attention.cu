@@ -32,14 +32,6 @@
 
 namespace ffb {
 
-// Warp barrier between tcgen05.wait::ld / wait::st and the elected lane's arrive in the softmax tiles.  Both waits are .sync.aligned (the
-// whole warp passes them together), so the barrier is arguably redundant; -DFFB_ATT_NO_SYNCWARP drops it (A/B only, not the product).
-#ifdef FFB_ATT_NO_SYNCWARP
-#define ATT_TILE_SYNCWARP() ((void)0)
-#else
-#define ATT_TILE_SYNCWARP() __syncwarp()
-#endif
-
 constexpr int ATT_BM = 128;     // query rows per sub-tile
 constexpr int ATT_NSUB = 3;     // sub-tiles per CTA
 constexpr int ATT_QB = ATT_NSUB * ATT_BM;   // query rows per CTA
@@ -243,6 +235,12 @@ attention_kernel(const __grid_constant__ AttnParams p) {
           tmem_st16(tPx, pk);                          // P_x(j) columns [0, 16): keys 0-31
           softmax_exp32<true, true, true, PolyD64>(s1, t.sc2, t.mneg2, t.sums2, pk);
           tmem_st16(tPx + 16, pk);                     // columns [16, 32): keys 32-63
+        } else if (!kFirst && !kLast && !t.fast && t.poly && !t.rescale && PolyD64G::num > 0) {   // the same for unscaled keys (op-level entry, hooks)
+          softmax_exp32<false, true, true, PolyD64G>(s0, t.sc2, t.mneg2, t.sums2, pk);
+          wait_p_free();
+          tmem_st16(tPx, pk);
+          softmax_exp32<false, true, true, PolyD64G>(s1, t.sc2, t.mneg2, t.sums2, pk);
+          tmem_st16(tPx + 16, pk);
         } else {
           softmax_half<PolyD64, PolyD64G>(s0, t, pk);
           wait_p_free();

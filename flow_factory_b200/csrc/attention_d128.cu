@@ -226,6 +226,12 @@ attention_d128_kernel(const __grid_constant__ AttnParams p) {
           tmem_st16(tPx, pk);                          // P_x(j) columns [0, 16): keys 0-31
           softmax_exp32<true, true, true, PolyD128>(s1, t.sc2, t.mneg2, t.sums2, pk);
           tmem_st16(tPx + 16, pk);                     // columns [16, 32): keys 32-63
+        } else if (!kFirst && !kLast && !t.fast && t.poly && !t.rescale && PolyD128G::num > 0) {   // the same for unscaled keys (op-level entry, hooks)
+          softmax_exp32<false, true, true, PolyD128G>(s0, t.sc2, t.mneg2, t.sums2, pk);
+          wait_p_free();
+          tmem_st16(tPx, pk);
+          softmax_exp32<false, true, true, PolyD128G>(s1, t.sc2, t.mneg2, t.sums2, pk);
+          tmem_st16(tPx + 16, pk);
         } else {
           softmax_half<PolyD128, PolyD128G>(s0, t, pk);
           wait_p_free();

@@ -221,4 +221,12 @@ __device__ __forceinline__ void softmax_final_check(float l_run) {
 }
 
 
+// Warp barrier between tcgen05.wait::ld / wait::st and the elected lane's arrive in the softmax tiles.  Both waits are .sync.aligned (the
+// whole warp passes them together), so the barrier is arguably redundant; -DFFB_ATT_NO_SYNCWARP drops it (A/B only, not the product).
+#ifdef FFB_ATT_NO_SYNCWARP
+#define ATT_TILE_SYNCWARP() ((void)0)
+#else
+#define ATT_TILE_SYNCWARP() __syncwarp()
+#endif
+
 }  // namespace ffb
