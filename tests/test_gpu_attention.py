@@ -26,7 +26,7 @@ def test_attention_matches_sdpa(B, S, H):
     torch.cuda.synchronize()
     ref = _ref(qkv, H)
     rep = err_report(out.reshape(-1, 64 * H), ref.reshape(-1, 64 * H), f"attn_{B}_{S}_{H}")
-    ok = rep["n_nan"] == 0 and rep["max_abs"] <= 5e-3     # measured on B200: <= 3.8e-3 (profiles/r02_parity_measured.jsonl)
+    ok = rep["n_nan"] == 0 and rep["max_abs"] <= 5e-3 * max(1.0, rep["ref_absmax"])     # measured on B200: <= 4.2e-3 of that scale (bf16 P and bf16 output rounding; profiles/r02_parity_measured.jsonl)
     if not ok:
         rep["device_error"] = device_error()
         dump(f"diag_attn_{B}_{S}_{H}.json", rep)
@@ -67,7 +67,7 @@ def test_attention_d128_matches_sdpa(B, S, H):
     torch.cuda.synchronize()
     ref = _ref_d(qkv, H, 128)
     rep = err_report(out.reshape(-1, 128 * H), ref.reshape(-1, 128 * H), f"attn128_{B}_{S}_{H}")
-    ok = rep["n_nan"] == 0 and rep["max_abs"] <= 7.5e-3   # measured on B200: <= 5.8e-3
+    ok = rep["n_nan"] == 0 and rep["max_abs"] <= 5e-3 * max(1.0, rep["ref_absmax"])   # measured on B200: <= 3.1e-3 of that scale
     if not ok:
         rep["device_error"] = device_error()
         dump(f"diag_attn128_{B}_{S}_{H}.json", rep)
