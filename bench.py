@@ -270,8 +270,8 @@ def run_reference(args):
 
 def time_roofline_kernels(cfg, args, dev, B, cfg_on, ni):
     """Isolated launches of the two roofline kernels at the bench shapes (CUDA events on the launching stream, 256 MB L2 flush between
-    repetitions, median of 10 after 3 warm-ups): the MLP-up GEMM (bias + GELU epilogue) and the joint attention in the engine's layout
-    (keys pre-scaled by softmax_scale * log2(e) in the QKV GEMM epilogue, csrc/softmax.cuh).  Returns (gemm_ms, (M, N, K), att_ms | None, note)."""
+    repetitions, median of 10 after 3 warm-ups): the MLP-up GEMM (bias + GELU epilogue) and the joint attention exactly as the engine
+    launches it (RMS-normed q / k heads, keys pre-scaled by softmax_scale * log2(e) in the QKV GEMM epilogue, csrc/softmax.cuh).  Returns (gemm_ms, (M, N, K), att_ms | None, note)."""
     from flow_factory_b200.ops import linear as op_linear
     Bp = B * (2 if cfg_on else 1)
     M, N, K = Bp * ni, 4 * cfg.inner_dim, cfg.inner_dim
@@ -293,13 +293,18 @@ def time_roofline_kernels(cfg, args, dev, B, cfg_on, ni):
     del A, Wt, oo
     att_ms, note = None, None
     try:
-        from flow_factory_b200.ops import attention as op_attention
+        # the engine's own launch (ffb200_attention_normed): q / k heads as the QKV epilogue leaves them - per-head RMS-normed (unit weights
+        # here, as in the random-init model), keys pre-scaled by softmax_scale * log2(e)
+        from flow_factory_b200.ops import attention_normed as op_attention
         S_joint, Hh = ni + args.n_text, cfg.num_attention_heads
-        qkv = torch.randn(Bp, S_joint, 3 * cfg.inner_dim, device=dev)
-        qkv[..., cfg.inner_dim: 2 * cfg.inner_dim] *= 64 ** -0.5 * 1.4426950408889634
-        qkv = qkv.bfloat16()
+        x = torch.randn(Bp, S_joint, 3, Hh, 64, device=dev)
+        x[:, :, :2] = x[:, :, :2] * torch.rsqrt(x[:, :, :2].pow(2).mean(-1, keepdim=True) + 1e-6)
+        x[:, :, 1] *= 64 ** -0.5 * 1.4426950408889634
+        qkv = x.reshape(Bp, S_joint, 3 * cfg.inner_dim).bfloat16()
+        del x
+        w_norm = torch.ones(64, device=dev).bfloat16()
         ao = torch.empty(Bp, S_joint, cfg.inner_dim, device=dev, dtype=torch.bfloat16)
-        att_ms = median_ms(lambda: op_attention(qkv, Hh, ao, k_prescaled=True))
+        att_ms = median_ms(lambda: op_attention(qkv, Hh, w_norm, w_norm, out=ao))
         del qkv, ao
     except Exception as exc:   # the attention micro-timing is reporting only: never lose the bench line over it
         note = f"{type(exc).__name__}: {exc}"

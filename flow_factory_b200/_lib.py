@@ -85,6 +85,7 @@ def lib() -> C.CDLL:
     L.ffb200_attention.argtypes = [vp, ci, ci, ci, vp, vp]
     L.ffb200_attention_ex.argtypes = [vp, ci, ci, ci, ci, vp, ci, vp]
     L.ffb200_attention_scaled.argtypes = [vp, ci, ci, ci, ci, vp, ci, cf, ci, vp]
+    L.ffb200_attention_normed.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, vp, vp]
     L.ffb200_ln_modulate.argtypes = [vp, ci, ci, ci, cf, vp, vp, vp, vp, vp, vp, cll, vp]
     L.ffb200_small_linear.argtypes = [vp, ci, ci, cll, vp, vp, ci, vp, cll, vp, cll, ci, vp]
     L.ffb200_sde_step.argtypes = [vp, vp, ci, ci, ci, ci, C.POINTER(StepCoef), vp, cull, ci, vp, vp, vp, vp, vp, vp]
@@ -99,7 +100,7 @@ EXPORTED_SYMBOLS = (
     "ffb200_engine_set_weights", "ffb200_engine_destroy", "ffb200_engine_mod_rows", "ffb200_plan_create",
     "ffb200_plan_destroy", "ffb200_plan_workspace_bytes", "ffb200_plan_set_prompts", "ffb200_transformer_forward",
     "ffb200_step", "ffb200_rollout", "ffb200_rollout_host", "ffb200_last_launch_count", "ffb200_linear",
-    "ffb200_linear_qkv_rope", "ffb200_attention", "ffb200_attention_ex", "ffb200_attention_scaled", "ffb200_ln_modulate", "ffb200_small_linear", "ffb200_sde_step", "ffb200_sde_step_ex", "ffb200_plan_set_latent_dtype",
+    "ffb200_linear_qkv_rope", "ffb200_attention", "ffb200_attention_ex", "ffb200_attention_scaled", "ffb200_attention_normed", "ffb200_ln_modulate", "ffb200_small_linear", "ffb200_sde_step", "ffb200_sde_step_ex", "ffb200_plan_set_latent_dtype",
     # FLUX.1: bound in flow_factory_b200/flux.py
     "ffb200_flux_engine_create", "ffb200_flux_engine_set_weights", "ffb200_flux_engine_destroy", "ffb200_flux_engine_mod_rows",
     "ffb200_flux_plan_create", "ffb200_flux_plan_create_ex", "ffb200_flux_set_text_lengths", "ffb200_flux_plan_destroy", "ffb200_flux_plan_workspace_bytes", "ffb200_flux_set_prompts",

@@ -65,6 +65,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
   uint64_t* p_free = p_full + ATT_NSUB;          // [3]  P V of tile j retired: P_x may be overwritten, O_x is quiescent
   uint64_t* o_full = p_free + ATT_NSUB;          // [3]  final O_x complete
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + ATT_NSUB);
+  uint32_t* bounded_smem = tmem_ptr_smem + 1;         // 1: |exponent| <= 126 proven for this launch (see AttnParams::bound_wq)
 
   // warp index through a shuffle: ptxas then knows it is warp-uniform and keeps everything derived from it (TMEM addresses, barrier
   // addresses, role tests) in uniform registers - no R2UR in front of every LDTM / STTM / SYNCS of the softmax loop (round 2, call 19:
@@ -101,6 +102,26 @@ attention_kernel(const __grid_constant__ AttnParams p) {
     fence_barrier_init();
   }
   if (warp == 13) tmem_alloc(tmem_ptr_smem, ATT_TMEM_COLS);
+  if (warp == 14) {
+    // Range proof for the polynomial exp2 slots (softmax.cuh): with keys pre-scaled by scale_log2 and both q and k RMS-normed per head,
+    // |q . k'| <= ||q|| ||k'|| <= (8 max|w_q|) (8 max|w_k| scale_log2); 1.016 covers the bf16 roundings of the epilogue that produced them.
+    float wq = 0.f, wk = 0.f;
+    bool known = p.k_prescaled != 0 && p.bound_wq[0] != nullptr && p.bound_wk[0] != nullptr;
+    if (known) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (p.bound_wq[i]) wq = fmaxf(wq, fmaxf(fabsf(__bfloat162float(p.bound_wq[i][lane])), fabsf(__bfloat162float(p.bound_wq[i][lane + 32]))));
+        if (p.bound_wk[i]) wk = fmaxf(wk, fmaxf(fabsf(__bfloat162float(p.bound_wk[i][lane])), fabsf(__bfloat162float(p.bound_wk[i][lane + 32]))));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        wq = fmaxf(wq, __shfl_xor_sync(0xffffffffu, wq, o));
+        wk = fmaxf(wk, __shfl_xor_sync(0xffffffffu, wk, o));
+      }
+    }
+    const float bound = 64.0f * 1.016f * wq * wk * p.scale_log2;
+    if (lane == 0) *bounded_smem = (known && bound <= 120.0f) ? 1u : 0u;     // NaN / inf weights fail the comparison: guard stays
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -190,6 +211,7 @@ attention_kernel(const __grid_constant__ AttnParams p) {
       const uint32_t tOx = tmem_base + lane_off + ATT_TMEM_O + x * ATT_D;
       const float sc = p.scale_log2;
       const bool pre = p.k_prescaled != 0;              // the scores already are base-2 exponents (softmax.cuh)
+      const bool bounded = *bounded_smem != 0;          // warp-uniform: the range guard of the polynomial slots is proven unnecessary
       SoftmaxState sm;
       const long long pc0 = prof_begin();
       long long lap = prof_begin();
@@ -221,7 +243,8 @@ attention_kernel(const __grid_constant__ AttnParams p) {
         prof_lap(&lap, 0x62);                          // TMEM waits, arrives
 
         SoftmaxTile t;
-        softmax_begin<PolyD64, PolyD64G>(s0, s1, kLast ? S - j * ATT_BN : ATT_BN, sc, pre, kFirst, sm, t);
+        // the range proof covers real keys only: the ragged last tile carries -inf for the keys beyond the sequence, so it keeps the guard
+        softmax_begin<PolyD64, PolyD64G>(s0, s1, kLast ? S - j * ATT_BN : ATT_BN, sc, pre, kFirst, sm, t, bounded && !kLast);
         uint32_t pk[16];                               // P(j), one half at a time, as packed bf16 pairs
         auto wait_p_free = [&]() {                     // P V of tile j-1 (released at the end of that tile) retired: P_x free, O_x quiescent
           if (!kFirst) {

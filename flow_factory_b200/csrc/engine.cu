@@ -324,11 +324,20 @@ static int add_gemm(ffb200_plan* p, const GemmSpec& s) {
   p->fwd_ops.push_back([gp, sms](cudaStream_t st) { ++g_launch_count; return launch_gemm(gp, sms, st); });
   return 0;
 }
-static int add_attn(ffb200_plan* p, const void* qkv, int seq, void* out) {
+// wq / wk: the per-head RMSNorm weights of the QKV epilogues that write this attention's q and k (image stream, text stream or null):
+// the kernel derives a bound on every exponent from them and drops the range guard of its polynomial slots when the bound allows
+// (AttnParams::bound_wq; FFB200_NO_SCORE_BOUND=1 withholds them for A/B runs).
+static int add_attn(ffb200_plan* p, const void* qkv, int seq, void* out, const void* wq0, const void* wk0, const void* wq1 = nullptr,
+                    const void* wk1 = nullptr) {
   AttnParams ap;
   int r = build_attn(qkv, p->Bp, seq, p->e->cfg.num_heads, out, &ap);
   if (r) return r;
   ap.k_prescaled = engine_prescale() ? 1 : 0;       // every QKV GEMM of this engine folds the scale into k (below)
+  static const bool with_bound = getenv("FFB200_NO_SCORE_BOUND") == nullptr;
+  if (with_bound && ap.k_prescaled) {
+    ap.bound_wq[0] = static_cast<const bf16*>(wq0); ap.bound_wk[0] = static_cast<const bf16*>(wk0);
+    ap.bound_wq[1] = static_cast<const bf16*>(wq1); ap.bound_wk[1] = static_cast<const bf16*>(wk1);
+  }
   p->fwd_ops.push_back([ap](cudaStream_t st) { ++g_launch_count; return launch_attention(ap, st); });
   return 0;
 }
@@ -443,7 +452,7 @@ int ffb200_plan_create(ffb200_engine* e, int batch, int cfg, int lat_h, int lat_
                    EPI_QKV_RMSNORM, nullptr, 0, L.norm_added_q, L.norm_added_k, D, 1e-6f, nullptr};
     sc.k_scale = engine_prescale() ? 0.125f * 1.4426950408889634f : 0.f;
     if ((r = add_gemm(p, sc))) break;
-    if ((r = add_attn(p, p->qkv, S, p->att))) break;
+    if ((r = add_attn(p, p->qkv, S, p->att, L.norm_q, L.norm_k, L.norm_added_q, L.norm_added_k))) break;
     // to_out + gate_msa residual (image rows of the joint attention output)
     GemmSpec so = {p->att, Bp, Ni, static_cast<long>(S) * D, D, D, L.out_w, D, L.out_b, p->h_img, static_cast<long>(Ni) * D, 0, D,
                    EPI_GATE_RESIDUAL, m1 + 2 * D, R, nullptr, nullptr, 0, 0.f, nullptr};
@@ -458,7 +467,7 @@ int ffb200_plan_create(ffb200_engine* e, int batch, int cfg, int lat_h, int lat_
                      EPI_QKV_RMSNORM, nullptr, 0, L.norm_q2, L.norm_k2, D, 1e-6f, nullptr};
       s2.k_scale = engine_prescale() ? 0.125f * 1.4426950408889634f : 0.f;
       if ((r = add_gemm(p, s2))) break;
-      if ((r = add_attn(p, p->qkv2, Ni, p->att2))) break;
+      if ((r = add_attn(p, p->qkv2, Ni, p->att2, L.norm_q2, L.norm_k2))) break;
       GemmSpec so2 = {p->att2, Bp, Ni, 0, D, D, L.out2_w, D, L.out2_b, p->h_img, static_cast<long>(Ni) * D, 0, D,
                       EPI_GATE_RESIDUAL, m1 + 8 * D, R, nullptr, nullptr, 0, 0.f, nullptr};
       if ((r = add_gemm(p, so2))) break;
@@ -797,6 +806,20 @@ int ffb200_attention_scaled(const void* qkv, int batch, int seq_len, int num_hea
   ap.k_prescaled = k_prescaled ? 1 : 0;
   g_launch_count = 1;
   FFB_CUDA(head_dim == 64 ? launch_attention(ap, static_cast<cudaStream_t>(stream)) : launch_attention_d128(ap, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int ffb200_attention_normed(const void* qkv, int batch, int seq_len, int num_heads, void* out, const void* wq0, const void* wk0,
+                            const void* wq1, const void* wk1, void* stream) {
+  FFB_CHECK(qkv && out && wq0 && wk0 && batch > 0 && seq_len > 0 && num_heads > 0, "bad argument");
+  AttnParams ap;
+  int r = build_attn(qkv, batch, seq_len, num_heads, out, &ap);
+  if (r) return r;
+  ap.k_prescaled = 1;
+  ap.bound_wq[0] = static_cast<const bf16*>(wq0); ap.bound_wk[0] = static_cast<const bf16*>(wk0);
+  ap.bound_wq[1] = static_cast<const bf16*>(wq1); ap.bound_wk[1] = static_cast<const bf16*>(wk1);
+  g_launch_count = 1;
+  FFB_CUDA(launch_attention(ap, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -71,6 +71,12 @@ struct AttnParams {
   // cross-attention (head_dim 128 kernel, launch_attention_d128_cross only): tmQKV addresses the query tensor [B, seq_len, >= D]
   // (head h at column q_col + 128 h), tmKV the key / value tensor [B, kv_len, ...] (columns k_col + 128 h / v_col + 128 h)
   int kv_len, q_col, k_col, v_col;
+  // optional (head_dim 64 kernel, pre-scaled keys): the per-head RMSNorm weights [64] that PRODUCED q and k (up to two sets: image and text
+  // stream of a joint attention; unused slots null).  RMS-normed heads have ||q|| <= 8 max|w_q| and ||k'|| <= 8 max|w_k| scale_log2, so
+  // |exponent| <= 64 max|w_q| max|w_k| scale_log2 (Cauchy-Schwarz): when that proves |exponent| <= 126 for the whole launch, the kernel
+  // skips the per-tile range guard of its polynomial exp2 slots.  All null: no proof, the guard stays (op-level entry, hooks).
+  const bf16* bound_wq[2];
+  const bf16* bound_wk[2];
 };
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);        // head_dim 64  (SD3.x)
 cudaError_t launch_attention_d128(const AttnParams& p, cudaStream_t stream);   // head_dim 128 (FLUX.1)

@@ -136,9 +136,10 @@ struct SoftmaxTile {
 //   sc    : softmax_scale * log2(e); ignored when `pre`.
 //   pre   : warp-uniform; the scores already are base-2 exponents (keys pre-scaled by the producer).
 //   first : warp-uniform; first KV tile of the row block.
+//   bounded : warp-uniform; every exponent of this launch is proven to lie within +-126 as long as the reference is 0 (fast path).
 template <class Poly, class PolyG = Poly>
 __device__ __forceinline__ void softmax_begin(uint32_t (&s0)[32], uint32_t (&s1)[32], int kv_valid, float sc, bool pre, bool first,
-                                              SoftmaxState& st, SoftmaxTile& t) {
+                                              SoftmaxState& st, SoftmaxTile& t, bool bounded = false) {
   if (kv_valid < 64) {
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
@@ -174,7 +175,8 @@ __device__ __forceinline__ void softmax_begin(uint32_t (&s0)[32], uint32_t (&s1)
   // and only a warp that saw one of them sorts out which (the common tile pays a single VOTE + branch for its bookkeeping)
   const bool grow = !first && !(st.l_run <= ATT_SHIFT_AT);       // also true for inf / NaN
   bool over = false;
-  if (Poly::num > 0 || PolyG::num > 0) {      // the general path (exponent = s * sc - ref: one more FFMA2 per pair) has its own slot policy
+  // `bounded` (warp-uniform): the launch PROVED |exponent| <= 126 for pre-scaled keys with reference 0 (AttnParams::bound_w*): no range guard
+  if ((Poly::num > 0 || PolyG::num > 0) && !(bounded && t.fast)) {   // general path: its own slot policy (one more FFMA2 per pair there)
     const float amax = t.fast ? softmax_poly_absmax<true, Poly>(s0, s1, sce, 0.f) : softmax_poly_absmax<false, PolyG>(s0, s1, sce, st.m_run);
     over = !(amax <= 126.0f);
   }

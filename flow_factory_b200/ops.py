@@ -62,6 +62,18 @@ def attention(qkv: torch.Tensor, num_heads: int, out: Optional[torch.Tensor] = N
     return out
 
 
+def attention_normed(qkv: torch.Tensor, num_heads: int, wq: torch.Tensor, wk: torch.Tensor, wq_text: Optional[torch.Tensor] = None,
+                     wk_text: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """head_dim 64 attention over pre-scaled keys whose q / k heads came out of a per-head RMSNorm with the bf16 weights `wq` / `wk` [64]
+    (and `wq_text` / `wk_text` for the text rows of a joint attention): the call the SD3.5 engine makes (ffb200_attention_normed)."""
+    B, S, _ = qkv.shape
+    if out is None:
+        out = torch.empty((B, S, 64 * num_heads), dtype=torch.bfloat16, device=qkv.device)
+    _lib.check(_lib.lib().ffb200_attention_normed(_ptr(qkv), B, S, num_heads, _ptr(out), _ptr(wq), _ptr(wk), _ptr(wq_text), _ptr(wk_text),
+                                                  _stream(qkv)), "ffb200_attention_normed")
+    return out
+
+
 def ln_modulate(x, shift1, scale1, out1, shift2=None, scale2=None, out2=None, *, mod_batch_stride, eps=1e-6) -> None:
     B, R, D = x.shape
     _lib.check(_lib.lib().ffb200_ln_modulate(_ptr(x), B, R, D, eps, _ptr(shift1), _ptr(scale1), _ptr(out1), _ptr(shift2),

@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define FFB200_ABI_VERSION 2   /* 2: + ffb200_attention_scaled, ffb200_plan_set_latent_dtype, ffb200_sde_step_ex (additions only) */
+#define FFB200_ABI_VERSION 3   /* 2: + ffb200_attention_scaled, ffb200_plan_set_latent_dtype, ffb200_sde_step_ex; 3: + ffb200_attention_normed (additions only) */
 
 /* ---------------------------------------------------------------- errors */
 const char* ffb200_last_error(void);
@@ -182,6 +182,14 @@ int ffb200_attention_ex(const void* qkv, int batch, int seq_len, int num_heads, 
  * (what the engines' QKV projection epilogue does), so the kernel takes the q.k scores as base-2 exponents and skips the per-score multiply. */
 int ffb200_attention_scaled(const void* qkv, int batch, int seq_len, int num_heads, int head_dim, void* out, int out_row_stride,
                             float softmax_scale, int k_prescaled, void* stream);
+/* head_dim 64, keys pre-scaled, q and k produced by a per-head RMSNorm (DF/models/attention_processor.py:1456-1459, 1470-1473: `norm_q`,
+ * `norm_k`, `norm_added_q`, `norm_added_k`) whose weights [64] the caller names: wq0 / wk0 (image stream) and optionally wq1 / wk1 (text
+ * stream of a joint attention; may be null).  RMS-normed heads bound every score (Cauchy-Schwarz: |q.k'| <= 64 max|wq| max|wk| scale*log2e),
+ * which lets the kernel skip the per-tile range check of its polynomial exp2 when that bound is <= 2^126's exponent; results are identical to
+ * ffb200_attention_scaled(k_prescaled = 1).  This is the call the SD3.5 engine makes internally; passing weights that did NOT produce q / k
+ * voids the bound (then use ffb200_attention_scaled). */
+int ffb200_attention_normed(const void* qkv, int batch, int seq_len, int num_heads, void* out, const void* wq0, const void* wk0,
+                            const void* wq1, const void* wk1, void* stream);
 /* LayerNorm(no affine) * (1 + scale) + shift  (DF/models/normalization.py:120-126). vectors: [num_batch, *] with stride. */
 int ffb200_ln_modulate(const void* x, int num_batch, int rows_per_batch, int D, float eps, const void* shift1,
                        const void* scale1, void* out1, const void* shift2, const void* scale2, void* out2,

@@ -159,3 +159,40 @@ def test_attention_large_first_tile_takes_a_nonzero_reference():
     ref = torch.nn.functional.scaled_dot_product_attention(qb, kb, vb).transpose(1, 2).reshape(B, S, H * d)
     assert torch.isfinite(out.float()).all()
     assert float((out.float() - ref).norm() / ref.norm()) <= 4e-3
+
+
+@pytest.mark.parametrize("B,S,H", [(1, 333, 3), (2, 589, 2), (1, 4429, 2)])
+@pytest.mark.parametrize("w_scale", [1.0, 2.5, 4.0])
+def test_attention_normed_range_proof_is_bit_identical(B, S, H, w_scale):
+    """ffb200_attention_normed: q / k heads produced by a per-head RMSNorm with weights wq / wk (attention_processor.py:1456-1473).  The
+    kernel proves |q.k'| <= 64 max|wq| max|wk| scale*log2(e) and, when that is within the polynomial exp2's range, skips the per-tile
+    range check: the output must equal the checked kernel's bit for bit - with weights small enough for the proof (w_scale 1, 2.5:
+    bounds 12 .. 73) and with weights too large for it (w_scale 4: 188 > 120, the check stays)."""
+    from flow_factory_b200 import ops
+    d = 64
+    g = torch.Generator(device="cuda").manual_seed(11 * S + H)
+    wq = (w_scale * (1.0 + 0.1 * torch.randn(d, device="cuda", generator=g)).clamp(0.5, 1.0)).bfloat16()     # max|w| <= w_scale
+    wk = (w_scale * (1.0 + 0.1 * torch.randn(d, device="cuda", generator=g)).clamp(0.5, 1.0)).bfloat16()
+    wqt, wkt = (0.9 * wq.float()).bfloat16(), (0.9 * wk.float()).bfloat16()
+
+    def rms(x, w):                                             # the QKV epilogue: bf16(bf16(x * rsqrt(mean x^2 + eps)) * w)
+        xf = x.float().reshape(B, -1, H, d)
+        n = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).bfloat16().float()
+        return (n * w.float()).reshape(B, -1, H * d)
+    n_text = S // 5
+    x = torch.randn(B, S, 3 * H * d, device="cuda", generator=g)
+    q = torch.cat([rms(x[:, n_text:, : H * d], wq), rms(x[:, :n_text, : H * d], wqt)], dim=1).bfloat16()
+    k = torch.cat([rms(x[:, n_text:, H * d: 2 * H * d], wk), rms(x[:, :n_text, H * d: 2 * H * d], wkt)], dim=1)
+    kp = (k * (d ** -0.5 * LOG2E)).bfloat16()                  # keys pre-scaled, ONE rounding
+    qkv = torch.cat([q, kp, x[..., 2 * H * d:].bfloat16()], dim=-1).contiguous()
+    checked = ops.attention(qkv, H, head_dim=d, k_prescaled=True)
+    proven = ops.attention_normed(qkv, H, wq, wk, wqt, wkt)
+    torch.cuda.synchronize()
+    assert torch.isfinite(proven.float()).all()
+    assert torch.equal(checked, proven)
+    sp = lambda t: t.float().reshape(B, S, H, d).transpose(1, 2)
+    ref = torch.nn.functional.scaled_dot_product_attention(sp(q), sp(kp), sp(qkv[..., 2 * H * d:]), scale=1.0 / LOG2E).transpose(1, 2).reshape(B, S, H * d)
+    assert float((proven.float() - ref).abs().max()) <= 2e-2 * max(1.0, float(ref.abs().max()))
+    # the bound itself: no score of this input exceeds it
+    bound = 64 * 1.016 * float(wq.float().abs().max()) * float(wk.float().abs().max()) * d ** -0.5 * LOG2E
+    assert float((sp(q) @ sp(kp).transpose(-1, -2)).abs().max()) <= bound

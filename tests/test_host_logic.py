@@ -116,7 +116,7 @@ def test_filter_kwargs_is_the_abi():
 
 def test_c_abi_library_loads_and_exports_every_declared_symbol():
     L = _lib.lib()
-    assert L.ffb200_abi_version() == 2
+    assert L.ffb200_abi_version() == 3
     with open(os.path.join(ROOT, "include", "ffb200.h")) as f:
         hdr = f.read()
     declared = set(re.findall(r"\b(ffb200_[a-z_0-9]+)\s*\(", hdr))

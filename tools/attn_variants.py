@@ -48,6 +48,41 @@ def trend_error(d):
     return float((out.float() - ref).norm() / ref.norm())
 
 
+def timed_normed(B, S, H):
+    """head_dim 64 through ffb200_attention_normed (unit RMSNorm weights: the range proof holds and the per-tile guard is skipped)."""
+    torch.manual_seed(0)
+    d = 64
+    x = torch.randn(B, S, 3, H, d, device="cuda")
+    x[:, :, :2] = x[:, :, :2] * torch.rsqrt(x[:, :, :2].pow(2).mean(-1, keepdim=True) + 1e-6)       # RMS-normed q and k heads
+    x[:, :, 1] *= d ** -0.5 * 1.4426950408889634
+    qkv = x.reshape(B, S, 3 * H * d).bfloat16()
+    w = torch.ones(d, device="cuda").bfloat16()
+    out = torch.empty(B, S, d * H, device="cuda", dtype=torch.bfloat16)
+    ts = []
+    for i in range(9):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); ops.attention_normed(qkv, H, w, w, out=out); b.record(); torch.cuda.synchronize()
+        if i >= 2:
+            ts.append(a.elapsed_time(b))
+    ts.sort()
+    ms = ts[len(ts) // 2]
+    t_chk = []
+    for i in range(9):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); ops.attention(qkv, H, out, head_dim=d, k_prescaled=True); b.record(); torch.cuda.synchronize()
+        if i >= 2:
+            t_chk.append(a.elapsed_time(b))
+    t_chk.sort()
+    fl = 4.0 * B * H * S * S * d
+    return fl / (ms * 1e-3) / 1e12, fl / (t_chk[len(t_chk) // 2] * 1e-3) / 1e12
+
+
 r64, r128 = timed(8, 4429, 24, 64), timed(2, 4608, 24, 128)
+try:
+    normed_tf, checked_tf = timed_normed(8, 4429, 24)
+except Exception as exc:      # older variant libraries do not export the entry
+    normed_tf, checked_tf = None, None
 print(json.dumps({"lib": os.path.basename(os.environ.get("FFB200_LIB", "libffb200.so")), "prescaled_keys": PRE, "d64_kernel": os.environ.get("FFB200_ATT_VARIANT", "row3"), "ms": r64[0], "tflops": r64[1],
-                  "d128_ms": r128[0], "d128_tflops": r128[1], "trend_rel_err_d64": trend_error(64), "trend_rel_err_d128": trend_error(128)}))
+                  "d128_ms": r128[0], "d128_tflops": r128[1], "d64_normed_tflops": normed_tf, "d64_same_input_checked_tflops": checked_tf, "trend_rel_err_d64": trend_error(64), "trend_rel_err_d128": trend_error(128)}))
