@@ -185,8 +185,8 @@ int ffb200_attention_scaled(const void* qkv, int batch, int seq_len, int num_hea
 /* head_dim 64, keys pre-scaled, q and k produced by a per-head RMSNorm (DF/models/attention_processor.py:1456-1459, 1470-1473: `norm_q`,
  * `norm_k`, `norm_added_q`, `norm_added_k`) whose weights [64] the caller names: wq0 / wk0 (image stream) and optionally wq1 / wk1 (text
  * stream of a joint attention; may be null).  RMS-normed heads bound every score (Cauchy-Schwarz: |q.k'| <= 64 max|wq| max|wk| scale*log2e),
- * which lets the kernel skip the per-tile range check of its polynomial exp2 when that bound is <= 2^126's exponent; results are identical to
- * ffb200_attention_scaled(k_prescaled = 1).  This is the call the SD3.5 engine makes internally; passing weights that did NOT produce q / k
+ * which lets the kernel skip the per-tile range check of its polynomial exp2 (valid for |exponent| <= 126) when that bound stays below 120;
+ * results are bit-identical to ffb200_attention_scaled(k_prescaled = 1).  This is the call the SD3.5 engine makes internally; passing weights that did NOT produce q / k
  * voids the bound (then use ffb200_attention_scaled). */
 int ffb200_attention_normed(const void* qkv, int batch, int seq_len, int num_heads, void* out, const void* wq0, const void* wk0,
                             const void* wq1, const void* wk1, void* stream);
