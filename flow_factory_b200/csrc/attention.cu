@@ -23,8 +23,10 @@
 //     the running sum passes 2^64), which for RMS-normed q / k never happens.
 // The softmax itself (softmax.cuh) is the cost of this kernel: at d = 64 the tensor core needs 8 cycles per SM for 256 scores, the MUFU
 // unit alone 16.  What is left per score on the product path (keys pre-scaled by softmax_scale * log2(e) in the QKV GEMM epilogue,
-// reference 0): one MUFU.EX2 or, for 2 of every 8 pairs, a polynomial exp2 on the FMA pipe; half a packed add for the row sum; half a
-// bf16 pack.  Measured history, rejected alternatives and the ncu picture: profiles/r02_attention_experiments.md.
+// reference 0): one MUFU.EX2 or, for 3 of every 8 pairs, a polynomial exp2 on the FMA pipe; half a packed add for the row sum; half a
+// bf16 pack - and a steady-state tile whose skeleton is as small as it gets: compile-time first / last tiles, one common-path body, elected-lane
+// arrives, warp-uniform addresses, and no range check of the polynomial slots when the RMSNorm weights prove the range (AttnParams::bound_wq).
+// Measured history (778 -> 1018 TFLOP/s in round 2), rejected alternatives and the ncu picture: profiles/r02_attention_experiments.md.
 #include <type_traits>
 #include "common.cuh"
 #include "kernels.h"

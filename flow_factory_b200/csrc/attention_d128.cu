@@ -5,7 +5,7 @@
 // token-major [B, S, 3D] buffer (RMSNorm and RoPE already applied to q and k by the QKV GEMM epilogue) with 3-D TMA boxes.
 //
 // Same design as attention.cu (see there): thread = query row = TMEM lane; P in its own TMEM columns; Q K^T of tile j+1 issued as
-// soon as the softmax warps hold S(j) in registers; P V accumulates O in TMEM with a lazily adopted running max.  Differences:
+// soon as the softmax warps hold S(j) in registers; P V accumulates O in TMEM; no per-tile row maximum (softmax.cuh).  Differences:
 //   * two 128-row sub-tiles per CTA (TMEM: per sub-tile S 64 + P 32 + O 128 columns = 448 of 512), 12 warps:
 //     warps 0-3 / 4-7 softmax of sub-tile 0 / 1, warp 8 TMA, warps 9 / 10 MMA issuers;
 //   * Q / K / V tiles are two 64-column SWIZZLE_128B panels each (a TMA box cannot be wider than the 128-byte swizzle span):
