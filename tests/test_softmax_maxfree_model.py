@@ -1,6 +1,9 @@
-"""CPU model of the max-free online softmax experiment (flow_factory_b200/csrc/softmax.cuh, -DFFB_ATT_MAXFREE): only the first KV tile
-takes its exact row maximum, later tiles keep the reference and move it by a power of two when the running sum passes 2^24.  The model
-restates the kernel's state update in fp32 numpy and checks it against an exact softmax on score rows that force several shifts."""
+"""CPU models of the attention softmax (flow_factory_b200/csrc/softmax.cuh, attention.cu), fp32 numpy / torch in the device code's operation order:
+  * the max-free online softmax: only the first KV tile takes its exact row maximum, later tiles keep the reference and move it by an exact
+    power of two when the running sum passes a threshold (the model shifts at 2^24 so that a short row exercises the path; the kernels at
+    2^64) - checked against an exact softmax on score rows that force several shifts;
+  * the polynomial exp2 of the FMA-pipe slots: accuracy inside its valid range, garbage outside it;
+  * the range proof that lets the head_dim-64 kernel drop the per-tile range check: RMS-normed heads bound every score."""
 import numpy as np
 import pytest
 
