@@ -13,7 +13,17 @@ if pre:
     qkv[..., d * H: 2 * d * H] *= d ** -0.5 * 1.4426950408889634
 qkv = qkv.bfloat16()
 out = torch.empty(B, S, d * H, device="cuda", dtype=torch.bfloat16)
+normed = os.environ.get("ATT_NORMED", "0") == "1" and d == 64      # the engine's launch: RMS-normed heads + the range proof (ffb200_attention_normed)
+if normed:
+    x = torch.randn(B, S, 3, H, d, device="cuda")
+    x[:, :, :2] = x[:, :, :2] * torch.rsqrt(x[:, :, :2].pow(2).mean(-1, keepdim=True) + 1e-6)
+    x[:, :, 1] *= d ** -0.5 * 1.4426950408889634
+    qkv = x.reshape(B, S, 3 * d * H).bfloat16()
+    w = torch.ones(d, device="cuda").bfloat16()
 for _ in range(4):
-    ops.attention(qkv, H, out, head_dim=d, k_prescaled=pre)
+    if normed:
+        ops.attention_normed(qkv, H, w, w, out=out)
+    else:
+        ops.attention(qkv, H, out, head_dim=d, k_prescaled=pre)
 torch.cuda.synchronize()
 print("done", d, pre, float(out.float().abs().mean()))
