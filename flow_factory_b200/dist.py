@@ -78,12 +78,14 @@ def gather_sharded_state_dict(state_dict, group=None, dtype: Optional[torch.dtyp
     the tail padded / empty - SURVEY.md section 8(e), BASELINE config 5).  The rollout engine wants replicated weights, and the path
     wants ONE collective per rollout, not one per block: all local shards are packed into a single flat buffer, gathered with one
     all_gather_into_tensor, and unpacked into full tensors (cast to `dtype` BEFORE the gather, so the payload is the bf16 model:
-    40 GB for Qwen-Image 20 B = ~50 ms over NVLink 5).  Plain tensors in the dict are passed through (already replicated)."""
+    40.9 GB for Qwen-Image 20 B; measured at N = 2 over NCCL with the first version of the packing - per-parameter staging buffers +
+    torch.cat -: 207 ms per rollout, profiles/r02_bench_qwen_n2.json).  Plain tensors in the dict are passed through (already replicated)."""
     if not (dist.is_available() and dist.is_initialized()):
         raise RuntimeError("gather_sharded_state_dict needs an initialised process group")
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    plan, parts = [], []
+    plan, locals_ = [], []
     out = {}
+    total, dev, dt = 0, None, None
     for name, t in state_dict.items():
         local, full = _local_shard(t)
         if local is None:
@@ -94,13 +96,25 @@ def gather_sharded_state_dict(state_dict, group=None, dtype: Optional[torch.dtyp
         rest = 1
         for d in full[1:]:
             rest *= d
-        buf = torch.zeros(chunk * rest, dtype=dtype or local.dtype, device=local.device)
-        buf[: local.numel()] = local.reshape(-1).to(buf.dtype)     # ranks past the tail hold fewer (or zero) rows
         plan.append((name, full, chunk, rest))
-        parts.append(buf)
-    if not parts:
+        locals_.append(local)
+        total += chunk * rest
+        if dtype is None and dt is not None and local.dtype != dt:
+            raise NotImplementedError("gather_sharded_state_dict(dtype=None) needs one parameter dtype; pass the dtype the engine wants")
+        dev, dt = local.device, (dtype or local.dtype)
+    if not plan:
         return out
-    flat = torch.cat(parts)
+    # every local shard goes straight into its slice of ONE flat send buffer (cast on the way; no per-parameter staging buffers, no cat):
+    # one copy kernel per parameter, and the tail padding is zeroed only where a shard is short (ranks past the tail hold fewer or no rows)
+    flat = torch.empty(total, dtype=dt, device=dev)
+    off = 0
+    for (name, full, chunk, rest), local in zip(plan, locals_):
+        sz, n = chunk * rest, local.numel()
+        if n:
+            flat[off: off + n].copy_(local.reshape(-1))
+        if n < sz:
+            flat[off + n: off + sz].zero_()
+        off += sz
     gathered = torch.empty(world * flat.numel(), dtype=flat.dtype, device=flat.device)
     dist.all_gather_into_tensor(gathered, flat, group=group)       # the one collective
     gathered = gathered.view(world, flat.numel())
